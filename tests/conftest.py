@@ -1,0 +1,55 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "offshore-sph_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+STEP_CASES = ['dambreak20_wendland', 'dambreak20_cubic', 'tank30_cubic_dynh',
+              'tank24_wendland_coupled', 'tank16_gaussian', 'block20_cubic_nobnd']
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """Load tests/golden/<name>.npz -> (dict of arrays, meta dict, particle array)."""
+    from oracle.oracle import particle_dtype
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    meta = json.loads(bytes(g['meta']).decode())
+    pA = None
+    if 'aos' in g:
+        pA = np.frombuffer(g['aos'].tobytes(), dtype=particle_dtype).copy()
+    return g, meta, pA
+
+
+def field_err(got, ref):
+    """Norm-wise relative error: |got-ref| / max(|ref_i|, |ref|_inf)  (hard part 2)."""
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    scale = np.maximum(np.abs(ref), np.max(np.abs(ref)) if ref.size else 0.0)
+    scale = np.where(scale > 0, scale, 1.0)
+    return float(np.max(np.abs(got - ref) / scale)) if ref.size else 0.0
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden

@@ -1,0 +1,203 @@
+"""Freeze golden vectors from the UNMODIFIED reference (numba path) for the WCSPH step.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  The reference has no test that pins the composed step,
+the neighbour order or the cell assignment, so these files are
+the pin: the oracle (oracle/wcsph_oracle.c) is checked against them on CPU, and the
+CUDA path is checked against both on the GPU box (where the reference is absent).
+
+Each case stores
+  aos        the input particle array as raw bytes (n x 154), state right after
+             Solver.setup()-style initialisation + deterministic jitter
+  meta       json: constants, kernel, integrator flags, versions
+  grid       xmin xmax ymin ymax cell_size ncx ncy   (NNLinkedList after update())
+  cell_ids   flat reference cell of every active particle (from heads/nexts)
+  nbr_off / nbr_idx   CSR neighbour lists of the fluid rows, reference order
+  loop_*     p c drho ax ay xsphx xsphy after one `_loop`
+  step_*     x y vx vy rho drho ax ay after each of `nsteps` whole steps driven in
+             the order of src/Solver.py:366-399, and the (dt, dt_c, dt_f) series
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "offshore-sph_b200"))
+
+from oracle import refshim  # noqa: E402
+from osph_b200 import workloads as W  # noqa: E402
+
+ref = refshim.load()
+FLUID = 0
+
+
+def ref_kernel(name):
+    return {'cubic': ref.CubicSpline, 'wendland': ref.Wendland, 'gaussian': ref.Gaussian}[name]()
+
+
+def cells_from_lists(nn, n):
+    cid = np.full(n, -1, dtype=np.int64)
+    for c in range(nn.n_cells):
+        j = nn.heads[c]
+        while j != -1:
+            cid[j] = c
+            j = nn.nexts[j]
+    return cid
+
+
+def neighbours(nn, pA):
+    off = np.zeros(len(pA) + 1, dtype=np.int64)
+    idx = []
+    for i in range(len(pA)):
+        off[i] = len(idx)
+        if pA[i]['label'] == FLUID:
+            _, _, _, nb = nn.near(i, pA)
+            idx.extend(int(v) for v in nb)
+    off[len(pA)] = len(idx)
+    return off, np.asarray(idx, dtype=np.int32)
+
+
+def loop_gaussian(pA, method, nn):
+    """`_loop` cannot take the Gaussian ufuncs (numba typing); compose it from the reference's pieces."""
+    G = ref.Gaussian
+    pA['p'] = method.compute_pressure(pA)
+    pA['c'] = method.compute_speed_of_sound(pA)
+    for i in range(len(pA)):
+        if pA[i]['label'] != FLUID:
+            continue
+        h_i, q_i, dist, near = nn.near(i, pA)
+        if len(near) == 0:
+            continue
+        comp = ref._assignProps(i, pA, near, h_i, q_i, dist)
+        comp['w'] = G.evaluate(comp['r'], comp['h'])
+        comp['dw_x'] = G.gradient(comp['x'], comp['r'], comp['h'])
+        comp['dw_y'] = G.gradient(comp['y'], comp['r'], comp['h'])
+        pA[i]['drho'] = method.compute_density_change(pA[i], comp)
+        a = method.compute_acceleration(pA[i], comp)
+        b = ref.BoundaryForce(method.r0, method.D, method.p1, method.p2, pA[i], comp)
+        pA[i]['ax'] = a[0] + b[0]
+        pA[i]['ay'] = a[1] + b[1]
+        v = method.compute_velocity(pA[i], comp)
+        pA[i]['vx'], pA[i]['vy'], pA[i]['xsphx'], pA[i]['xsphy'] = v
+    return pA
+
+
+def run_loop(pA, kernel, method, nn):
+    if kernel == 'gaussian':
+        return loop_gaussian(pA, method, nn)
+    k = ref_kernel(kernel)
+    return ref._loop(pA, k.evaluate, k.gradient, method, nn)
+
+
+def make_case(name, case, kernel, useXSPH, damping, nsteps, strict=False, scale=2.0):
+    pA0 = case['pA'].copy()
+    c = case['consts']
+    n = len(pA0)
+    fixed_h = case['h']
+    method = ref.WCSPH(c['height'], c['r0'], c['rho0'], useXSPH, c['Pb'], False)
+    assert method.co == c['co'] and method.B == c['B'] and method.D == c['D']
+    integ = ref.PEC(useXSPH, strict)
+    out = dict(aos=np.frombuffer(pA0.tobytes(), dtype=np.uint8).reshape(n, 154).copy())
+
+    # --- neighbour structure + one force evaluation on the input state ------------------------
+    pA = pA0.copy().view(ref.particle_dtype)
+    nn = ref.NNLinkedList(scale)
+    nn.update(pA)
+    out['grid'] = np.array([nn.xmin, nn.xmax, nn.ymin, nn.ymax, nn.cell_size,
+                            nn.ncells_per_dim[0], nn.ncells_per_dim[1]], dtype=np.float64)
+    out['cell_ids'] = cells_from_lists(nn, n)
+    out['nbr_off'], out['nbr_idx'] = neighbours(nn, pA)
+    pA = run_loop(pA, kernel, method, nn)
+    for f in ('p', 'c', 'drho', 'ax', 'ay', 'xsphx', 'xsphy'):
+        out['loop_' + f] = pA[f].copy()
+
+    # --- whole steps, same order as Solver.run() ---------------------------------------------
+    pA = pA0.copy().view(ref.particle_dtype)
+    fi = pA['label'] == FLUID
+    nf = int(fi.sum())
+    dts = []
+    cols = ('x', 'y', 'vx', 'vy', 'rho', 'drho', 'ax', 'ay', 'xsphx', 'xsphy', 'p', 'h')
+    hist = {f: [] for f in cols}
+    for _ in range(nsteps):
+        m, dc, df = ref.TimeStep().compute(nf, pA[fi], 0.25, 0.25)
+        dts.append((m, dc, df))
+        pA[fi] = integ.predict(m, pA[fi], damping)
+        nn.update(pA)
+        if fixed_h is None:
+            pA['h'][fi] = ref.computeH(1.3, nf, pA[fi]['m'], pA[fi]['rho'])
+        else:
+            pA['h'][fi] = fixed_h
+        pA = run_loop(pA, kernel, method, nn)
+        pA[fi] = integ.correct(m, pA[fi], damping)
+        for f in cols:
+            hist[f].append(pA[f].copy())
+    out['dts'] = np.asarray(dts, dtype=np.float64).reshape(nsteps, 3)
+    for f in cols:
+        out['step_' + f] = np.stack(hist[f]) if nsteps else np.zeros((0, n))
+    import numba
+    out['meta'] = np.frombuffer(json.dumps(dict(
+        name=name, kernel=kernel, useXSPH=bool(useXSPH), strict=bool(strict), damping=damping,
+        nsteps=nsteps, fixed_h=fixed_h, scale=scale, consts=c, n=n, n_fluid=nf,
+        numba=numba.__version__, numpy=np.__version__)).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print('%-28s n=%5d fluid=%5d pairs=%7d grid=%dx%d cs=%g  -> %.0f kB' % (
+        name, n, nf, len(out['nbr_idx']), out['grid'][5], out['grid'][6], out['grid'][4],
+        os.path.getsize(path) / 1e3))
+
+
+def solver_run_case(name, N, kernel, duration, maxSettle):
+    """The reference's own Solver.setup()/run() on the dam break, end state only."""
+    r0, pA = W.dam_break(N)
+    pA = pA.view(ref.particle_dtype)
+    k = ref_kernel(kernel)
+    method = ref.WCSPH(height=25.0, r0=r0, rho0=1000.0, useXSPH=True, Pb=0, useSummationDensity=False)
+    integ = ref.PEC(useXSPH=True, strict=False)
+    S = ref.Solver
+    S.particleArray = None; S.data = []; S.export = {}; S.dt_a = []; S.dt_c = []; S.dt_f = []
+    s = S(method, integ, k, duration, incrementalWriteout=False, h=1.6 * r0, maxSettle=maxSettle)
+    s.addParticles(pA.copy())
+    s.setup()
+    s.run()
+    out = dict(
+        final=np.frombuffer(s.particleArray.tobytes(), dtype=np.uint8).reshape(len(pA), 154).copy(),
+        dt_a=np.asarray(s.dt_a), dt_c=np.asarray(s.dt_c), dt_f=np.asarray(s.dt_f),
+        t_step=np.int64(s.t_step), t=np.float64(s.t), settleTime=np.float64(s.settleTime),
+        export_x_last=np.asarray(s.export['x'][-1]), n_export=np.int64(len(s.export['x'])),
+        meta=np.frombuffer(json.dumps(dict(name=name, N=N, kernel=kernel, duration=duration,
+                                           maxSettle=maxSettle, hfac=1.6)).encode(), dtype=np.uint8))
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print('%-28s steps=%d t=%.5f settle=%.5f -> %.0f kB' % (name, s.t_step, s.t, s.settleTime,
+                                                            os.path.getsize(path) / 1e3))
+
+
+def main():
+    # regime A: 3h > reference cell (1.0): the 3x3 coarse walk truncates the neighbourhood
+    make_case('dambreak20_wendland', W.dam_break_case(20), 'wendland', True, 0.05, 3)
+    make_case('dambreak20_cubic', W.dam_break_case(20, seed=1), 'cubic', True, 0.0, 3)
+    # regime B: 3h < cell; dynamic h (Containment-like: h=None, XSPH off, cubic)
+    make_case('tank30_cubic_dynh', W.tank_case(30, h=None, useXSPH=False), 'cubic', False, 0.05, 3)
+    # coupled (ice-like) row with mass, XSPH on, Wendland, strict density clamp
+    make_case('tank24_wendland_coupled', W.tank_case(24, h=1.6 / 24, useXSPH=True, coupled_row=True, seed=2),
+              'wendland', True, 0.0, 2, strict=True)
+    # Gaussian: composed oracle, one force evaluation + one step
+    make_case('tank16_gaussian', W.tank_case(16, h=1.3 / 16, useXSPH=True, seed=3), 'gaussian', True, 0.05, 1)
+    # no boundary particles: every h > 0, so the reference cell is 2*hmin instead of the 1.0 fallback
+    blk = W.tank_case(20, h=1.5 / 20, useXSPH=True, seed=4)
+    keep = blk['pA']['label'] == FLUID
+    blk['pA'] = blk['pA'][keep]
+    make_case('block20_cubic_nobnd', blk, 'cubic', True, 0.0, 2)
+    # the reference Solver end to end (settle -> gate removal -> time stepping)
+    solver_run_case('solver_dambreak12_wendland', 12, 'wendland', 0.03, 6)
+
+
+if __name__ == '__main__':
+    main()
