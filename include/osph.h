@@ -1,0 +1,198 @@
+/*
+ * osph.h -- C ABI of libosph_b200.so: the B200-native (sm_100a) WCSPH time step that
+ * replaces the numba hot path of KoningJasper/Offshore-SPH.
+ *
+ * The reference has no FFI: its "plugin API" is a set of duck-typed Python call sites inside
+ * Solver.run() (reference src/Solver.py:366-399).  Every entry point below replaces one of those
+ * call sites; the citation after "replaces:" is file:line in the reference tree.  Host Python
+ * binds this header with ctypes (offshore-sph_b200/osph_b200/capi.py); INTEGRATION.md shows the
+ * few lines a maintainer of the reference would add to src/Solver.py.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative OSPH_E_* code on failure; osph_last_error()
+ *     gives the text.  There is no CPU fallback: without a CUDA device osph_create() fails.
+ *   - the caller owns host buffers, the library owns device buffers.  Host arrays of particles
+ *     are the reference's packed `particle_dtype` records (src/Common.py:26-57): 1 byte deleted,
+ *     1 byte label, 19 doubles at byte offsets 2 + 8*k, record stride 154 unless stated.
+ *   - "active" particles are the rows with deleted == 0, in row order; index spaces that the
+ *     reference exposes (neighbour indices, cell ids, per-particle columns) are positions in that
+ *     compacted active array, exactly as in the reference's `pA[indexes]` (src/Solver.py:238,254).
+ *   - one host thread per context; all work is enqueued on one CUDA stream per context and a call
+ *     blocks only when it returns data to the host.
+ */
+#ifndef OSPH_H
+#define OSPH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSPH_VERSION 1
+
+/* arithmetic of the pair kernel; integrator state is always double */
+#define OSPH_FP64 0   /* validation mode: exact reference neighbour predicate, fields <= 1e-10 */
+#define OSPH_FP32 1   /* performance mode: pair arithmetic in float on anchor-relative positions */
+
+/* smoothing kernel -- replaces: src/Kernels/CubicSpline.py:10-70, Wendland.py:9-64, Gaussian.py:16-59 */
+#define OSPH_KERNEL_CUBIC    0
+#define OSPH_KERNEL_WENDLAND 1
+#define OSPH_KERNEL_GAUSSIAN 2
+
+/* integrator -- replaces: src/Integrators/PEC.py:12-88, Euler.py:7-26, Verlet.py:8-55 */
+#define OSPH_INTEGRATOR_PEC    0
+#define OSPH_INTEGRATOR_EULER  1
+#define OSPH_INTEGRATOR_VERLET 2
+
+/* smoothing-length refresh of Solver._compute (src/Solver.py:242-246) */
+#define OSPH_H_FIXED   0   /* Solver(h=value): h[fluid] = fixed_h */
+#define OSPH_H_DYNAMIC 1   /* Solver(h=None): h[fluid] = h_sigma * sqrt(m/rho), computeH (SolverTools.py:106-118) */
+#define OSPH_H_KEEP    2   /* leave h as uploaded (stand-alone nn.update / _loop calls) */
+
+/* particle labels, src/Common.py:8-12 */
+#define OSPH_FLUID 0
+#define OSPH_BOUNDARY 1
+#define OSPH_TEMP_BOUNDARY 2
+#define OSPH_COUPLED 3
+
+/* real-valued columns of particle_dtype, in record order (byte offset = 2 + 8 * id) */
+enum osph_field {
+    OSPH_F_M = 0, OSPH_F_RHO, OSPH_F_P, OSPH_F_C, OSPH_F_DRHO, OSPH_F_H, OSPH_F_X, OSPH_F_Y,
+    OSPH_F_VX, OSPH_F_VY, OSPH_F_AX, OSPH_F_AY, OSPH_F_XSPHX, OSPH_F_XSPHY, OSPH_F_X0, OSPH_F_Y0,
+    OSPH_F_VX0, OSPH_F_VY0, OSPH_F_RHO0, OSPH_NUM_FIELDS
+};
+
+#define OSPH_E_INVALID   (-1)  /* bad argument / call order */
+#define OSPH_E_CUDA      (-2)  /* CUDA runtime error (text in osph_last_error) */
+#define OSPH_E_NO_DEVICE (-3)  /* no usable CUDA device: the library has no CPU path */
+#define OSPH_E_CAPACITY  (-4)  /* a caller-provided buffer is too small */
+#define OSPH_E_NO_FLUID  (-5)  /* time-step reduction over zero fluid particles */
+#define OSPH_E_GRID      (-6)  /* the reference grid would need more cells than can be tabulated */
+
+/* status bits reported by osph_sync() */
+#define OSPH_S_NONFINITE   1u  /* a NaN/Inf acceleration or density was produced */
+#define OSPH_S_SMALL_DT    2u  /* dt < 1e-6 (reference src/Solver.py:220-224 records this as ts_error) */
+#define OSPH_S_UNBINNED    4u  /* a particle's reference cell id fell outside the table (reference: OOB write) */
+#define OSPH_S_GRID_COARSE 8u  /* acceleration grid was coarsened to fit the allocated cell table */
+
+typedef struct osph_ctx osph_ctx;
+
+/*
+ * Everything the reference spreads over the constructors of WCSPH (src/Methods/WCSPH.py:35-79),
+ * PEC/Verlet (src/Integrators/PEC.py:13-28), Solver (src/Solver.py:46,109,215) and the kernel choice.
+ */
+typedef struct osph_config {
+    int32_t struct_size;          /* sizeof(osph_config), checked */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t precision;            /* OSPH_FP64 | OSPH_FP32 */
+    int32_t kernel;               /* OSPH_KERNEL_* */
+    int32_t integrator;           /* OSPH_INTEGRATOR_* */
+    int32_t method_xsph;          /* WCSPH.useXSPH */
+    int32_t integrator_xsph;      /* PEC.useXSPH / Verlet.useXSPH */
+    int32_t strict;               /* PEC.strict: clamp rho >= 0 */
+    int32_t summation_density;    /* WCSPH.useSummationDensity (Jacobi pass on device) */
+    int32_t dynamic_h;            /* OSPH_H_*: how the fluid smoothing length is refreshed before each force evaluation */
+    int32_t reorder_every;        /* physical re-sort cadence of the device state, steps; 0 = default */
+    int32_t reserved0;
+    double  fixed_h;              /* Solver(h=...) when dynamic_h == 0 */
+    double  h_sigma;              /* 1.3 */
+    double  nn_scale;             /* NNLinkedList(scale=2.0), src/Solver.py:109 */
+    double  gamma, B, rho0, Pb, co;       /* Tait EOS */
+    double  alpha, beta;                  /* artificial viscosity */
+    double  epsilon;                      /* XSPH */
+    double  r0, D, p1, p2;                /* Lennard-Jones boundary force */
+    double  gravity;                      /* 9.81, subtracted from ay (WCSPH.py:168-169) */
+    double  cfl_courant, cfl_force;       /* 0.25, 0.25 (src/Solver.py:215) */
+} osph_config;
+
+/* Fill *cfg with the reference defaults for WCSPH(height, r0, rho0, ...). replaces: src/Methods/WCSPH.py:56-79 */
+int osph_default_config(osph_config *cfg, double height, double r0, double rho0);
+
+int osph_create(const osph_config *cfg, osph_ctx **out);
+int osph_destroy(osph_ctx *ctx);
+const char *osph_last_error(const osph_ctx *ctx);   /* ctx may be NULL: error of the last failed osph_create */
+int osph_version(void);
+
+/* ---- host <-> device state ------------------------------------------------------------------ */
+
+/*
+ * Upload the whole particle array (n rows, `stride` bytes apart).  Rows with deleted != 0 are kept
+ * verbatim in a device mirror and never touched.  replaces: the `self.particleArray[self.indexes]`
+ * fancy-index copies handed to nn.update/_loop (src/Solver.py:238,254).
+ */
+int osph_upload_aos(osph_ctx *ctx, const void *pA, int64_t n, int64_t stride);
+/* Write the current device state back into the caller's array (same n/stride as the upload). */
+int osph_download_aos(osph_ctx *ctx, void *pA, int64_t n, int64_t stride);
+/* Same, but the caller supplies the device-side view: nothing crosses PCIe.  d_pA is a device pointer. */
+int osph_import_device_aos(osph_ctx *ctx, const void *d_pA, int64_t n, int64_t stride);
+int osph_export_device_aos(osph_ctx *ctx, void *d_pA, int64_t n, int64_t stride);
+/*
+ * Download `nfields` columns (enum osph_field) of the ACTIVE particles, in active order, into
+ * cols[k][0..n_active).  replaces: the per-step `np.copy(self.particleArray[key])` of Solver._store
+ * (src/Solver.py:477-482) without moving the other 150 bytes of every record.
+ */
+int osph_download_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, double *const *cols);
+/* Overwrite columns of the active particles from host arrays in active order (coupling write-back). */
+int osph_upload_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, const double *const *cols);
+int64_t osph_num_active(const osph_ctx *ctx);
+int64_t osph_num_fluid(const osph_ctx *ctx);
+
+/* ---- the five per-step calls of Solver.run() ------------------------------------------------- */
+
+/* out = {min(dt_c, dt_f), dt_c, dt_f}.  replaces: TimeStep().compute(...) src/Equations/TimeStep.py:11-91 via Solver._minTimeStep (src/Solver.py:210-230) */
+int osph_timestep(osph_ctx *ctx, double out[3]);
+/* replaces: integrator.predict(dt, pA[f_indexes], damping)  src/Solver.py:380 */
+int osph_predict(osph_ctx *ctx, double dt, double damping);
+/* replaces: nn.update(pA[indexes]) + the h refresh  src/Solver.py:238-246 (NNLinkedList.py:37-39,86-141) */
+int osph_build_neighbours(osph_ctx *ctx);
+/* replaces: _loop(pA[indexes], kernel.evaluate, kernel.gradient, method, nn)  src/Solver.py:254 (SolverTools.py:120-174) */
+int osph_compute(osph_ctx *ctx);
+/* replaces: integrator.correct(dt, pA[f_indexes], damping)  src/Solver.py:396 */
+int osph_correct(osph_ctx *ctx, double dt, double damping);
+/*
+ * nsteps whole steps (timestep -> predict -> neighbours -> compute -> correct) without host round
+ * trips; fixed_dt <= 0 selects the dynamic time step.  replaces: the body of the while loop
+ * src/Solver.py:366-399 for runs without coupling.  The (dt, dt_c, dt_f) series is kept on the device
+ * and fetched with osph_get_dt_log.
+ */
+int osph_step(osph_ctx *ctx, int32_t nsteps, double fixed_dt, double damping);
+/* Up to cap triples of the series recorded by osph_step since the last call; returns the count via *count. */
+int osph_get_dt_log(osph_ctx *ctx, double *out, int64_t cap, int64_t *count);
+/* replaces: KineticEnergy(J, pA[f_indexes])  src/Equations/KineticEnergy.py:6-12 (sum over the fluid rows) */
+int osph_kinetic_energy(osph_ctx *ctx, double *ke);
+/* Block until all enqueued work is done; *status receives the OSPH_S_* bits accumulated since the last call. */
+int osph_sync(osph_ctx *ctx, uint32_t *status);
+
+/* ---- validation / query entry points --------------------------------------------------------- */
+
+/*
+ * Reference grid of the last osph_build_neighbours: grid = {xmin, xmax, ymin, ymax, cell_size, ncx, ncy}
+ * and, per active particle, the flat cell id the reference's _bin computes (NNLinkedList.py:129-141).
+ */
+int osph_get_cells(osph_ctx *ctx, double grid[7], int64_t *cell_ids);
+/*
+ * CSR neighbour lists (reference predicate: 3x3 cells AND r/h_ij <= 3.0, NNLinkedList.py:50-71) of the
+ * fluid rows, indices in active order, each list sorted ascending.  offsets has n_active+1 entries.
+ * Pass idx == NULL to obtain only offsets/total.  replaces: nn.near(i, pA) for every i.
+ */
+int osph_get_neighbours_csr(osph_ctx *ctx, int64_t *offsets, int64_t *idx, int64_t cap, int64_t *total);
+/*
+ * Neighbours of an arbitrary point; same predicate, results sorted by index.  Returns the count in
+ * *count (may exceed cap).  replaces: nn.nearPos(x, y, h, pA)  NNLinkedList.py:41-80 (IceBreak pressure probe).
+ */
+int osph_near_pos(osph_ctx *ctx, double x, double y, double h, int64_t cap,
+                  int64_t *idx, double *r, double *q, double *hij, int64_t *count);
+/* Device time of each phase since creation, ms: {timestep, predict, neighbours, compute, correct, transfer}. */
+int osph_get_timers(osph_ctx *ctx, double out_ms[6]);
+/* Kernel launches issued by this context since creation (bench.py reports them as gpu_launches). */
+int64_t osph_launch_count(const osph_ctx *ctx);
+/* CUDA stream of the context as a uintptr (so callers can record their own events on it). */
+uint64_t osph_stream(const osph_ctx *ctx);
+/* Average device time of the fused pair kernel over the launches since the last call, microseconds. */
+int osph_pair_kernel_time(osph_ctx *ctx, double *avg_us, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSPH_H */

@@ -1,0 +1,571 @@
+// api.cu -- the extern "C" surface declared in include/osph.h: context life cycle, host<->device
+// transfers of the reference's packed particle records, the five per-step calls of Solver.run()
+// (reference src/Solver.py:366-399), the fused multi-step loop and the validation queries.
+// There is deliberately no CPU implementation behind any entry point.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "step.cuh"
+
+static std::string g_create_error;
+
+enum { T_TIMESTEP = 0, T_PREDICT, T_NEIGHBOURS, T_COMPUTE, T_CORRECT, T_TRANSFER };
+
+struct PhaseTimer {
+    osph_ctx *ctx; int id; int slot;
+    PhaseTimer(osph_ctx *c, int id_) : ctx(c), id(id_), slot(-1)
+    {
+        if ((int)ctx->phase_ev.size() / 2 >= 2048) drain(ctx);
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        ctx->phase_ev.push_back(a); ctx->phase_ev.push_back(b); ctx->phase_id.push_back(id);
+        slot = (int)ctx->phase_id.size() - 1;
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~PhaseTimer() { if (slot >= 0) cudaEventRecord(ctx->phase_ev[2 * slot + 1], ctx->stream); }
+    static void drain(osph_ctx *ctx)
+    {
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t k = 0; k < ctx->phase_id.size(); k++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->phase_ev[2 * k], ctx->phase_ev[2 * k + 1]) == cudaSuccess)
+                ctx->timers_ms[ctx->phase_id[k]] += ms;
+            cudaEventDestroy(ctx->phase_ev[2 * k]); cudaEventDestroy(ctx->phase_ev[2 * k + 1]);
+        }
+        ctx->phase_ev.clear(); ctx->phase_id.clear();
+    }
+};
+
+static void free_particles(osph_ctx *ctx)
+{
+    cudaFree(ctx->d_aos); cudaFree(ctx->d_row); cudaFree(ctx->d_act); cudaFree(ctx->d_slot_of_act);
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) { cudaFree(ctx->f[k]); ctx->f[k] = nullptr; }
+    cudaFree(ctx->label); cudaFree(ctx->scratch); cudaFree(ctx->d_stage);
+    cudaFree(ctx->s_coarse); cudaFree(ctx->s_gcell); cudaFree(ctx->s_pos); cudaFree(ctx->s_vel);
+    cudaFree(ctx->s_rm); cudaFree(ctx->s_hp); cudaFree(ctx->s_info); cudaFree(ctx->u_coarse); cudaFree(ctx->u_gcell);
+    cudaFree(ctx->d_partial);
+    osph_sort_free(ctx);
+    ctx->d_aos = nullptr; ctx->d_row = ctx->d_act = ctx->d_slot_of_act = nullptr; ctx->label = nullptr;
+    ctx->scratch = ctx->d_stage = nullptr; ctx->s_coarse = nullptr; ctx->s_gcell = nullptr; ctx->s_pos = nullptr;
+    ctx->s_vel = ctx->s_rm = ctx->s_hp = nullptr; ctx->s_info = nullptr; ctx->u_coarse = nullptr; ctx->u_gcell = nullptr;
+    ctx->d_partial = nullptr;
+    ctx->cap = 0; ctx->aos_bytes = 0;
+}
+
+static int alloc_particles(osph_ctx *ctx, int64_t n_active, int64_t n_total, int64_t stride)
+{
+    size_t aos_bytes = (size_t)n_total * (size_t)stride;
+    if (n_active <= ctx->cap && aos_bytes <= ctx->aos_bytes) return 0;
+    free_particles(ctx);
+    int64_t cap = std::max<int64_t>(n_active, 1024);
+    const size_t rs = ctx->cfg.precision == OSPH_FP64 ? sizeof(double2) : sizeof(float2);
+    OSPH_CUDA(cudaMalloc(&ctx->d_aos, std::max<size_t>(aos_bytes, 16)));
+    OSPH_CUDA(cudaMalloc(&ctx->d_row, sizeof(int) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->d_act, sizeof(int) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->d_slot_of_act, sizeof(int) * cap));
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) OSPH_CUDA(cudaMalloc(&ctx->f[k], sizeof(double) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->label, cap));
+    OSPH_CUDA(cudaMalloc(&ctx->scratch, sizeof(double) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->d_stage, sizeof(double) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->s_coarse, sizeof(int4) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->s_gcell, sizeof(int2) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->s_pos, sizeof(double2) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->s_vel, rs * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->s_rm, rs * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->s_hp, rs * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->s_info, sizeof(int) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->u_coarse, sizeof(int4) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->u_gcell, sizeof(int2) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->d_partial, sizeof(double) * (div_up(cap, 256) + 1)));
+    int rc = osph_sort_alloc(ctx, cap);
+    if (rc) return rc;
+    ctx->cap = cap; ctx->aos_bytes = aos_bytes;
+    return 0;
+}
+
+extern "C" int osph_version(void) { return OSPH_VERSION; }
+
+extern "C" int osph_default_config(osph_config *cfg, double height, double r0, double rho0)
+{
+    if (!cfg) return OSPH_E_INVALID;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (int32_t)sizeof(osph_config);
+    cfg->precision = OSPH_FP64; cfg->kernel = OSPH_KERNEL_CUBIC; cfg->integrator = OSPH_INTEGRATOR_PEC;
+    cfg->method_xsph = 1; cfg->integrator_xsph = 1; cfg->strict = 1;
+    cfg->dynamic_h = 1; cfg->fixed_h = 0.0; cfg->h_sigma = 1.3; cfg->nn_scale = 2.0;
+    cfg->gamma = 7.0;
+    cfg->co = 10.0 * sqrt(2 * 9.81 * height);          // TaitEOS_co, reference src/Equations/TaitEOS.py:40-44
+    cfg->B = cfg->co * cfg->co * rho0 / cfg->gamma;    // TaitEOS_B, :33-38
+    cfg->rho0 = rho0; cfg->Pb = 0.0;
+    cfg->alpha = 0.01; cfg->beta = 0.0; cfg->epsilon = 0.5;
+    cfg->r0 = r0; cfg->D = 5 * 9.81 * height; cfg->p1 = 4; cfg->p2 = 2;
+    cfg->gravity = 9.81; cfg->cfl_courant = 0.25; cfg->cfl_force = 0.25;
+    return 0;
+}
+
+extern "C" const char *osph_last_error(const osph_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int osph_create(const osph_config *cfg, osph_ctx **out)
+{
+    if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(osph_config)) {
+        g_create_error = "osph_create: null argument or osph_config.struct_size mismatch";
+        return OSPH_E_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        g_create_error = std::string("osph_create: no usable CUDA device (") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range") +
+                         "); libosph_b200 has no CPU path";
+        cudaGetLastError();
+        return OSPH_E_NO_DEVICE;
+    }
+    if (cfg->precision != OSPH_FP64 && cfg->precision != OSPH_FP32) { g_create_error = "bad precision"; return OSPH_E_INVALID; }
+    if (cfg->kernel < 0 || cfg->kernel > 2 || cfg->integrator < 0 || cfg->integrator > 2) {
+        g_create_error = "bad kernel / integrator id"; return OSPH_E_INVALID;
+    }
+    osph_ctx *ctx = new osph_ctx();
+    ctx->cfg = *cfg; ctx->device = cfg->device;
+    auto fail = [&](const char *what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete ctx; return OSPH_E_CUDA;
+    };
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    for (int k = 0; k < 2 * OSPH_PAIR_EVENTS; k++)
+        if ((e = cudaEventCreate(&ctx->pair_ev[k])) != cudaSuccess) return fail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_grid, sizeof(GridParams))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_sc, sizeof(StepScalars))) != cudaSuccess) return fail("cudaMalloc", e);
+    ctx->dt_log_cap = 1 << 16;
+    if ((e = cudaMalloc(&ctx->d_dt_log, sizeof(double) * 3 * ctx->dt_log_cap)) != cudaSuccess) return fail("cudaMalloc", e);
+    if (osph_init_scalars(ctx) != 0) { g_create_error = ctx->err; delete ctx; return OSPH_E_CUDA; }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int osph_destroy(osph_ctx *ctx)
+{
+    if (!ctx) return OSPH_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    PhaseTimer::drain(ctx);
+    free_particles(ctx);
+    cudaFree(ctx->cell_range); cudaFree(ctx->d_grid); cudaFree(ctx->d_sc); cudaFree(ctx->d_dt_log);
+    for (int k = 0; k < 2 * OSPH_PAIR_EVENTS; k++) if (ctx->pair_ev[k]) cudaEventDestroy(ctx->pair_ev[k]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+#define CHECK_CTX()                                                        \
+    if (!ctx) return OSPH_E_INVALID;                                       \
+    OSPH_CUDA(cudaSetDevice(ctx->device))
+#define NEED_PARTICLES()                                                   \
+    if (ctx->n <= 0) { ctx->err = "no particles uploaded"; return OSPH_E_INVALID; }
+
+static void invalidate_state(osph_ctx *ctx)
+{
+    ctx->prepared = false; ctx->neighbours_valid = false; ctx->reductions_valid = false;
+}
+
+// ---- transfers ---------------------------------------------------------------------------------
+
+static int ingest(osph_ctx *ctx, const unsigned char *flags_host, const void *src, bool src_on_device, int64_t n,
+                  int64_t stride)
+{
+    // flags_host: n*2 bytes (deleted, label) gathered from the records
+    std::vector<int> rows; rows.reserve((size_t)n);
+    int64_t nf = 0;
+    for (int64_t r = 0; r < n; r++)
+        if (!flags_host[2 * r]) { rows.push_back((int)r); nf += (flags_host[2 * r + 1] == OSPH_FLUID); }
+    int64_t na = (int64_t)rows.size();
+    int rc = alloc_particles(ctx, na, n, stride);
+    if (rc) return rc;
+    if (na != ctx->n || n != ctx->n_total) { ctx->sized = false; }
+    ctx->n = na; ctx->n_total = n; ctx->stride = stride; ctx->n_fluid = nf;
+    OSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, src, (size_t)n * stride,
+                              src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (na > 0) {
+        std::vector<int> act((size_t)na);
+        for (int64_t k = 0; k < na; k++) act[k] = (int)k;
+        OSPH_CUDA(cudaMemcpyAsync(ctx->d_row, rows.data(), sizeof(int) * na, cudaMemcpyHostToDevice, ctx->stream));
+        OSPH_CUDA(cudaMemcpyAsync(ctx->d_act, act.data(), sizeof(int) * na, cudaMemcpyHostToDevice, ctx->stream));
+        OSPH_CUDA(cudaStreamSynchronize(ctx->stream));     // rows/act are stack-owned
+        rc = osph_launch_unpack(ctx);
+        if (rc) return rc;
+    }
+    ctx->c_uniform = false; ctx->have_perm = false; ctx->build_counter = 0; ctx->slot_of_act_valid = false;
+    invalidate_state(ctx);
+    return 0;
+}
+
+extern "C" int osph_upload_aos(osph_ctx *ctx, const void *pA, int64_t n, int64_t stride)
+{
+    CHECK_CTX();
+    if (!pA || n < 0 || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_upload_aos: bad arguments"; return OSPH_E_INVALID; }
+    PhaseTimer t(ctx, T_TRANSFER);
+    std::vector<unsigned char> flags((size_t)n * 2);
+    const unsigned char *p = (const unsigned char *)pA;
+    for (int64_t r = 0; r < n; r++) { flags[2 * r] = p[r * stride]; flags[2 * r + 1] = p[r * stride + 1]; }
+    return ingest(ctx, flags.data(), pA, false, n, stride);
+}
+
+extern "C" int osph_import_device_aos(osph_ctx *ctx, const void *d_pA, int64_t n, int64_t stride)
+{
+    CHECK_CTX();
+    if (!d_pA || n < 0 || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_import_device_aos: bad arguments"; return OSPH_E_INVALID; }
+    PhaseTimer t(ctx, T_TRANSFER);
+    std::vector<unsigned char> flags((size_t)n * 2);
+    OSPH_CUDA(cudaMemcpy2D(flags.data(), 2, d_pA, (size_t)stride, 2, (size_t)n, cudaMemcpyDeviceToHost));
+    return ingest(ctx, flags.data(), d_pA, true, n, stride);
+}
+
+extern "C" int osph_download_aos(osph_ctx *ctx, void *pA, int64_t n, int64_t stride)
+{
+    CHECK_CTX();
+    if (!pA || n != ctx->n_total || stride != ctx->stride) { ctx->err = "osph_download_aos: shape differs from the upload"; return OSPH_E_INVALID; }
+    PhaseTimer t(ctx, T_TRANSFER);
+    int rc = osph_launch_pack(ctx);
+    if (rc) return rc;
+    OSPH_CUDA(cudaMemcpyAsync(pA, ctx->d_aos, (size_t)n * stride, cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int osph_export_device_aos(osph_ctx *ctx, void *d_pA, int64_t n, int64_t stride)
+{
+    CHECK_CTX();
+    if (!d_pA || n != ctx->n_total || stride != ctx->stride) { ctx->err = "osph_export_device_aos: shape differs from the import"; return OSPH_E_INVALID; }
+    int rc = osph_launch_pack(ctx);
+    if (rc) return rc;
+    OSPH_CUDA(cudaMemcpyAsync(d_pA, ctx->d_aos, (size_t)n * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int osph_download_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, double *const *cols)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    PhaseTimer t(ctx, T_TRANSFER);
+    for (int k = 0; k < nfields; k++) {
+        if (fields[k] < 0 || fields[k] >= OSPH_NUM_FIELDS || !cols[k]) { ctx->err = "osph_download_fields: bad field"; return OSPH_E_INVALID; }
+        int rc = osph_launch_col_to_active(ctx, fields[k], ctx->d_stage);
+        if (rc) return rc;
+        OSPH_CUDA(cudaMemcpyAsync(cols[k], ctx->d_stage, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+        OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+extern "C" int osph_upload_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, const double *const *cols)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    PhaseTimer t(ctx, T_TRANSFER);
+    for (int k = 0; k < nfields; k++) {
+        if (fields[k] < 0 || fields[k] >= OSPH_NUM_FIELDS || !cols[k]) { ctx->err = "osph_upload_fields: bad field"; return OSPH_E_INVALID; }
+        OSPH_CUDA(cudaMemcpyAsync(ctx->d_stage, cols[k], sizeof(double) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = osph_launch_col_from_active(ctx, fields[k], ctx->d_stage);
+        if (rc) return rc;
+        OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    invalidate_state(ctx);
+    return 0;
+}
+
+extern "C" int64_t osph_num_active(const osph_ctx *ctx) { return ctx ? ctx->n : 0; }
+extern "C" int64_t osph_num_fluid(const osph_ctx *ctx) { return ctx ? ctx->n_fluid : 0; }
+
+// ---- the per-step calls --------------------------------------------------------------------------
+
+// First build after an upload: size the cell table from the grid the device would like to use.
+static int size_cell_table(osph_ctx *ctx)
+{
+    if (ctx->sized) return 0;
+    int64_t saved = ctx->cell_cap;
+    ctx->cell_cap = (int64_t)1 << OSPH_MAX_CELL_BITS;         // "unlimited" for the sizing pass
+    int rc = osph_launch_grid_params(ctx);
+    ctx->cell_cap = saved;
+    if (rc) return rc;
+    GridParams g;
+    OSPH_CUDA(cudaMemcpyAsync(&g, ctx->d_grid, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    int64_t need = (int64_t)g.gnx * g.gny + 1;
+    if (g.regime_a && need > ((int64_t)1 << OSPH_MAX_CELL_BITS)) {
+        ctx->err = "reference grid needs more cells than can be tabulated"; return OSPH_E_GRID;
+    }
+    int64_t want = std::min<int64_t>((int64_t)1 << OSPH_MAX_CELL_BITS, need + need / 2 + 1024);
+    if (want > ctx->cell_cap) {
+        cudaFree(ctx->cell_range); ctx->cell_range = nullptr;
+        OSPH_CUDA(cudaMalloc(&ctx->cell_range, sizeof(int2) * (size_t)want));
+        ctx->cell_cap = want;
+    }
+    int bits = 1;
+    while (((int64_t)1 << bits) < ctx->cell_cap + 1) bits++;
+    ctx->key_bits = bits;
+    ctx->sized = true;
+    return 0;
+}
+
+static int ensure_reductions(osph_ctx *ctx)
+{
+    if (ctx->reductions_valid) return 0;
+    int rc = osph_launch_correct(ctx, false, 0.0, 0.0, false);
+    if (rc) return rc;
+    ctx->reductions_valid = true;
+    return 0;
+}
+
+extern "C" int osph_timestep(osph_ctx *ctx, double out[3])
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    if (ctx->n_fluid == 0) { ctx->err = "osph_timestep: no fluid particles"; return OSPH_E_NO_FLUID; }
+    int rc;
+    {
+        PhaseTimer t(ctx, T_TIMESTEP);
+        if ((rc = ensure_reductions(ctx))) return rc;
+        if ((rc = osph_launch_timestep(ctx, -1.0, false))) return rc;
+    }
+    StepScalars sc;
+    OSPH_CUDA(cudaMemcpyAsync(&sc, ctx->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    out[0] = sc.dt[0]; out[1] = sc.dt[1]; out[2] = sc.dt[2];
+    return 0;
+}
+
+extern "C" int osph_predict(osph_ctx *ctx, double dt, double damping)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    PhaseTimer t(ctx, T_PREDICT);
+    int rc = osph_launch_prepare(ctx, true, dt, damping, false);
+    if (rc) return rc;
+    invalidate_state(ctx);
+    ctx->prepared = true;
+    return 0;
+}
+
+static int build_neighbours(osph_ctx *ctx)
+{
+    int rc;
+    if (!ctx->prepared) {
+        if ((rc = osph_launch_prepare(ctx, false, 0.0, 0.0, false))) return rc;
+        ctx->prepared = true;
+    }
+    if ((rc = size_cell_table(ctx))) return rc;
+    if ((rc = osph_launch_build(ctx))) return rc;
+    ctx->neighbours_valid = true;
+    return 0;
+}
+
+extern "C" int osph_build_neighbours(osph_ctx *ctx)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    PhaseTimer t(ctx, T_NEIGHBOURS);
+    return build_neighbours(ctx);
+}
+
+extern "C" int osph_compute(osph_ctx *ctx)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    int rc;
+    if (!ctx->neighbours_valid) {
+        PhaseTimer t(ctx, T_NEIGHBOURS);
+        if ((rc = build_neighbours(ctx))) return rc;
+    }
+    PhaseTimer t(ctx, T_COMPUTE);
+    if ((rc = osph_launch_pair(ctx))) return rc;
+    ctx->c_uniform = true;
+    ctx->reductions_valid = false;
+    return 0;
+}
+
+extern "C" int osph_correct(osph_ctx *ctx, double dt, double damping)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    PhaseTimer t(ctx, T_CORRECT);
+    int rc = osph_launch_correct(ctx, true, dt, damping, false);
+    if (rc) return rc;
+    invalidate_state(ctx);
+    ctx->reductions_valid = true;
+    return 0;
+}
+
+extern "C" int osph_step(osph_ctx *ctx, int32_t nsteps, double fixed_dt, double damping)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    if (ctx->n_fluid == 0 && !(fixed_dt > 0)) { ctx->err = "osph_step: no fluid particles"; return OSPH_E_NO_FLUID; }
+    int rc;
+    for (int s = 0; s < nsteps; s++) {
+        if ((rc = ensure_reductions(ctx))) return rc;
+        if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true))) return rc;
+        if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true))) return rc;
+        ctx->prepared = true;
+        if ((rc = size_cell_table(ctx))) return rc;
+        if ((rc = osph_launch_build(ctx))) return rc;
+        if ((rc = osph_launch_pair(ctx))) return rc;
+        ctx->c_uniform = true;
+        if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true))) return rc;
+        invalidate_state(ctx);
+        ctx->reductions_valid = true;
+        ctx->step_counter++;
+    }
+    return 0;
+}
+
+extern "C" int osph_get_dt_log(osph_ctx *ctx, double *out, int64_t cap, int64_t *count)
+{
+    CHECK_CTX();
+    StepScalars sc;
+    OSPH_CUDA(cudaMemcpyAsync(&sc, ctx->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    int64_t have = std::min<int64_t>(sc.dt_log_count, ctx->dt_log_cap);
+    int64_t take = std::min<int64_t>(have, cap);
+    if (take > 0 && out) OSPH_CUDA(cudaMemcpy(out, ctx->d_dt_log, sizeof(double) * 3 * take, cudaMemcpyDeviceToHost));
+    if (count) *count = sc.dt_log_count;
+    long long zero = 0;
+    OSPH_CUDA(cudaMemcpy((char *)ctx->d_sc + offsetof(StepScalars, dt_log_count), &zero, sizeof(zero), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int osph_kinetic_energy(osph_ctx *ctx, double *ke)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    int rc = osph_launch_ke(ctx);
+    if (rc) return rc;
+    StepScalars sc;
+    OSPH_CUDA(cudaMemcpyAsync(&sc, ctx->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ke = sc.ke;
+    return 0;
+}
+
+extern "C" int osph_sync(osph_ctx *ctx, uint32_t *status)
+{
+    CHECK_CTX();
+    StepScalars sc;
+    OSPH_CUDA(cudaMemcpyAsync(&sc, ctx->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (sc.status & 0x80000000u) { ctx->err = "reference grid needs more cells than the allocated table"; return OSPH_E_GRID; }
+    if (status) *status = sc.status;
+    unsigned int zero = 0;
+    OSPH_CUDA(cudaMemcpy((char *)ctx->d_sc + offsetof(StepScalars, status), &zero, sizeof(zero), cudaMemcpyHostToDevice));
+    if (sc.status & OSPH_S_GRID_COARSE) ctx->sized = false;    // re-size the cell table at the next build
+    return 0;
+}
+
+// ---- validation / queries -----------------------------------------------------------------------
+
+extern "C" int osph_get_cells(osph_ctx *ctx, double grid[7], int64_t *cell_ids)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    int rc;
+    if (!ctx->neighbours_valid && (rc = build_neighbours(ctx))) return rc;
+    GridParams g;
+    OSPH_CUDA(cudaMemcpyAsync(&g, ctx->d_grid, sizeof(g), cudaMemcpyDeviceToHost, ctx->stream));
+    long long *d_out = nullptr;
+    if (cell_ids) {
+        OSPH_CUDA(cudaMalloc(&d_out, sizeof(long long) * ctx->n));
+        if ((rc = osph_launch_cells(ctx, d_out))) { cudaFree(d_out); return rc; }
+        cudaError_t e = cudaMemcpyAsync(cell_ids, d_out, sizeof(long long) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d_out); ctx->err = cudaGetErrorString(e); return OSPH_E_CUDA; }
+    }
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_out);
+    if (grid) {
+        grid[0] = g.xmin; grid[1] = g.xmax; grid[2] = g.ymin; grid[3] = g.ymax; grid[4] = g.cell_size;
+        grid[5] = (double)g.ncx; grid[6] = (double)g.ncy;
+    }
+    return 0;
+}
+
+extern "C" int osph_get_neighbours_csr(osph_ctx *ctx, int64_t *offsets, int64_t *idx, int64_t cap, int64_t *total)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    if (!offsets) { ctx->err = "osph_get_neighbours_csr: offsets is NULL"; return OSPH_E_INVALID; }
+    int rc;
+    if (!ctx->neighbours_valid && (rc = build_neighbours(ctx))) return rc;
+    int64_t n = ctx->n;
+    long long *d_counts = nullptr, *d_out = nullptr;
+    OSPH_CUDA(cudaMalloc(&d_counts, sizeof(long long) * (n + 1)));
+    if ((rc = osph_launch_neighbours(ctx, 0, d_counts, nullptr, nullptr))) { cudaFree(d_counts); return rc; }
+    std::vector<long long> counts((size_t)n + 1);
+    cudaError_t e = cudaMemcpyAsync(counts.data(), d_counts, sizeof(long long) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_counts); ctx->err = cudaGetErrorString(e); return OSPH_E_CUDA; }
+    long long run = 0;
+    for (int64_t i = 0; i < n; i++) { long long c = counts[i]; offsets[i] = run; counts[i] = run; run += c; }
+    offsets[n] = run; counts[n] = run;
+    if (total) *total = run;
+    if (idx) {
+        if (cap < run) { cudaFree(d_counts); ctx->err = "osph_get_neighbours_csr: idx buffer too small"; return OSPH_E_CAPACITY; }
+        e = cudaMalloc(&d_out, sizeof(long long) * std::max<long long>(run, 1));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_counts, counts.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d_counts); cudaFree(d_out); ctx->err = cudaGetErrorString(e); return OSPH_E_CUDA; }
+        rc = osph_launch_neighbours(ctx, 1, nullptr, d_counts, d_out);
+        if (!rc) {
+            e = cudaMemcpyAsync(idx, d_out, sizeof(long long) * run, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OSPH_E_CUDA; }
+        }
+    }
+    cudaFree(d_counts); cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int osph_near_pos(osph_ctx *ctx, double x, double y, double h, int64_t cap, int64_t *idx, double *r,
+                             double *q, double *hij, int64_t *count)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    int rc;
+    if (!ctx->neighbours_valid && (rc = build_neighbours(ctx))) return rc;
+    int64_t c = std::max<int64_t>(cap, 1);
+    long long *d_idx = nullptr, *d_count = nullptr; double *d_r = nullptr;
+    OSPH_CUDA(cudaMalloc(&d_idx, sizeof(long long) * c));
+    OSPH_CUDA(cudaMalloc(&d_r, sizeof(double) * 3 * c));
+    OSPH_CUDA(cudaMalloc(&d_count, sizeof(long long)));
+    rc = osph_launch_near_pos(ctx, x, y, h, cap, d_idx, d_r, d_r + c, d_r + 2 * c, d_count);
+    long long cnt = 0;
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        int64_t take = std::min<int64_t>(cnt, cap);
+        if (e == cudaSuccess && take > 0) {
+            if (idx) cudaMemcpy(idx, d_idx, sizeof(long long) * take, cudaMemcpyDeviceToHost);
+            if (r) cudaMemcpy(r, d_r, sizeof(double) * take, cudaMemcpyDeviceToHost);
+            if (q) cudaMemcpy(q, d_r + c, sizeof(double) * take, cudaMemcpyDeviceToHost);
+            if (hij) cudaMemcpy(hij, d_r + 2 * c, sizeof(double) * take, cudaMemcpyDeviceToHost);
+        }
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OSPH_E_CUDA; }
+    }
+    if (count) *count = cnt;
+    cudaFree(d_idx); cudaFree(d_r); cudaFree(d_count);
+    return rc;
+}
+
+extern "C" int osph_get_timers(osph_ctx *ctx, double out_ms[6])
+{
+    CHECK_CTX();
+    PhaseTimer::drain(ctx);
+    for (int k = 0; k < 6; k++) out_ms[k] = ctx->timers_ms[k];
+    return 0;
+}
+
+extern "C" int64_t osph_launch_count(const osph_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t osph_stream(const osph_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+extern "C" int osph_pair_kernel_time(osph_ctx *ctx, double *avg_us, int64_t *launches)
+{
+    CHECK_CTX();
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    double sum = 0; int cnt = 0;
+    for (int k = 0; k < ctx->pair_ev_used; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->pair_ev[2 * k], ctx->pair_ev[2 * k + 1]) == cudaSuccess) { sum += ms; cnt++; }
+    }
+    ctx->pair_ev_used = 0;
+    if (avg_us) *avg_us = cnt ? sum * 1000.0 / cnt : 0.0;
+    if (launches) *launches = cnt;
+    return 0;
+}

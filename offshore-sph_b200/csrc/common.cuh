@@ -1,0 +1,199 @@
+// common.cuh -- context, device-side scalars and small device helpers shared by all
+// translation units of libosph_b200.so (sm_100a only; no other architecture is built).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/osph.h"
+
+#define OSPH_CAP_STAGE 512            // candidates staged in shared memory per batch of the pair kernel
+#define OSPH_PAIR_THREADS 256         // one CTA of the pair kernel owns this many consecutive sorted particles
+#define OSPH_MAX_CELL_BITS 28
+#define OSPH_PAIR_EVENTS 512           // pair-kernel launches timed between two osph_pair_kernel_time calls
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident scalars.  Everything the step needs between kernels lives here so that a whole
+// step is enqueued without a host round trip (and can be captured in a CUDA graph).
+// ---------------------------------------------------------------------------------------------
+struct GridParams {
+    // reference grid (NNLinkedList._init, reference src/Tools/NNLinkedList.py:86-127)
+    double xmin, xmax, ymin, ymax, cell_size;
+    long long ncx, ncy, n_cells;
+    // acceleration grid used on the device (regime A: identical to the reference grid;
+    // regime B: cells of the pair-interaction radius)
+    double gsize, ginv;
+    int gnx, gny;
+    int regime_a;          // 1: acceleration grid == reference grid (ids by the reference formula)
+    int reach_set;         // cells to walk per side to cover q <= 3 (neighbour-set emitter)
+    double hmax;           // max h over active particles after the refresh
+    double pair_r2;        // square of the radius inside which a pair can contribute
+};
+
+struct StepScalars {
+    // order-preserving encodings (see enc_f64) so that atomicMin/atomicMax work on doubles
+    unsigned long long xmin, xmax, ymin, ymax;   // bounds of active particles
+    unsigned long long hmin_all;                 // min h over ALL active (cell size rule), before refresh
+    unsigned long long hmax_all;                 // max h over active, after refresh
+    unsigned long long hmin_fluid, cmax_fluid, a2max_fluid;   // TimeStep.computeVars
+    unsigned int status;                         // OSPH_S_* bits
+    unsigned int n_fluid_seen;
+    double dt[3];                                // {dt, dt_c, dt_f} of the current step
+    double ke;
+    long long dt_log_count;
+};
+
+struct osph_ctx {
+    osph_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    int64_t n_total = 0;      // rows of the host array
+    int64_t stride = 154;
+    int64_t n = 0;            // active particles resident on the device
+    int64_t n_fluid = 0;
+    int64_t cap = 0;          // allocated particle capacity
+
+    // raw record mirror + maps
+    unsigned char *d_aos = nullptr;  // n_total * stride bytes
+    int *d_row = nullptr;            // storage slot -> row of the host array
+    int *d_act = nullptr;            // storage slot -> index in the compacted active array
+    int *d_slot_of_act = nullptr;    // active index -> storage slot (rebuilt lazily)
+    bool slot_of_act_valid = false;
+
+    // state, SoA, storage order (OSPH_NUM_FIELDS columns of doubles + label)
+    double *f[OSPH_NUM_FIELDS] = {nullptr};
+    signed char *label = nullptr;
+    double *scratch = nullptr;       // one spare column for the physical reorder
+    double *d_stage = nullptr;       // one spare column for column transfers
+    size_t aos_bytes = 0;
+    bool c_uniform = false;          // c == co for every active particle (true after the first compute)
+
+    // sort workspace
+    unsigned int *key[2] = {nullptr, nullptr};
+    unsigned int *idx[2] = {nullptr, nullptr};   // sorted position -> storage slot
+    int sorted_buf = 0;
+    unsigned int *hist = nullptr;    // [256][nblocks]
+    unsigned int *digit_tot = nullptr;
+    int sort_blocks = 0;
+    int key_bits = 0;
+
+    // cell table of the acceleration grid: (begin, end) per cell
+    int2 *cell_range = nullptr;
+    int64_t cell_cap = 0;
+
+    // per-particle cell info in sorted order
+    int4 *s_coarse = nullptr;        // reference grid: (bin_cx, bin_cy, query_cx, query_cy); bin_cx < 0: unbinned
+    int2 *s_gcell = nullptr;         // acceleration-grid query cell
+    // pair-kernel inputs in sorted order (Real = double or float)
+    double2 *s_pos = nullptr;
+    void *s_vel = nullptr, *s_rm = nullptr, *s_hp = nullptr;   // Real2 each
+    int *s_info = nullptr;           // bit0: fluid
+    // scratch in storage order produced by the key kernel
+    int4 *u_coarse = nullptr;
+    int2 *u_gcell = nullptr;
+
+    GridParams *d_grid = nullptr;
+    StepScalars *d_sc = nullptr;
+    double *d_dt_log = nullptr;
+    int64_t dt_log_cap = 0;
+    double *d_partial = nullptr;     // block partials for deterministic sums
+
+    bool neighbours_valid = false;
+    bool prepared = false;           // bounds / h refresh done for the current positions
+    bool sized = false;              // cell table sized for the current particle set
+    bool reductions_valid = false;   // hmin_fluid/cmax/a2max describe the current state
+    int64_t step_counter = 0;
+    int64_t build_counter = 0;
+    bool have_perm = false;          // idx[sorted_buf] is a valid permutation of the current storage order
+    int64_t launches = 0;
+
+    // timers
+    std::vector<cudaEvent_t> phase_ev;   // (start, stop) pairs of the per-phase timers
+    std::vector<int> phase_id;
+    double timers_ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t pair_ev[2 * OSPH_PAIR_EVENTS] = {nullptr};   // (start, stop) per pair-kernel launch
+    int pair_ev_used = 0;
+    bool time_pair = true;
+
+    // pinned staging for transfers
+    unsigned char *h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+};
+
+#define OSPH_CUDA(call)                                                                    \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                \
+            return OSPH_E_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define OSPH_LAUNCH_CHECK()                                                                \
+    do {                                                                                   \
+        ctx->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess) {                                                          \
+            ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e__);           \
+            return OSPH_E_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Monotone map double -> uint64 so that unsigned atomicMin/atomicMax order doubles correctly.
+__device__ __forceinline__ unsigned long long enc_f64(double v)
+{
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u & 0x8000000000000000ULL) ? ~u : (u | 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ double dec_f64(unsigned long long u)
+{
+    u = (u & 0x8000000000000000ULL) ? (u & 0x7fffffffffffffffULL) : ~u;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)u);
+#else
+    double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+#define ENC_POS_INF 0xfff0000000000000ULL   // enc(+inf)
+#define ENC_NEG_INF 0x000fffffffffffffULL   // enc(-inf)
+
+__device__ __forceinline__ double warp_min(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max_i(int v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// launchers implemented in the other translation units
+// ---------------------------------------------------------------------------------------------
+int osph_sort_pairs(osph_ctx *ctx, int64_t n, int bits);                 // sort.cu: key[sorted_buf], idx[sorted_buf]
+int osph_sort_alloc(osph_ctx *ctx, int64_t cap);
+void osph_sort_free(osph_ctx *ctx);
+int osph_launch_pair(osph_ctx *ctx);                                      // pair.cu

@@ -1,0 +1,19 @@
+// pair.cuh -- argument block of the fused pair kernel (pair.cu)
+#pragma once
+#include "common.cuh"
+
+struct PairArgs {
+    int n;
+    const unsigned int *idx;          // sorted position -> storage slot
+    const double2 *s_pos;
+    const void *s_vel, *s_rm, *s_hp;  // Real2 arrays: (vx,vy), (rho,m), (h, p/rho^2)
+    const int *s_info;
+    const int4 *s_coarse;
+    const int2 *s_gcell;
+    const int2 *cell_range;
+    const GridParams *gp;
+    const double *vx, *vy;            // state columns (storage order), for xsph = v + correction
+    double *drho, *ax, *ay, *xsphx, *xsphy;
+    double alpha, beta, c_half, eps, r0, D, p1, p2, gravity;
+    int lj_42, method_xsph, summation_density;
+};

@@ -1,0 +1,790 @@
+// step.cu -- everything of the WCSPH step except the radix sort and the fused pair kernel:
+// record (un)packing, predictor / corrector with their fused reductions, grid parameters, cell keys,
+// cell table, gather of the pair-kernel inputs, neighbour-list emitter and point query.
+//
+// All arithmetic that the reference evaluates in strict IEEE double (neighbour search, time step:
+// numba jitclass without fastmath) uses __dadd_rn/__dmul_rn/__ddiv_rn/__dsqrt_rn so that nvcc cannot
+// contract it into FMAs; integrator updates do the same so they are bit-identical to the CPU oracle.
+#include "common.cuh"
+#include "step.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K10: packed 154-byte records <-> SoA columns.  Doubles sit at byte offset 2 + 8k (2-byte aligned
+// only), so they are moved as four 16-bit words.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double load_f64_unaligned(const unsigned char *p)
+{
+    const unsigned short *s = reinterpret_cast<const unsigned short *>(p);
+    unsigned long long u = (unsigned long long)s[0] | ((unsigned long long)s[1] << 16) |
+                           ((unsigned long long)s[2] << 32) | ((unsigned long long)s[3] << 48);
+    return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ void store_f64_unaligned(unsigned char *p, double v)
+{
+    unsigned short *s = reinterpret_cast<unsigned short *>(p);
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    s[0] = (unsigned short)u; s[1] = (unsigned short)(u >> 16);
+    s[2] = (unsigned short)(u >> 32); s[3] = (unsigned short)(u >> 48);
+}
+
+struct Columns { double *f[OSPH_NUM_FIELDS]; };
+
+__global__ void k_unpack_aos(const unsigned char *__restrict__ aos, long long stride, const int *__restrict__ row,
+                             int n, Columns c, signed char *__restrict__ label)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char *rec = aos + (long long)row[i] * stride;
+    label[i] = (signed char)rec[1];
+#pragma unroll
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) c.f[k][i] = load_f64_unaligned(rec + 2 + 8 * k);
+}
+
+__global__ void k_pack_aos(unsigned char *__restrict__ aos, long long stride, const int *__restrict__ row, int n,
+                           Columns c, int c_uniform, double co)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char *rec = aos + (long long)row[i] * stride;
+#pragma unroll
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) {
+        double v = c.f[k][i];
+        if (k == OSPH_F_C && c_uniform) v = co;
+        store_f64_unaligned(rec + 2 + 8 * k, v);
+    }
+}
+
+// column of the active particles in active order <-> storage order
+__global__ void k_col_to_active(const double *__restrict__ col, const int *__restrict__ act, int n,
+                                double *__restrict__ out, int fill, double fill_value)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[act[i]] = fill ? fill_value : col[i];
+}
+__global__ void k_col_from_active(double *__restrict__ col, const int *__restrict__ act, int n,
+                                  const double *__restrict__ in)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) col[i] = in[act[i]];
+}
+
+__global__ void k_fill_c(double *__restrict__ c, int n, double co)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) c[i] = co;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalars
+// ---------------------------------------------------------------------------------------------
+__global__ void k_reset_prepare_scalars(StepScalars *sc)
+{
+    sc->xmin = ENC_POS_INF; sc->ymin = ENC_POS_INF; sc->xmax = ENC_NEG_INF; sc->ymax = ENC_NEG_INF;
+    sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF;
+}
+__global__ void k_reset_dt_scalars(StepScalars *sc)
+{
+    sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF;
+    sc->n_fluid_seen = 0;
+}
+__global__ void k_init_scalars(StepScalars *sc)
+{
+    sc->status = 0; sc->dt[0] = sc->dt[1] = sc->dt[2] = 0.0; sc->ke = 0.0; sc->dt_log_count = 0;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_minmax_atomic(double (&vmin)[NV], unsigned long long *const (&pmin)[NV],
+                                                    int nmin)
+{
+    // vmin[k] for k < nmin are minima, the rest maxima
+    __shared__ double sh[NV][32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double v = k < nmin ? warp_min(vmin[k]) : warp_max(vmin[k]);
+        if (lane == 0) sh[k][w] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double v = lane < nw ? sh[k][lane] : (k < nmin ? INFINITY : -INFINITY);
+            v = k < nmin ? warp_min(v) : warp_max(v);
+            if (lane == 0) {
+                if (k < nmin) { if (v < INFINITY) atomicMin(pmin[k], enc_f64(v)); }
+                else { if (v > -INFINITY) atomicMax(pmin[k], enc_f64(v)); }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 + K2: predictor (PEC: reference src/Integrators/PEC.py:32-60, Verlet.py:28-36, Euler: identity)
+// fused with the reductions NNLinkedList._init needs (bounds of ALL active particles,
+// NNLinkedList.py:89-93; min h before the refresh, :103-110) and with the smoothing-length refresh of
+// Solver._compute (src/Solver.py:242-246, computeH SolverTools.py:106-118).
+// dt is read from device memory so a multi-step loop needs no host round trip.
+// ---------------------------------------------------------------------------------------------
+template <int INTEG, bool PREDICT>
+__global__ void __launch_bounds__(256)
+k_prepare(PrepareArgs a)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double bx = INFINITY, by = INFINITY, hmn = INFINITY, Bx = -INFINITY, By = -INFINITY, hmx = -INFINITY;
+    if (i < a.n) {
+        bool fluid = a.label[i] == OSPH_FLUID;
+        double x = a.x[i], y = a.y[i], h = a.h[i];
+        hmn = h;
+        if (fluid) {
+            double rho = a.rho[i];
+            if (PREDICT) {
+                const double dt = a.use_dev_dt ? a.sc->dt[0] : a.dt;
+                const double hdt = __dmul_rn(0.5, dt);
+                double vx = a.vx[i], vy = a.vy[i];
+                if (INTEG == OSPH_INTEGRATOR_PEC) {
+                    a.x0[i] = x; a.y0[i] = y; a.vx0[i] = vx; a.vy0[i] = vy;
+                    double ux = vx, uy = vy;
+                    if (a.integ_xsph) { ux = a.xsphx[i]; uy = a.xsphy[i]; }
+                    x = __dadd_rn(x, __dmul_rn(hdt, ux));
+                    y = __dadd_rn(y, __dmul_rn(hdt, uy));
+                    const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
+                    a.vx[i] = __ddiv_rn(__dadd_rn(vx, __dmul_rn(hdt, a.ax[i])), den);
+                    a.vy[i] = __ddiv_rn(__dadd_rn(vy, __dmul_rn(hdt, a.ay[i])), den);
+                    a.rho0[i] = rho;
+                    rho = __dadd_rn(rho, __dmul_rn(hdt, a.drho[i]));
+                    if (a.strict && rho < 0.0) rho = 0.0;
+                    a.rho[i] = rho;
+                } else if (INTEG == OSPH_INTEGRATOR_VERLET) {
+                    x = __dadd_rn(x, __dmul_rn(hdt, vx));
+                    y = __dadd_rn(y, __dmul_rn(hdt, vy));
+                }
+                a.x[i] = x; a.y[i] = y;
+            }
+            // smoothing-length refresh
+            if (a.dynamic_h == OSPH_H_DYNAMIC) {
+                double m = a.m[i];
+                h = 0.0;
+                if (rho > 1e-12) h = __dmul_rn(a.h_sigma, sqrt(__ddiv_rn(m, rho)));
+                a.h[i] = h;
+            } else if (a.dynamic_h == OSPH_H_FIXED) {
+                h = a.fixed_h;
+                a.h[i] = h;
+            }
+        }
+        bx = x; Bx = x; by = y; By = y; hmx = h;
+    }
+    double v[6] = {bx, by, hmn, Bx, By, hmx};
+    unsigned long long *const p[6] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all,
+                                      &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all};
+    block_minmax_atomic<6>(v, p, 3);
+}
+
+template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, true>(PrepareArgs);
+template __global__ void k_prepare<OSPH_INTEGRATOR_VERLET, true>(PrepareArgs);
+template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, false>(PrepareArgs);
+
+// ---------------------------------------------------------------------------------------------
+// Grid parameters: the reference grid (NNLinkedList.py:86-127) and the acceleration grid.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, double pair_radius_q, double r0,
+                              long long cell_cap)
+{
+    double xmin = dec_f64(sc->xmin), xmax = dec_f64(sc->xmax), ymin = dec_f64(sc->ymin), ymax = dec_f64(sc->ymax);
+    double hmin = dec_f64(sc->hmin_all), hmax = dec_f64(sc->hmax_all);
+    g->xmin = xmin; g->xmax = xmax; g->ymin = ymin; g->ymax = ymax; g->hmax = hmax;
+    double cs = __dmul_rn(hmin, nn_scale);           // :104-105
+    if (cs < 1e-6) cs = 1.0;                          // :107-108
+    g->cell_size = cs;
+    double inv = __ddiv_rn(1.0, cs);                  // :113
+    long long ncx = (long long)ceil(__dmul_rn(inv, __dadd_rn(xmax, -xmin)));
+    long long ncy = (long long)ceil(__dmul_rn(inv, __dadd_rn(ymax, -ymin)));
+    if (ncx < 1) ncx = 1;
+    if (ncy < 1) ncy = 1;
+    g->ncx = ncx; g->ncy = ncy; g->n_cells = ncx * ncy;
+
+    // Radius inside which a pair can contribute: kernel support (q < 2 cubic/Wendland, q <= 3 Gaussian)
+    // and the Lennard-Jones range min(r0, 3 h_ij); h_ij <= hmax.
+    double lj = fmin(r0, 3.0 * hmax);
+    double R = fmax(pair_radius_q * hmax, lj) * (1.0 + 1e-6);
+    if (!(R > 0.0)) R = cs;
+    g->pair_r2 = R * R;
+    int regime_a = (R >= cs) ? 1 : 0;
+    double gs = regime_a ? cs : R;
+    long long gnx, gny;
+    if (regime_a) { gnx = ncx; gny = ncy; }
+    else {
+        for (int it = 0; it < 64; it++) {
+            gnx = (long long)floor((xmax - xmin) / gs) + 1;
+            gny = (long long)floor((ymax - ymin) / gs) + 1;
+            if (gnx * gny + 1 <= cell_cap) break;
+            gs *= 1.25;                                // coarsen until the table fits
+            atomicOr(&sc->status, OSPH_S_GRID_COARSE);
+        }
+    }
+    if (gnx * gny + 1 > cell_cap) {                    // regime A cannot be coarsened
+        atomicOr(&sc->status, 0x80000000u);
+        gnx = 1; gny = 1; gs = fmax(xmax - xmin, ymax - ymin) + 1.0; regime_a = 0;
+    }
+    g->regime_a = regime_a; g->gsize = gs; g->ginv = 1.0 / gs; g->gnx = (int)gnx; g->gny = (int)gny;
+    double rs = 3.0 * hmax * (1.0 + 1e-6);
+    int reach = regime_a ? 1 : (int)ceil(rs / gs);
+    if (reach < 1) reach = 1;
+    g->reach_set = reach;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: cell keys.  Reference cell id (NNLinkedList.py:129-141, 164-176, 200-208) in strict IEEE.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_keys(const double *__restrict__ x, const double *__restrict__ y, int n, const GridParams *__restrict__ gp,
+       StepScalars *sc, unsigned int *__restrict__ key, unsigned int *__restrict__ idx,
+       int4 *__restrict__ u_coarse, int2 *__restrict__ u_gcell)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridParams g = *gp;
+    double rx = __dadd_rn(x[i], -g.xmin), ry = __dadd_rn(y[i], -g.ymin);
+    long long cx = (long long)floor(__ddiv_rn(rx, g.cell_size));
+    long long cy = (long long)floor(__ddiv_rn(ry, g.cell_size));
+    long long flat = cx + g.ncx * cy;
+    int4 co;
+    bool binned = flat >= 0 && flat < g.n_cells;
+    co.x = binned ? (int)(flat % g.ncx) : -1000000;
+    co.y = binned ? (int)(flat / g.ncx) : -1000000;
+    co.z = (int)cx; co.w = (int)cy;
+    if (!binned) atomicOr(&sc->status, OSPH_S_UNBINNED);
+    int gx, gy;
+    unsigned int k;
+    if (g.regime_a) {
+        gx = (int)cx; gy = (int)cy;                                   // query cell: raw reference ids
+        k = binned ? (unsigned int)flat : (unsigned int)g.n_cells;    // bin cell: the reference's flat id
+    } else {
+        gx = (int)floor(rx * g.ginv); gy = (int)floor(ry * g.ginv);
+        gx = min(max(gx, 0), g.gnx - 1); gy = min(max(gy, 0), g.gny - 1);
+        k = (unsigned int)gy * (unsigned int)g.gnx + (unsigned int)gx;
+    }
+    key[i] = k; idx[i] = (unsigned int)i;
+    u_coarse[i] = co; u_gcell[i] = make_int2(gx, gy);
+}
+
+// K6: cell table from the sorted keys (table is zeroed first: empty cells have begin == end == 0)
+__global__ void __launch_bounds__(256)
+k_cell_table(const unsigned int *__restrict__ key, int n, int2 *__restrict__ cell_range)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    unsigned int k = key[s];
+    if (s == 0 || key[s - 1] != k) cell_range[k].x = s;
+    if (s == n - 1 || key[s + 1] != k) cell_range[k].y = s + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: gather of the pair-kernel inputs into sorted order, fused with the Tait EOS
+// (reference WCSPH.compute_pressure, src/Methods/WCSPH.py:131-149; TaitEOS.py:6-31).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tait_ratio_pow(double ratio, double gamma)
+{
+    if (gamma == 7.0) { double r2 = ratio * ratio, r4 = r2 * r2; return r4 * r2 * ratio; }
+    return pow(ratio, gamma);
+}
+
+template <typename Real2>
+__global__ void __launch_bounds__(256)
+k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_hp)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    int i = (int)a.idx[s];
+    bool fluid = a.label[i] == OSPH_FLUID;
+    double rho = a.rho[i];
+    double p = a.Pb;
+    if (fluid) p = (tait_ratio_pow(rho / a.rho0, a.gamma) - 1.0) * a.B + a.Pb;
+    a.p[i] = p;
+    double pr2 = fluid ? p / (rho * rho) : 0.0;
+    a.s_pos[s] = make_double2(a.x[i], a.y[i]);
+    typedef decltype(Real2().x) Real;
+    Real2 v; v.x = (Real)a.vx[i]; v.y = (Real)a.vy[i]; s_vel[s] = v;
+    Real2 rm; rm.x = (Real)rho; rm.y = (Real)a.m[i]; s_rm[s] = rm;
+    Real2 hp; hp.x = (Real)a.h[i]; hp.y = (Real)pr2; s_hp[s] = hp;
+    a.s_info[s] = fluid ? 1 : 0;
+    a.s_coarse[s] = a.u_coarse[i];
+    a.s_gcell[s] = a.u_gcell[i];
+}
+template __global__ void k_gather<double2>(GatherArgs, double2 *, double2 *, double2 *);
+template __global__ void k_gather<float2>(GatherArgs, float2 *, float2 *, float2 *);
+
+// physical reorder of one column: dst[s] = src[idx[s]]
+template <typename T>
+__global__ void k_permute(const T *__restrict__ src, const unsigned int *__restrict__ idx, int n, T *__restrict__ dst)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) dst[s] = src[idx[s]];
+}
+template __global__ void k_permute<double>(const double *, const unsigned int *, int, double *);
+template __global__ void k_permute<int>(const int *, const unsigned int *, int, int *);
+template __global__ void k_permute<signed char>(const signed char *, const unsigned int *, int, signed char *);
+
+__global__ void k_iota(unsigned int *__restrict__ idx, int n)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) idx[s] = (unsigned int)s;
+}
+__global__ void k_invert_act(const int *__restrict__ act, int n, int *__restrict__ slot_of_act)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot_of_act[act[i]] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: corrector (PEC.py:62-88, Euler.py:17-26, Verlet.py:38-55) fused with the reduction TimeStep
+// needs for the NEXT step (TimeStep.computeVars, src/Equations/TimeStep.py:58-91) and the
+// non-finite check.
+// ---------------------------------------------------------------------------------------------
+template <int INTEG, bool CORRECT>
+__global__ void __launch_bounds__(256)
+k_correct(CorrectArgs a)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double hmn = INFINITY, cmx = -INFINITY, amx = -INFINITY;
+    if (i < a.n && a.label[i] == OSPH_FLUID) {
+        double ax = a.ax[i], ay = a.ay[i];
+        if (CORRECT) {
+            const double dt = a.use_dev_dt ? a.sc->dt[0] : a.dt;
+            double drho = a.drho[i];
+            double x, y, vx, vy, rho;
+            if (INTEG == OSPH_INTEGRATOR_PEC) {
+                const double hdt = __dmul_rn(0.5, dt);
+                double x0 = a.x0[i], y0 = a.y0[i], vx0 = a.vx0[i], vy0 = a.vy0[i], rho0 = a.rho0[i];
+                double ux, uy;
+                if (a.integ_xsph) { ux = a.xsphx[i]; uy = a.xsphy[i]; } else { ux = a.vx[i]; uy = a.vy[i]; }
+                double mx = __dadd_rn(x0, __dmul_rn(hdt, ux));
+                double my = __dadd_rn(y0, __dmul_rn(hdt, uy));
+                const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
+                double mvx = __ddiv_rn(__dadd_rn(vx0, __dmul_rn(hdt, ax)), den);
+                double mvy = __ddiv_rn(__dadd_rn(vy0, __dmul_rn(hdt, ay)), den);
+                x = __dadd_rn(__dmul_rn(2.0, mx), -x0);
+                y = __dadd_rn(__dmul_rn(2.0, my), -y0);
+                vx = __dadd_rn(__dmul_rn(2.0, mvx), -vx0);
+                vy = __dadd_rn(__dmul_rn(2.0, mvy), -vy0);
+                double mrho = __dadd_rn(rho0, __dmul_rn(hdt, drho));
+                rho = __dadd_rn(__dmul_rn(2.0, mrho), -rho0);
+                if (a.strict && rho < 0.0) rho = 0.0;
+            } else if (INTEG == OSPH_INTEGRATOR_EULER) {
+                x = a.x[i]; y = a.y[i]; vx = a.vx[i]; vy = a.vy[i]; rho = a.rho[i];
+                const double hdt2 = __dmul_rn(__dmul_rn(0.5, dt), dt);
+                x = __dadd_rn(__dadd_rn(x, __dmul_rn(dt, vx)), __dmul_rn(hdt2, ax));
+                y = __dadd_rn(__dadd_rn(y, __dmul_rn(dt, vy)), __dmul_rn(hdt2, ay));
+                vx = __dadd_rn(vx, __dmul_rn(dt, ax));
+                vy = __dadd_rn(vy, __dmul_rn(dt, ay));
+                rho = __dadd_rn(rho, __dmul_rn(dt, drho));
+            } else {
+                const double hdt = __dmul_rn(0.5, dt);
+                x = a.x[i]; y = a.y[i]; vx = a.vx[i]; vy = a.vy[i]; rho = a.rho[i];
+                vx = __dadd_rn(vx, __dmul_rn(dt, ax));
+                vy = __dadd_rn(vy, __dmul_rn(dt, ay));
+                double ux = vx, uy = vy;
+                if (a.integ_xsph) { ux = a.xsphx[i]; uy = a.xsphy[i]; }
+                x = __dadd_rn(x, __dmul_rn(hdt, ux));
+                y = __dadd_rn(y, __dmul_rn(hdt, uy));
+            }
+            a.x[i] = x; a.y[i] = y; a.vx[i] = vx; a.vy[i] = vy; a.rho[i] = rho;
+            if (!(isfinite(x) && isfinite(y) && isfinite(vx) && isfinite(vy) && isfinite(rho)))
+                atomicOr(&a.sc->status, OSPH_S_NONFINITE);
+        }
+        hmn = a.h[i];
+        cmx = a.c_uniform ? a.co : a.c[i];
+        amx = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+        if (!(amx == amx)) amx = INFINITY;
+    }
+    double v[3] = {hmn, cmx, amx};
+    unsigned long long *const p[3] = {&a.sc->hmin_fluid, &a.sc->cmax_fluid, &a.sc->a2max_fluid};
+    block_minmax_atomic<3>(v, p, 1);
+}
+template __global__ void k_correct<OSPH_INTEGRATOR_PEC, true>(CorrectArgs);
+template __global__ void k_correct<OSPH_INTEGRATOR_EULER, true>(CorrectArgs);
+template __global__ void k_correct<OSPH_INTEGRATOR_VERLET, true>(CorrectArgs);
+template __global__ void k_correct<OSPH_INTEGRATOR_PEC, false>(CorrectArgs);
+
+// TimeStep.compute / courant / force (src/Equations/TimeStep.py:11-56), strict IEEE.
+__global__ void k_timestep(StepScalars *sc, double gamma_c, double gamma_f, double fixed_dt,
+                           double *dt_log, long long dt_log_cap)
+{
+    double out0, c = 0.0, f = 0.0;
+    if (fixed_dt > 0.0) { out0 = fixed_dt; }
+    else {
+        double hmin = dec_f64(sc->hmin_fluid), cmax = dec_f64(sc->cmax_fluid), a2 = dec_f64(sc->a2max_fluid);
+        c = __ddiv_rn(__dmul_rn(gamma_c, hmin), cmax);
+        f = (a2 < 1e-12) ? 1e10 : __dmul_rn(gamma_f, __dsqrt_rn(__ddiv_rn(hmin, a2)));
+        out0 = c < f ? c : f;
+        if (out0 < 1e-6) atomicOr(&sc->status, OSPH_S_SMALL_DT);
+    }
+    sc->dt[0] = out0; sc->dt[1] = c; sc->dt[2] = f;
+    if (dt_log) {
+        long long k = sc->dt_log_count;
+        if (k < dt_log_cap) { dt_log[3 * k] = out0; dt_log[3 * k + 1] = c; dt_log[3 * k + 2] = f; }
+        sc->dt_log_count = k + 1;
+    }
+}
+
+// KineticEnergy (src/Equations/KineticEnergy.py:6-12) over the fluid rows; deterministic two-stage sum.
+__global__ void __launch_bounds__(256)
+k_ke_partial(const double *__restrict__ m, const double *__restrict__ vx, const double *__restrict__ vy,
+             const signed char *__restrict__ label, int n, double *__restrict__ partial)
+{
+    __shared__ double sh[256];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double k = 0.0;
+    if (i < n && label[i] == OSPH_FLUID) k = 0.5 * m[i] * (vx[i] * vx[i] + vy[i] * vy[i]);
+    sh[threadIdx.x] = k;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256)
+k_ke_final(const double *__restrict__ partial, int nb, StepScalars *sc)
+{
+    __shared__ double sh[256];
+    double k = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 256) k += partial[b];
+    sh[threadIdx.x] = k;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sc->ke = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11 / K12: neighbour sets with the reference predicate (NNLinkedList.py:50-71):
+//   j is binned in one of the 3x3 valid reference cells around i's raw cell  AND  r / h_ij <= 3.0,
+// all in strict IEEE double.  Used for parity tests and for the nearPos point query.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ref_accept(double px, double py, double ph, int qcx, int qcy, double2 pj, double hj,
+                                           int4 cj, double *r_out, double *q_out, double *h_out)
+{
+    if (abs(cj.x - qcx) > 1 || abs(cj.y - qcy) > 1) return false;
+    double dx = __dadd_rn(px, -pj.x), dy = __dadd_rn(py, -pj.y);
+    double r = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    double hij = __dmul_rn(0.5, __dadd_rn(ph, hj));
+    double q = __ddiv_rn(r, hij);
+    if (!(q <= 3.0)) return false;
+    if (r_out) { *r_out = r; *q_out = q; *h_out = hij; }
+    return true;
+}
+
+// Walks the acceleration grid around (gx, gy) with `reach` cells per side and calls f(s) per candidate.
+template <typename F>
+__device__ __forceinline__ void walk_cells(const GridParams &g, const int2 *__restrict__ cell_range, int gx, int gy,
+                                           int reach, F f)
+{
+    for (int dy = -reach; dy <= reach; dy++) {
+        int cy = gy + dy;
+        if (cy < 0 || cy >= g.gny) continue;
+        int x0 = max(gx - reach, 0), x1 = min(gx + reach, g.gnx - 1);
+        for (int cx = x0; cx <= x1; cx++) {
+            int2 r = cell_range[(long long)cy * g.gnx + cx];
+            for (int s = r.x; s < r.y; s++) f(s);
+        }
+    }
+}
+
+// mode 0: count per active index; mode 1: fill (ascending active index within each list)
+__global__ void __launch_bounds__(128)
+k_neighbours(NeighbourArgs a, int mode)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    int i = (int)a.idx[s];
+    int ai = a.act[i];
+    if (!(a.s_info[s] & 1)) { if (mode == 0) a.counts[ai] = 0; return; }
+    const GridParams g = *a.gp;
+    double2 pi = a.s_pos[s];
+    double hi = a.h[i];
+    int4 ci = a.s_coarse[s];
+    int2 gc = a.s_gcell[s];
+    long long base = mode ? a.offsets[ai] : 0;
+    int cnt = 0;
+    walk_cells(g, a.cell_range, gc.x, gc.y, g.reach_set, [&](int t) {
+        if (ref_accept(pi.x, pi.y, hi, ci.z, ci.w, a.s_pos[t], a.h[a.idx[t]], a.s_coarse[t], nullptr, nullptr, nullptr)) {
+            if (mode) {
+                long long aj = a.act[a.idx[t]];
+                long long k = cnt;                       // insertion sort keeps the list ascending
+                while (k > 0 && a.out[base + k - 1] > aj) { a.out[base + k] = a.out[base + k - 1]; k--; }
+                a.out[base + k] = aj;
+            }
+            cnt++;
+        }
+    });
+    if (mode == 0) a.counts[ai] = cnt;
+}
+
+__global__ void k_near_pos(NeighbourArgs a, double px, double py, double ph, long long cap, long long *out_idx,
+                           double *out_r, double *out_q, double *out_h, long long *out_count)
+{
+    const GridParams g = *a.gp;
+    double rx = __dadd_rn(px, -g.xmin), ry = __dadd_rn(py, -g.ymin);
+    int qcx = (int)floor(__ddiv_rn(rx, g.cell_size)), qcy = (int)floor(__ddiv_rn(ry, g.cell_size));
+    int gx, gy, reach;
+    if (g.regime_a) { gx = qcx; gy = qcy; reach = 1; }
+    else {
+        gx = (int)floor(rx * g.ginv); gy = (int)floor(ry * g.ginv);
+        double rs = 1.5 * (ph + g.hmax) * (1.0 + 1e-6);
+        reach = (int)ceil(rs / g.gsize); if (reach < 1) reach = 1;
+    }
+    long long cnt = 0;
+    walk_cells(g, a.cell_range, gx, gy, reach, [&](int t) {
+        double r, q, h;
+        if (ref_accept(px, py, ph, qcx, qcy, a.s_pos[t], a.h[a.idx[t]], a.s_coarse[t], &r, &q, &h)) {
+            long long aj = a.act[a.idx[t]];
+            if (cnt < cap) {
+                long long k = cnt;
+                while (k > 0 && out_idx[k - 1] > aj) {
+                    out_idx[k] = out_idx[k - 1]; out_r[k] = out_r[k - 1]; out_q[k] = out_q[k - 1]; out_h[k] = out_h[k - 1];
+                    k--;
+                }
+                out_idx[k] = aj; out_r[k] = r; out_q[k] = q; out_h[k] = h;
+            }
+            cnt++;
+        }
+    });
+    *out_count = cnt;
+}
+
+__global__ void k_cells_to_active(const int4 *__restrict__ s_coarse, const unsigned int *__restrict__ idx,
+                                  const int *__restrict__ act, int n, const GridParams *__restrict__ gp,
+                                  long long *__restrict__ out)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int4 c = s_coarse[s];
+    out[act[idx[s]]] = (long long)c.z + gp->ncx * (long long)c.w;   // the unclamped value _bin computes
+}
+
+// =============================================================================================
+// host launchers
+// =============================================================================================
+static Columns columns_of(osph_ctx *ctx)
+{
+    Columns c;
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) c.f[k] = ctx->f[k];
+    return c;
+}
+
+int osph_init_scalars(osph_ctx *ctx)
+{
+    k_init_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    k_reset_dt_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_unpack(osph_ctx *ctx)
+{
+    if (ctx->n == 0) return 0;
+    k_unpack_aos<<<div_up(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, ctx->d_row, (int)ctx->n,
+                                                                columns_of(ctx), ctx->label);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_pack(osph_ctx *ctx)
+{
+    if (ctx->n == 0) return 0;
+    k_pack_aos<<<div_up(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, ctx->d_row, (int)ctx->n,
+                                                              columns_of(ctx), ctx->c_uniform ? 1 : 0, ctx->cfg.co);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt)
+{
+    PrepareArgs a;
+    a.n = (int)ctx->n; a.label = ctx->label;
+    a.x = ctx->f[OSPH_F_X]; a.y = ctx->f[OSPH_F_Y]; a.vx = ctx->f[OSPH_F_VX]; a.vy = ctx->f[OSPH_F_VY];
+    a.rho = ctx->f[OSPH_F_RHO]; a.h = ctx->f[OSPH_F_H]; a.m = ctx->f[OSPH_F_M];
+    a.ax = ctx->f[OSPH_F_AX]; a.ay = ctx->f[OSPH_F_AY]; a.drho = ctx->f[OSPH_F_DRHO];
+    a.xsphx = ctx->f[OSPH_F_XSPHX]; a.xsphy = ctx->f[OSPH_F_XSPHY];
+    a.x0 = ctx->f[OSPH_F_X0]; a.y0 = ctx->f[OSPH_F_Y0]; a.vx0 = ctx->f[OSPH_F_VX0]; a.vy0 = ctx->f[OSPH_F_VY0];
+    a.rho0 = ctx->f[OSPH_F_RHO0];
+    a.sc = ctx->d_sc; a.dt = dt; a.damping = damping; a.fixed_h = ctx->cfg.fixed_h; a.h_sigma = ctx->cfg.h_sigma;
+    a.use_dev_dt = use_dev_dt ? 1 : 0; a.integ_xsph = ctx->cfg.integrator_xsph; a.strict = ctx->cfg.strict;
+    a.dynamic_h = ctx->cfg.dynamic_h;
+    k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    int grid = div_up(ctx->n, 256);
+    int integ = ctx->cfg.integrator;
+    if (predict && integ == OSPH_INTEGRATOR_PEC) k_prepare<OSPH_INTEGRATOR_PEC, true><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (predict && integ == OSPH_INTEGRATOR_VERLET) k_prepare<OSPH_INTEGRATOR_VERLET, true><<<grid, 256, 0, ctx->stream>>>(a);
+    else k_prepare<OSPH_INTEGRATOR_PEC, false><<<grid, 256, 0, ctx->stream>>>(a);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+static double pair_radius_q(const osph_ctx *ctx) { return ctx->cfg.kernel == OSPH_KERNEL_GAUSSIAN ? 3.0 : 2.0; }
+
+// Physical reorder of the whole state into the order of the last sort.  Runs at the START of a build,
+// before new keys are formed, so only the state columns and the row/act maps have to move.
+static int reorder_state(osph_ctx *ctx)
+{
+    const unsigned int *idx = ctx->idx[ctx->sorted_buf];
+    int n = (int)ctx->n, grid = div_up(ctx->n, 256);
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) {
+        k_permute<double><<<grid, 256, 0, ctx->stream>>>(ctx->f[k], idx, n, ctx->scratch); OSPH_LAUNCH_CHECK();
+        double *t = ctx->f[k]; ctx->f[k] = ctx->scratch; ctx->scratch = t;
+    }
+    // label / row / act / u_coarse / u_gcell go through the same spare column (it is 8 bytes wide)
+    k_permute<signed char><<<grid, 256, 0, ctx->stream>>>(ctx->label, idx, n, (signed char *)ctx->scratch); OSPH_LAUNCH_CHECK();
+    OSPH_CUDA(cudaMemcpyAsync(ctx->label, ctx->scratch, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_row, idx, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
+    OSPH_CUDA(cudaMemcpyAsync(ctx->d_row, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_act, idx, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
+    OSPH_CUDA(cudaMemcpyAsync(ctx->d_act, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->slot_of_act_valid = false;
+    return 0;
+}
+
+int osph_launch_grid_params(osph_ctx *ctx)
+{
+    k_grid_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->d_grid, ctx->cfg.nn_scale, pair_radius_q(ctx), ctx->cfg.r0,
+                                            (long long)ctx->cell_cap);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_build(osph_ctx *ctx)
+{
+    int n = (int)ctx->n, grid = div_up(ctx->n, 256);
+    int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
+    if (ctx->have_perm && (ctx->build_counter % every) == (1 % every)) {
+        int rc0 = reorder_state(ctx);
+        if (rc0) return rc0;
+    }
+    ctx->build_counter++;
+    int rcg = osph_launch_grid_params(ctx);
+    if (rcg) return rcg;
+    ctx->sorted_buf = 0;
+    k_keys<<<grid, 256, 0, ctx->stream>>>(ctx->f[OSPH_F_X], ctx->f[OSPH_F_Y], n, ctx->d_grid, ctx->d_sc, ctx->key[0],
+                                          ctx->idx[0], ctx->u_coarse, ctx->u_gcell);
+    OSPH_LAUNCH_CHECK();
+    int rc = osph_sort_pairs(ctx, n, ctx->key_bits);
+    if (rc) return rc;
+    OSPH_CUDA(cudaMemsetAsync(ctx->cell_range, 0, sizeof(int2) * (size_t)ctx->cell_cap, ctx->stream));
+    k_cell_table<<<grid, 256, 0, ctx->stream>>>(ctx->key[ctx->sorted_buf], n, ctx->cell_range);
+    OSPH_LAUNCH_CHECK();
+    ctx->have_perm = true;
+
+    GatherArgs g;
+    g.n = n; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label;
+    g.x = ctx->f[OSPH_F_X]; g.y = ctx->f[OSPH_F_Y]; g.vx = ctx->f[OSPH_F_VX]; g.vy = ctx->f[OSPH_F_VY];
+    g.rho = ctx->f[OSPH_F_RHO]; g.m = ctx->f[OSPH_F_M]; g.h = ctx->f[OSPH_F_H]; g.p = ctx->f[OSPH_F_P];
+    g.u_coarse = ctx->u_coarse; g.u_gcell = ctx->u_gcell;
+    g.s_pos = ctx->s_pos; g.s_info = ctx->s_info; g.s_coarse = ctx->s_coarse; g.s_gcell = ctx->s_gcell;
+    g.gamma = ctx->cfg.gamma; g.B = ctx->cfg.B; g.rho0 = ctx->cfg.rho0; g.Pb = ctx->cfg.Pb;
+    if (ctx->cfg.precision == OSPH_FP64)
+        k_gather<double2><<<grid, 256, 0, ctx->stream>>>(g, (double2 *)ctx->s_vel, (double2 *)ctx->s_rm, (double2 *)ctx->s_hp);
+    else
+        k_gather<float2><<<grid, 256, 0, ctx->stream>>>(g, (float2 *)ctx->s_vel, (float2 *)ctx->s_rm, (float2 *)ctx->s_hp);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt)
+{
+    CorrectArgs a;
+    a.n = (int)ctx->n; a.label = ctx->label;
+    a.x = ctx->f[OSPH_F_X]; a.y = ctx->f[OSPH_F_Y]; a.vx = ctx->f[OSPH_F_VX]; a.vy = ctx->f[OSPH_F_VY];
+    a.rho = ctx->f[OSPH_F_RHO]; a.h = ctx->f[OSPH_F_H]; a.c = ctx->f[OSPH_F_C];
+    a.ax = ctx->f[OSPH_F_AX]; a.ay = ctx->f[OSPH_F_AY]; a.drho = ctx->f[OSPH_F_DRHO];
+    a.xsphx = ctx->f[OSPH_F_XSPHX]; a.xsphy = ctx->f[OSPH_F_XSPHY];
+    a.x0 = ctx->f[OSPH_F_X0]; a.y0 = ctx->f[OSPH_F_Y0]; a.vx0 = ctx->f[OSPH_F_VX0]; a.vy0 = ctx->f[OSPH_F_VY0];
+    a.rho0 = ctx->f[OSPH_F_RHO0];
+    a.sc = ctx->d_sc; a.dt = dt; a.damping = damping; a.co = ctx->cfg.co;
+    a.use_dev_dt = use_dev_dt ? 1 : 0; a.integ_xsph = ctx->cfg.integrator_xsph; a.strict = ctx->cfg.strict;
+    a.c_uniform = ctx->c_uniform ? 1 : 0;
+    k_reset_dt_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    int grid = div_up(ctx->n, 256);
+    if (!correct) k_correct<OSPH_INTEGRATOR_PEC, false><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (ctx->cfg.integrator == OSPH_INTEGRATOR_PEC) k_correct<OSPH_INTEGRATOR_PEC, true><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (ctx->cfg.integrator == OSPH_INTEGRATOR_EULER) k_correct<OSPH_INTEGRATOR_EULER, true><<<grid, 256, 0, ctx->stream>>>(a);
+    else k_correct<OSPH_INTEGRATOR_VERLET, true><<<grid, 256, 0, ctx->stream>>>(a);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log)
+{
+    k_timestep<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->cfg.cfl_courant, ctx->cfg.cfl_force, fixed_dt,
+                                         log ? ctx->d_dt_log : nullptr, (long long)ctx->dt_log_cap);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_ke(osph_ctx *ctx)
+{
+    int nb = div_up(ctx->n, 256);
+    k_ke_partial<<<nb, 256, 0, ctx->stream>>>(ctx->f[OSPH_F_M], ctx->f[OSPH_F_VX], ctx->f[OSPH_F_VY], ctx->label,
+                                              (int)ctx->n, ctx->d_partial);
+    OSPH_LAUNCH_CHECK();
+    k_ke_final<<<1, 256, 0, ctx->stream>>>(ctx->d_partial, nb, ctx->d_sc);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+static NeighbourArgs neighbour_args(osph_ctx *ctx)
+{
+    NeighbourArgs a;
+    a.n = (int)ctx->n; a.idx = ctx->idx[ctx->sorted_buf]; a.act = ctx->d_act; a.h = ctx->f[OSPH_F_H];
+    a.s_pos = ctx->s_pos; a.s_info = ctx->s_info; a.s_coarse = ctx->s_coarse; a.s_gcell = ctx->s_gcell;
+    a.cell_range = ctx->cell_range; a.gp = ctx->d_grid; a.counts = nullptr; a.offsets = nullptr; a.out = nullptr;
+    return a;
+}
+
+int osph_launch_neighbours(osph_ctx *ctx, int mode, long long *d_counts, const long long *d_offsets, long long *d_out)
+{
+    NeighbourArgs a = neighbour_args(ctx);
+    a.counts = d_counts; a.offsets = d_offsets; a.out = d_out;
+    k_neighbours<<<div_up(ctx->n, 128), 128, 0, ctx->stream>>>(a, mode);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_near_pos(osph_ctx *ctx, double x, double y, double h, long long cap, long long *d_idx, double *d_r,
+                         double *d_q, double *d_h, long long *d_count)
+{
+    NeighbourArgs a = neighbour_args(ctx);
+    k_near_pos<<<1, 1, 0, ctx->stream>>>(a, x, y, h, cap, d_idx, d_r, d_q, d_h, d_count);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_cells(osph_ctx *ctx, long long *d_out)
+{
+    k_cells_to_active<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->s_coarse, ctx->idx[ctx->sorted_buf], ctx->d_act,
+                                                                    (int)ctx->n, ctx->d_grid, d_out);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_col_to_active(osph_ctx *ctx, int field, double *d_out)
+{
+    int fill = (field == OSPH_F_C && ctx->c_uniform) ? 1 : 0;
+    k_col_to_active<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->f[field], ctx->d_act, (int)ctx->n, d_out, fill,
+                                                                  ctx->cfg.co);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_col_from_active(osph_ctx *ctx, int field, const double *d_in)
+{
+    if (field == OSPH_F_C && ctx->c_uniform) {      // materialise c before a caller overwrites it
+        k_fill_c<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->f[OSPH_F_C], (int)ctx->n, ctx->cfg.co);
+        OSPH_LAUNCH_CHECK();
+        ctx->c_uniform = false;
+    }
+    k_col_from_active<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->f[field], ctx->d_act, (int)ctx->n, d_in);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}

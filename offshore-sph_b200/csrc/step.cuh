@@ -1,0 +1,71 @@
+// step.cuh -- argument blocks and host launchers of step.cu
+#pragma once
+#include "common.cuh"
+
+struct PrepareArgs {
+    int n;
+    const signed char *label;
+    double *x, *y, *vx, *vy, *rho, *h;
+    const double *m, *ax, *ay, *drho, *xsphx, *xsphy;
+    double *x0, *y0, *vx0, *vy0, *rho0;
+    StepScalars *sc;
+    double dt, damping, fixed_h, h_sigma;
+    int use_dev_dt, integ_xsph, strict, dynamic_h;
+};
+
+struct CorrectArgs {
+    int n;
+    const signed char *label;
+    double *x, *y, *vx, *vy, *rho;
+    const double *h, *c, *ax, *ay, *drho, *xsphx, *xsphy, *x0, *y0, *vx0, *vy0, *rho0;
+    StepScalars *sc;
+    double dt, damping, co;
+    int use_dev_dt, integ_xsph, strict, c_uniform;
+};
+
+struct GatherArgs {
+    int n;
+    const unsigned int *idx;
+    const signed char *label;
+    const double *x, *y, *vx, *vy, *rho, *m, *h;
+    double *p;
+    const int4 *u_coarse;
+    const int2 *u_gcell;
+    double2 *s_pos;
+    int *s_info;
+    int4 *s_coarse;
+    int2 *s_gcell;
+    double gamma, B, rho0, Pb;
+};
+
+struct NeighbourArgs {
+    int n;
+    const unsigned int *idx;
+    const int *act;
+    const double *h;          // state column, storage order (exact FP64 h in both precisions)
+    const double2 *s_pos;
+    const int *s_info;
+    const int4 *s_coarse;
+    const int2 *s_gcell;
+    const int2 *cell_range;
+    const GridParams *gp;
+    long long *counts;        // per active index
+    const long long *offsets;
+    long long *out;
+};
+
+int osph_launch_unpack(osph_ctx *ctx);
+int osph_launch_pack(osph_ctx *ctx);
+int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt);
+int osph_launch_build(osph_ctx *ctx);            // grid params, keys, sort, cell table, (reorder), gather
+int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt);
+int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log);
+int osph_launch_grid_params(osph_ctx *ctx);
+int osph_launch_ke(osph_ctx *ctx);
+int osph_launch_neighbours(osph_ctx *ctx, int mode, long long *d_counts, const long long *d_offsets, long long *d_out);
+int osph_launch_near_pos(osph_ctx *ctx, double x, double y, double h, long long cap, long long *d_idx, double *d_r,
+                         double *d_q, double *d_h, long long *d_count);
+int osph_launch_cells(osph_ctx *ctx, long long *d_out);
+int osph_launch_col_to_active(osph_ctx *ctx, int field, double *d_out);
+int osph_launch_col_from_active(osph_ctx *ctx, int field, const double *d_in);
+int osph_init_scalars(osph_ctx *ctx);

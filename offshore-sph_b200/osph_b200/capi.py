@@ -1,0 +1,302 @@
+"""ctypes binding of libosph_b200.so (include/osph.h).
+
+This is the thin C-ABI layer named by the north star: host Python hands the
+reference's packed ``particle_dtype`` array to hand-written sm_100a kernels and
+gets it back.  There is no CPU fallback anywhere in this module: if the shared
+library is missing or no CUDA device is present, construction raises.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(PKG_ROOT, "csrc")
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libosph_b200.so")
+HEADER = os.path.join(os.path.dirname(PKG_ROOT), "include", "osph.h")
+
+FP64, FP32 = 0, 1
+KERNELS = {'cubic': 0, 'wendland': 1, 'gaussian': 2}
+INTEGRATORS = {'pec': 0, 'euler': 1, 'verlet': 2}
+FIELDS = ['m', 'rho', 'p', 'c', 'drho', 'h', 'x', 'y', 'vx', 'vy', 'ax', 'ay',
+          'xsphx', 'xsphy', 'x0', 'y0', 'vx0', 'vy0', 'rho0']
+FIELD_ID = {f: i for i, f in enumerate(FIELDS)}
+
+S_NONFINITE, S_SMALL_DT, S_UNBINNED, S_GRID_COARSE = 1, 2, 4, 8
+
+
+class OsphError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("libosph_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in
+                ('struct_size', 'device', 'precision', 'kernel', 'integrator', 'method_xsph',
+                 'integrator_xsph', 'strict', 'summation_density', 'dynamic_h', 'reorder_every', 'reserved0')] + \
+               [(k, C.c_double) for k in
+                ('fixed_h', 'h_sigma', 'nn_scale', 'gamma', 'B', 'rho0', 'Pb', 'co', 'alpha', 'beta', 'epsilon',
+                 'r0', 'D', 'p1', 'p2', 'gravity', 'cfl_courant', 'cfl_force')]
+
+
+def build(force=False, verbose=False):
+    """Compile libosph_b200.so for sm_100a with nvcc (csrc/Makefile). Works without a GPU."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))] + [HEADER]
+    stale = force or not os.path.exists(LIB_PATH) or \
+        os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
+    if stale:
+        out = subprocess.run(["make", "-C", CSRC] + (["-B"] if force else []), capture_output=True, text=True)
+        if verbose or out.returncode != 0:
+            print(out.stdout + out.stderr)
+        if out.returncode != 0:
+            raise RuntimeError("nvcc build of libosph_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (never builds implicitly on a box without the sources' toolchain)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError("libosph_b200.so not found at %s: run __graft_entry__.build() (nvcc, sm_100a). "
+                      "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    ctx = C.c_void_p
+    i64, i32, dbl = C.c_int64, C.c_int32, C.c_double
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    sig = {
+        'osph_version': (C.c_int, []),
+        'osph_default_config': (C.c_int, [C.POINTER(Config), dbl, dbl, dbl]),
+        'osph_create': (C.c_int, [C.POINTER(Config), C.POINTER(ctx)]),
+        'osph_destroy': (C.c_int, [ctx]),
+        'osph_last_error': (C.c_char_p, [ctx]),
+        'osph_upload_aos': (C.c_int, [ctx, C.c_void_p, i64, i64]),
+        'osph_download_aos': (C.c_int, [ctx, C.c_void_p, i64, i64]),
+        'osph_import_device_aos': (C.c_int, [ctx, C.c_void_p, i64, i64]),
+        'osph_export_device_aos': (C.c_int, [ctx, C.c_void_p, i64, i64]),
+        'osph_download_fields': (C.c_int, [ctx, i32, C.POINTER(i32), C.POINTER(dp)]),
+        'osph_upload_fields': (C.c_int, [ctx, i32, C.POINTER(i32), C.POINTER(dp)]),
+        'osph_num_active': (i64, [ctx]),
+        'osph_num_fluid': (i64, [ctx]),
+        'osph_timestep': (C.c_int, [ctx, dp]),
+        'osph_predict': (C.c_int, [ctx, dbl, dbl]),
+        'osph_build_neighbours': (C.c_int, [ctx]),
+        'osph_compute': (C.c_int, [ctx]),
+        'osph_correct': (C.c_int, [ctx, dbl, dbl]),
+        'osph_step': (C.c_int, [ctx, i32, dbl, dbl]),
+        'osph_get_dt_log': (C.c_int, [ctx, dp, i64, ip]),
+        'osph_kinetic_energy': (C.c_int, [ctx, dp]),
+        'osph_sync': (C.c_int, [ctx, C.POINTER(C.c_uint32)]),
+        'osph_get_cells': (C.c_int, [ctx, dp, ip]),
+        'osph_get_neighbours_csr': (C.c_int, [ctx, ip, ip, i64, ip]),
+        'osph_near_pos': (C.c_int, [ctx, dbl, dbl, dbl, i64, ip, dp, dp, dp, ip]),
+        'osph_get_timers': (C.c_int, [ctx, dp]),
+        'osph_launch_count': (i64, [ctx]),
+        'osph_stream': (C.c_uint64, [ctx]),
+        'osph_pair_kernel_time': (C.c_int, [ctx, dp, ip]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._osph_signatures = sig
+    _lib = L
+    return L
+
+
+def default_config(height, r0, rho0=1000.0):
+    cfg = Config()
+    rc = lib().osph_default_config(C.byref(cfg), float(height), float(r0), float(rho0))
+    if rc != 0:
+        raise OsphError(rc, "osph_default_config")
+    return cfg
+
+
+H_FIXED, H_DYNAMIC, H_KEEP = 0, 1, 2
+
+
+def make_config(consts, kernel='cubic', integrator='pec', precision=FP64, fixed_h=None, integrator_xsph=None,
+                strict=False, device=0, reorder_every=0, keep_h=False):
+    """Config from a dict of WCSPH constants (workloads.wcsph_constants / a src.Methods.WCSPH object's fields)."""
+    cfg = default_config(consts['height'], consts['r0'], consts['rho0'])
+    for k in ('gamma', 'B', 'Pb', 'co', 'alpha', 'beta', 'epsilon', 'D', 'p1', 'p2'):
+        setattr(cfg, k, float(consts[k]))
+    cfg.device = device
+    cfg.precision = precision
+    cfg.kernel = KERNELS[kernel] if isinstance(kernel, str) else int(kernel)
+    cfg.integrator = INTEGRATORS[integrator] if isinstance(integrator, str) else int(integrator)
+    cfg.method_xsph = int(bool(consts['useXSPH']))
+    cfg.integrator_xsph = int(bool(consts['useXSPH'] if integrator_xsph is None else integrator_xsph))
+    cfg.strict = int(bool(strict))
+    cfg.summation_density = int(bool(consts.get('useSummationDensity', False)))
+    cfg.dynamic_h = H_KEEP if keep_h else (H_DYNAMIC if fixed_h is None else H_FIXED)
+    cfg.fixed_h = 0.0 if fixed_h is None else float(fixed_h)
+    cfg.reorder_every = reorder_every
+    return cfg
+
+
+class Context:
+    """One device-resident particle set + the kernels of the WCSPH step (one per GPU)."""
+
+    def __init__(self, cfg):
+        self._L = lib()
+        self._h = C.c_void_p()
+        self.cfg = cfg
+        rc = self._L.osph_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise OsphError(rc, self._L.osph_last_error(None).decode())
+        self._shape = None
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self._L.osph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise OsphError(rc, self._L.osph_last_error(self._h).decode())
+
+    # ---- transfers ----
+    def upload(self, pA):
+        assert pA.dtype.itemsize >= 154 and pA.flags['C_CONTIGUOUS']
+        self._shape = (len(pA), pA.dtype.itemsize)
+        self._ck(self._L.osph_upload_aos(self._h, pA.ctypes.data, len(pA), pA.dtype.itemsize))
+
+    def download(self, pA):
+        self._ck(self._L.osph_download_aos(self._h, pA.ctypes.data, len(pA), pA.dtype.itemsize))
+        return pA
+
+    def import_device(self, ptr, n, stride=154):
+        self._shape = (n, stride)
+        self._ck(self._L.osph_import_device_aos(self._h, C.c_void_p(ptr), n, stride))
+
+    def export_device(self, ptr, n, stride=154):
+        self._ck(self._L.osph_export_device_aos(self._h, C.c_void_p(ptr), n, stride))
+
+    def download_fields(self, names):
+        n = self.num_active
+        cols = [np.empty(n, dtype=np.float64) for _ in names]
+        ids = (C.c_int32 * len(names))(*[FIELD_ID[f] for f in names])
+        ptrs = (C.POINTER(C.c_double) * len(names))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
+        self._ck(self._L.osph_download_fields(self._h, len(names), ids, ptrs))
+        return dict(zip(names, cols))
+
+    def upload_fields(self, cols):
+        names = list(cols)
+        arrs = [np.ascontiguousarray(cols[f], dtype=np.float64) for f in names]
+        assert all(len(a) == self.num_active for a in arrs)
+        ids = (C.c_int32 * len(names))(*[FIELD_ID[f] for f in names])
+        ptrs = (C.POINTER(C.c_double) * len(names))(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in arrs])
+        self._ck(self._L.osph_upload_fields(self._h, len(names), ids, ptrs))
+
+    @property
+    def num_active(self):
+        return int(self._L.osph_num_active(self._h))
+
+    @property
+    def num_fluid(self):
+        return int(self._L.osph_num_fluid(self._h))
+
+    # ---- the per-step calls ----
+    def timestep(self):
+        out = (C.c_double * 3)()
+        self._ck(self._L.osph_timestep(self._h, out))
+        return out[0], out[1], out[2]
+
+    def predict(self, dt, damping):
+        self._ck(self._L.osph_predict(self._h, dt, damping))
+
+    def build_neighbours(self):
+        self._ck(self._L.osph_build_neighbours(self._h))
+
+    def compute(self):
+        self._ck(self._L.osph_compute(self._h))
+
+    def correct(self, dt, damping):
+        self._ck(self._L.osph_correct(self._h, dt, damping))
+
+    def step(self, nsteps=1, fixed_dt=None, damping=0.0):
+        self._ck(self._L.osph_step(self._h, nsteps, -1.0 if fixed_dt is None else fixed_dt, damping))
+
+    def dt_log(self, cap=65536):
+        out = np.zeros((cap, 3))
+        cnt = C.c_int64(0)
+        self._ck(self._L.osph_get_dt_log(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(cnt)))
+        return out[:min(cnt.value, cap)]
+
+    def kinetic_energy(self):
+        ke = C.c_double(0)
+        self._ck(self._L.osph_kinetic_energy(self._h, C.byref(ke)))
+        return ke.value
+
+    def sync(self):
+        st = C.c_uint32(0)
+        self._ck(self._L.osph_sync(self._h, C.byref(st)))
+        return st.value
+
+    # ---- validation / queries ----
+    def cells(self):
+        grid = (C.c_double * 7)()
+        ids = np.zeros(self.num_active, dtype=np.int64)
+        self._ck(self._L.osph_get_cells(self._h, grid, ids.ctypes.data_as(C.POINTER(C.c_int64))))
+        g = dict(xmin=grid[0], xmax=grid[1], ymin=grid[2], ymax=grid[3], cell_size=grid[4],
+                 ncx=int(grid[5]), ncy=int(grid[6]))
+        return g, ids
+
+    def neighbours_csr(self):
+        n = self.num_active
+        off = np.zeros(n + 1, dtype=np.int64)
+        total = C.c_int64(0)
+        ip = C.POINTER(C.c_int64)
+        self._ck(self._L.osph_get_neighbours_csr(self._h, off.ctypes.data_as(ip), None, 0, C.byref(total)))
+        idx = np.zeros(max(total.value, 1), dtype=np.int64)
+        self._ck(self._L.osph_get_neighbours_csr(self._h, off.ctypes.data_as(ip), idx.ctypes.data_as(ip),
+                                                 len(idx), C.byref(total)))
+        return off, idx[:total.value]
+
+    def near_pos(self, x, y, h, cap=256):
+        ip, dp = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+        while True:
+            idx = np.zeros(cap, dtype=np.int64); r = np.zeros(cap); q = np.zeros(cap); hh = np.zeros(cap)
+            cnt = C.c_int64(0)
+            self._ck(self._L.osph_near_pos(self._h, x, y, h, cap, idx.ctypes.data_as(ip), r.ctypes.data_as(dp),
+                                           q.ctypes.data_as(dp), hh.ctypes.data_as(dp), C.byref(cnt)))
+            if cnt.value <= cap:
+                k = cnt.value
+                return hh[:k], q[:k], r[:k], idx[:k]
+            cap = int(cnt.value)
+
+    def timers(self):
+        out = (C.c_double * 6)()
+        self._ck(self._L.osph_get_timers(self._h, out))
+        return dict(zip(('time_step', 'integrate_prediction', 'neighbour_hood', 'compute',
+                         'integrate_correction', 'transfer'), [v * 1e-3 for v in out]))
+
+    @property
+    def launch_count(self):
+        return int(self._L.osph_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return int(self._L.osph_stream(self._h))
+
+    def pair_kernel_time(self):
+        us = C.c_double(0); n = C.c_int64(0)
+        self._ck(self._L.osph_pair_kernel_time(self._h, C.byref(us), C.byref(n)))
+        return us.value, n.value

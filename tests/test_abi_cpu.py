@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/osph.h declares.
+No compute call is made here (there is no GPU in the build container and the library has no CPU path)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from osph_b200 import capi
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    return capi.build()
+
+
+def test_header_symbols_exported(libpath):
+    hdr = open(os.path.join(ROOT, "include", "osph.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(osph_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = C.CDLL(libpath)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    bound = set(capi.lib()._osph_signatures)
+    assert declared == bound, declared ^ bound
+
+
+def test_config_layout_and_defaults(libpath):
+    cfg = capi.default_config(25.0, 0.5, 1000.0)
+    assert cfg.struct_size == C.sizeof(capi.Config)
+    assert cfg.co == 221.47234590350104 and cfg.B == 7007142.857142859 and cfg.D == 1226.25
+    assert (cfg.gamma, cfg.alpha, cfg.beta, cfg.epsilon, cfg.p1, cfg.p2) == (7.0, 0.01, 0.0, 0.5, 4.0, 2.0)
+    assert (cfg.nn_scale, cfg.h_sigma, cfg.cfl_courant, cfg.cfl_force, cfg.gravity) == (2.0, 1.3, 0.25, 0.25, 9.81)
+    assert capi.lib().osph_version() == 1
+
+
+def test_no_cpu_fallback(libpath):
+    """Without a CUDA device context creation must fail loudly; with one it must succeed."""
+    import torch
+    cfg = capi.default_config(25.0, 0.5)
+    if torch.cuda.is_available():
+        capi.Context(cfg).close()
+    else:
+        with pytest.raises(capi.OsphError) as e:
+            capi.Context(cfg)
+        assert e.value.code == -3 and "no CPU path" in str(e.value)
+
+
+def test_bad_struct_size_rejected(libpath):
+    cfg = capi.default_config(25.0, 0.5)
+    cfg.struct_size = 8
+    with pytest.raises(capi.OsphError) as e:
+        capi.Context(cfg)
+    assert e.value.code == -1
+
+
+def test_product_never_touches_oracle():
+    """The product package must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "offshore-sph_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h', 'Makefile')):
+                txt = open(os.path.join(d, f), errors='ignore').read()
+                if re.search(r"\boracle\b", txt) and 'oracle' in txt.replace("CPU oracle", ""):
+                    for line in txt.splitlines():
+                        if re.search(r"^\s*(from|import)\s+oracle|liboracle|oracle/", line):
+                            bad.append((f, line.strip()))
+    assert not bad, bad

@@ -1,0 +1,279 @@
+"""GPU: the CUDA path (through the C ABI) against the golden vectors frozen from the reference and
+against the CPU oracle on the same seeded inputs.
+
+Bars (north star): cell assignment and neighbour SETS bit-exact; FP64 fields within 1e-10
+(norm-wise, conftest.field_err) per step; dt within 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import STEP_CASES, field_err, load_golden
+from oracle import oracle as O
+from osph_b200 import capi
+from osph_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+LOOP_FIELDS = ('p', 'c', 'drho', 'ax', 'ay', 'xsphx', 'xsphy')
+STATE_FIELDS = ('x', 'y', 'vx', 'vy', 'rho', 'drho', 'ax', 'ay', 'xsphx', 'xsphy', 'p', 'h')
+
+
+def _ctx(meta, precision=capi.FP64, keep_h=False, integrator='pec', kernel=None, reorder_every=0):
+    cfg = capi.make_config(meta['consts'] | {'useXSPH': meta['useXSPH']}, kernel or meta['kernel'], integrator,
+                           precision, meta['fixed_h'], strict=meta['strict'], keep_h=keep_h,
+                           reorder_every=reorder_every)
+    return capi.Context(cfg)
+
+
+def _sorted_lists(off, idx):
+    return [np.sort(idx[off[i]:off[i + 1]]) for i in range(len(off) - 1)]
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_cells_and_neighbour_sets_bit_exact(name):
+    g, meta, pA = load_golden(name)
+    with _ctx(meta, keep_h=True) as ctx:
+        ctx.upload(pA)
+        ctx.build_neighbours()
+        grid, cells = ctx.cells()
+        assert [grid['xmin'], grid['xmax'], grid['ymin'], grid['ymax'], grid['cell_size']] == list(g['grid'][:5])
+        assert (grid['ncx'], grid['ncy']) == (int(g['grid'][5]), int(g['grid'][6]))
+        assert np.array_equal(cells, g['cell_ids'])
+        off, idx = ctx.neighbours_csr()
+        assert np.array_equal(off, g['nbr_off'])
+        want = _sorted_lists(g['nbr_off'], g['nbr_idx'].astype(np.int64))
+        got = _sorted_lists(off, idx)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        assert ctx.sync() == 0
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_loop_fields_vs_golden(name):
+    g, meta, pA = load_golden(name)
+    with _ctx(meta, keep_h=True) as ctx:
+        ctx.upload(pA)
+        ctx.compute()
+        out = ctx.download(pA.copy())
+        for f in LOOP_FIELDS:
+            assert field_err(out[f], g['loop_' + f]) <= TOL, f
+        # columns the loop does not write come back bit-identical
+        for f in ('x', 'y', 'vx', 'vy', 'rho', 'm', 'h', 'x0', 'rho0'):
+            assert np.array_equal(out[f], pA[f]), f
+        assert np.array_equal(out['label'], pA['label']) and np.array_equal(out['deleted'], pA['deleted'])
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_whole_steps_vs_golden(name):
+    g, meta, pA = load_golden(name)
+    with _ctx(meta) as ctx:
+        ctx.upload(pA)
+        for s in range(meta['nsteps']):
+            dt, dc, df = ctx.timestep()
+            assert np.allclose([dt, dc, df], g['dts'][s], rtol=1e-10, atol=0)
+            ctx.predict(dt, meta['damping'])
+            ctx.build_neighbours()
+            ctx.compute()
+            ctx.correct(dt, meta['damping'])
+            cols = ctx.download_fields(list(STATE_FIELDS))
+            for f in STATE_FIELDS:
+                assert field_err(cols[f], g['step_' + f][s]) <= TOL, (s, f)
+        assert ctx.sync() == 0
+
+
+@pytest.mark.parametrize("name", ['dambreak20_wendland', 'tank30_cubic_dynh'])
+def test_fused_loop_equals_explicit_calls(name):
+    g, meta, pA = load_golden(name)
+    n = 4
+    with _ctx(meta) as a, _ctx(meta) as b:
+        a.upload(pA); b.upload(pA)
+        dts = []
+        for _ in range(n):
+            dt = a.timestep(); dts.append(dt)
+            a.predict(dt[0], meta['damping']); a.build_neighbours(); a.compute(); a.correct(dt[0], meta['damping'])
+        b.step(n, None, meta['damping'])
+        A = a.download(pA.copy()); B = b.download(pA.copy())
+        assert A.tobytes() == B.tobytes()
+        assert np.array_equal(b.dt_log(), np.asarray(dts))
+
+
+@pytest.mark.parametrize("integrator", ['euler', 'verlet'])
+def test_other_integrators_vs_oracle(integrator):
+    g, meta, pA = load_golden('dambreak20_cubic')
+    P = O.Particles.from_aos(pA)
+    w = O.wcsph(**{k: meta['consts'][k] for k in ('height', 'r0', 'rho0')}, useXSPH=True)
+    with _ctx(meta, integrator=integrator) as ctx:
+        ctx.upload(pA)
+        for s in range(3):
+            dt3, _ = O.step(P, w, 'cubic', integrator, True, False, 0.0, meta['fixed_h'])
+            ctx.step(1, None, 0.0)
+            cols = ctx.download_fields(list(STATE_FIELDS))
+            for f in STATE_FIELDS:
+                assert field_err(cols[f], getattr(P, f)) <= TOL, (s, f)
+        assert np.allclose(ctx.dt_log()[-1], dt3, rtol=1e-10)
+
+
+@pytest.mark.parametrize("N,kernel", [(60, 'wendland'), (150, 'cubic'), (150, 'gaussian'), (150, 'wendland')])
+def test_dam_break_vs_oracle(N, kernel):
+    """Larger seeded dam breaks: N=60 is the truncating regime (3h > cell), N=150 the fine-cell regime."""
+    case = W.dam_break_case(N, seed=5)
+    pA, c = case['pA'], case['consts']
+    P = O.Particles.from_aos(pA)
+    w = O.wcsph(c['height'], c['r0'], c['rho0'], True)
+    cfg = capi.make_config(c, kernel, 'pec', capi.FP64, case['h'])
+    with capi.Context(cfg) as ctx:
+        ctx.upload(pA)
+        ctx.build_neighbours()
+        grid, cells = ctx.cells()
+        og = O.Grid(P)
+        assert np.array_equal(cells, og.cell_ids())
+        off, idx = ctx.neighbours_csr()
+        ooff, oidx = og.neighbours_csr()
+        assert np.array_equal(off, ooff)
+        assert all(np.array_equal(a, b) for a, b in zip(_sorted_lists(off, idx), _sorted_lists(ooff, oidx)))
+        for s in range(2):
+            dt3, _ = O.step(P, w, kernel, 'pec', True, False, 0.05, case['h'])
+            ctx.step(1, None, 0.05)
+            cols = ctx.download_fields(list(STATE_FIELDS))
+            for f in STATE_FIELDS:
+                assert field_err(cols[f], getattr(P, f)) <= TOL, (s, f)
+            assert np.allclose(ctx.dt_log()[-1], dt3, rtol=1e-10)
+
+
+def test_reorder_cadence_does_not_change_results():
+    """Physical re-sorting of the device state only permutes storage: fields agree to summation order."""
+    case = W.dam_break_case(40, seed=6)
+    outs = []
+    for every in (1, 3, 1000):
+        cfg = capi.make_config(case['consts'], 'wendland', 'pec', capi.FP64, case['h'], reorder_every=every)
+        with capi.Context(cfg) as ctx:
+            ctx.upload(case['pA'])
+            ctx.step(7, None, 0.05)
+            outs.append(ctx.download(case['pA'].copy()))
+    for o in outs[1:]:
+        for f in STATE_FIELDS:
+            assert field_err(o[f], outs[0][f]) <= 1e-11, f
+
+
+def test_fp32_mode_close_to_fp64():
+    """Performance mode: float pair arithmetic on anchor-relative positions; drift bounded and reported."""
+    case = W.dam_break_case(100, seed=7)
+    res = {}
+    for prec in (capi.FP64, capi.FP32):
+        cfg = capi.make_config(case['consts'], 'wendland', 'pec', prec, case['h'])
+        with capi.Context(cfg) as ctx:
+            ctx.upload(case['pA'])
+            ctx.step(20, None, 0.05)
+            res[prec] = ctx.download(case['pA'].copy())
+    a, b = res[capi.FP64], res[capi.FP32]
+    r0 = case['r0']
+    assert np.max(np.hypot(a['x'] - b['x'], a['y'] - b['y'])) < 1e-4 * r0      # position drift after 20 steps
+    assert field_err(b['rho'], a['rho']) < 1e-6
+    assert field_err(b['ax'], a['ax']) < 5e-3 and field_err(b['ay'], a['ay']) < 5e-3
+
+
+def test_deleted_rows_untouched_and_index_space():
+    """Deleted rows never reach the kernels and come back verbatim; indices are in compacted active order."""
+    g, meta, pA = load_golden('dambreak20_wendland')
+    pB = pA.copy()
+    dead = np.flatnonzero(pB['label'] == 2)          # remove the temporary gate, as Solver.run() does after settling
+    pB['deleted'][dead] = True
+    pB['p'][dead] = -1e15
+    act = pB[~pB['deleted']]
+    P = O.Particles.from_aos(act)
+    og = O.Grid(P)
+    with _ctx(meta, keep_h=True) as ctx:
+        ctx.upload(pB)
+        assert ctx.num_active == len(act) and ctx.num_fluid == int((act['label'] == 0).sum())
+        ctx.compute()
+        off, idx = ctx.neighbours_csr()
+        ooff, oidx = og.neighbours_csr()
+        assert np.array_equal(off, ooff)
+        assert all(np.array_equal(a, b) for a, b in zip(_sorted_lists(off, idx), _sorted_lists(ooff, oidx)))
+        out = ctx.download(pB.copy())
+        assert out[dead].tobytes() == pB[dead].tobytes()
+        w = O.wcsph(**{k: meta['consts'][k] for k in ('height', 'r0', 'rho0')}, useXSPH=True)
+        O.loop(P, w, og, 'wendland')
+        for f in LOOP_FIELDS:
+            assert field_err(out[f][~pB['deleted']], getattr(P, f)) <= TOL, f
+
+
+def test_near_pos_matches_oracle():
+    g, meta, pA = load_golden('tank24_wendland_coupled')
+    P = O.Particles.from_aos(pA)
+    og = O.Grid(P)
+    rng = np.random.default_rng(1)
+    with _ctx(meta, keep_h=True) as ctx:
+        ctx.upload(pA)
+        ctx.build_neighbours()
+        for _ in range(20):
+            x, y = rng.uniform(0, 1, 2)
+            h = float(rng.uniform(0.03, 0.12))
+            hh, q, r, idx = ctx.near_pos(x, y, h)
+            oh, oq, orr, oidx = og.near_pos(x, y, h)
+            order = np.argsort(oidx)
+            assert np.array_equal(idx, oidx[order])
+            assert np.array_equal(r, orr[order]) and np.array_equal(q, oq[order]) and np.array_equal(hh, oh[order])
+
+
+def test_kinetic_energy_and_timestep_edges():
+    g, meta, pA = load_golden('dambreak20_cubic')
+    P = O.Particles.from_aos(pA)
+    with _ctx(meta) as ctx:
+        ctx.upload(pA)
+        assert ctx.kinetic_energy() == pytest.approx(O.kinetic_energy(P, P.fluid), rel=1e-13)
+        assert ctx.timestep() == O.timestep(P, P.fluid)          # strict-IEEE reduction: bit-exact
+    # no fluid particle: the reference raises from np.min([]); the ABI returns OSPH_E_NO_FLUID
+    walls = pA[pA['label'] != 0]
+    with _ctx(meta) as ctx:
+        ctx.upload(walls)
+        with pytest.raises(capi.OsphError) as e:
+            ctx.timestep()
+        assert e.value.code == -5
+    # nothing uploaded
+    with _ctx(meta) as ctx:
+        with pytest.raises(capi.OsphError):
+            ctx.compute()
+
+
+def test_upload_fields_roundtrip_and_single_particle():
+    g, meta, pA = load_golden('block20_cubic_nobnd')
+    with _ctx(meta) as ctx:
+        ctx.upload(pA)
+        cols = ctx.download_fields(['x', 'vy', 'c'])
+        assert np.array_equal(cols['x'], pA['x']) and np.array_equal(cols['c'], pA['c'])
+        ctx.upload_fields({'vy': cols['vy'] * 2.0})
+        assert np.array_equal(ctx.download_fields(['vy'])['vy'], pA['vy'] * 2.0)
+    one = pA[:1].copy()
+    with _ctx(meta) as ctx:                                       # a lone particle only sees itself
+        ctx.upload(one)
+        ctx.compute()
+        off, idx = ctx.neighbours_csr()
+        assert list(off) == [0, 1] and list(idx) == [0]
+        out = ctx.download(one.copy())
+        assert out['ax'][0] == 0.0 and out['ay'][0] == -9.81 and out['drho'][0] == 0.0
+
+
+def test_particle_on_upper_grid_edge():
+    """Extent an exact multiple of the cell: the reference bins x == xmax into column ncx, which
+    wraps into the next row (or past the table).  The CUDA path reproduces the wrap bit for bit."""
+    c = W.wcsph_constants(2.0, 0.25, 1000.0, True)
+    xs, ys = np.meshgrid(np.linspace(0.0, 2.0, 9), np.linspace(0.0, 3.0, 13), indexing='ij')
+    pA = np.zeros(xs.size, dtype=O.particle_dtype)
+    pA['x'] = xs.ravel(); pA['y'] = ys.ravel() + 0.01 * np.sin(7 * xs.ravel())
+    pA['y'][0] = 0.0; pA['y'][-1] = 3.0
+    pA['m'] = 62.5; pA['rho'] = 1000.0; pA['h'] = 0.5
+    pA['label'][:13] = 1; pA['h'][:13] = 0.0
+    P = O.Particles.from_aos(pA)
+    og = O.Grid(P)
+    cfg = capi.make_config(c, 'cubic', 'pec', capi.FP64, 0.5, keep_h=True)
+    with capi.Context(cfg) as ctx:
+        ctx.upload(pA)
+        ctx.build_neighbours()
+        grid, cells = ctx.cells()
+        assert grid['cell_size'] == 1.0 and (grid['ncx'], grid['ncy']) == (og.params['ncx'], og.params['ncy'])
+        assert np.array_equal(cells, og.cell_ids())
+        off, idx = ctx.neighbours_csr()
+        ooff, oidx = og.neighbours_csr()
+        assert np.array_equal(off, ooff)
+        assert all(np.array_equal(a, b) for a, b in zip(_sorted_lists(off, idx), _sorted_lists(ooff, oidx)))
+        assert (ctx.sync() & capi.S_UNBINNED) == (capi.S_UNBINNED if og.rc != 0 else 0)
