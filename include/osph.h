@@ -104,6 +104,7 @@ typedef struct osph_config {
     double  r0, D, p1, p2;                /* Lennard-Jones boundary force */
     double  gravity;                      /* 9.81, subtracted from ay (WCSPH.py:168-169) */
     double  cfl_courant, cfl_force;       /* 0.25, 0.25 (src/Solver.py:215) */
+    double  height;                       /* WCSPH.height: fluid column height of the hydrostatic initialisation */
 } osph_config;
 
 /* Fill *cfg with the reference defaults for WCSPH(height, r0, rho0, ...). replaces: src/Methods/WCSPH.py:56-79 */
@@ -137,6 +138,13 @@ int osph_download_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, 
 int osph_upload_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, const double *const *cols);
 int64_t osph_num_active(const osph_ctx *ctx);
 int64_t osph_num_fluid(const osph_ctx *ctx);
+
+/*
+ * Initialise the fluid rows as Solver.setup() does: h (fixed or computeH on the uploaded rho), hydrostatic
+ * density rho0 (1 + rho0 g (H - y) / B)^(1/gamma), pressure and speed of sound.
+ * replaces: src/Solver.py:184-196 (WCSPH.initialize src/Methods/WCSPH.py:82-108, TaitEOS.py:46-65).
+ */
+int osph_initialize(osph_ctx *ctx);
 
 /* ---- the five per-step calls of Solver.run() ------------------------------------------------- */
 
@@ -191,6 +199,22 @@ int64_t osph_launch_count(const osph_ctx *ctx);
 uint64_t osph_stream(const osph_ctx *ctx);
 /* Average device time of the fused pair kernel over the launches since the last call, microseconds. */
 int osph_pair_kernel_time(osph_ctx *ctx, double *avg_us, int64_t *launches);
+
+/* ---- stand-alone leaf functions on host arrays (context-free; `device` is a CUDA ordinal) ---------- */
+
+/* what == 0: kernel.evaluate(r, h); what == 1: kernel.gradient(x, r, h).
+ * replaces: src/Kernels/CubicSpline.py:10-70, Wendland.py:9-64, Gaussian.py:16-59 */
+int osph_leaf_kernel(int device, int kernel, int what, int64_t n, const double *x, const double *r,
+                     const double *h, double *out);
+/* replaces: WCSPH.compute_pressure src/Methods/WCSPH.py:131-149 (TaitEOS ufunc, TaitEOS.py:6-31) */
+int osph_leaf_tait_pressure(int device, int64_t n, const double *rho, const int8_t *label, double gamma,
+                            double B, double rho0, double Pb, double *out);
+/* replaces: TaitEOS_height src/Equations/TaitEOS.py:46-65 */
+int osph_leaf_tait_height(int device, int64_t n, const double *y, double rho0, double H, double B,
+                          double gamma, double *out);
+/* replaces: computeH src/Tools/SolverTools.py:106-118 */
+int osph_leaf_compute_h(int device, int64_t n, double sigma, const double *m, const double *rho, double *out);
+const char *osph_leaf_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -102,7 +102,7 @@ extern "C" int osph_default_config(osph_config *cfg, double height, double r0, d
     cfg->rho0 = rho0; cfg->Pb = 0.0;
     cfg->alpha = 0.01; cfg->beta = 0.0; cfg->epsilon = 0.5;
     cfg->r0 = r0; cfg->D = 5 * 9.81 * height; cfg->p1 = 4; cfg->p2 = 2;
-    cfg->gravity = 9.81; cfg->cfl_courant = 0.25; cfg->cfl_force = 0.25;
+    cfg->gravity = 9.81; cfg->cfl_courant = 0.25; cfg->cfl_force = 0.25; cfg->height = height;
     return 0;
 }
 
@@ -277,6 +277,16 @@ extern "C" int osph_upload_fields(osph_ctx *ctx, int32_t nfields, const int32_t 
 
 extern "C" int64_t osph_num_active(const osph_ctx *ctx) { return ctx ? ctx->n : 0; }
 extern "C" int64_t osph_num_fluid(const osph_ctx *ctx) { return ctx ? ctx->n_fluid : 0; }
+
+extern "C" int osph_initialize(osph_ctx *ctx)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    int rc = osph_launch_setup(ctx);
+    if (rc) return rc;
+    if (ctx->c_uniform) ctx->c_uniform = false;     // c now holds per-row values again (non-fluid rows keep theirs)
+    invalidate_state(ctx);
+    return 0;
+}
 
 // ---- the per-step calls --------------------------------------------------------------------------
 

@@ -21,75 +21,7 @@
 #include "common.cuh"
 #include "pair.cuh"
 
-#define PI_D 3.14159265358979323846
-
-template <typename Real> struct R2;
-template <> struct R2<double> { typedef double2 type; };
-template <> struct R2<float> { typedef float2 type; };
-
-// ---- fast reciprocal / rsqrt in double: MUFU seed + Newton, ~1 ulp, no special-case branches ----------
-__device__ __forceinline__ double rcp_fast(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0); y = fma(y, e, y);
-    e = fma(-x, y, 1.0); y = fma(y, e, y);
-    e = fma(-x, y, 1.0); y = fma(y, e, y);
-    return y;
-}
-__device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
-
-__device__ __forceinline__ double rsqrt_fast(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    // Newton for 1/sqrt(x): y <- y + y*(1 - x*y*y)/2
-    double hx = 0.5 * x;
-    double e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
-    e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
-    e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
-    return y;
-}
-__device__ __forceinline__ float rsqrt_fast(float x) { return rsqrtf(x); }
-
-__device__ __forceinline__ double exp_neg(double x) { return exp(-x); }
-__device__ __forceinline__ float exp_neg(float x) { return __expf(-x); }
-
-__device__ __forceinline__ double pow_gen(double a, double b) { return pow(a, b); }
-__device__ __forceinline__ float pow_gen(float a, float b) { return __powf(a, b); }
-
-// ---- smoothing kernels: value w and gradient factor g with  grad W = g * (dx, dy) ---------------------
-// reference: CubicSpline.py:10-70, Wendland.py:9-64, Gaussian.py:16-59.  inv_r == 0 encodes r < 1e-10
-// (the reference zeroes the gradient there).
-template <typename Real, int KID>
-__device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
-{
-    const Real ih2 = inv_h * inv_h;
-    if (KID == OSPH_KERNEL_CUBIC) {
-        const Real alpha = Real(10.0 / (7.0 * PI_D)) * ih2;
-        Real wv, gv;
-        if (q > Real(1)) { Real t = Real(2) - q; Real t2 = t * t; wv = Real(0.25) * t2 * t; gv = Real(-0.75) * t2; }
-        else { wv = Real(1) - Real(1.5) * q * q * (Real(1) - Real(0.5) * q); gv = Real(-3) * q * (Real(1) - Real(0.75) * q); }
-        if (q > Real(2)) { wv = Real(0); gv = Real(0); }
-        w = alpha * wv;
-        g = alpha * gv * inv_h * inv_r;
-    } else if (KID == OSPH_KERNEL_WENDLAND) {
-        const Real alpha = Real(9.0 / (4.0 * PI_D)) * ih2;
-        Real in = Real(1) - Real(0.5) * q;
-        Real in2 = in * in, in4 = in2 * in2, in5 = in4 * in;
-        Real wv = in5 * in * (Real(35.0 / 12.0) * q * q + Real(3) * q + Real(1));
-        Real gv = in5 * Real(-14.0 / 3.0) * q * (Real(1) + Real(2.5) * q);
-        if (q >= Real(2)) { wv = Real(0); gv = Real(0); }
-        w = alpha * wv;
-        g = alpha * gv * inv_h * inv_r;
-    } else {
-        const Real alpha = Real(1.0 / PI_D) * ih2;
-        Real e = exp_neg(q * q);
-        Real wv = alpha * e;                          // q <= 3 is decided by the caller (set membership)
-        w = wv;
-        g = Real(-2) * q * wv * inv_h * inv_r;      // dwdq / (r h) ; inv_r == 0 also covers r*h <= 1e-12
-    }
-}
+#include "sph_math.cuh"
 
 template <typename Real, int KID, bool EXACT>
 __global__ void __launch_bounds__(OSPH_PAIR_THREADS)

@@ -74,6 +74,24 @@ __global__ void k_fill_c(double *__restrict__ c, int n, double co)
     if (i < n) c[i] = co;
 }
 
+// Solver.setup() on the fluid rows (reference src/Solver.py:184-196): smoothing length from the uploaded
+// density, hydrostatic density (WCSPH.initialize, TaitEOS_height), then pressure and speed of sound.
+__global__ void k_setup(int n, const signed char *__restrict__ label, const double *__restrict__ m,
+                        const double *__restrict__ y, double *__restrict__ rho, double *__restrict__ h,
+                        double *__restrict__ p, double *__restrict__ c, int dynamic_h, double fixed_h, double h_sigma,
+                        double rho0, double H, double B, double gamma, double Pb, double co)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || label[i] != OSPH_FLUID) return;
+    if (dynamic_h == OSPH_H_DYNAMIC) h[i] = rho[i] > 1e-12 ? h_sigma * sqrt(m[i] / rho[i]) : 0.0;
+    else if (dynamic_h == OSPH_H_FIXED) h[i] = fixed_h;
+    double frac = rho0 * 9.81 * (H - y[i]) / B;
+    double r = rho0 * pow(1.0 + frac, 1.0 / gamma);
+    rho[i] = r;
+    p[i] = (pow(r / rho0, gamma) - 1.0) * B + Pb;
+    c[i] = co;
+}
+
 // ---------------------------------------------------------------------------------------------
 // scalars
 // ---------------------------------------------------------------------------------------------
@@ -579,6 +597,17 @@ int osph_init_scalars(osph_ctx *ctx)
     k_init_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
     k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
     k_reset_dt_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_setup(osph_ctx *ctx)
+{
+    const osph_config &c = ctx->cfg;
+    k_setup<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>((int)ctx->n, ctx->label, ctx->f[OSPH_F_M], ctx->f[OSPH_F_Y],
+                                                          ctx->f[OSPH_F_RHO], ctx->f[OSPH_F_H], ctx->f[OSPH_F_P],
+                                                          ctx->f[OSPH_F_C], c.dynamic_h, c.fixed_h, c.h_sigma, c.rho0,
+                                                          c.height, c.B, c.gamma, c.Pb, c.co);
+    OSPH_LAUNCH_CHECK();
     return 0;
 }
 

@@ -54,6 +54,7 @@ struct NeighbourArgs {
     long long *out;
 };
 
+int osph_launch_setup(osph_ctx *ctx);
 int osph_launch_unpack(osph_ctx *ctx);
 int osph_launch_pack(osph_ctx *ctx);
 int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt);

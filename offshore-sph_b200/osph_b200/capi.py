@@ -40,7 +40,7 @@ class Config(C.Structure):
                  'integrator_xsph', 'strict', 'summation_density', 'dynamic_h', 'reorder_every', 'reserved0')] + \
                [(k, C.c_double) for k in
                 ('fixed_h', 'h_sigma', 'nn_scale', 'gamma', 'B', 'rho0', 'Pb', 'co', 'alpha', 'beta', 'epsilon',
-                 'r0', 'D', 'p1', 'p2', 'gravity', 'cfl_courant', 'cfl_force')]
+                 'r0', 'D', 'p1', 'p2', 'gravity', 'cfl_courant', 'cfl_force', 'height')]
 
 
 def build(force=False, verbose=False):
@@ -86,6 +86,7 @@ def lib():
         'osph_upload_fields': (C.c_int, [ctx, i32, C.POINTER(i32), C.POINTER(dp)]),
         'osph_num_active': (i64, [ctx]),
         'osph_num_fluid': (i64, [ctx]),
+        'osph_initialize': (C.c_int, [ctx]),
         'osph_timestep': (C.c_int, [ctx, dp]),
         'osph_predict': (C.c_int, [ctx, dbl, dbl]),
         'osph_build_neighbours': (C.c_int, [ctx]),
@@ -102,6 +103,11 @@ def lib():
         'osph_launch_count': (i64, [ctx]),
         'osph_stream': (C.c_uint64, [ctx]),
         'osph_pair_kernel_time': (C.c_int, [ctx, dp, ip]),
+        'osph_leaf_kernel': (C.c_int, [C.c_int, C.c_int, C.c_int, i64, dp, dp, dp, dp]),
+        'osph_leaf_tait_pressure': (C.c_int, [C.c_int, i64, dp, C.POINTER(C.c_int8), dbl, dbl, dbl, dbl, dp]),
+        'osph_leaf_tait_height': (C.c_int, [C.c_int, i64, dp, dbl, dbl, dbl, dbl, dp]),
+        'osph_leaf_compute_h': (C.c_int, [C.c_int, i64, dbl, dp, dp, dp]),
+        'osph_leaf_last_error': (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -213,6 +219,9 @@ class Context:
     def num_fluid(self):
         return int(self._L.osph_num_fluid(self._h))
 
+    def initialize(self):
+        self._ck(self._L.osph_initialize(self._h))
+
     # ---- the per-step calls ----
     def timestep(self):
         out = (C.c_double * 3)()
@@ -300,3 +309,50 @@ class Context:
         us = C.c_double(0); n = C.c_int64(0)
         self._ck(self._L.osph_pair_kernel_time(self._h, C.byref(us), C.byref(n)))
         return us.value, n.value
+
+
+# ---- stand-alone leaf functions (host arrays in, host arrays out; computed on the device) ----------
+
+def _leaf_ck(rc):
+    if rc != 0:
+        raise OsphError(rc, lib().osph_leaf_last_error().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def default_device():
+    return int(os.environ.get("OSPH_DEVICE", "0"))
+
+
+def leaf_kernel(kernel, what, x, r, h):
+    r = _f64(r); h = _f64(np.broadcast_to(h, r.shape)); out = np.empty_like(r)
+    x = _f64(np.broadcast_to(x, r.shape)) if x is not None else None
+    _leaf_ck(lib().osph_leaf_kernel(default_device(), KERNELS[kernel], what, r.size,
+                                    _ptr(x) if x is not None else None, _ptr(r), _ptr(h), _ptr(out)))
+    return out
+
+
+def leaf_tait_pressure(rho, label, gamma, B, rho0, Pb=0.0):
+    rho = _f64(rho); lab = np.ascontiguousarray(np.broadcast_to(label, rho.shape), dtype=np.int8)
+    out = np.empty_like(rho)
+    _leaf_ck(lib().osph_leaf_tait_pressure(default_device(), rho.size, _ptr(rho),
+                                           lab.ctypes.data_as(C.POINTER(C.c_int8)), gamma, B, rho0, Pb, _ptr(out)))
+    return out
+
+
+def leaf_tait_height(y, rho0, H, B, gamma):
+    y = _f64(y); out = np.empty_like(y)
+    _leaf_ck(lib().osph_leaf_tait_height(default_device(), y.size, _ptr(y), rho0, H, B, gamma, _ptr(out)))
+    return out
+
+
+def leaf_compute_h(sigma, m, rho):
+    m = _f64(m); rho = _f64(rho); out = np.empty_like(m)
+    _leaf_ck(lib().osph_leaf_compute_h(default_device(), m.size, sigma, _ptr(m), _ptr(rho), _ptr(out)))
+    return out
