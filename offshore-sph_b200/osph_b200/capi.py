@@ -330,6 +330,15 @@ def default_device():
     return int(os.environ.get("OSPH_DEVICE", "0"))
 
 
+def precision_from_env():
+    """OSPH_PRECISION=fp64 (default, validation mode) | fp32 (performance mode): selects the pair-kernel arithmetic
+    without editing example scripts."""
+    v = os.environ.get("OSPH_PRECISION", "fp64").lower()
+    if v not in ("fp64", "fp32"):
+        raise ValueError("OSPH_PRECISION must be fp64 or fp32")
+    return FP64 if v == "fp64" else FP32
+
+
 def leaf_kernel(kernel, what, x, r, h):
     r = _f64(r); h = _f64(np.broadcast_to(h, r.shape)); out = np.empty_like(r)
     x = _f64(np.broadcast_to(x, r.shape)) if x is not None else None

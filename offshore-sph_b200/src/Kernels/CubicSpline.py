@@ -1,0 +1,22 @@
+"""2-D cubic spline, alpha = 10/(7 pi h^2), support q <= 2 (reference src/Kernels/CubicSpline.py:10-70).
+
+Inside Solver.run() the kernel is evaluated inline by the fused pair kernel (csrc/pair.cu); the
+array methods below serve callers that use the kernel object on its own (e.g. the IceBreak pressure
+probe) and run on the device through osph_leaf_kernel.
+"""
+import numpy as np
+
+from src.Kernels.Kernel import Kernel
+from osph_b200 import capi
+
+
+class CubicSpline(Kernel):
+    osph_name = 'cubic'
+
+    @staticmethod
+    def evaluate(r: np.array, h: np.array):
+        return capi.leaf_kernel('cubic', 0, None, r, h)
+
+    @staticmethod
+    def gradient(x: np.array, r: np.array, h: np.array):
+        return capi.leaf_kernel('cubic', 1, x, r, h)

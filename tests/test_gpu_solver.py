@@ -1,0 +1,136 @@
+"""GPU: the re-hosted Solver and the plugin objects used stand-alone, against the reference's own
+Solver.run() (golden end state) and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import field_err, load_golden
+from oracle import oracle as O
+from osph_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def test_solver_run_matches_reference_solver(monkeypatch):
+    """Settling -> gate removal -> time stepping of the 12x12 dam break, vs the unmodified reference Solver."""
+    monkeypatch.setenv("OSPH_QUIET", "1")
+    from src.Solver import Solver
+    from src.Methods.WCSPH import WCSPH
+    from src.Kernels.Wendland import Wendland
+    from src.Integrators.PEC import PEC
+    g, meta, _ = load_golden('solver_dambreak12_wendland')
+    r0, pA = W.dam_break(meta['N'])
+    method = WCSPH(height=25.0, r0=r0, rho0=1000.0, useXSPH=True, Pb=0, useSummationDensity=False)
+    s = Solver(method, PEC(useXSPH=True, strict=False), Wendland(), meta['duration'], incrementalWriteout=False,
+               h=meta['hfac'] * r0, maxSettle=meta['maxSettle'])
+    s.addParticles(pA)
+    s.setup()
+    s.run()
+    ref = np.frombuffer(g['final'].tobytes(), dtype=O.particle_dtype)
+    assert s.t_step == int(g['t_step'])
+    assert np.allclose(s.dt_a, g['dt_a'], rtol=1e-10, atol=0)
+    assert s.settleTime == pytest.approx(float(g['settleTime']), rel=1e-10)
+    assert s.t == pytest.approx(float(g['t']), rel=1e-10)
+    assert np.array_equal(s.particleArray['deleted'], ref['deleted'])
+    act = ~ref['deleted']
+    for f in ('x', 'y', 'vx', 'vy', 'rho', 'p', 'ax', 'ay', 'drho', 'h', 'c'):
+        assert field_err(s.particleArray[f][act], ref[f][act]) <= 1e-9, f
+    assert np.all(s.particleArray['p'][~act] == -1e15)
+    assert len(s.export['x']) == int(g['n_export'])
+    assert field_err(s.export['x'][-1], g['export_x_last']) <= 1e-9
+    assert s.timing_data['total'] > 0 and set(s.timing_data) >= {'compute', 'neighbour_hood', 'time_step'}
+
+
+def test_containment_example_runs(monkeypatch):
+    """Dynamic h, XSPH off, WCSPH() without useSummationDensity: the shipped Containment call pattern."""
+    monkeypatch.setenv("OSPH_QUIET", "1")
+    import importlib.util, os
+    from conftest import PKG
+    spec = importlib.util.spec_from_file_location("ex_containment", os.path.join(PKG, "examples", "containment.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    s = mod.main(['--nx', '20', '--duration', '0.002', '--max-settle', '5'])
+    pa = s.particleArray
+    assert s.t >= 0.002 and np.all(np.isfinite(pa['x'])) and np.all(np.isfinite(pa['rho']))
+    fluid = pa['label'] == 0
+    assert np.all(pa['h'][fluid] > 0) and pa['y'][fluid].min() > -1.0 / 20        # nothing fell through the floor
+    assert len(s.export['vx']) == s.t_step
+
+
+def test_kernel_objects_standalone():
+    """reference test/test_kernels_cubic.py closed forms + oracle, through the device leaf entry points."""
+    from src.Kernels.CubicSpline import CubicSpline
+    from src.Kernels.Wendland import Wendland
+    from src.Kernels.Gaussian import Gaussian
+    rng = np.random.default_rng(3)
+    r = rng.uniform(0, 0.9, 500); h = rng.uniform(0.2, 0.4, 500); x = rng.uniform(-1, 1, 500) * r
+    r[:3] = [0.0, 1e-11, 0.5]; h[:3] = [0.25, 0.25, 0.25]
+    for K, name in ((CubicSpline, 'cubic'), (Wendland, 'wendland'), (Gaussian, 'gaussian')):
+        assert np.allclose(K.evaluate(r, h), O.kernel_evaluate(name, r, h), rtol=1e-13, atol=1e-300)
+        assert np.allclose(K.gradient(x, r, h), O.kernel_gradient(name, x, r, h), rtol=1e-13, atol=1e-300)
+    a = 10 / (7 * np.pi)
+    assert np.allclose(CubicSpline.evaluate(np.array([0.5, 1.0, 1.5, 2.0, 3.0]), np.ones(5)),
+                       [a * (1 - 1.5 * .25 * .75), a * .25, a * .25 * .125, 0, 0], rtol=1e-14)
+
+
+def test_method_and_tools_standalone():
+    from src.Methods.WCSPH import WCSPH
+    from src.Tools.SolverTools import computeH, findActive, _loop
+    from src.Tools.NNLinkedList import NNLinkedList
+    from src.Kernels.CubicSpline import CubicSpline
+    from src.Equations.TimeStep import TimeStep
+    from src.Equations.KineticEnergy import KineticEnergy
+    from src.Equations.TaitEOS import TaitEOS, TaitEOS_height
+    g, meta, pA = load_golden('dambreak20_cubic')
+    c = meta['consts']
+    m = WCSPH(c['height'], c['r0'], c['rho0'], True, 0)
+    assert (m.co, m.B, m.D) == (c['co'], c['B'], c['D'])
+    w = O.wcsph(c['height'], c['r0'], c['rho0'], True)
+    fluid = pA[pA['label'] == 0]
+    assert np.allclose(m.initialize(fluid.copy())['rho'], O.initialize_density(w, fluid['y']), rtol=1e-14)
+    L = O.lib()
+    want = np.array([L.oracle_tait_p(7.0, c['B'], c['rho0'], float(r), int(l)) for r, l in zip(pA['rho'], pA['label'])])
+    assert np.allclose(m.compute_pressure(pA), want, rtol=1e-12, atol=1e-6)
+    assert np.allclose(TaitEOS(7.0, c['B'], c['rho0'], pA['rho'], pA['label']), want, rtol=1e-12, atol=1e-6)
+    assert np.allclose(TaitEOS_height(c['rho0'], c['height'], c['B'], 7.0, fluid['y']),
+                       O.initialize_density(w, fluid['y']), rtol=1e-14)
+    assert np.allclose(computeH(1.3, len(fluid), fluid['m'], fluid['rho']), O.compute_h(1.3, fluid['m'], fluid['rho']),
+                       rtol=1e-15)
+    cnt, mask = findActive(0, pA)
+    assert cnt == len(pA) and mask.all()
+    # neighbour search object
+    nn = NNLinkedList(2.0)
+    nn.update(pA)
+    assert nn.cell_size == g['grid'][4] and list(nn.ncells_per_dim) == [int(g['grid'][5]), int(g['grid'][6])]
+    i = 7
+    hh, q, r, idx = nn.near(i, pA)
+    want_idx = np.sort(g['nbr_idx'][g['nbr_off'][i]:g['nbr_off'][i + 1]])
+    assert idx.dtype == np.uint64 and np.array_equal(idx.astype(np.int64), want_idx)
+    # _loop as a stand-alone call
+    out = _loop(pA.copy(), CubicSpline.evaluate, CubicSpline.gradient, m, nn)
+    for f in ('p', 'c', 'drho', 'ax', 'ay', 'xsphx', 'xsphy'):
+        assert field_err(out[f], g['loop_' + f]) <= 1e-10, f
+    # time step / kinetic energy on host arrays
+    P = O.Particles.from_aos(fluid)
+    assert TimeStep().compute(len(fluid), fluid, 0.25, 0.25) == O.timestep(P, P.fluid)
+    assert KineticEnergy(len(fluid), fluid) == pytest.approx(O.kinetic_energy(P), rel=1e-13)
+
+
+def test_integrator_objects_standalone():
+    """reference test/test_integrators_pec.py known answers through the device kernels."""
+    from src.Integrators.PEC import PEC
+    from src.Integrators.Euler import Euler
+    from src.Common import particle_dtype
+    def some(label):
+        p = np.zeros(1, dtype=particle_dtype)
+        p['label'] = label; p['vx'] = 1.0; p['vy'] = 3.0; p['ax'] = 5.0; p['drho'] = 10
+        return 2.0, p
+    i = PEC(useXSPH=False)
+    dt, p = some(0)
+    p2 = i.predict(dt, p, 0)
+    assert (p2['x'][0], p2['y'][0], p2['rho'][0]) == (dt * 0.5, dt * 0.5 * 3.0, dt * 0.5 * 10.0)
+    p3 = i.correct(dt, p2, 0)
+    assert p3['x'][0] == pytest.approx(dt * 1.0 + 0.5 * 5 * 2 * 2) and p3['y'][0] == pytest.approx(dt * 3.0)
+    assert p3['rho'][0] == pytest.approx(10 * dt)
+    dt, pe = some(0)
+    pe = Euler().correct(dt, Euler().predict(dt, pe, 0), 0)
+    for f in ('x', 'y', 'vx', 'vy', 'rho'):
+        assert p3[f][0] == pytest.approx(pe[f][0])
