@@ -248,14 +248,6 @@ def run_gpu(args):
                 "avg_launch_us": pair_us, "launches_timed": pair_n, "share_of_step": pair_us * 1e-6 * args.steps / t_dev,
                 "algorithmic_bytes_per_particle": 13 * F + 1,
                 "note": "pair kernel is FP-pipe bound (SURVEY 8d): ~70 flop/pair; see fp_pipe"}
-    fp_pipe = None
-    try:
-        off_total = None
-        if n <= 2_000_000 and prec == capi.FP64:
-            pass
-    except Exception:
-        pass
-
     # ---- CPU baseline: oracle port on a bounded sample ----------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
@@ -292,6 +284,9 @@ def main():
     ap.add_argument("--kernel", default="cubic", choices=["cubic", "wendland", "gaussian"])
     ap.add_argument("--particles-per-side", type=int, default=1000,
                     help="N of the dam-break generator (N x N fluid particles); 1000 = BASELINE configs[1]")
+    ap.add_argument("--total-side", action="store_true",
+                    help="multi-GPU: --particles-per-side is the TOTAL problem (strong scaling) instead of per-GPU "
+                         "N*sqrt(gpus) (weak scaling, default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()

@@ -200,6 +200,47 @@ uint64_t osph_stream(const osph_ctx *ctx);
 /* Average device time of the fused pair kernel over the launches since the last call, microseconds. */
 int osph_pair_kernel_time(osph_ctx *ctx, double *avg_us, int64_t *launches);
 
+/* ---- 1-D slab decomposition: one context per GPU, exchange buffers owned by the caller -------------------
+ *
+ * The reference is single-process; this section has no counterpart there.  A rank owns
+ * the particles with x_lo <= x < x_hi.  Buffers passed here are DEVICE pointers owned by the caller (torch
+ * tensors that NCCL sends from / receives into); records are doubles:
+ *   halo / ghost record  OSPH_WIRE_HALO = 8  : x y vx vy rho m h label
+ *   migrant record       OSPH_WIRE_FULL = 21 : the 19 columns (enum osph_field order), label, global row id
+ * Per step:  osph_slab_step_begin -> osph_slab_pack -> [exchange] -> osph_slab_commit -> osph_slab_step_end.
+ */
+#define OSPH_WIRE_HALO 8
+#define OSPH_WIRE_FULL 21
+/* Reserve room for `particle_capacity` owned + ghost particles at the next upload (slabs grow by migration). */
+int osph_reserve(osph_ctx *ctx, int64_t particle_capacity);
+/* Replace the row ids recorded at upload (0..n_active-1) by global ids, so migrants keep their identity. */
+int osph_set_row_ids(osph_ctx *ctx, const int32_t *ids, int64_t n);
+/* Enter slab mode; d_ghost has room for ghost_capacity halo records. */
+int osph_slab_configure(osph_ctx *ctx, double x_lo, double x_hi, void *d_ghost, int64_t ghost_capacity);
+/* d_out3 (device) <- local {h_min, -c_max, -a2_max} over the owned fluid rows (all-reduce with MIN). */
+int osph_slab_dt_local(osph_ctx *ctx, double *d_out3);
+/* Install the all-reduced triple (device pointer, may be NULL to keep the local one), form dt on the device
+ * (fixed_dt <= 0: dynamic) and run the predictor + local grid reductions. */
+int osph_slab_step_begin(osph_ctx *ctx, const double *d_dt_reduced3, double fixed_dt, double damping);
+/* Classify the owned particles: migrants (x outside the slab) are packed as full records and kept as this
+ * rank's first ghosts; particles within halo_width of a face are packed as halo records.  d_meta (device, 12
+ * doubles) <- {mig_left, mig_right, halo_left, halo_right, xmin, -xmax, ymin, -ymax, hmin_all, -hmax, overflow, 0}. */
+int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
+                   void *d_halo_left, void *d_halo_right, int64_t halo_cap, double *d_meta);
+/* Drop the n_mig_out migrants recorded by osph_slab_pack (hole filling), append the n_mig_in received ones,
+ * declare n_ghost records present in the ghost buffer and install the all-reduced grid scalars
+ * {xmin, -xmax, ymin, -ymax, hmin_all, -hmax} so that every rank forms the same reference grid. */
+int osph_slab_commit(osph_ctx *ctx, int64_t n_mig_out, const void *d_mig_in, int64_t n_mig_in, int64_t n_ghost,
+                     const double global_bounds[6]);
+/* Neighbour structure over owned + ghost particles, fused pair kernel for the owned fluid rows, corrector. */
+int osph_slab_step_end(osph_ctx *ctx, double damping);
+/* Host copy of the owned particles as packed records in storage order (deleted = 0) and their global ids;
+ * the pair (pA, ids) is valid input for osph_upload_aos + osph_set_row_ids. */
+int osph_download_owned(osph_ctx *ctx, void *pA, int64_t cap_rows, int64_t stride, int32_t *ids, int64_t *n_out);
+/* Copy ids, labels and columns of the owned particles (storage order) into caller-owned device buffers. */
+int osph_slab_export(osph_ctx *ctx, int32_t *d_ids, int8_t *d_label, int32_t nfields, const int32_t *fields,
+                     double *const *d_cols);
+
 /* ---- stand-alone leaf functions on host arrays (context-free; `device` is a CUDA ordinal) ---------- */
 
 /* what == 0: kernel.evaluate(r, h); what == 1: kernel.gradient(x, r, h).

@@ -45,22 +45,22 @@ static void free_particles(osph_ctx *ctx)
     for (int k = 0; k < OSPH_NUM_FIELDS; k++) { cudaFree(ctx->f[k]); ctx->f[k] = nullptr; }
     cudaFree(ctx->label); cudaFree(ctx->scratch); cudaFree(ctx->d_stage);
     cudaFree(ctx->s_coarse); cudaFree(ctx->s_gcell); cudaFree(ctx->s_pos); cudaFree(ctx->s_vel);
-    cudaFree(ctx->s_rm); cudaFree(ctx->s_hp); cudaFree(ctx->s_info); cudaFree(ctx->u_coarse); cudaFree(ctx->u_gcell);
+    cudaFree(ctx->s_rm); cudaFree(ctx->s_hp); cudaFree(ctx->s_info);
     cudaFree(ctx->d_partial);
     osph_sort_free(ctx);
     ctx->d_aos = nullptr; ctx->d_row = ctx->d_act = ctx->d_slot_of_act = nullptr; ctx->label = nullptr;
     ctx->scratch = ctx->d_stage = nullptr; ctx->s_coarse = nullptr; ctx->s_gcell = nullptr; ctx->s_pos = nullptr;
-    ctx->s_vel = ctx->s_rm = ctx->s_hp = nullptr; ctx->s_info = nullptr; ctx->u_coarse = nullptr; ctx->u_gcell = nullptr;
+    ctx->s_vel = ctx->s_rm = ctx->s_hp = nullptr; ctx->s_info = nullptr;
     ctx->d_partial = nullptr;
     ctx->cap = 0; ctx->aos_bytes = 0;
 }
 
 static int alloc_particles(osph_ctx *ctx, int64_t n_active, int64_t n_total, int64_t stride)
 {
-    size_t aos_bytes = (size_t)n_total * (size_t)stride;
-    if (n_active <= ctx->cap && aos_bytes <= ctx->aos_bytes) return 0;
+    size_t aos_bytes = (size_t)std::max<int64_t>(n_total, ctx->reserve) * (size_t)stride;
+    if (std::max<int64_t>(n_active, ctx->reserve) <= ctx->cap && aos_bytes <= ctx->aos_bytes) return 0;
     free_particles(ctx);
-    int64_t cap = std::max<int64_t>(n_active, 1024);
+    int64_t cap = std::max<int64_t>(std::max<int64_t>(n_active, ctx->reserve), 1024);
     const size_t rs = ctx->cfg.precision == OSPH_FP64 ? sizeof(double2) : sizeof(float2);
     OSPH_CUDA(cudaMalloc(&ctx->d_aos, std::max<size_t>(aos_bytes, 16)));
     OSPH_CUDA(cudaMalloc(&ctx->d_row, sizeof(int) * cap));
@@ -77,8 +77,6 @@ static int alloc_particles(osph_ctx *ctx, int64_t n_active, int64_t n_total, int
     OSPH_CUDA(cudaMalloc(&ctx->s_rm, rs * cap));
     OSPH_CUDA(cudaMalloc(&ctx->s_hp, rs * cap));
     OSPH_CUDA(cudaMalloc(&ctx->s_info, sizeof(int) * cap));
-    OSPH_CUDA(cudaMalloc(&ctx->u_coarse, sizeof(int4) * cap));
-    OSPH_CUDA(cudaMalloc(&ctx->u_gcell, sizeof(int2) * cap));
     OSPH_CUDA(cudaMalloc(&ctx->d_partial, sizeof(double) * (div_up(cap, 256) + 1)));
     int rc = osph_sort_alloc(ctx, cap);
     if (rc) return rc;
@@ -154,6 +152,8 @@ extern "C" int osph_destroy(osph_ctx *ctx)
     PhaseTimer::drain(ctx);
     free_particles(ctx);
     cudaFree(ctx->cell_range); cudaFree(ctx->d_grid); cudaFree(ctx->d_sc); cudaFree(ctx->d_dt_log);
+    cudaFree(ctx->scan_block); cudaFree(ctx->d_slab_counters); cudaFree(ctx->d_mig_slots); cudaFree(ctx->d_tail_flag);
+    cudaFree(ctx->d_holes); cudaFree(ctx->d_fillers);
     for (int k = 0; k < 2 * OSPH_PAIR_EVENTS; k++) if (ctx->pair_ev[k]) cudaEventDestroy(ctx->pair_ev[k]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -197,7 +197,7 @@ static int ingest(osph_ctx *ctx, const unsigned char *flags_host, const void *sr
         rc = osph_launch_unpack(ctx);
         if (rc) return rc;
     }
-    ctx->c_uniform = false; ctx->have_perm = false; ctx->build_counter = 0; ctx->slot_of_act_valid = false;
+    ctx->c_uniform = false; ctx->build_counter = 0; ctx->n_ghost = 0; ctx->slab = false; ctx->slot_of_act_valid = false;
     invalidate_state(ctx);
     return 0;
 }
@@ -232,6 +232,23 @@ extern "C" int osph_download_aos(osph_ctx *ctx, void *pA, int64_t n, int64_t str
     if (rc) return rc;
     OSPH_CUDA(cudaMemcpyAsync(pA, ctx->d_aos, (size_t)n * stride, cudaMemcpyDeviceToHost, ctx->stream));
     OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int osph_download_owned(osph_ctx *ctx, void *pA, int64_t cap_rows, int64_t stride, int32_t *ids, int64_t *n_out)
+{
+    CHECK_CTX();
+    if (!pA || !ids || stride != ctx->stride || cap_rows < ctx->n || (size_t)ctx->n * stride > ctx->aos_bytes) {
+        ctx->err = "osph_download_owned: buffer too small or stride differs from the upload"; return OSPH_E_CAPACITY;
+    }
+    PhaseTimer t(ctx, T_TRANSFER);
+    int *d_ids = (int *)ctx->d_stage;
+    int rc = osph_launch_pack_owned(ctx, d_ids);
+    if (rc) return rc;
+    OSPH_CUDA(cudaMemcpyAsync(pA, ctx->d_aos, (size_t)ctx->n * stride, cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaMemcpyAsync(ids, d_ids, sizeof(int) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = ctx->n;
     return 0;
 }
 
@@ -291,7 +308,7 @@ extern "C" int osph_initialize(osph_ctx *ctx)
 // ---- the per-step calls --------------------------------------------------------------------------
 
 // First build after an upload: size the cell table from the grid the device would like to use.
-static int size_cell_table(osph_ctx *ctx)
+int osph_size_cell_table(osph_ctx *ctx)
 {
     if (ctx->sized) return 0;
     int64_t saved = ctx->cell_cap;
@@ -363,7 +380,7 @@ static int build_neighbours(osph_ctx *ctx)
         if ((rc = osph_launch_prepare(ctx, false, 0.0, 0.0, false))) return rc;
         ctx->prepared = true;
     }
-    if ((rc = size_cell_table(ctx))) return rc;
+    if ((rc = osph_size_cell_table(ctx))) return rc;
     if ((rc = osph_launch_build(ctx))) return rc;
     ctx->neighbours_valid = true;
     return 0;
@@ -412,7 +429,7 @@ extern "C" int osph_step(osph_ctx *ctx, int32_t nsteps, double fixed_dt, double 
         if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true))) return rc;
         if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true))) return rc;
         ctx->prepared = true;
-        if ((rc = size_cell_table(ctx))) return rc;
+        if ((rc = osph_size_cell_table(ctx))) return rc;
         if ((rc = osph_launch_build(ctx))) return rc;
         if ((rc = osph_launch_pair(ctx))) return rc;
         ctx->c_uniform = true;

@@ -11,6 +11,8 @@
 #define OSPH_CAP_STAGE 512            // candidates staged in shared memory per batch of the pair kernel
 #define OSPH_PAIR_THREADS 256         // one CTA of the pair kernel owns this many consecutive sorted particles
 #define OSPH_MAX_CELL_BITS 28
+#define OSPH_WIRE_HALO 8               // doubles per ghost record: x y vx vy rho m h label
+#define OSPH_WIRE_FULL 21              // doubles per migrant record: 19 columns, label, global id
 #define OSPH_PAIR_EVENTS 512           // pair-kernel launches timed between two osph_pair_kernel_time calls
 
 // ---------------------------------------------------------------------------------------------
@@ -91,9 +93,17 @@ struct osph_ctx {
     double2 *s_pos = nullptr;
     void *s_vel = nullptr, *s_rm = nullptr, *s_hp = nullptr;   // Real2 each
     int *s_info = nullptr;           // bit0: fluid
-    // scratch in storage order produced by the key kernel
-    int4 *u_coarse = nullptr;
-    int2 *u_gcell = nullptr;
+    // slab mode: ghost particles as light wire records (OSPH_WIRE_HALO doubles each), appended after the owned ones
+    double *d_ghost = nullptr;
+    int64_t n_ghost = 0, ghost_cap = 0;
+    bool ghost_external = false;
+    unsigned int *scan_block = nullptr;   // block sums of the scan utility
+    bool slab = false;
+    double x_lo = 0, x_hi = 0;
+    int *d_slab_counters = nullptr, *d_mig_slots = nullptr, *d_tail_flag = nullptr, *d_holes = nullptr, *d_fillers = nullptr;
+    int64_t slab_list_cap = 0;
+    int64_t reserve = 0;              // particle capacity requested by osph_reserve
+    int64_t scan_cap = 0;
 
     GridParams *d_grid = nullptr;
     StepScalars *d_sc = nullptr;
@@ -107,7 +117,6 @@ struct osph_ctx {
     bool reductions_valid = false;   // hmin_fluid/cmax/a2max describe the current state
     int64_t step_counter = 0;
     int64_t build_counter = 0;
-    bool have_perm = false;          // idx[sorted_buf] is a valid permutation of the current storage order
     int64_t launches = 0;
 
     // timers

@@ -65,7 +65,7 @@ k_pair(PairArgs a)
         Real2 v = g_vel[s]; vxi = v.x; vyi = v.y;
         Real2 rm = g_rm[s]; rhoi = rm.x;
         Real2 hp = g_hp[s]; hi = hp.x; slf = hp.y;
-        fluid_i = (a.s_info[s] & 1) != 0;
+        fluid_i = (a.s_info[s] & 3) == 3;          // fluid AND owned (ghosts of a slab are sources only)
         if constexpr (EXACT) { int4 c = a.s_coarse[s]; qcx = c.z; qcy = c.w; }
         if (fluid_i) {
             int2 gc = a.s_gcell[s];
@@ -230,7 +230,7 @@ static int launch_kid(osph_ctx *ctx, const PairArgs &a, int grid)
 int osph_launch_pair(osph_ctx *ctx)
 {
     PairArgs a;
-    a.n = (int)ctx->n;
+    a.n = (int)(ctx->n + ctx->n_ghost);
     a.idx = ctx->idx[ctx->sorted_buf];
     a.s_pos = ctx->s_pos; a.s_vel = ctx->s_vel; a.s_rm = ctx->s_rm; a.s_hp = ctx->s_hp;
     a.s_info = ctx->s_info; a.s_coarse = ctx->s_coarse; a.s_gcell = ctx->s_gcell;
@@ -243,7 +243,7 @@ int osph_launch_pair(osph_ctx *ctx)
     a.r0 = c.r0; a.D = c.D; a.p1 = c.p1; a.p2 = c.p2; a.gravity = c.gravity;
     a.lj_42 = (c.p1 == 4.0 && c.p2 == 2.0) ? 1 : 0;
     a.method_xsph = c.method_xsph; a.summation_density = c.summation_density;
-    int grid = div_up(ctx->n, OSPH_PAIR_THREADS);
+    int grid = div_up(ctx->n + ctx->n_ghost, OSPH_PAIR_THREADS);
     const bool timed = ctx->time_pair && ctx->pair_ev_used < OSPH_PAIR_EVENTS;
     if (timed) cudaEventRecord(ctx->pair_ev[2 * ctx->pair_ev_used], ctx->stream);
     if (c.precision == OSPH_FP64) launch_kid<double, true>(ctx, a, grid);

@@ -1,0 +1,302 @@
+// slab.cu -- 1-D slab decomposition along x across the GPUs of one box.
+// One context per GPU owns the particles with x_lo <= x < x_hi.  Per step, after the predictor:
+//   osph_slab_pack    classifies the owned particles, packs migrants (full records) and halo particles (light
+//                     records) for both neighbours into caller-owned device buffers (torch tensors that NCCL
+//                     sends straight from), and keeps light copies of the migrants as this rank's first ghosts;
+//   [the caller exchanges counts + payloads over NCCL/NVLink; halos are received directly into the ghost buffer]
+//   osph_slab_commit  removes the migrants from the owned set (hole filling), appends the received ones and
+//                     installs the all-reduced grid scalars, so every rank forms the SAME reference grid.
+// The reference has no counterpart: it is a single-threaded, single-process code.
+#include "common.cuh"
+#include "step.cuh"
+
+struct SlabPackArgs {
+    int n;
+    const signed char *label;
+    const int *row;
+    const double *f[OSPH_NUM_FIELDS];
+    double x_lo, x_hi, width;
+    double *mig_left, *mig_right, *halo_left, *halo_right, *ghost;
+    int mig_cap, halo_cap, ghost_cap;
+    int *counters;      // [0] mig_left [1] mig_right [2] halo_left [3] halo_right [4] ghosts [5] overflow flag
+    int *mig_slots;     // slots of the migrants (unordered)
+};
+
+__device__ __forceinline__ void write_light(double *dst, const SlabPackArgs &a, int i)
+{
+    dst[0] = a.f[OSPH_F_X][i]; dst[1] = a.f[OSPH_F_Y][i]; dst[2] = a.f[OSPH_F_VX][i]; dst[3] = a.f[OSPH_F_VY][i];
+    dst[4] = a.f[OSPH_F_RHO][i]; dst[5] = a.f[OSPH_F_M][i]; dst[6] = a.f[OSPH_F_H][i]; dst[7] = (double)a.label[i];
+}
+__device__ __forceinline__ void write_full(double *dst, const SlabPackArgs &a, int i)
+{
+#pragma unroll
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) dst[k] = a.f[k][i];
+    dst[OSPH_NUM_FIELDS] = (double)a.label[i];
+    dst[OSPH_NUM_FIELDS + 1] = (double)a.row[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_slab_pack(SlabPackArgs a)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    double x = a.f[OSPH_F_X][i];
+    int side = x < a.x_lo ? 0 : (x >= a.x_hi ? 1 : -1);
+    if (side >= 0) {
+        int k = atomicAdd(&a.counters[side], 1);
+        int g = atomicAdd(&a.counters[4], 1);
+        int m = atomicAdd(&a.counters[6], 1);
+        if (k < a.mig_cap && g < a.ghost_cap) {
+            write_full((side ? a.mig_right : a.mig_left) + (size_t)k * OSPH_WIRE_FULL, a, i);
+            write_light(a.ghost + (size_t)g * OSPH_WIRE_HALO, a, i);
+            a.mig_slots[m] = i;
+        } else a.counters[5] = 1;
+        return;
+    }
+    if (x < a.x_lo + a.width) {
+        int k = atomicAdd(&a.counters[2], 1);
+        if (k < a.halo_cap) write_light(a.halo_left + (size_t)k * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1;
+    }
+    if (x >= a.x_hi - a.width) {
+        int k = atomicAdd(&a.counters[3], 1);
+        if (k < a.halo_cap) write_light(a.halo_right + (size_t)k * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1;
+    }
+}
+
+__global__ void k_slab_meta(const int *counters, const StepScalars *sc, double *meta)
+{
+    meta[0] = counters[0]; meta[1] = counters[1]; meta[2] = counters[2]; meta[3] = counters[3];
+    meta[4] = dec_f64(sc->xmin); meta[5] = -dec_f64(sc->xmax); meta[6] = dec_f64(sc->ymin); meta[7] = -dec_f64(sc->ymax);
+    meta[8] = dec_f64(sc->hmin_all); meta[9] = -dec_f64(sc->hmax_all);
+    meta[10] = counters[5];
+    meta[11] = 0.0;
+}
+
+__global__ void k_slab_set_bounds(StepScalars *sc, double xmin, double nxmax, double ymin, double nymax, double hmin,
+                                  double nhmax)
+{
+    sc->xmin = enc_f64(xmin); sc->xmax = enc_f64(-nxmax); sc->ymin = enc_f64(ymin); sc->ymax = enc_f64(-nymax);
+    sc->hmin_all = enc_f64(hmin); sc->hmax_all = enc_f64(-nhmax);
+}
+
+// hole filling: the m migrants leave; the last m slots are vacated, their non-migrant occupants fill the holes
+__global__ void k_slab_mark(const int *__restrict__ mig_slots, int m, int n_new, int *__restrict__ tail_flag,
+                            int *__restrict__ holes, int *__restrict__ nh)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    int h = mig_slots[k];
+    if (h >= n_new) tail_flag[h - n_new] = 1;
+    else holes[atomicAdd(nh, 1)] = h;
+}
+__global__ void k_slab_fillers(const int *__restrict__ tail_flag, int m, int n_new, int *__restrict__ fillers,
+                               int *__restrict__ nf)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    if (!tail_flag[t]) fillers[atomicAdd(nf, 1)] = n_new + t;
+}
+struct SlabMoveArgs { double *f[OSPH_NUM_FIELDS]; signed char *label; int *row; };
+__global__ void k_slab_move(SlabMoveArgs a, const int *__restrict__ holes, const int *__restrict__ fillers,
+                            const int *__restrict__ nh, int m)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = t / (OSPH_NUM_FIELDS + 2), c = t % (OSPH_NUM_FIELDS + 2);
+    if (k >= m || k >= *nh) return;
+    int dst = holes[k], src = fillers[k];
+    if (c < OSPH_NUM_FIELDS) a.f[c][dst] = a.f[c][src];
+    else if (c == OSPH_NUM_FIELDS) a.label[dst] = a.label[src];
+    else a.row[dst] = a.row[src];
+}
+__global__ void k_slab_append(SlabMoveArgs a, const double *__restrict__ rec, int n_in, int base)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = t / (OSPH_NUM_FIELDS + 2), c = t % (OSPH_NUM_FIELDS + 2);
+    if (k >= n_in) return;
+    double v = rec[(size_t)k * OSPH_WIRE_FULL + c];
+    if (c < OSPH_NUM_FIELDS) a.f[c][base + k] = v;
+    else if (c == OSPH_NUM_FIELDS) a.label[base + k] = (signed char)v;
+    else a.row[base + k] = (int)v;
+}
+
+__global__ void k_slab_dt_local(const StepScalars *sc, double *out)
+{
+    out[0] = dec_f64(sc->hmin_fluid); out[1] = -dec_f64(sc->cmax_fluid); out[2] = -dec_f64(sc->a2max_fluid);
+}
+__global__ void k_slab_dt_set(StepScalars *sc, const double *in)
+{
+    sc->hmin_fluid = enc_f64(in[0]); sc->cmax_fluid = enc_f64(-in[1]); sc->a2max_fluid = enc_f64(-in[2]);
+}
+__global__ void k_slab_ids(const int *__restrict__ row, const signed char *__restrict__ label, int n,
+                           int *__restrict__ ids, signed char *__restrict__ lab)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ids[i] = row[i]; if (lab) lab[i] = label[i]; }
+}
+
+static SlabMoveArgs move_args(osph_ctx *ctx)
+{
+    SlabMoveArgs a;
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) a.f[k] = ctx->f[k];
+    a.label = ctx->label; a.row = ctx->d_row;
+    return a;
+}
+
+#define CHECK_CTX()                                                        \
+    if (!ctx) return OSPH_E_INVALID;                                       \
+    OSPH_CUDA(cudaSetDevice(ctx->device))
+
+extern "C" int osph_slab_configure(osph_ctx *ctx, double x_lo, double x_hi, void *d_ghost, int64_t ghost_capacity)
+{
+    CHECK_CTX();
+    if (!(x_lo < x_hi) || !d_ghost || ghost_capacity <= 0) { ctx->err = "osph_slab_configure: bad arguments"; return OSPH_E_INVALID; }
+    ctx->slab = true; ctx->x_lo = x_lo; ctx->x_hi = x_hi;
+    ctx->d_ghost = (double *)d_ghost; ctx->ghost_cap = ghost_capacity; ctx->n_ghost = 0;
+    if (!ctx->d_slab_counters) {
+        OSPH_CUDA(cudaMalloc(&ctx->d_slab_counters, sizeof(int) * 16));
+    }
+    return 0;
+}
+
+extern "C" int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
+                              void *d_halo_left, void *d_halo_right, int64_t halo_cap, double *d_meta)
+{
+    CHECK_CTX();
+    if (!ctx->slab || ctx->n <= 0) { ctx->err = "osph_slab_pack: context is not in slab mode"; return OSPH_E_INVALID; }
+    if (mig_cap > ctx->slab_list_cap) {
+        cudaFree(ctx->d_mig_slots); cudaFree(ctx->d_tail_flag); cudaFree(ctx->d_holes); cudaFree(ctx->d_fillers);
+        OSPH_CUDA(cudaMalloc(&ctx->d_mig_slots, sizeof(int) * mig_cap * 2));
+        OSPH_CUDA(cudaMalloc(&ctx->d_tail_flag, sizeof(int) * mig_cap * 2));
+        OSPH_CUDA(cudaMalloc(&ctx->d_holes, sizeof(int) * mig_cap * 2));
+        OSPH_CUDA(cudaMalloc(&ctx->d_fillers, sizeof(int) * mig_cap * 2));
+        ctx->slab_list_cap = mig_cap;
+    }
+    OSPH_CUDA(cudaMemsetAsync(ctx->d_slab_counters, 0, sizeof(int) * 16, ctx->stream));
+    SlabPackArgs a;
+    a.n = (int)ctx->n; a.label = ctx->label; a.row = ctx->d_row;
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) a.f[k] = ctx->f[k];
+    a.x_lo = ctx->x_lo; a.x_hi = ctx->x_hi; a.width = halo_width;
+    a.mig_left = (double *)d_mig_left; a.mig_right = (double *)d_mig_right;
+    a.halo_left = (double *)d_halo_left; a.halo_right = (double *)d_halo_right; a.ghost = ctx->d_ghost;
+    a.mig_cap = (int)mig_cap; a.halo_cap = (int)halo_cap; a.ghost_cap = (int)ctx->ghost_cap;
+    a.counters = ctx->d_slab_counters; a.mig_slots = ctx->d_mig_slots;
+    k_slab_pack<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(a); OSPH_LAUNCH_CHECK();
+    k_slab_meta<<<1, 1, 0, ctx->stream>>>(ctx->d_slab_counters, ctx->d_sc, d_meta); OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int osph_slab_commit(osph_ctx *ctx, int64_t n_mig_out, const void *d_mig_in, int64_t n_mig_in,
+                                int64_t n_ghost, const double global_bounds[6])
+{
+    CHECK_CTX();
+    if (!ctx->slab) { ctx->err = "osph_slab_commit: context is not in slab mode"; return OSPH_E_INVALID; }
+    int64_t n_new = ctx->n - n_mig_out;
+    if (n_new < 0 || n_new + n_mig_in + n_ghost > ctx->cap || n_ghost > ctx->ghost_cap) {
+        ctx->err = "osph_slab_commit: particle capacity exceeded (osph_reserve a larger capacity)"; return OSPH_E_CAPACITY;
+    }
+    int m = (int)n_mig_out;
+    if (m > 0) {
+        int *nh = ctx->d_slab_counters + 8, *nf = ctx->d_slab_counters + 9;
+        OSPH_CUDA(cudaMemsetAsync(nh, 0, sizeof(int) * 2, ctx->stream));
+        OSPH_CUDA(cudaMemsetAsync(ctx->d_tail_flag, 0, sizeof(int) * m, ctx->stream));
+        k_slab_mark<<<div_up(m, 256), 256, 0, ctx->stream>>>(ctx->d_mig_slots, m, (int)n_new, ctx->d_tail_flag, ctx->d_holes, nh);
+        OSPH_LAUNCH_CHECK();
+        k_slab_fillers<<<div_up(m, 256), 256, 0, ctx->stream>>>(ctx->d_tail_flag, m, (int)n_new, ctx->d_fillers, nf);
+        OSPH_LAUNCH_CHECK();
+        k_slab_move<<<div_up((int64_t)m * (OSPH_NUM_FIELDS + 2), 256), 256, 0, ctx->stream>>>(move_args(ctx), ctx->d_holes,
+                                                                                            ctx->d_fillers, nh, m);
+        OSPH_LAUNCH_CHECK();
+    }
+    if (n_mig_in > 0) {
+        k_slab_append<<<div_up(n_mig_in * (OSPH_NUM_FIELDS + 2), 256), 256, 0, ctx->stream>>>(
+            move_args(ctx), (const double *)d_mig_in, (int)n_mig_in, (int)n_new);
+        OSPH_LAUNCH_CHECK();
+    }
+    ctx->n = n_new + n_mig_in;
+    ctx->n_ghost = n_ghost;
+    if (global_bounds) {
+        k_slab_set_bounds<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, global_bounds[0], global_bounds[1], global_bounds[2],
+                                                    global_bounds[3], global_bounds[4], global_bounds[5]);
+        OSPH_LAUNCH_CHECK();
+    }
+    ctx->prepared = true;
+    return 0;
+}
+
+extern "C" int osph_slab_dt_local(osph_ctx *ctx, double *d_out3)
+{
+    CHECK_CTX();
+    if (!ctx->reductions_valid) {
+        int rc = osph_launch_correct(ctx, false, 0.0, 0.0, false);
+        if (rc) return rc;
+        ctx->reductions_valid = true;
+    }
+    k_slab_dt_local<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, d_out3); OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int osph_slab_step_begin(osph_ctx *ctx, const double *d_dt_reduced3, double fixed_dt, double damping)
+{
+    CHECK_CTX();
+    if (!ctx->slab) { ctx->err = "osph_slab_step_begin: context is not in slab mode"; return OSPH_E_INVALID; }
+    int rc;
+    if (d_dt_reduced3) { k_slab_dt_set<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, d_dt_reduced3); OSPH_LAUNCH_CHECK(); }
+    if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true))) return rc;
+    if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true))) return rc;
+    ctx->neighbours_valid = false; ctx->reductions_valid = false;
+    return 0;
+}
+
+int osph_size_cell_table(osph_ctx *ctx);     // api.cu
+
+extern "C" int osph_slab_step_end(osph_ctx *ctx, double damping)
+{
+    CHECK_CTX();
+    if (!ctx->slab) { ctx->err = "osph_slab_step_end: context is not in slab mode"; return OSPH_E_INVALID; }
+    int rc;
+    if ((rc = osph_size_cell_table(ctx))) return rc;
+    if ((rc = osph_launch_build(ctx))) return rc;
+    if ((rc = osph_launch_pair(ctx))) return rc;
+    ctx->c_uniform = true;
+    if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true))) return rc;
+    ctx->prepared = false; ctx->neighbours_valid = false; ctx->reductions_valid = true;
+    ctx->step_counter++;
+    return 0;
+}
+
+extern "C" int osph_slab_export(osph_ctx *ctx, int32_t *d_ids, int8_t *d_label, int32_t nfields, const int32_t *fields,
+                                double *const *d_cols)
+{
+    CHECK_CTX();
+    if (ctx->n <= 0) return 0;
+    k_slab_ids<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->d_row, ctx->label, (int)ctx->n, d_ids, (signed char *)d_label);
+    OSPH_LAUNCH_CHECK();
+    for (int k = 0; k < nfields; k++) {
+        if (fields[k] < 0 || fields[k] >= OSPH_NUM_FIELDS) { ctx->err = "osph_slab_export: bad field"; return OSPH_E_INVALID; }
+        if (fields[k] == OSPH_F_C && ctx->c_uniform) {
+            int rc = osph_launch_fill(ctx, d_cols[k], ctx->cfg.co);
+            if (rc) return rc;
+        } else {
+            OSPH_CUDA(cudaMemcpyAsync(d_cols[k], ctx->f[fields[k]], sizeof(double) * ctx->n, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int osph_set_row_ids(osph_ctx *ctx, const int32_t *ids, int64_t n)
+{
+    CHECK_CTX();
+    if (n != ctx->n || !ids) { ctx->err = "osph_set_row_ids: need one id per active particle"; return OSPH_E_INVALID; }
+    OSPH_CUDA(cudaMemcpyAsync(ctx->d_row, ids, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int osph_reserve(osph_ctx *ctx, int64_t particle_capacity)
+{
+    CHECK_CTX();
+    if (particle_capacity < 0) return OSPH_E_INVALID;
+    ctx->reserve = particle_capacity;
+    return 0;
+}

@@ -54,6 +54,24 @@ __global__ void k_pack_aos(unsigned char *__restrict__ aos, long long stride, co
     }
 }
 
+// owned particles in storage order as complete records (deleted = 0), plus their global ids
+__global__ void k_pack_owned(unsigned char *__restrict__ aos, long long stride, int n, Columns c,
+                             const signed char *__restrict__ label, const int *__restrict__ row, int *__restrict__ ids,
+                             int c_uniform, double co)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char *rec = aos + (long long)i * stride;
+    rec[0] = 0; rec[1] = (unsigned char)label[i];
+#pragma unroll
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) {
+        double v = c.f[k][i];
+        if (k == OSPH_F_C && c_uniform) v = co;
+        store_f64_unaligned(rec + 2 + 8 * k, v);
+    }
+    ids[i] = row[i];
+}
+
 // column of the active particles in active order <-> storage order
 __global__ void k_col_to_active(const double *__restrict__ col, const int *__restrict__ act, int n,
                                 double *__restrict__ out, int fill, double fill_value)
@@ -252,37 +270,49 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
 
 // ---------------------------------------------------------------------------------------------
 // K3: cell keys.  Reference cell id (NNLinkedList.py:129-141, 164-176, 200-208) in strict IEEE.
+// The same function is re-evaluated by the gather kernel (deterministic, so the ids agree) instead of
+// carrying 24 bytes of cell info per particle through the sort.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_keys(const double *__restrict__ x, const double *__restrict__ y, int n, const GridParams *__restrict__ gp,
-       StepScalars *sc, unsigned int *__restrict__ key, unsigned int *__restrict__ idx,
-       int4 *__restrict__ u_coarse, int2 *__restrict__ u_gcell)
+struct CellInfo { int4 coarse; int2 gcell; unsigned int key; bool binned; };
+
+__device__ __forceinline__ CellInfo cell_of(double x, double y, const GridParams &g)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const GridParams g = *gp;
-    double rx = __dadd_rn(x[i], -g.xmin), ry = __dadd_rn(y[i], -g.ymin);
+    CellInfo c;
+    double rx = __dadd_rn(x, -g.xmin), ry = __dadd_rn(y, -g.ymin);
     long long cx = (long long)floor(__ddiv_rn(rx, g.cell_size));
     long long cy = (long long)floor(__ddiv_rn(ry, g.cell_size));
     long long flat = cx + g.ncx * cy;
-    int4 co;
-    bool binned = flat >= 0 && flat < g.n_cells;
-    co.x = binned ? (int)(flat % g.ncx) : -1000000;
-    co.y = binned ? (int)(flat / g.ncx) : -1000000;
-    co.z = (int)cx; co.w = (int)cy;
-    if (!binned) atomicOr(&sc->status, OSPH_S_UNBINNED);
-    int gx, gy;
-    unsigned int k;
+    c.binned = flat >= 0 && flat < g.n_cells;
+    c.coarse.x = c.binned ? (int)(flat % g.ncx) : -1000000;
+    c.coarse.y = c.binned ? (int)(flat / g.ncx) : -1000000;
+    c.coarse.z = (int)cx; c.coarse.w = (int)cy;
     if (g.regime_a) {
-        gx = (int)cx; gy = (int)cy;                                   // query cell: raw reference ids
-        k = binned ? (unsigned int)flat : (unsigned int)g.n_cells;    // bin cell: the reference's flat id
+        c.gcell = make_int2((int)cx, (int)cy);                                  // query cell: raw reference ids
+        c.key = c.binned ? (unsigned int)flat : (unsigned int)g.n_cells;        // bin cell: the reference's flat id
     } else {
-        gx = (int)floor(rx * g.ginv); gy = (int)floor(ry * g.ginv);
+        int gx = (int)floor(rx * g.ginv), gy = (int)floor(ry * g.ginv);
         gx = min(max(gx, 0), g.gnx - 1); gy = min(max(gy, 0), g.gny - 1);
-        k = (unsigned int)gy * (unsigned int)g.gnx + (unsigned int)gx;
+        c.gcell = make_int2(gx, gy);
+        c.key = (unsigned int)gy * (unsigned int)g.gnx + (unsigned int)gx;
     }
-    key[i] = k; idx[i] = (unsigned int)i;
-    u_coarse[i] = co; u_gcell[i] = make_int2(gx, gy);
+    return c;
+}
+
+// ghosts (slab mode) are light wire records of OSPH_WIRE_HALO doubles: x y vx vy rho m h label
+__global__ void __launch_bounds__(256)
+k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, const double *__restrict__ ghost,
+       int n_all, const GridParams *__restrict__ gp, StepScalars *sc, unsigned int *__restrict__ key,
+       unsigned int *__restrict__ idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_all) return;
+    const GridParams g = *gp;
+    double px, py;
+    if (i < n_owned) { px = x[i]; py = y[i]; }
+    else { const double *r = ghost + (size_t)(i - n_owned) * OSPH_WIRE_HALO; px = r[0]; py = r[1]; }
+    CellInfo c = cell_of(px, py, g);
+    if (!c.binned) atomicOr(&sc->status, OSPH_S_UNBINNED);
+    key[i] = c.key; idx[i] = (unsigned int)i;
 }
 
 // K6: cell table from the sorted keys (table is zeroed first: empty cells have begin == end == 0)
@@ -311,22 +341,31 @@ __global__ void __launch_bounds__(256)
 k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_hp)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n) return;
+    if (s >= a.n_all) return;
     int i = (int)a.idx[s];
-    bool fluid = a.label[i] == OSPH_FLUID;
-    double rho = a.rho[i];
+    double x, y, vx, vy, rho, m, h;
+    int lab, info;
+    if (i < a.n_owned) {
+        x = a.x[i]; y = a.y[i]; vx = a.vx[i]; vy = a.vy[i]; rho = a.rho[i]; m = a.m[i]; h = a.h[i];
+        lab = a.label[i]; info = 2;                                   // bit1: owned = a target of the pair kernel
+    } else {
+        const double *r = a.ghost + (size_t)(i - a.n_owned) * OSPH_WIRE_HALO;
+        x = r[0]; y = r[1]; vx = r[2]; vy = r[3]; rho = r[4]; m = r[5]; h = r[6]; lab = (int)r[7]; info = 0;
+    }
+    bool fluid = lab == OSPH_FLUID;
     double p = a.Pb;
     if (fluid) p = (tait_ratio_pow(rho / a.rho0, a.gamma) - 1.0) * a.B + a.Pb;
-    a.p[i] = p;
+    if (i < a.n_owned) a.p[i] = p;
     double pr2 = fluid ? p / (rho * rho) : 0.0;
-    a.s_pos[s] = make_double2(a.x[i], a.y[i]);
+    a.s_pos[s] = make_double2(x, y);
     typedef decltype(Real2().x) Real;
-    Real2 v; v.x = (Real)a.vx[i]; v.y = (Real)a.vy[i]; s_vel[s] = v;
-    Real2 rm; rm.x = (Real)rho; rm.y = (Real)a.m[i]; s_rm[s] = rm;
-    Real2 hp; hp.x = (Real)a.h[i]; hp.y = (Real)pr2; s_hp[s] = hp;
-    a.s_info[s] = fluid ? 1 : 0;
-    a.s_coarse[s] = a.u_coarse[i];
-    a.s_gcell[s] = a.u_gcell[i];
+    Real2 v; v.x = (Real)vx; v.y = (Real)vy; s_vel[s] = v;
+    Real2 rm; rm.x = (Real)rho; rm.y = (Real)m; s_rm[s] = rm;
+    Real2 hp; hp.x = (Real)h; hp.y = (Real)pr2; s_hp[s] = hp;
+    a.s_info[s] = info | (fluid ? 1 : 0);
+    CellInfo c = cell_of(x, y, *a.gp);
+    a.s_coarse[s] = c.coarse;
+    a.s_gcell[s] = c.gcell;
 }
 template __global__ void k_gather<double2>(GatherArgs, double2 *, double2 *, double2 *);
 template __global__ void k_gather<float2>(GatherArgs, float2 *, float2 *, float2 *);
@@ -629,6 +668,16 @@ int osph_launch_pack(osph_ctx *ctx)
     return 0;
 }
 
+int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids)
+{
+    if (ctx->n == 0) return 0;
+    k_pack_owned<<<div_up(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, (int)ctx->n, columns_of(ctx),
+                                                                ctx->label, ctx->d_row, d_ids, ctx->c_uniform ? 1 : 0,
+                                                                ctx->cfg.co);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
 int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt)
 {
     PrepareArgs a;
@@ -654,22 +703,47 @@ int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, 
 
 static double pair_radius_q(const osph_ctx *ctx) { return ctx->cfg.kernel == OSPH_KERNEL_GAUSSIAN ? 3.0 : 2.0; }
 
-// Physical reorder of the whole state into the order of the last sort.  Runs at the START of a build,
-// before new keys are formed, so only the state columns and the row/act maps have to move.
+// Physical reorder of the owned state into sorted (cell) order, right after the sort.  `perm` maps new slot ->
+// old slot.  Afterwards idx[] is rewritten so that it refers to the new slots.
+__global__ void k_owned_flags(const unsigned int *__restrict__ idx, int n_all, int n_owned, unsigned int *__restrict__ flag)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_all) flag[s] = idx[s] < (unsigned int)n_owned ? 1u : 0u;
+}
+__global__ void k_owned_perm(unsigned int *__restrict__ idx, const unsigned int *__restrict__ pos, int n_all, int n_owned,
+                             unsigned int *__restrict__ perm)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_all) return;
+    unsigned int i = idx[s];
+    if (i < (unsigned int)n_owned) { perm[pos[s]] = i; idx[s] = pos[s]; }
+}
+
 static int reorder_state(osph_ctx *ctx)
 {
-    const unsigned int *idx = ctx->idx[ctx->sorted_buf];
-    int n = (int)ctx->n, grid = div_up(ctx->n, 256);
+    unsigned int *idx = ctx->idx[ctx->sorted_buf];
+    unsigned int *perm = ctx->idx[ctx->sorted_buf ^ 1];          // the other sort buffer is free after the sort
+    int n = (int)ctx->n, n_all = (int)(ctx->n + ctx->n_ghost), grid = div_up(ctx->n, 256);
+    if (ctx->n_ghost == 0) {
+        OSPH_CUDA(cudaMemcpyAsync(perm, idx, sizeof(unsigned int) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_iota<<<grid, 256, 0, ctx->stream>>>(idx, n); OSPH_LAUNCH_CHECK();
+    } else {
+        unsigned int *flag = ctx->key[ctx->sorted_buf ^ 1];
+        k_owned_flags<<<div_up(n_all, 256), 256, 0, ctx->stream>>>(idx, n_all, n, flag); OSPH_LAUNCH_CHECK();
+        int rc = osph_scan_exclusive(ctx, flag, n_all);
+        if (rc) return rc;
+        k_owned_perm<<<div_up(n_all, 256), 256, 0, ctx->stream>>>(idx, flag, n_all, n, perm); OSPH_LAUNCH_CHECK();
+    }
     for (int k = 0; k < OSPH_NUM_FIELDS; k++) {
-        k_permute<double><<<grid, 256, 0, ctx->stream>>>(ctx->f[k], idx, n, ctx->scratch); OSPH_LAUNCH_CHECK();
+        k_permute<double><<<grid, 256, 0, ctx->stream>>>(ctx->f[k], perm, n, ctx->scratch); OSPH_LAUNCH_CHECK();
         double *t = ctx->f[k]; ctx->f[k] = ctx->scratch; ctx->scratch = t;
     }
-    // label / row / act / u_coarse / u_gcell go through the same spare column (it is 8 bytes wide)
-    k_permute<signed char><<<grid, 256, 0, ctx->stream>>>(ctx->label, idx, n, (signed char *)ctx->scratch); OSPH_LAUNCH_CHECK();
+    // label / row / act go through the same spare column (it is 8 bytes wide)
+    k_permute<signed char><<<grid, 256, 0, ctx->stream>>>(ctx->label, perm, n, (signed char *)ctx->scratch); OSPH_LAUNCH_CHECK();
     OSPH_CUDA(cudaMemcpyAsync(ctx->label, ctx->scratch, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_row, idx, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
+    k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_row, perm, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
     OSPH_CUDA(cudaMemcpyAsync(ctx->d_row, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_act, idx, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
+    k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_act, perm, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
     OSPH_CUDA(cudaMemcpyAsync(ctx->d_act, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->slot_of_act_valid = false;
     return 0;
@@ -685,31 +759,26 @@ int osph_launch_grid_params(osph_ctx *ctx)
 
 int osph_launch_build(osph_ctx *ctx)
 {
-    int n = (int)ctx->n, grid = div_up(ctx->n, 256);
-    int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
-    if (ctx->have_perm && (ctx->build_counter % every) == (1 % every)) {
-        int rc0 = reorder_state(ctx);
-        if (rc0) return rc0;
-    }
-    ctx->build_counter++;
-    int rcg = osph_launch_grid_params(ctx);
-    if (rcg) return rcg;
-    ctx->sorted_buf = 0;
-    k_keys<<<grid, 256, 0, ctx->stream>>>(ctx->f[OSPH_F_X], ctx->f[OSPH_F_Y], n, ctx->d_grid, ctx->d_sc, ctx->key[0],
-                                          ctx->idx[0], ctx->u_coarse, ctx->u_gcell);
-    OSPH_LAUNCH_CHECK();
-    int rc = osph_sort_pairs(ctx, n, ctx->key_bits);
+    int n = (int)ctx->n, n_all = (int)(ctx->n + ctx->n_ghost), grid = div_up(n_all, 256);
+    int rc = osph_launch_grid_params(ctx);
     if (rc) return rc;
-    OSPH_CUDA(cudaMemsetAsync(ctx->cell_range, 0, sizeof(int2) * (size_t)ctx->cell_cap, ctx->stream));
-    k_cell_table<<<grid, 256, 0, ctx->stream>>>(ctx->key[ctx->sorted_buf], n, ctx->cell_range);
+    ctx->sorted_buf = 0;
+    k_keys<<<grid, 256, 0, ctx->stream>>>(ctx->f[OSPH_F_X], ctx->f[OSPH_F_Y], n, ctx->d_ghost, n_all, ctx->d_grid,
+                                          ctx->d_sc, ctx->key[0], ctx->idx[0]);
     OSPH_LAUNCH_CHECK();
-    ctx->have_perm = true;
+    if ((rc = osph_sort_pairs(ctx, n_all, ctx->key_bits))) return rc;
+    OSPH_CUDA(cudaMemsetAsync(ctx->cell_range, 0, sizeof(int2) * (size_t)ctx->cell_cap, ctx->stream));
+    k_cell_table<<<grid, 256, 0, ctx->stream>>>(ctx->key[ctx->sorted_buf], n_all, ctx->cell_range);
+    OSPH_LAUNCH_CHECK();
+    int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
+    if (ctx->build_counter % every == 0 && (rc = reorder_state(ctx))) return rc;
+    ctx->build_counter++;
 
     GatherArgs g;
-    g.n = n; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label;
+    g.n_owned = n; g.n_all = n_all; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label; g.ghost = ctx->d_ghost;
     g.x = ctx->f[OSPH_F_X]; g.y = ctx->f[OSPH_F_Y]; g.vx = ctx->f[OSPH_F_VX]; g.vy = ctx->f[OSPH_F_VY];
     g.rho = ctx->f[OSPH_F_RHO]; g.m = ctx->f[OSPH_F_M]; g.h = ctx->f[OSPH_F_H]; g.p = ctx->f[OSPH_F_P];
-    g.u_coarse = ctx->u_coarse; g.u_gcell = ctx->u_gcell;
+    g.gp = ctx->d_grid;
     g.s_pos = ctx->s_pos; g.s_info = ctx->s_info; g.s_coarse = ctx->s_coarse; g.s_gcell = ctx->s_gcell;
     g.gamma = ctx->cfg.gamma; g.B = ctx->cfg.B; g.rho0 = ctx->cfg.rho0; g.Pb = ctx->cfg.Pb;
     if (ctx->cfg.precision == OSPH_FP64)
@@ -765,7 +834,7 @@ int osph_launch_ke(osph_ctx *ctx)
 static NeighbourArgs neighbour_args(osph_ctx *ctx)
 {
     NeighbourArgs a;
-    a.n = (int)ctx->n; a.idx = ctx->idx[ctx->sorted_buf]; a.act = ctx->d_act; a.h = ctx->f[OSPH_F_H];
+    a.n = (int)ctx->n; a.idx = ctx->idx[ctx->sorted_buf]; a.act = ctx->d_act; a.h = ctx->f[OSPH_F_H];   // single-GPU validation path: no ghosts
     a.s_pos = ctx->s_pos; a.s_info = ctx->s_info; a.s_coarse = ctx->s_coarse; a.s_gcell = ctx->s_gcell;
     a.cell_range = ctx->cell_range; a.gp = ctx->d_grid; a.counts = nullptr; a.offsets = nullptr; a.out = nullptr;
     return a;
@@ -802,6 +871,13 @@ int osph_launch_col_to_active(osph_ctx *ctx, int field, double *d_out)
     int fill = (field == OSPH_F_C && ctx->c_uniform) ? 1 : 0;
     k_col_to_active<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(ctx->f[field], ctx->d_act, (int)ctx->n, d_out, fill,
                                                                   ctx->cfg.co);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_fill(osph_ctx *ctx, double *d_col, double value)
+{
+    k_fill_c<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(d_col, (int)ctx->n, value);
     OSPH_LAUNCH_CHECK();
     return 0;
 }

@@ -24,13 +24,13 @@ struct CorrectArgs {
 };
 
 struct GatherArgs {
-    int n;
+    int n_owned, n_all;
     const unsigned int *idx;
     const signed char *label;
+    const double *ghost;
     const double *x, *y, *vx, *vy, *rho, *m, *h;
     double *p;
-    const int4 *u_coarse;
-    const int2 *u_gcell;
+    const GridParams *gp;
     double2 *s_pos;
     int *s_info;
     int4 *s_coarse;
@@ -57,6 +57,7 @@ struct NeighbourArgs {
 int osph_launch_setup(osph_ctx *ctx);
 int osph_launch_unpack(osph_ctx *ctx);
 int osph_launch_pack(osph_ctx *ctx);
+int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids);
 int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt);
 int osph_launch_build(osph_ctx *ctx);            // grid params, keys, sort, cell table, (reorder), gather
 int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt);
@@ -70,3 +71,5 @@ int osph_launch_cells(osph_ctx *ctx, long long *d_out);
 int osph_launch_col_to_active(osph_ctx *ctx, int field, double *d_out);
 int osph_launch_col_from_active(osph_ctx *ctx, int field, const double *d_in);
 int osph_init_scalars(osph_ctx *ctx);
+int osph_launch_fill(osph_ctx *ctx, double *d_col, double value);
+int osph_scan_exclusive(osph_ctx *ctx, unsigned int *d_data, int n);     // scan.cu, in place

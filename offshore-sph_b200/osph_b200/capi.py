@@ -103,6 +103,16 @@ def lib():
         'osph_launch_count': (i64, [ctx]),
         'osph_stream': (C.c_uint64, [ctx]),
         'osph_pair_kernel_time': (C.c_int, [ctx, dp, ip]),
+        'osph_reserve': (C.c_int, [ctx, i64]),
+        'osph_set_row_ids': (C.c_int, [ctx, C.POINTER(i32), i64]),
+        'osph_slab_configure': (C.c_int, [ctx, dbl, dbl, C.c_void_p, i64]),
+        'osph_slab_dt_local': (C.c_int, [ctx, C.c_void_p]),
+        'osph_slab_step_begin': (C.c_int, [ctx, C.c_void_p, dbl, dbl]),
+        'osph_slab_pack': (C.c_int, [ctx, dbl, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]),
+        'osph_slab_commit': (C.c_int, [ctx, i64, C.c_void_p, i64, i64, dp]),
+        'osph_slab_step_end': (C.c_int, [ctx, dbl]),
+        'osph_download_owned': (C.c_int, [ctx, C.c_void_p, i64, i64, C.POINTER(i32), ip]),
+        'osph_slab_export': (C.c_int, [ctx, C.c_void_p, C.c_void_p, i32, C.POINTER(i32), C.POINTER(C.c_void_p)]),
         'osph_leaf_kernel': (C.c_int, [C.c_int, C.c_int, C.c_int, i64, dp, dp, dp, dp]),
         'osph_leaf_tait_pressure': (C.c_int, [C.c_int, i64, dp, C.POINTER(C.c_int8), dbl, dbl, dbl, dbl, dp]),
         'osph_leaf_tait_height': (C.c_int, [C.c_int, i64, dp, dbl, dbl, dbl, dbl, dp]),
@@ -290,6 +300,48 @@ class Context:
                 k = cnt.value
                 return hh[:k], q[:k], r[:k], idx[:k]
             cap = int(cnt.value)
+
+    # ---- slab decomposition (device pointers of caller-owned buffers) ----
+    def reserve(self, capacity):
+        self._ck(self._L.osph_reserve(self._h, int(capacity)))
+
+    def set_row_ids(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self._ck(self._L.osph_set_row_ids(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), len(ids)))
+
+    def slab_configure(self, x_lo, x_hi, ghost_ptr, ghost_capacity):
+        self._ck(self._L.osph_slab_configure(self._h, x_lo, x_hi, C.c_void_p(ghost_ptr), ghost_capacity))
+
+    def slab_dt_local(self, out_ptr):
+        self._ck(self._L.osph_slab_dt_local(self._h, C.c_void_p(out_ptr)))
+
+    def slab_step_begin(self, dt_ptr, fixed_dt, damping):
+        self._ck(self._L.osph_slab_step_begin(self._h, C.c_void_p(dt_ptr) if dt_ptr else None,
+                                              -1.0 if fixed_dt is None else fixed_dt, damping))
+
+    def slab_pack(self, width, mig_l, mig_r, mig_cap, halo_l, halo_r, halo_cap, meta_ptr):
+        self._ck(self._L.osph_slab_pack(self._h, width, C.c_void_p(mig_l), C.c_void_p(mig_r), mig_cap,
+                                        C.c_void_p(halo_l), C.c_void_p(halo_r), halo_cap, C.c_void_p(meta_ptr)))
+
+    def slab_commit(self, n_mig_out, mig_in_ptr, n_mig_in, n_ghost, bounds):
+        b = (C.c_double * 6)(*bounds)
+        self._ck(self._L.osph_slab_commit(self._h, n_mig_out, C.c_void_p(mig_in_ptr) if mig_in_ptr else None,
+                                          n_mig_in, n_ghost, b))
+
+    def slab_step_end(self, damping):
+        self._ck(self._L.osph_slab_step_end(self._h, damping))
+
+    def download_owned(self, pA, ids):
+        n = C.c_int64(0)
+        self._ck(self._L.osph_download_owned(self._h, pA.ctypes.data, len(pA), pA.dtype.itemsize,
+                                             ids.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)))
+        return n.value
+
+    def slab_export(self, ids_ptr, label_ptr, fields, col_ptrs):
+        ids = (C.c_int32 * len(fields))(*[FIELD_ID[f] for f in fields])
+        ptrs = (C.c_void_p * len(fields))(*col_ptrs)
+        self._ck(self._L.osph_slab_export(self._h, C.c_void_p(ids_ptr), C.c_void_p(label_ptr) if label_ptr else None,
+                                          len(fields), ids, ptrs))
 
     def timers(self):
         out = (C.c_double * 6)()
