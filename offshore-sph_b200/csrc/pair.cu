@@ -23,20 +23,35 @@
 
 #include "sph_math.cuh"
 
+#define PAIR_LIST 24          // per-thread list of accepted candidates (16-bit shared-memory indices)
+#define PAIR_SCAN 4           // candidates tested between two warp votes
+#define PAIR_CAP 1024         // candidate records resident in shared memory at once
+
+// One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
+// every field at a compile-time offset.  40 B (float) / 80 B (double) keeps 8 / 16-byte vector alignment.
+template <typename Real, bool EXACT> struct Rec;
+template <> struct __align__(8) Rec<float, false> { float2 pos, vel, rm, hp; int info; int pad; };
+template <> struct __align__(16) Rec<double, true> { double2 pos, vel, rm, hp; int info; int cbx, cby; int pad; };
+
+template <typename Real, bool EXACT>
+constexpr size_t pair_smem_bytes()
+{
+    return sizeof(Rec<Real, EXACT>) * PAIR_CAP + sizeof(unsigned short) * PAIR_LIST * OSPH_PAIR_THREADS +
+           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6;
+}
+
 template <typename Real, int KID, bool EXACT>
-__global__ void __launch_bounds__(OSPH_PAIR_THREADS)
+__global__ void __launch_bounds__(OSPH_PAIR_THREADS, sizeof(Real) == 8 ? 2 : 3)
 k_pair(PairArgs a)
 {
     typedef typename R2<Real>::type Real2;
-    constexpr int CAP = OSPH_CAP_STAGE;
+    typedef Rec<Real, EXACT> RecT;
+    constexpr int CAP = PAIR_CAP;
     constexpr int NT = OSPH_PAIR_THREADS;
-    __shared__ Real2 sh_pos[CAP];
-    __shared__ Real2 sh_vel[CAP];
-    __shared__ Real2 sh_rm[CAP];
-    __shared__ Real2 sh_hp[CAP];
-    __shared__ int sh_info[CAP];
-    __shared__ int2 sh_cb[EXACT ? CAP : 1];
-    __shared__ int sh_red[NT / 32][6];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RecT *sh_rec = reinterpret_cast<RecT *>(smem_raw);
+    unsigned short *sh_list = reinterpret_cast<unsigned short *>(smem_raw + sizeof(RecT) * CAP);
+    int(*sh_red)[6] = reinterpret_cast<int(*)[6]>(smem_raw + sizeof(RecT) * CAP + sizeof(unsigned short) * PAIR_LIST * NT);
 
     const Real2 *__restrict__ g_vel = reinterpret_cast<const Real2 *>(a.s_vel);
     const Real2 *__restrict__ g_rm = reinterpret_cast<const Real2 *>(a.s_rm);
@@ -56,9 +71,7 @@ k_pair(PairArgs a)
     Real xi = 0, yi = 0, vxi = 0, vyi = 0, rhoi = 1, hi = 0, slf = 0;
     int qcx = 0, qcy = 0;
     bool fluid_i = false;
-    int ra[3], rb[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) { ra[d] = 0x7fffffff; rb[d] = 0; }
+    int ra0 = 0x7fffffff, ra1 = 0x7fffffff, ra2 = 0x7fffffff, rb0 = 0, rb1 = 0, rb2 = 0;
     if (valid) {
         double2 p = a.s_pos[s];
         xi = (Real)(p.x - anchor.x); yi = (Real)(p.y - anchor.y);
@@ -73,128 +86,177 @@ k_pair(PairArgs a)
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 int cy = gc.y + d - 1;
-                if (cy < 0 || cy >= gny || x0 > x1) continue;
-                const int2 *row = a.cell_range + (long long)cy * gnx;
                 int lo = 0x7fffffff, hiE = 0;
-                for (int cx = x0; cx <= x1; cx++) {
-                    int2 r = row[cx];
-                    if (r.y > r.x) { lo = min(lo, r.x); hiE = max(hiE, r.y); }
+                if (cy >= 0 && cy < gny && x0 <= x1) {
+                    const int2 *row = a.cell_range + (long long)cy * gnx;
+                    for (int cx = x0; cx <= x1; cx++) {
+                        int2 r = row[cx];
+                        if (r.y > r.x) { lo = min(lo, r.x); hiE = max(hiE, r.y); }
+                    }
                 }
-                ra[d] = lo; rb[d] = hiE;
+                if (d == 0) { ra0 = lo; rb0 = hiE; } else if (d == 1) { ra1 = lo; rb1 = hiE; } else { ra2 = lo; rb2 = hiE; }
             }
         }
     }
     // CTA-wide union of the runs, per row offset
     {
         int lane = tid & 31, w = tid >> 5;
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            int lo = warp_min_i(ra[d]), hiE = warp_max_i(rb[d]);
-            if (lane == 0) { sh_red[w][d] = lo; sh_red[w][3 + d] = hiE; }
+        int lo0 = warp_min_i(ra0), lo1 = warp_min_i(ra1), lo2 = warp_min_i(ra2);
+        int hi0 = warp_max_i(rb0), hi1 = warp_max_i(rb1), hi2 = warp_max_i(rb2);
+        if (lane == 0) {
+            sh_red[w][0] = lo0; sh_red[w][1] = lo1; sh_red[w][2] = lo2;
+            sh_red[w][3] = hi0; sh_red[w][4] = hi1; sh_red[w][5] = hi2;
         }
         __syncthreads();
     }
-    int ulo[3], uhi[3];
+    int ulo0 = 0x7fffffff, ulo1 = 0x7fffffff, ulo2 = 0x7fffffff, uhi0 = 0, uhi1 = 0, uhi2 = 0;
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-        int lo = 0x7fffffff, hiE = 0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; w++) { lo = min(lo, sh_red[w][d]); hiE = max(hiE, sh_red[w][3 + d]); }
-        ulo[d] = lo; uhi[d] = hiE;
+    for (int w = 0; w < NT / 32; w++) {
+        ulo0 = min(ulo0, sh_red[w][0]); ulo1 = min(ulo1, sh_red[w][1]); ulo2 = min(ulo2, sh_red[w][2]);
+        uhi0 = max(uhi0, sh_red[w][3]); uhi1 = max(uhi1, sh_red[w][4]); uhi2 = max(uhi2, sh_red[w][5]);
     }
+    const int len0 = max(uhi0 - ulo0, 0), len1 = max(uhi1 - ulo1, 0), len2 = max(uhi2 - ulo2, 0);
 
     const Real alpha_c = (Real)(a.alpha * a.c_half);      // alpha * 0.5 * c_i  (comp.c is never filled)
     const Real beta = (Real)a.beta;
     const Real r0 = (Real)a.r0, r0sq = r0 * r0;
+    const Real neg_eps = -(Real)a.eps;
+    const bool use_xsph = a.method_xsph != 0;
     Real drho = 0, ax = 0, ay = 0, bx = 0, by = 0, xs = 0, ys = 0;
 
-#pragma unroll 1
-    for (int d = 0; d < 3; d++) {
-#pragma unroll 1
-        for (int base = ulo[d]; base < uhi[d]; base += CAP) {
-            const int cnt = min(CAP, uhi[d] - base);
-            __syncthreads();
-            for (int t = tid; t < cnt; t += NT) {
-                int g = base + t;
-                double2 p = a.s_pos[g];
-                Real2 pr; pr.x = (Real)(p.x - anchor.x); pr.y = (Real)(p.y - anchor.y);
-                sh_pos[t] = pr;
-                sh_vel[t] = g_vel[g];
-                sh_rm[t] = g_rm[g];
-                sh_hp[t] = g_hp[g];
-                sh_info[t] = a.s_info[g];
-                if constexpr (EXACT) { int4 c = a.s_coarse[g]; sh_cb[t] = make_int2(c.x, c.y); }
+    // stage sorted particles [g0, g0 + cnt) into records [dst, dst + cnt)
+    auto stage = [&](int g0, int cnt, int dst) {
+        for (int t = tid; t < cnt; t += NT) {
+            const int g = g0 + t;
+            RecT rec;
+            double2 p = a.s_pos[g];
+            rec.pos.x = (Real)(p.x - anchor.x); rec.pos.y = (Real)(p.y - anchor.y);
+            rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
+            if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
+            rec.pad = 0;
+            sh_rec[dst + t] = rec;
+        }
+    };
+
+    // One accepted candidate: everything the reference evaluates per neighbour, fused.
+    auto interact = [&](const int j) {
+        const RecT *__restrict__ rj = sh_rec + j;
+        const Real2 pj = rj->pos;
+        const Real dx = xi - pj.x, dy = yi - pj.y;
+        const Real r2 = dx * dx + dy * dy;
+        const Real2 hpj = rj->hp;
+        const Real hij = Real(0.5) * (hi + hpj.x);
+        const bool fluid_j = (rj->info & 1) != 0;
+        const Real sup = (KID == OSPH_KERNEL_GAUSSIAN ? Real(3) : Real(2)) * hij;
+        // Gaussian: the cut IS the set boundary, keep the band for the exact test below
+        const bool kern = r2 <= sup * sup * (KID == OSPH_KERNEL_GAUSSIAN ? Real(1.0 + 1e-6) : Real(1));
+        const bool lj = !fluid_j && r2 <= r0sq;
+        if (!(kern || lj)) return;
+        // membership in the reference neighbour set: q <= 3 (matters for LJ and the Gaussian cut)
+        {
+            const Real t9 = Real(9) * hij * hij;
+            if constexpr (EXACT) {
+                if (r2 > t9 * (1.0 - 1e-13)) {
+                    if (r2 > t9 * (1.0 + 1e-13)) return;
+                    double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+                    if (!(__ddiv_rn(rr, (double)hij) <= 3.0)) return;
+                }
+                if (abs(rj->cbx - qcx) > 1 || abs(rj->cby - qcy) > 1) return;
+            } else {
+                if (r2 > t9) return;
             }
-            __syncthreads();
-            if (!fluid_i) continue;
-            const int j0 = max(ra[d], base) - base, j1 = min(rb[d], base + cnt) - base;
+        }
+        const Real inv_rt = r2 > Real(1e-24) ? rsqrt_fast(r2) : Real(0);   // LJ guard: r > 1e-12
+        const Real inv_r = r2 > Real(1e-20) ? inv_rt : Real(0);            // gradient guard: r >= 1e-10
+        const Real r = r2 * inv_rt;
+        const Real inv_h = rcp_fast(hij);
+        const Real q = r * inv_h;
+        Real w, g;
+        sph_kernel<Real, KID>(q, inv_h, inv_r, w, g);
+        const Real dwx = g * dx, dwy = g * dy;
+        const Real2 vj = rj->vel;
+        const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
+        const Real2 rmj = rj->rm;
+        const Real mj = rmj.y;
+        const Real inv_rbar = rcp_fast(Real(0.5) * (rhoi + rmj.x));
+        if (fluid_j) {
+            drho += mj * (dvx * dwx + dvy * dwy);
+            // artificial viscosity only for approaching pairs: min(dot, 0) makes it branch-free
+            const Real dot = fmin(dvx * dx + dvy * dy, Real(0));
+            const Real hbar = Real(0.5) * (hi + hij);          // h averaged twice (Momentum.py:43)
+            const Real mu = hbar * dot * rcp_fast(r2 + Real(0.01) * hbar * hbar);
+            const Real PIij = mu * (beta * mu - alpha_c) * inv_rbar;
+            const Real fac = mj * (slf + hpj.y + PIij);
+            ax -= fac * dwx; ay -= fac * dwy;
+        } else if (lj && r2 > Real(1e-24)) {
+            const Real frac = r0 * inv_rt;
+            Real tmp;
+            if (a.lj_42) { const Real f2 = frac * frac; tmp = f2 * f2 - f2; }
+            else tmp = pow_gen(frac, (Real)a.p1) - pow_gen(frac, (Real)a.p2);
+            const Real fac = (Real)a.D * tmp * inv_rt * inv_rt;
+            bx += fac * dx; by += fac * dy;
+        }
+        if (use_xsph) {
+            const Real fac = neg_eps * mj * w * inv_rbar;
+            xs += fac * dvx; ys += fac * dvy;
+        }
+    };
+
+    // Two-phase walk, warp-synchronous.  (1) scan: cheap distance test over the thread's own sub-interval of
+    // the staged records, accepted candidates appended to a per-thread list.  (2) flush: when any lane's list
+    // is nearly full every lane evaluates its list.  The heavy body then runs with most lanes active instead
+    // of the ~35-45% a fused test-and-evaluate loop achieves (profiles/r01).
+    int nl = 0;
+    auto flush = [&]() {
 #pragma unroll 1
-            for (int j = j0; j < j1; j++) {
-                const Real2 pj = sh_pos[j];
-                const Real dx = xi - pj.x, dy = yi - pj.y;
-                const Real r2 = dx * dx + dy * dy;
-                if (!(r2 <= pair_r2)) continue;
-                const Real2 hpj = sh_hp[j];
-                const Real hij = Real(0.5) * (hi + hpj.x);
-                const bool fluid_j = (sh_info[j] & 1) != 0;
-                const Real sup = (KID == OSPH_KERNEL_GAUSSIAN ? Real(3) : Real(2)) * hij;
-                // Gaussian: the cut IS the set boundary, keep the band for the exact test below
-                const bool kern = r2 <= sup * sup * (KID == OSPH_KERNEL_GAUSSIAN ? Real(1.0 + 1e-6) : Real(1));
-                const bool lj = !fluid_j && r2 <= r0sq;
-                if (!(kern || lj)) continue;
-                // membership in the reference neighbour set: q <= 3 (matters for LJ and the Gaussian cut)
-                {
-                    const Real t9 = Real(9) * hij * hij;
-                    if constexpr (EXACT) {
-                        if (r2 > t9 * (1.0 - 1e-13)) {
-                            if (r2 > t9 * (1.0 + 1e-13)) continue;
-                            double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
-                            if (!(__ddiv_rn(rr, (double)hij) <= 3.0)) continue;
-                        }
-                        const int2 cb = sh_cb[j];
-                        if (abs(cb.x - qcx) > 1 || abs(cb.y - qcy) > 1) continue;
-                    } else {
-                        if (r2 > t9) continue;
-                    }
+        for (int k = 0; k < nl; k++) interact((int)sh_list[k * NT + tid]);
+        nl = 0;
+    };
+    auto scan = [&](int j, const int j1) {          // all 32 lanes of a warp call this together
+        bool warp_more = __any_sync(0xffffffffu, j < j1);
+#pragma unroll 1
+        while (warp_more) {
+#pragma unroll
+            for (int u = 0; u < PAIR_SCAN; u++) {
+                if (j < j1) {
+                    const Real2 pj = sh_rec[j].pos;
+                    const Real dx = xi - pj.x, dy = yi - pj.y;
+                    if (dx * dx + dy * dy <= pair_r2) { sh_list[nl * NT + tid] = (unsigned short)j; nl++; }
+                    j++;
                 }
-                const Real inv_rt = r2 > Real(1e-24) ? rsqrt_fast(r2) : Real(0);   // LJ guard: r > 1e-12
-                const Real inv_r = r2 > Real(1e-20) ? inv_rt : Real(0);            // gradient guard: r >= 1e-10
-                const Real r = r2 * inv_rt;
-                const Real inv_h = rcp_fast(hij);
-                const Real q = r * inv_h;
-                Real w, g;
-                sph_kernel<Real, KID>(q, inv_h, inv_r, w, g);
-                const Real dwx = g * dx, dwy = g * dy;
-                const Real2 vj = sh_vel[j];
-                const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
-                const Real2 rmj = sh_rm[j];
-                const Real mj = rmj.y;
-                Real inv_rbar = 0;
-                if (fluid_j) {
-                    drho += mj * (dvx * dwx + dvy * dwy);
-                    const Real dot = dvx * dx + dvy * dy;
-                    Real PIij = 0;
-                    if (dot < Real(0)) {
-                        inv_rbar = rcp_fast(Real(0.5) * (rhoi + rmj.x));
-                        const Real hbar = Real(0.5) * (hi + hij);          // h averaged twice (Momentum.py:43)
-                        const Real mu = hbar * dot * rcp_fast(r2 + Real(0.01) * hbar * hbar);
-                        PIij = mu * (beta * mu - alpha_c) * inv_rbar;
-                    }
-                    const Real fac = mj * (slf + hpj.y + PIij);
-                    ax -= fac * dwx; ay -= fac * dwy;
-                } else if (lj && r2 > Real(1e-24)) {
-                    const Real frac = r0 * inv_rt;
-                    Real tmp;
-                    if (a.lj_42) { const Real f2 = frac * frac; tmp = f2 * f2 - f2; }
-                    else tmp = pow_gen(frac, (Real)a.p1) - pow_gen(frac, (Real)a.p2);
-                    const Real fac = (Real)a.D * tmp * inv_rt * inv_rt;
-                    bx += fac * dx; by += fac * dy;
-                }
-                if (a.method_xsph && mj != Real(0)) {
-                    if (inv_rbar == Real(0)) inv_rbar = rcp_fast(Real(0.5) * (rhoi + rmj.x));
-                    const Real fac = -(Real)a.eps * mj * w * inv_rbar;
-                    xs += fac * dvx; ys += fac * dvy;
-                }
+            }
+            if (__any_sync(0xffffffffu, nl > PAIR_LIST - PAIR_SCAN)) flush();
+            warp_more = __any_sync(0xffffffffu, j < j1);
+        }
+    };
+
+    if (len0 + len1 + len2 <= CAP) {
+        // common case: the three runs of the CTA fit in shared memory together; one staging pass, the
+        // candidate list persists across the rows and is flushed only when full and once at the end
+        const int o1 = len0, o2 = len0 + len1;
+        stage(ulo0, len0, 0); stage(ulo1, len1, o1); stage(ulo2, len2, o2);
+        __syncthreads();
+        // (an empty run is ra = INT_MAX, rb = 0: test it before doing index arithmetic on it)
+        const bool h0 = fluid_i && rb0 > ra0, h1 = fluid_i && rb1 > ra1, h2 = fluid_i && rb2 > ra2;
+        scan(h0 ? ra0 - ulo0 : 0, h0 ? rb0 - ulo0 : 0);
+        scan(h1 ? ra1 - ulo1 + o1 : 0, h1 ? rb1 - ulo1 + o1 : 0);
+        scan(h2 ? ra2 - ulo2 + o2 : 0, h2 ? rb2 - ulo2 + o2 : 0);
+        flush();
+    } else {
+        // rare: a run longer than the buffer (very dense cells or sparse rows spanning the domain): batches
+#pragma unroll 1
+        for (int d = 0; d < 3; d++) {
+            const int ulo = d == 0 ? ulo0 : (d == 1 ? ulo1 : ulo2), uhi = d == 0 ? uhi0 : (d == 1 ? uhi1 : uhi2);
+            const int ra = d == 0 ? ra0 : (d == 1 ? ra1 : ra2), rb = d == 0 ? rb0 : (d == 1 ? rb1 : rb2);
+#pragma unroll 1
+            for (int base = ulo; base < uhi; base += CAP) {
+                const int cnt = min(CAP, uhi - base);
+                __syncthreads();
+                stage(base, cnt, 0);
+                __syncthreads();
+                const bool has = fluid_i && rb > ra;
+                scan(has ? max(ra, base) - base : 0, has ? min(rb, base + cnt) - base : 0);
+                flush();
             }
         }
     }
@@ -213,17 +275,30 @@ k_pair(PairArgs a)
     }
 }
 
+template <typename Real, int KID, bool EXACT>
+static cudaError_t launch_one(const PairArgs &a, int grid, cudaStream_t stream)
+{
+    static bool configured = false;
+    constexpr size_t smem = pair_smem_bytes<Real, EXACT>();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_pair<Real, KID, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_pair<Real, KID, EXACT><<<grid, OSPH_PAIR_THREADS, smem, stream>>>(a);
+    return cudaSuccess;
+}
+
 template <typename Real, bool EXACT>
 static int launch_kid(osph_ctx *ctx, const PairArgs &a, int grid)
 {
+    cudaError_t e;
     switch (ctx->cfg.kernel) {
-    case OSPH_KERNEL_CUBIC:
-        k_pair<Real, OSPH_KERNEL_CUBIC, EXACT><<<grid, OSPH_PAIR_THREADS, 0, ctx->stream>>>(a); break;
-    case OSPH_KERNEL_WENDLAND:
-        k_pair<Real, OSPH_KERNEL_WENDLAND, EXACT><<<grid, OSPH_PAIR_THREADS, 0, ctx->stream>>>(a); break;
-    default:
-        k_pair<Real, OSPH_KERNEL_GAUSSIAN, EXACT><<<grid, OSPH_PAIR_THREADS, 0, ctx->stream>>>(a); break;
+    case OSPH_KERNEL_CUBIC: e = launch_one<Real, OSPH_KERNEL_CUBIC, EXACT>(a, grid, ctx->stream); break;
+    case OSPH_KERNEL_WENDLAND: e = launch_one<Real, OSPH_KERNEL_WENDLAND, EXACT>(a, grid, ctx->stream); break;
+    default: e = launch_one<Real, OSPH_KERNEL_GAUSSIAN, EXACT>(a, grid, ctx->stream); break;
     }
+    if (e != cudaSuccess) { ctx->err = std::string("pair kernel configuration: ") + cudaGetErrorString(e); return OSPH_E_CUDA; }
     return 0;
 }
 
@@ -246,8 +321,8 @@ int osph_launch_pair(osph_ctx *ctx)
     int grid = div_up(ctx->n + ctx->n_ghost, OSPH_PAIR_THREADS);
     const bool timed = ctx->time_pair && ctx->pair_ev_used < OSPH_PAIR_EVENTS;
     if (timed) cudaEventRecord(ctx->pair_ev[2 * ctx->pair_ev_used], ctx->stream);
-    if (c.precision == OSPH_FP64) launch_kid<double, true>(ctx, a, grid);
-    else launch_kid<float, false>(ctx, a, grid);
+    int rc = c.precision == OSPH_FP64 ? launch_kid<double, true>(ctx, a, grid) : launch_kid<float, false>(ctx, a, grid);
+    if (rc) return rc;
     OSPH_LAUNCH_CHECK();
     if (timed) { cudaEventRecord(ctx->pair_ev[2 * ctx->pair_ev_used + 1], ctx->stream); ctx->pair_ev_used++; }
     return 0;

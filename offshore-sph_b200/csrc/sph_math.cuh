@@ -4,6 +4,9 @@
 #include "common.cuh"
 
 #define PI_D 3.14159265358979323846
+#ifndef OSPH_NEWTON_STEPS
+#define OSPH_NEWTON_STEPS 2      // refinement steps after the 2^-20 MUFU seed: 2^-40, then full double (tools/mufu_accuracy.cu)
+#endif
 
 template <typename Real> struct R2;
 template <> struct R2<double> { typedef double2 type; };
@@ -16,7 +19,9 @@ __device__ __forceinline__ double rcp_fast(double x)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0); y = fma(y, e, y);
     e = fma(-x, y, 1.0); y = fma(y, e, y);
+#if OSPH_NEWTON_STEPS > 2
     e = fma(-x, y, 1.0); y = fma(y, e, y);
+#endif
     return y;
 }
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
@@ -29,7 +34,9 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     double hx = 0.5 * x;
     double e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
     e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+#if OSPH_NEWTON_STEPS > 2
     e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
+#endif
     return y;
 }
 __device__ __forceinline__ float rsqrt_fast(float x) { return rsqrtf(x); }
