@@ -23,9 +23,22 @@
 
 #include "sph_math.cuh"
 
-#define PAIR_LIST 24          // per-thread list of accepted candidates (16-bit shared-memory indices)
+#ifndef PAIR_LIST64
+#define PAIR_LIST64 48        // per-thread list of accepted candidates (16-bit shared-memory indices), double
+#endif
+#ifndef PAIR_LIST32
+#define PAIR_LIST32 48        // same, float instantiation
+#endif
+#ifndef PAIR_MINB64
+#define PAIR_MINB64 2         // __launch_bounds__ min CTAs per SM, double
+#endif
+#ifndef PAIR_MINB32
+#define PAIR_MINB32 3
+#endif
 #define PAIR_SCAN 4           // candidates tested between two warp votes
+#ifndef PAIR_CAP
 #define PAIR_CAP 1024         // candidate records resident in shared memory at once
+#endif
 
 // One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
 // every field at a compile-time offset.  40 B (float) / 80 B (double) keeps 8 / 16-byte vector alignment.
@@ -36,16 +49,17 @@ template <> struct __align__(16) Rec<double, true> { double2 pos, vel, rm, hp; i
 template <typename Real, bool EXACT>
 constexpr size_t pair_smem_bytes()
 {
-    return sizeof(Rec<Real, EXACT>) * PAIR_CAP + sizeof(unsigned short) * PAIR_LIST * OSPH_PAIR_THREADS +
+    return sizeof(Rec<Real, EXACT>) * PAIR_CAP + sizeof(unsigned short) * (sizeof(Real) == 8 ? PAIR_LIST64 : PAIR_LIST32) * OSPH_PAIR_THREADS +
            sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6;
 }
 
 template <typename Real, int KID, bool EXACT>
-__global__ void __launch_bounds__(OSPH_PAIR_THREADS, sizeof(Real) == 8 ? 2 : 3)
+__global__ void __launch_bounds__(OSPH_PAIR_THREADS, sizeof(Real) == 8 ? PAIR_MINB64 : PAIR_MINB32)
 k_pair(PairArgs a)
 {
     typedef typename R2<Real>::type Real2;
     typedef Rec<Real, EXACT> RecT;
+    constexpr int PAIR_LIST = sizeof(Real) == 8 ? PAIR_LIST64 : PAIR_LIST32;
     constexpr int CAP = PAIR_CAP;
     constexpr int NT = OSPH_PAIR_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,67 +152,74 @@ k_pair(PairArgs a)
         }
     };
 
-    // One accepted candidate: everything the reference evaluates per neighbour, fused.
+    // One listed candidate: everything the reference evaluates per neighbour, fused.  Written as one straight
+    // line (all shared-memory loads first, one early exit, the four reciprocal / rsqrt Newton chains independent of
+    // each other, fluid-only terms masked instead of branched) so the scheduler can overlap the FP64 latencies;
+    // only the rare paths (exact-predicate band, Lennard-Jones wall force) branch.
     auto interact = [&](const int j) {
         const RecT *__restrict__ rj = sh_rec + j;
         const Real2 pj = rj->pos;
+        const Real2 hpj = rj->hp;
+        const Real2 vj = rj->vel;
+        const Real2 rmj = rj->rm;
+        const int info_j = rj->info;
+        int cbx = 0, cby = 0;
+        if constexpr (EXACT) { cbx = rj->cbx; cby = rj->cby; }
         const Real dx = xi - pj.x, dy = yi - pj.y;
         const Real r2 = dx * dx + dy * dy;
-        const Real2 hpj = rj->hp;
         const Real hij = Real(0.5) * (hi + hpj.x);
-        const bool fluid_j = (rj->info & 1) != 0;
-        const Real sup = (KID == OSPH_KERNEL_GAUSSIAN ? Real(3) : Real(2)) * hij;
-        // Gaussian: the cut IS the set boundary, keep the band for the exact test below
-        const bool kern = r2 <= sup * sup * (KID == OSPH_KERNEL_GAUSSIAN ? Real(1.0 + 1e-6) : Real(1));
+        const Real h2 = hij * hij;
+        const bool fluid_j = (info_j & 1) != 0;
+        // kernel support (q <= 2, or the q <= 3 cut of the Gaussian, which IS the set boundary: keep a band for the
+        // exact test) and Lennard-Jones range
+        const bool kern = r2 <= h2 * (KID == OSPH_KERNEL_GAUSSIAN ? Real(9.0 * (1.0 + 1e-6)) : Real(4));
         const bool lj = !fluid_j && r2 <= r0sq;
-        if (!(kern || lj)) return;
-        // membership in the reference neighbour set: q <= 3 (matters for LJ and the Gaussian cut)
-        {
-            const Real t9 = Real(9) * hij * hij;
-            if constexpr (EXACT) {
-                if (r2 > t9 * (1.0 - 1e-13)) {
-                    if (r2 > t9 * (1.0 + 1e-13)) return;
-                    double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
-                    if (!(__ddiv_rn(rr, (double)hij) <= 3.0)) return;
-                }
-                if (abs(rj->cbx - qcx) > 1 || abs(rj->cby - qcy) > 1) return;
-            } else {
-                if (r2 > t9) return;
+        bool ok = kern || lj;
+        // membership in the reference neighbour set: q <= 3 (it can only fail for LJ pairs and at the Gaussian cut)
+        if constexpr (EXACT) {
+            ok = ok && abs(cbx - qcx) <= 1 && abs(cby - qcy) <= 1 && r2 <= h2 * (9.0 * (1.0 + 1e-13));
+            if (ok && r2 > h2 * (9.0 * (1.0 - 1e-13))) {          // within 1e-13 of the threshold: decide in strict IEEE
+                double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+                ok = __ddiv_rn(rr, (double)hij) <= 3.0;
             }
+        } else {
+            ok = ok && r2 <= h2 * Real(9);
         }
-        const Real inv_rt = r2 > Real(1e-24) ? rsqrt_fast(r2) : Real(0);   // LJ guard: r > 1e-12
-        const Real inv_r = r2 > Real(1e-20) ? inv_rt : Real(0);            // gradient guard: r >= 1e-10
-        const Real r = r2 * inv_rt;
+        if (!ok) return;
+        const Real rs = rsqrt_fast(fmax(r2, Real(1e-30)));
         const Real inv_h = rcp_fast(hij);
+        const Real rbar = Real(0.5) * (rhoi + rmj.x);
+        const Real inv_rbar = rcp_fast(rbar);
+        const Real hbar = Real(0.5) * (hi + hij);                 // h averaged twice (Momentum.py:43)
+        const Real inv_den = rcp_fast(r2 + Real(0.01) * hbar * hbar);
+        const Real inv_rt = r2 > Real(1e-24) ? rs : Real(0);       // LJ guard: r > 1e-12
+        const Real inv_r = r2 > Real(1e-20) ? rs : Real(0);        // gradient guard: r >= 1e-10
+        const Real r = r2 * inv_rt;
         const Real q = r * inv_h;
         Real w, g;
         sph_kernel<Real, KID>(q, inv_h, inv_r, w, g);
         const Real dwx = g * dx, dwy = g * dy;
-        const Real2 vj = rj->vel;
         const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
-        const Real2 rmj = rj->rm;
         const Real mj = rmj.y;
-        const Real inv_rbar = rcp_fast(Real(0.5) * (rhoi + rmj.x));
-        if (fluid_j) {
-            drho += mj * (dvx * dwx + dvy * dwy);
-            // artificial viscosity only for approaching pairs: min(dot, 0) makes it branch-free
-            const Real dot = fmin(dvx * dx + dvy * dy, Real(0));
-            const Real hbar = Real(0.5) * (hi + hij);          // h averaged twice (Momentum.py:43)
-            const Real mu = hbar * dot * rcp_fast(r2 + Real(0.01) * hbar * hbar);
-            const Real PIij = mu * (beta * mu - alpha_c) * inv_rbar;
-            const Real fac = mj * (slf + hpj.y + PIij);
-            ax -= fac * dwx; ay -= fac * dwy;
-        } else if (lj && r2 > Real(1e-24)) {
+        const Real mjf = fluid_j ? mj : Real(0);                   // continuity and momentum: fluid neighbours only
+        drho += mjf * (dvx * dwx + dvy * dwy);
+        // artificial viscosity only for approaching pairs: min(dot, 0) makes it branch-free
+        const Real dot = fmin(dvx * dx + dvy * dy, Real(0));
+        const Real mu = hbar * dot * inv_den;
+        const Real PIij = mu * (beta * mu - alpha_c) * inv_rbar;
+        const Real fac = mjf * (slf + hpj.y + PIij);
+        ax -= fac * dwx; ay -= fac * dwy;
+        if (use_xsph) {
+            const Real fx = neg_eps * mj * w * inv_rbar;
+            xs += fx * dvx; ys += fx * dvy;
+        }
+        if (lj && r2 > Real(1e-24)) {                              // wall / coupled particle inside r0
             const Real frac = r0 * inv_rt;
             Real tmp;
             if (a.lj_42) { const Real f2 = frac * frac; tmp = f2 * f2 - f2; }
             else tmp = pow_gen(frac, (Real)a.p1) - pow_gen(frac, (Real)a.p2);
-            const Real fac = (Real)a.D * tmp * inv_rt * inv_rt;
-            bx += fac * dx; by += fac * dy;
-        }
-        if (use_xsph) {
-            const Real fac = neg_eps * mj * w * inv_rbar;
-            xs += fac * dvx; ys += fac * dvy;
+            const Real fl = (Real)a.D * tmp * inv_rt * inv_rt;
+            bx += fl * dx; by += fl * dy;
         }
     };
 

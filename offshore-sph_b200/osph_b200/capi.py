@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(PKG_ROOT, "csrc")
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libosph_b200.so")
+LIB_PATH = os.environ.get("OSPH_LIB") or os.path.join(PKG_ROOT, "lib", "libosph_b200.so")
 HEADER = os.path.join(os.path.dirname(PKG_ROOT), "include", "osph.h")
 
 FP64, FP32 = 0, 1
