@@ -173,30 +173,25 @@ static void invalidate_state(osph_ctx *ctx)
 
 // ---- transfers ---------------------------------------------------------------------------------
 
-static int ingest(osph_ctx *ctx, const unsigned char *flags_host, const void *src, bool src_on_device, int64_t n,
-                  int64_t stride)
+// Upload path: raw records -> device mirror; the list of active rows is built ON the device (flags, exclusive
+// scan, compaction) so the host touches nothing but two counters.
+static int ingest(osph_ctx *ctx, const void *src, bool src_on_device, int64_t n, int64_t stride)
 {
-    // flags_host: n*2 bytes (deleted, label) gathered from the records
-    std::vector<int> rows; rows.reserve((size_t)n);
-    int64_t nf = 0;
-    for (int64_t r = 0; r < n; r++)
-        if (!flags_host[2 * r]) { rows.push_back((int)r); nf += (flags_host[2 * r + 1] == OSPH_FLUID); }
-    int64_t na = (int64_t)rows.size();
-    int rc = alloc_particles(ctx, na, n, stride);
+    int rc = alloc_particles(ctx, n, n, stride);          // capacity for the case that every row is active
     if (rc) return rc;
-    if (na != ctx->n || n != ctx->n_total) { ctx->sized = false; }
-    ctx->n = na; ctx->n_total = n; ctx->stride = stride; ctx->n_fluid = nf;
+    if (n != ctx->n_total) ctx->sized = false;
+    ctx->n_total = n; ctx->stride = stride;
     OSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, src, (size_t)n * stride,
                               src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-    if (na > 0) {
-        std::vector<int> act((size_t)na);
-        for (int64_t k = 0; k < na; k++) act[k] = (int)k;
-        OSPH_CUDA(cudaMemcpyAsync(ctx->d_row, rows.data(), sizeof(int) * na, cudaMemcpyHostToDevice, ctx->stream));
-        OSPH_CUDA(cudaMemcpyAsync(ctx->d_act, act.data(), sizeof(int) * na, cudaMemcpyHostToDevice, ctx->stream));
-        OSPH_CUDA(cudaStreamSynchronize(ctx->stream));     // rows/act are stack-owned
-        rc = osph_launch_unpack(ctx);
-        if (rc) return rc;
-    }
+    int *d_counters = (int *)ctx->d_partial;
+    OSPH_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int) * 2, ctx->stream));
+    if ((rc = osph_launch_active_list(ctx, (int)n, d_counters))) return rc;
+    int counters[2] = {0, 0};
+    OSPH_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (counters[0] != ctx->n) ctx->sized = false;
+    ctx->n = counters[0]; ctx->n_fluid = counters[1];
+    if (ctx->n > 0 && (rc = osph_launch_unpack(ctx))) return rc;
     ctx->c_uniform = false; ctx->build_counter = 0; ctx->n_ghost = 0; ctx->slab = false; ctx->slot_of_act_valid = false;
     invalidate_state(ctx);
     return 0;
@@ -205,22 +200,17 @@ static int ingest(osph_ctx *ctx, const unsigned char *flags_host, const void *sr
 extern "C" int osph_upload_aos(osph_ctx *ctx, const void *pA, int64_t n, int64_t stride)
 {
     CHECK_CTX();
-    if (!pA || n < 0 || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_upload_aos: bad arguments"; return OSPH_E_INVALID; }
+    if (!pA || n < 0 || n > 0x7fffffff || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_upload_aos: bad arguments"; return OSPH_E_INVALID; }
     PhaseTimer t(ctx, T_TRANSFER);
-    std::vector<unsigned char> flags((size_t)n * 2);
-    const unsigned char *p = (const unsigned char *)pA;
-    for (int64_t r = 0; r < n; r++) { flags[2 * r] = p[r * stride]; flags[2 * r + 1] = p[r * stride + 1]; }
-    return ingest(ctx, flags.data(), pA, false, n, stride);
+    return ingest(ctx, pA, false, n, stride);
 }
 
 extern "C" int osph_import_device_aos(osph_ctx *ctx, const void *d_pA, int64_t n, int64_t stride)
 {
     CHECK_CTX();
-    if (!d_pA || n < 0 || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_import_device_aos: bad arguments"; return OSPH_E_INVALID; }
+    if (!d_pA || n < 0 || n > 0x7fffffff || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_import_device_aos: bad arguments"; return OSPH_E_INVALID; }
     PhaseTimer t(ctx, T_TRANSFER);
-    std::vector<unsigned char> flags((size_t)n * 2);
-    OSPH_CUDA(cudaMemcpy2D(flags.data(), 2, d_pA, (size_t)stride, 2, (size_t)n, cudaMemcpyDeviceToHost));
-    return ingest(ctx, flags.data(), d_pA, true, n, stride);
+    return ingest(ctx, d_pA, true, n, stride);
 }
 
 extern "C" int osph_download_aos(osph_ctx *ctx, void *pA, int64_t n, int64_t stride)

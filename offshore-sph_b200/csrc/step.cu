@@ -29,6 +29,29 @@ __device__ __forceinline__ void store_f64_unaligned(unsigned char *p, double v)
 
 struct Columns { double *f[OSPH_NUM_FIELDS]; };
 
+// Active-row list on the device: flag = !deleted, exclusive scan (scan.cu), then compaction.  counters[0] = number
+// of active rows, counters[1] = number of fluid rows among them.
+__global__ void k_active_flags(const unsigned char *__restrict__ aos, long long stride, int n, unsigned int *__restrict__ flag)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) flag[r] = aos[(long long)r * stride] ? 0u : 1u;
+}
+__global__ void k_active_compact(const unsigned char *__restrict__ aos, long long stride, int n,
+                                 const unsigned int *__restrict__ pos, int *__restrict__ row, int *__restrict__ act,
+                                 int *__restrict__ counters)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int fluid = 0;
+    if (r < n) {
+        const unsigned char *rec = aos + (long long)r * stride;
+        bool alive = rec[0] == 0;
+        if (alive) { unsigned int p = pos[r]; row[p] = r; act[p] = (int)p; fluid = rec[1] == OSPH_FLUID; }
+        if (r == n - 1) counters[0] = (int)pos[r] + (alive ? 1 : 0);
+    }
+    unsigned int m = __ballot_sync(0xffffffffu, fluid);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[1], __popc(m));
+}
+
 __global__ void k_unpack_aos(const unsigned char *__restrict__ aos, long long stride, const int *__restrict__ row,
                              int n, Columns c, signed char *__restrict__ label)
 {
@@ -40,36 +63,39 @@ __global__ void k_unpack_aos(const unsigned char *__restrict__ aos, long long st
     for (int k = 0; k < OSPH_NUM_FIELDS; k++) c.f[k][i] = load_f64_unaligned(rec + 2 + 8 * k);
 }
 
-__global__ void k_pack_aos(unsigned char *__restrict__ aos, long long stride, const int *__restrict__ row, int n,
-                           Columns c, int c_uniform, double co)
+// Pack: a CTA transposes 128 particles through shared memory (coalesced column reads -> packed records),
+// then each warp streams whole records to their rows with contiguous 16-bit stores.  `ids` (optional) receives
+// the row ids; `identity` writes record i to row i (owned-set export) and also sets deleted = 0 / label.
+#define PACK_ROWS 128
+__global__ void __launch_bounds__(PACK_ROWS)
+k_pack_aos(unsigned char *__restrict__ aos, long long stride, const int *__restrict__ row, int n, Columns c,
+           const signed char *__restrict__ label, int c_uniform, double co, int identity, int *__restrict__ ids)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    unsigned char *rec = aos + (long long)row[i] * stride;
+    __shared__ __align__(16) unsigned short sh[PACK_ROWS * 77];
+    __shared__ int sh_row[PACK_ROWS];
+    const int t = threadIdx.x, i0 = blockIdx.x * PACK_ROWS, i = i0 + t;
+    if (i < n) {
+        unsigned short *rec = sh + t * 77;
+        rec[0] = identity ? (unsigned short)((unsigned char)label[i]) << 8 : 0;      // bytes 0,1 = deleted(0), label
 #pragma unroll
-    for (int k = 0; k < OSPH_NUM_FIELDS; k++) {
-        double v = c.f[k][i];
-        if (k == OSPH_F_C && c_uniform) v = co;
-        store_f64_unaligned(rec + 2 + 8 * k, v);
+        for (int k = 0; k < OSPH_NUM_FIELDS; k++) {
+            double v = c.f[k][i];
+            if (k == OSPH_F_C && c_uniform) v = co;
+            unsigned long long u = (unsigned long long)__double_as_longlong(v);
+            rec[1 + 4 * k] = (unsigned short)u; rec[2 + 4 * k] = (unsigned short)(u >> 16);
+            rec[3 + 4 * k] = (unsigned short)(u >> 32); rec[4 + 4 * k] = (unsigned short)(u >> 48);
+        }
+        int r = row[i];
+        sh_row[t] = identity ? i : r;
+        if (ids) ids[i] = r;
     }
-}
-
-// owned particles in storage order as complete records (deleted = 0), plus their global ids
-__global__ void k_pack_owned(unsigned char *__restrict__ aos, long long stride, int n, Columns c,
-                             const signed char *__restrict__ label, const int *__restrict__ row, int *__restrict__ ids,
-                             int c_uniform, double co)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    unsigned char *rec = aos + (long long)i * stride;
-    rec[0] = 0; rec[1] = (unsigned char)label[i];
-#pragma unroll
-    for (int k = 0; k < OSPH_NUM_FIELDS; k++) {
-        double v = c.f[k][i];
-        if (k == OSPH_F_C && c_uniform) v = co;
-        store_f64_unaligned(rec + 2 + 8 * k, v);
+    __syncthreads();
+    const int lane = t & 31, w = t >> 5, rows = min(PACK_ROWS, n - i0);
+    for (int r = w; r < rows; r += PACK_ROWS / 32) {
+        unsigned short *dst = reinterpret_cast<unsigned short *>(aos + (long long)sh_row[r] * stride);
+        const unsigned short *src = sh + r * 77;
+        for (int hw = lane + (identity ? 0 : 1); hw < 77; hw += 32) dst[hw] = src[hw];
     }
-    ids[i] = row[i];
 }
 
 // column of the active particles in active order <-> storage order
@@ -650,6 +676,19 @@ int osph_launch_setup(osph_ctx *ctx)
     return 0;
 }
 
+int osph_launch_active_list(osph_ctx *ctx, int n_total, int *d_counters)
+{
+    if (n_total == 0) return 0;
+    unsigned int *flag = ctx->key[0];
+    k_active_flags<<<div_up(n_total, 256), 256, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, n_total, flag); OSPH_LAUNCH_CHECK();
+    int rc = osph_scan_exclusive(ctx, flag, n_total);
+    if (rc) return rc;
+    k_active_compact<<<div_up(n_total, 256), 256, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, n_total, flag, ctx->d_row,
+                                                                   ctx->d_act, d_counters);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
 int osph_launch_unpack(osph_ctx *ctx)
 {
     if (ctx->n == 0) return 0;
@@ -662,8 +701,9 @@ int osph_launch_unpack(osph_ctx *ctx)
 int osph_launch_pack(osph_ctx *ctx)
 {
     if (ctx->n == 0) return 0;
-    k_pack_aos<<<div_up(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, ctx->d_row, (int)ctx->n,
-                                                              columns_of(ctx), ctx->c_uniform ? 1 : 0, ctx->cfg.co);
+    k_pack_aos<<<div_up(ctx->n, PACK_ROWS), PACK_ROWS, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, ctx->d_row, (int)ctx->n,
+                                                                          columns_of(ctx), ctx->label, ctx->c_uniform ? 1 : 0,
+                                                                          ctx->cfg.co, 0, nullptr);
     OSPH_LAUNCH_CHECK();
     return 0;
 }
@@ -671,9 +711,9 @@ int osph_launch_pack(osph_ctx *ctx)
 int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids)
 {
     if (ctx->n == 0) return 0;
-    k_pack_owned<<<div_up(ctx->n, 128), 128, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, (int)ctx->n, columns_of(ctx),
-                                                                ctx->label, ctx->d_row, d_ids, ctx->c_uniform ? 1 : 0,
-                                                                ctx->cfg.co);
+    k_pack_aos<<<div_up(ctx->n, PACK_ROWS), PACK_ROWS, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, ctx->d_row, (int)ctx->n,
+                                                                          columns_of(ctx), ctx->label, ctx->c_uniform ? 1 : 0,
+                                                                          ctx->cfg.co, 1, d_ids);
     OSPH_LAUNCH_CHECK();
     return 0;
 }
@@ -771,7 +811,9 @@ int osph_launch_build(osph_ctx *ctx)
     k_cell_table<<<grid, 256, 0, ctx->stream>>>(ctx->key[ctx->sorted_buf], n_all, ctx->cell_range);
     OSPH_LAUNCH_CHECK();
     int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
-    if (ctx->build_counter % every == 0 && (rc = reorder_state(ctx))) return rc;
+    // physical re-sort on the 3rd build after an upload, then every `every` builds: a caller that uploads, steps once
+    // and downloads (the host-buffer plugin call pattern) never pays for it, a resident run gets it early
+    if (ctx->build_counter % every == (2 % every) && (rc = reorder_state(ctx))) return rc;
     ctx->build_counter++;
 
     GatherArgs g;

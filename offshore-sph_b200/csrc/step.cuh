@@ -56,6 +56,7 @@ struct NeighbourArgs {
 
 int osph_launch_setup(osph_ctx *ctx);
 int osph_launch_unpack(osph_ctx *ctx);
+int osph_launch_active_list(osph_ctx *ctx, int n_total, int *d_counters);
 int osph_launch_pack(osph_ctx *ctx);
 int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids);
 int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt);

@@ -172,9 +172,10 @@ class Context:
         self._shape = None
 
     def close(self):
-        if getattr(self, '_h', None) is not None and self._h:
-            self._L.osph_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, '_h', None)
+        if h is not None and h.value:
+            self._h = None
+            self._L.osph_destroy(h)
 
     __del__ = close
 
