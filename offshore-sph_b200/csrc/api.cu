@@ -416,14 +416,15 @@ extern "C" int osph_step(osph_ctx *ctx, int32_t nsteps, double fixed_dt, double 
     int rc;
     for (int s = 0; s < nsteps; s++) {
         if ((rc = ensure_reductions(ctx))) return rc;
-        if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true))) return rc;
-        if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true))) return rc;
+        // the two scalar resets ride along in k_timestep / k_grid_params on this fused path
+        if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true))) return rc;
+        if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true))) return rc;
         ctx->prepared = true;
         if ((rc = osph_size_cell_table(ctx))) return rc;
-        if ((rc = osph_launch_build(ctx))) return rc;
+        if ((rc = osph_launch_build(ctx, true))) return rc;
         if ((rc = osph_launch_pair(ctx))) return rc;
         ctx->c_uniform = true;
-        if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true))) return rc;
+        if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true, true))) return rc;
         invalidate_state(ctx);
         ctx->reductions_valid = true;
         ctx->step_counter++;

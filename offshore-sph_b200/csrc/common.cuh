@@ -202,7 +202,7 @@ __device__ __forceinline__ int warp_max_i(int v)
 // ---------------------------------------------------------------------------------------------
 // launchers implemented in the other translation units
 // ---------------------------------------------------------------------------------------------
-int osph_sort_pairs(osph_ctx *ctx, int64_t n, int bits);                 // sort.cu: key[sorted_buf], idx[sorted_buf]
+int osph_sort_pairs(osph_ctx *ctx, int64_t n, int bits, bool first_hist_done);   // sort.cu: key[sorted_buf], idx[sorted_buf]
 int osph_sort_alloc(osph_ctx *ctx, int64_t cap);
 void osph_sort_free(osph_ctx *ctx);
 int osph_launch_pair(osph_ctx *ctx);                                      // pair.cu

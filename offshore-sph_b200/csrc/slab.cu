@@ -241,8 +241,8 @@ extern "C" int osph_slab_step_begin(osph_ctx *ctx, const double *d_dt_reduced3, 
     if (!ctx->slab) { ctx->err = "osph_slab_step_begin: context is not in slab mode"; return OSPH_E_INVALID; }
     int rc;
     if (d_dt_reduced3) { k_slab_dt_set<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, d_dt_reduced3); OSPH_LAUNCH_CHECK(); }
-    if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true))) return rc;
-    if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true))) return rc;
+    if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true))) return rc;
+    if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true))) return rc;
     ctx->neighbours_valid = false; ctx->reductions_valid = false;
     return 0;
 }
@@ -255,10 +255,10 @@ extern "C" int osph_slab_step_end(osph_ctx *ctx, double damping)
     if (!ctx->slab) { ctx->err = "osph_slab_step_end: context is not in slab mode"; return OSPH_E_INVALID; }
     int rc;
     if ((rc = osph_size_cell_table(ctx))) return rc;
-    if ((rc = osph_launch_build(ctx))) return rc;
+    if ((rc = osph_launch_build(ctx, true))) return rc;
     if ((rc = osph_launch_pair(ctx))) return rc;
     ctx->c_uniform = true;
-    if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true))) return rc;
+    if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true, true))) return rc;
     ctx->prepared = false; ctx->neighbours_valid = false; ctx->reductions_valid = true;
     ctx->step_counter++;
     return 0;

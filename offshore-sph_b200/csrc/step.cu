@@ -7,6 +7,7 @@
 // contract it into FMAs; integrator updates do the same so they are bit-identical to the CPU oracle.
 #include "common.cuh"
 #include "step.cuh"
+#include "sort.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // K10: packed 154-byte records <-> SoA columns.  Doubles sit at byte offset 2 + 8k (2-byte aligned
@@ -249,8 +250,12 @@ template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, false>(PrepareArgs);
 // Grid parameters: the reference grid (NNLinkedList.py:86-127) and the acceleration grid.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, double pair_radius_q, double r0,
-                              long long cell_cap)
+                              long long cell_cap, int reset_dt)
 {
+    if (reset_dt) {           // folded k_reset_dt_scalars: the corrector of this step reduces into these
+        sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF;
+        sc->n_fluid_seen = 0;
+    }
     double xmin = dec_f64(sc->xmin), xmax = dec_f64(sc->xmax), ymin = dec_f64(sc->ymin), ymax = dec_f64(sc->ymax);
     double hmin = dec_f64(sc->hmin_all), hmax = dec_f64(sc->hmax_all);
     g->xmin = xmin; g->xmax = xmax; g->ymin = ymin; g->ymax = ymax; g->hmax = hmax;
@@ -324,32 +329,35 @@ __device__ __forceinline__ CellInfo cell_of(double x, double y, const GridParams
     return c;
 }
 
-// ghosts (slab mode) are light wire records of OSPH_WIRE_HALO doubles: x y vx vy rho m h label
-__global__ void __launch_bounds__(256)
+// ghosts (slab mode) are light wire records of OSPH_WIRE_HALO doubles: x y vx vy rho m h label.
+// The kernel walks the radix sort's tiles and also emits the first pass's per-tile digit histogram.
+template <int BITS>
+__global__ void __launch_bounds__(SORT_THREADS)
 k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, const double *__restrict__ ghost,
        int n_all, const GridParams *__restrict__ gp, StepScalars *sc, unsigned int *__restrict__ key,
-       unsigned int *__restrict__ idx)
+       unsigned int *__restrict__ idx, int nblocks, unsigned int *__restrict__ hist)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_all) return;
+    constexpr int RADIX = 1 << BITS;
+    __shared__ unsigned int cnt[RADIX];
+    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) cnt[d] = 0;
+    __syncthreads();
     const GridParams g = *gp;
-    double px, py;
-    if (i < n_owned) { px = x[i]; py = y[i]; }
-    else { const double *r = ghost + (size_t)(i - n_owned) * OSPH_WIRE_HALO; px = r[0]; py = r[1]; }
-    CellInfo c = cell_of(px, py, g);
-    if (!c.binned) atomicOr(&sc->status, OSPH_S_UNBINNED);
-    key[i] = c.key; idx[i] = (unsigned int)i;
-}
-
-// K6: cell table from the sorted keys (table is zeroed first: empty cells have begin == end == 0)
-__global__ void __launch_bounds__(256)
-k_cell_table(const unsigned int *__restrict__ key, int n, int2 *__restrict__ cell_range)
-{
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    unsigned int k = key[s];
-    if (s == 0 || key[s - 1] != k) cell_range[k].x = s;
-    if (s == n - 1 || key[s + 1] != k) cell_range[k].y = s + 1;
+    bool unbinned = false;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        int i = blockIdx.x * SORT_TILE + r * SORT_THREADS + threadIdx.x;
+        if (i >= n_all) continue;
+        double px, py;
+        if (i < n_owned) { px = x[i]; py = y[i]; }
+        else { const double *rec = ghost + (size_t)(i - n_owned) * OSPH_WIRE_HALO; px = rec[0]; py = rec[1]; }
+        CellInfo c = cell_of(px, py, g);
+        unbinned |= !c.binned;
+        key[i] = c.key; idx[i] = (unsigned int)i;
+        atomicAdd(&cnt[c.key & (RADIX - 1)], 1u);
+    }
+    if (unbinned) atomicOr(&sc->status, OSPH_S_UNBINNED);
+    __syncthreads();
+    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = cnt[d];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,6 +376,11 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n_all) return;
+    {   // K6 fused: cell table from the sorted keys (table zeroed before: empty cells have begin == end == 0)
+        unsigned int k = a.key[s];
+        if (s == 0 || a.key[s - 1] != k) a.cell_range[k].x = s;
+        if (s == a.n_all - 1 || a.key[s + 1] != k) a.cell_range[k].y = s + 1;
+    }
     int i = (int)a.idx[s];
     double x, y, vx, vy, rho, m, h;
     int lab, info;
@@ -490,8 +503,12 @@ template __global__ void k_correct<OSPH_INTEGRATOR_PEC, false>(CorrectArgs);
 
 // TimeStep.compute / courant / force (src/Equations/TimeStep.py:11-56), strict IEEE.
 __global__ void k_timestep(StepScalars *sc, double gamma_c, double gamma_f, double fixed_dt,
-                           double *dt_log, long long dt_log_cap)
+                           double *dt_log, long long dt_log_cap, int reset_prepare)
 {
+    if (reset_prepare) {      // folded k_reset_prepare_scalars: the predictor that follows reduces into these
+        sc->xmin = ENC_POS_INF; sc->ymin = ENC_POS_INF; sc->xmax = ENC_NEG_INF; sc->ymax = ENC_NEG_INF;
+        sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF;
+    }
     double out0, c = 0.0, f = 0.0;
     if (fixed_dt > 0.0) { out0 = fixed_dt; }
     else {
@@ -718,7 +735,7 @@ int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids)
     return 0;
 }
 
-int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt)
+int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset)
 {
     PrepareArgs a;
     a.n = (int)ctx->n; a.label = ctx->label;
@@ -731,7 +748,7 @@ int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, 
     a.sc = ctx->d_sc; a.dt = dt; a.damping = damping; a.fixed_h = ctx->cfg.fixed_h; a.h_sigma = ctx->cfg.h_sigma;
     a.use_dev_dt = use_dev_dt ? 1 : 0; a.integ_xsph = ctx->cfg.integrator_xsph; a.strict = ctx->cfg.strict;
     a.dynamic_h = ctx->cfg.dynamic_h;
-    k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    if (!skip_reset) { k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
     int grid = div_up(ctx->n, 256);
     int integ = ctx->cfg.integrator;
     if (predict && integ == OSPH_INTEGRATOR_PEC) k_prepare<OSPH_INTEGRATOR_PEC, true><<<grid, 256, 0, ctx->stream>>>(a);
@@ -789,27 +806,36 @@ static int reorder_state(osph_ctx *ctx)
     return 0;
 }
 
-int osph_launch_grid_params(osph_ctx *ctx)
+int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt)
 {
     k_grid_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->d_grid, ctx->cfg.nn_scale, pair_radius_q(ctx), ctx->cfg.r0,
-                                            (long long)ctx->cell_cap);
+                                            (long long)ctx->cell_cap, reset_dt ? 1 : 0);
     OSPH_LAUNCH_CHECK();
     return 0;
 }
 
-int osph_launch_build(osph_ctx *ctx)
+int osph_launch_build(osph_ctx *ctx, bool reset_dt)
 {
     int n = (int)ctx->n, n_all = (int)(ctx->n + ctx->n_ghost), grid = div_up(n_all, 256);
-    int rc = osph_launch_grid_params(ctx);
+    int rc = osph_launch_grid_params(ctx, reset_dt);
     if (rc) return rc;
     ctx->sorted_buf = 0;
-    k_keys<<<grid, 256, 0, ctx->stream>>>(ctx->f[OSPH_F_X], ctx->f[OSPH_F_Y], n, ctx->d_ghost, n_all, ctx->d_grid,
-                                          ctx->d_sc, ctx->key[0], ctx->idx[0]);
-    OSPH_LAUNCH_CHECK();
-    if ((rc = osph_sort_pairs(ctx, n_all, ctx->key_bits))) return rc;
+    {
+        const int nblocks = div_up(n_all, SORT_TILE), db = osph_sort_digit_bits(ctx->key_bits);
+        const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];
+        if (db == 8)
+            k_keys<8><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, n_all, ctx->d_grid, ctx->d_sc,
+                                                                 ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
+        else if (db == 10)
+            k_keys<10><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, n_all, ctx->d_grid, ctx->d_sc,
+                                                                  ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
+        else
+            k_keys<11><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, n_all, ctx->d_grid, ctx->d_sc,
+                                                                  ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
+        OSPH_LAUNCH_CHECK();
+    }
+    if ((rc = osph_sort_pairs(ctx, n_all, ctx->key_bits, true))) return rc;
     OSPH_CUDA(cudaMemsetAsync(ctx->cell_range, 0, sizeof(int2) * (size_t)ctx->cell_cap, ctx->stream));
-    k_cell_table<<<grid, 256, 0, ctx->stream>>>(ctx->key[ctx->sorted_buf], n_all, ctx->cell_range);
-    OSPH_LAUNCH_CHECK();
     int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
     // physical re-sort on the 3rd build after an upload, then every `every` builds: a caller that uploads, steps once
     // and downloads (the host-buffer plugin call pattern) never pays for it, a resident run gets it early
@@ -817,7 +843,7 @@ int osph_launch_build(osph_ctx *ctx)
     ctx->build_counter++;
 
     GatherArgs g;
-    g.n_owned = n; g.n_all = n_all; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label; g.ghost = ctx->d_ghost;
+    g.n_owned = n; g.n_all = n_all; g.key = ctx->key[ctx->sorted_buf]; g.cell_range = ctx->cell_range; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label; g.ghost = ctx->d_ghost;
     g.x = ctx->f[OSPH_F_X]; g.y = ctx->f[OSPH_F_Y]; g.vx = ctx->f[OSPH_F_VX]; g.vy = ctx->f[OSPH_F_VY];
     g.rho = ctx->f[OSPH_F_RHO]; g.m = ctx->f[OSPH_F_M]; g.h = ctx->f[OSPH_F_H]; g.p = ctx->f[OSPH_F_P];
     g.gp = ctx->d_grid;
@@ -831,7 +857,7 @@ int osph_launch_build(osph_ctx *ctx)
     return 0;
 }
 
-int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt)
+int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt, bool skip_reset)
 {
     CorrectArgs a;
     a.n = (int)ctx->n; a.label = ctx->label;
@@ -844,7 +870,7 @@ int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, 
     a.sc = ctx->d_sc; a.dt = dt; a.damping = damping; a.co = ctx->cfg.co;
     a.use_dev_dt = use_dev_dt ? 1 : 0; a.integ_xsph = ctx->cfg.integrator_xsph; a.strict = ctx->cfg.strict;
     a.c_uniform = ctx->c_uniform ? 1 : 0;
-    k_reset_dt_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK();
+    if (!skip_reset) { k_reset_dt_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
     int grid = div_up(ctx->n, 256);
     if (!correct) k_correct<OSPH_INTEGRATOR_PEC, false><<<grid, 256, 0, ctx->stream>>>(a);
     else if (ctx->cfg.integrator == OSPH_INTEGRATOR_PEC) k_correct<OSPH_INTEGRATOR_PEC, true><<<grid, 256, 0, ctx->stream>>>(a);
@@ -854,10 +880,10 @@ int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, 
     return 0;
 }
 
-int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log)
+int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare)
 {
     k_timestep<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->cfg.cfl_courant, ctx->cfg.cfl_force, fixed_dt,
-                                         log ? ctx->d_dt_log : nullptr, (long long)ctx->dt_log_cap);
+                                         log ? ctx->d_dt_log : nullptr, (long long)ctx->dt_log_cap, reset_prepare ? 1 : 0);
     OSPH_LAUNCH_CHECK();
     return 0;
 }

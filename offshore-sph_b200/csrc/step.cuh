@@ -25,6 +25,8 @@ struct CorrectArgs {
 
 struct GatherArgs {
     int n_owned, n_all;
+    const unsigned int *key;      // sorted keys (cell table is written from them)
+    int2 *cell_range;
     const unsigned int *idx;
     const signed char *label;
     const double *ghost;
@@ -59,11 +61,11 @@ int osph_launch_unpack(osph_ctx *ctx);
 int osph_launch_active_list(osph_ctx *ctx, int n_total, int *d_counters);
 int osph_launch_pack(osph_ctx *ctx);
 int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids);
-int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt);
-int osph_launch_build(osph_ctx *ctx);            // grid params, keys, sort, cell table, (reorder), gather
-int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt);
-int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log);
-int osph_launch_grid_params(osph_ctx *ctx);
+int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
+int osph_launch_build(osph_ctx *ctx, bool reset_dt = false);   // grid params, keys, sort, (reorder), gather + cell table
+int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
+int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare = false);
+int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt = false);
 int osph_launch_ke(osph_ctx *ctx);
 int osph_launch_neighbours(osph_ctx *ctx, int mode, long long *d_counts, const long long *d_offsets, long long *d_out);
 int osph_launch_near_pos(osph_ctx *ctx, double x, double y, double h, long long cap, long long *d_idx, double *d_r,
