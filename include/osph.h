@@ -241,6 +241,29 @@ int osph_download_owned(osph_ctx *ctx, void *pA, int64_t cap_rows, int64_t strid
 int osph_slab_export(osph_ctx *ctx, int32_t *d_ids, int8_t *d_label, int32_t nfields, const int32_t *fields,
                      double *const *d_cols);
 
+/*
+ * The same protocol sequenced inside the library with direct NCCL calls (no interpreter between the collectives).
+ * libnccl.so.2 is resolved at run time: the copy already loaded into the process (torch's) if any, else
+ * `libnccl_path`, else the system one.  Rendezvous stays with the caller: rank 0 obtains a unique id with
+ * osph_nccl_unique_id and distributes the 128 bytes (e.g. torch.distributed.broadcast).
+ */
+typedef struct osph_slab_comm osph_slab_comm;
+int osph_nccl_unique_id(const char *libnccl_path, char out[128]);
+const char *osph_nccl_last_error(void);
+/* Communicator + exchange buffers for a context that already holds this rank's particles (x_lo <= x < x_hi).
+ * hmax: largest smoothing length at start (halo width = 1.1 * pair radius, refreshed from the all-gathered h_max). */
+int osph_slab_comm_create(osph_ctx *ctx, const char *libnccl_path, const char unique_id[128], int rank, int world,
+                          double x_lo, double x_hi, double r0, double hmax, int64_t mig_cap, int64_t halo_cap,
+                          osph_slab_comm **out);
+int osph_slab_comm_destroy(osph_ctx *ctx, osph_slab_comm *comm);
+/* Re-enter slab mode after osph_upload_aos replaced the particle set (host-buffer call pattern). */
+int osph_slab_comm_attach(osph_ctx *ctx, osph_slab_comm *comm);
+/* nsteps slab-decomposed steps: all_reduce(dt) -> predict -> pack -> all_gather(counts, bounds) -> send/recv
+ * (migrants + halos) -> commit -> neighbours + pair kernel + correct. */
+int osph_slab_run(osph_ctx *ctx, osph_slab_comm *comm, int32_t nsteps, double fixed_dt, double damping);
+/* {mig_out l,r, halo_out l,r, mig_in l,r, halo_in l,r} of the last step */
+int osph_slab_last_counts(const osph_slab_comm *comm, int64_t out[8]);
+
 /* ---- stand-alone leaf functions on host arrays (context-free; `device` is a CUDA ordinal) ---------- */
 
 /* what == 0: kernel.evaluate(r, h); what == 1: kernel.gradient(x, r, h).

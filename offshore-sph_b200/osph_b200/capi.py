@@ -113,6 +113,14 @@ def lib():
         'osph_slab_step_end': (C.c_int, [ctx, dbl]),
         'osph_download_owned': (C.c_int, [ctx, C.c_void_p, i64, i64, C.POINTER(i32), ip]),
         'osph_slab_export': (C.c_int, [ctx, C.c_void_p, C.c_void_p, i32, C.POINTER(i32), C.POINTER(C.c_void_p)]),
+        'osph_nccl_unique_id': (C.c_int, [C.c_char_p, C.c_char_p]),
+        'osph_nccl_last_error': (C.c_char_p, []),
+        'osph_slab_comm_create': (C.c_int, [ctx, C.c_char_p, C.c_char_p, C.c_int, C.c_int, dbl, dbl, dbl, dbl, i64, i64,
+                                            C.POINTER(C.c_void_p)]),
+        'osph_slab_comm_destroy': (C.c_int, [ctx, C.c_void_p]),
+        'osph_slab_comm_attach': (C.c_int, [ctx, C.c_void_p]),
+        'osph_slab_run': (C.c_int, [ctx, C.c_void_p, i32, dbl, dbl]),
+        'osph_slab_last_counts': (C.c_int, [C.c_void_p, ip]),
         'osph_leaf_kernel': (C.c_int, [C.c_int, C.c_int, C.c_int, i64, dp, dp, dp, dp]),
         'osph_leaf_tait_pressure': (C.c_int, [C.c_int, i64, dp, C.POINTER(C.c_int8), dbl, dbl, dbl, dbl, dp]),
         'osph_leaf_tait_height': (C.c_int, [C.c_int, i64, dp, dbl, dbl, dbl, dbl, dp]),
@@ -344,6 +352,27 @@ class Context:
         self._ck(self._L.osph_slab_export(self._h, C.c_void_p(ids_ptr), C.c_void_p(label_ptr) if label_ptr else None,
                                           len(fields), ids, ptrs))
 
+    # ---- slab decomposition sequenced in the library (direct NCCL) ----
+    def slab_comm_create(self, unique_id, rank, world, x_lo, x_hi, r0, hmax, mig_cap, halo_cap):
+        comm = C.c_void_p()
+        self._ck(self._L.osph_slab_comm_create(self._h, nccl_library_path().encode(), bytes(unique_id), rank, world,
+                                               x_lo, x_hi, r0, hmax, mig_cap, halo_cap, C.byref(comm)))
+        return comm
+
+    def slab_comm_destroy(self, comm):
+        self._L.osph_slab_comm_destroy(self._h, comm)
+
+    def slab_comm_attach(self, comm):
+        self._ck(self._L.osph_slab_comm_attach(self._h, comm))
+
+    def slab_run(self, comm, nsteps, fixed_dt=None, damping=0.0):
+        self._ck(self._L.osph_slab_run(self._h, comm, nsteps, -1.0 if fixed_dt is None else fixed_dt, damping))
+
+    def slab_last_counts(self, comm):
+        out = (C.c_int64 * 8)()
+        self._L.osph_slab_last_counts(comm, out)
+        return list(out)
+
     def timers(self):
         out = (C.c_double * 6)()
         self._ck(self._L.osph_get_timers(self._h, out))
@@ -377,6 +406,24 @@ def _f64(a):
 
 def _ptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def nccl_library_path():
+    """Fallback path of libnccl.so.2 (the copy bundled with torch); the library prefers one already loaded."""
+    try:
+        import nvidia.nccl
+        p = os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so.2")
+        return p if os.path.exists(p) else ""
+    except Exception:
+        return ""
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = lib().osph_nccl_unique_id(nccl_library_path().encode(), buf)
+    if rc != 0:
+        raise OsphError(rc, lib().osph_nccl_last_error().decode())
+    return buf.raw
 
 
 def default_device():

@@ -167,6 +167,59 @@ class SlabRun:
         return ids[:n].cpu().numpy(), lab[:n].cpu().numpy(), {f: c[:n].cpu().numpy() for f, c in zip(fields, cols)}
 
 
+class NcclSlabRun:
+    """Same protocol as SlabRun, sequenced inside libosph_b200 with direct NCCL calls (osph_slab_run).
+    torch.distributed only distributes the 128-byte NCCL unique id."""
+
+    def __init__(self, ctx, cuts, local_pA, local_ids, kernel, r0, hmax, device, group=None,
+                 mig_frac=0.02, ghost_frac=0.25, min_cap=4096):
+        from osph_b200 import capi
+        self.ctx, self.kernel, self.r0 = ctx, kernel, r0
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.x_lo, self.x_hi = cuts[self.rank], cuts[self.rank + 1]
+        self.device = device
+        n = len(local_pA)
+        self.mig_cap = max(min_cap, int(n * mig_frac))
+        self.halo_cap = max(min_cap, int(n * ghost_frac))
+        self.ghost_cap = 2 * self.halo_cap + 2 * self.mig_cap
+        uid = torch.zeros(128, dtype=torch.uint8, device=device)
+        if self.rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0, group=group)
+        ctx.reserve(int(n * 1.3) + self.ghost_cap + 2 * self.mig_cap)
+        ctx.upload(local_pA)
+        ctx.set_row_ids(local_ids)
+        self.comm = ctx.slab_comm_create(bytes(uid.cpu().numpy().tobytes()), self.rank, self.world, self.x_lo, self.x_hi,
+                                         r0, float(hmax), self.mig_cap, self.halo_cap)
+        self.steps = 0
+
+    def step(self, nsteps=1, fixed_dt=None, damping=0.0):
+        self.ctx.slab_run(self.comm, nsteps, fixed_dt, damping)
+        self.steps += nsteps
+
+    @property
+    def last_counts(self):
+        c = self.ctx.slab_last_counts(self.comm)
+        return dict(mig_out=(c[0], c[1]), halo_out=(c[2], c[3]), mig_in=(c[4], c[5]), halo_in=(c[6], c[7]),
+                    ghosts=c[0] + c[1] + c[6] + c[7], owned=self.ctx.num_active)
+
+    def reattach(self):
+        self.ctx.slab_comm_attach(self.comm)
+
+    def export(self, fields):
+        n = self.ctx.num_active
+        ids = torch.zeros(max(n, 1), dtype=torch.int32, device=self.device)
+        lab = torch.zeros(max(n, 1), dtype=torch.int8, device=self.device)
+        cols = [torch.zeros(max(n, 1), dtype=torch.float64, device=self.device) for _ in fields]
+        self.ctx.slab_export(ids.data_ptr(), lab.data_ptr(), fields, [c.data_ptr() for c in cols])
+        return ids[:n].cpu().numpy(), lab[:n].cpu().numpy(), {f: c[:n].cpu().numpy() for f, c in zip(fields, cols)}
+
+    def close(self):
+        if self.comm is not None:
+            self.ctx.slab_comm_destroy(self.comm)
+            self.comm = None
+
+
 def partition(pA, world, rank):
     """Slab cuts from the fluid quantiles and this rank's rows of the global array."""
     act = ~pA['deleted']
@@ -213,8 +266,10 @@ def bench_multi_gpu(args, rank, world, local):
     ctx = capi.Context(cfg)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     torch.cuda.set_stream(stream)
-    comm = TorchComm()
-    run = SlabRun(ctx, comm, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+    if args.sequencer == 'python':
+        run = SlabRun(ctx, TorchComm(), cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+    else:
+        run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
 
     run.step(args.warmup, None, B.DAMPING)
     ctx.sync(); ctx.pair_kernel_time()
@@ -251,7 +306,10 @@ def bench_multi_gpu(args, rank, world, local):
     def e2e_step(n_rows):
         ctx.upload(host[:n_rows])
         ctx.set_row_ids(hids[:n_rows])
-        ctx.slab_configure(run.x_lo, run.x_hi, run.ghost.data_ptr(), run.ghost_cap)
+        if args.sequencer == 'python':
+            ctx.slab_configure(run.x_lo, run.x_hi, run.ghost.data_ptr(), run.ghost_cap)
+        else:
+            run.reattach()
         run.step(1, None, B.DAMPING)
         return ctx.download_owned(host, hids)
 
@@ -284,7 +342,8 @@ def bench_multi_gpu(args, rank, world, local):
                        "particles": n_total, "particles_per_gpu": [int(v) for v in per[:, 0]],
                        "ghosts_per_gpu": [int(v) for v in per[:, 1]], "damping": B.DAMPING, "dt": "dynamic",
                        "l2": "per-GPU working set exceeds the 126 MB L2",
-                       "parallelism": "1-D slabs along x, %d ranks, NCCL halo + migration, fluid-quantile cuts" % world},
+                       "parallelism": "1-D slabs along x, %d ranks, NCCL halo + migration (%s sequencer), fluid-quantile cuts"
+                                      % (world, args.sequencer)},
             "clocks": clk, "gpu_launches": int(per[:, 2].sum()),
             "e2e": {"value": n_total * e2e_steps / float(t_e2e.item()), "unit": B.UNIT,
                     "h2d_bytes_per_step": int(mv.item()), "d2h_bytes_per_step": int(mv.item()), "steps": e2e_steps,
@@ -300,5 +359,7 @@ def bench_multi_gpu(args, rank, world, local):
     dist.barrier()
     torch.cuda.synchronize()
     torch.cuda.set_stream(torch.cuda.default_stream())       # never leave torch on a stream about to be destroyed
+    if hasattr(run, 'close'):
+        run.close()
     ctx.close()
     dist.destroy_process_group()

@@ -33,7 +33,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok = True
-    for kernel, prec, tol in (('wendland', capi.FP64, 1e-11), ('cubic', capi.FP64, 1e-11), ('gaussian', capi.FP32, 2e-3)):
+    for kernel, prec, tol, seq in (('wendland', capi.FP64, 1e-11, 'nccl'), ('wendland', capi.FP64, 1e-11, 'python'),
+                                   ('cubic', capi.FP64, 1e-11, 'nccl'), ('gaussian', capi.FP32, 2e-3, 'nccl')):
         case = W.dam_break_case(a.side, seed=11)
         # give the fluid a push towards +x so particles cross the slab faces during the run
         f = case['pA']['label'] == 0
@@ -48,8 +49,11 @@ def main():
         ctx = capi.Context(cfg)
         torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.stream, device=local))
         cuts, local_pA, ids = slabs.partition(pA, world, rank)
-        run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'],
-                            torch.device('cuda', local))
+        if seq == 'python':
+            run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'],
+                                torch.device('cuda', local))
+        else:
+            run = slabs.NcclSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cuda', local))
         moved = 0
         for _ in range(a.steps):
             run.step(1, FIXED_DT, 0.05)
@@ -63,12 +67,14 @@ def main():
         good = bool(np.all(seen == 1)) and worst <= tol and status == 0 and \
             np.allclose(dts, ref_dt, rtol=1e-12 if prec == capi.FP64 else 1e-4, atol=0)
         if rank == 0:
-            print("%-9s %s ranks=%d n=%d steps=%d migrants=%d worst_err=%.2e (%s) dt_equal=%s -> %s" % (
-                kernel, 'fp64' if prec == capi.FP64 else 'fp32', world, len(pA), a.steps, int(tot_moved.item()), worst,
+            print("%-9s %s %-6s ranks=%d n=%d steps=%d migrants=%d worst_err=%.2e (%s) dt_equal=%s -> %s" % (
+                kernel, 'fp64' if prec == capi.FP64 else 'fp32', seq, world, len(pA), a.steps, int(tot_moved.item()), worst,
                 max(errs, key=errs.get), np.allclose(dts, ref_dt, rtol=1e-12, atol=0), 'OK' if good else 'FAIL'), flush=True)
         ok = ok and good and (a.steps < 10 or int(tot_moved.item()) > 0)
         torch.cuda.synchronize()
         torch.cuda.set_stream(torch.cuda.default_stream())      # never leave torch on a stream about to be destroyed
+        if hasattr(run, 'close'):
+            run.close()
         ctx.close()
     flag = torch.tensor([0 if ok else 1], device='cuda'); dist.all_reduce(flag)
     dist.barrier()
