@@ -191,6 +191,14 @@ int osph_get_neighbours_csr(osph_ctx *ctx, int64_t *offsets, int64_t *idx, int64
  */
 int osph_near_pos(osph_ctx *ctx, double x, double y, double h, int64_t cap,
                   int64_t *idx, double *r, double *q, double *hij, int64_t *count);
+/*
+ * SPH-interpolated density and Tait pressure at n arbitrary points (host arrays), all points in one launch:
+ * neighbours by the reference predicate with query smoothing length h, W(r, h), Shepard normalisation, summation
+ * density over the fluid neighbours.  replaces: pressure_SPH, examples/IceBreak.py:252-285 (nn.nearPos +
+ * kernel.evaluate + Shepard + SummationDensity + Tait, once per ice node per step on the host).
+ */
+int osph_probe_pressure(osph_ctx *ctx, int64_t n, const double *x, const double *y, double h, double *rho_out,
+                        double *p_out);
 /* Device time of each phase since creation, ms: {timestep, predict, neighbours, compute, correct, transfer}. */
 int osph_get_timers(osph_ctx *ctx, double out_ms[6]);
 /* Kernel launches issued by this context since creation (bench.py reports them as gpu_launches). */

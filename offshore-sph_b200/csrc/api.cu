@@ -562,6 +562,29 @@ extern "C" int osph_near_pos(osph_ctx *ctx, double x, double y, double h, int64_
     return rc;
 }
 
+extern "C" int osph_probe_pressure(osph_ctx *ctx, int64_t n, const double *x, const double *y, double h, double *rho_out,
+                                   double *p_out)
+{
+    CHECK_CTX(); NEED_PARTICLES();
+    if (n <= 0) return 0;
+    if (!x || !y || !rho_out || !p_out || !(h > 0) || ctx->n_ghost > 0) { ctx->err = "osph_probe_pressure: bad arguments"; return OSPH_E_INVALID; }
+    int rc;
+    if (!ctx->neighbours_valid && (rc = build_neighbours(ctx))) return rc;
+    double *d = nullptr;
+    OSPH_CUDA(cudaMalloc(&d, sizeof(double) * 4 * n));
+    cudaError_t e = cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    rc = e == cudaSuccess ? osph_launch_probe(ctx, (int)n, d, d + n, h, d + 2 * n, d + 3 * n) : OSPH_E_CUDA;
+    if (!rc) {
+        e = cudaMemcpyAsync(rho_out, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p_out, d + 3 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = OSPH_E_CUDA; }
+    cudaFree(d);
+    return rc;
+}
+
 extern "C" int osph_get_timers(osph_ctx *ctx, double out_ms[6])
 {
     CHECK_CTX();

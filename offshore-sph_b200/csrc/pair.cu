@@ -296,6 +296,72 @@ k_pair(PairArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Optional summation-density pass (reference src/Tools/SolverTools.py:129-140, SummationDensity.py:6-13):
+//   rho_i = sum over FLUID neighbours j of m_j W(r_ij, h_ij),  neighbours = the reference set (q <= 3).
+// The sum uses only m, W and h of the neighbours -- not their density -- so the reference's in-place, index-ordered
+// loop is order-independent and this parallel pass reproduces it exactly.  p keeps the value formed from the old
+// density (the reference evaluates the EOS before this pass); p / rho^2 is refreshed with the new density.
+// Off in every shipped example: a plain one-thread-per-particle walk, always in double.
+// ---------------------------------------------------------------------------------------------------------
+template <int KID, typename Real2>
+__global__ void __launch_bounds__(128)
+k_summation_density(PairArgs a, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_hp, const double *__restrict__ h64,
+                    const double *__restrict__ m64, double *__restrict__ rho_state, const double *__restrict__ p_state)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n || (a.s_info[s] & 3) != 3) return;
+    const GridParams g = *a.gp;
+    const int slot = (int)a.idx[s];
+    const double2 pi = a.s_pos[s];
+    const double hi = h64[slot];
+    const int4 ci = a.s_coarse[s];
+    const int2 gc = a.s_gcell[s];
+    double rho = 0.0;
+    const int reach = g.reach_set;
+    for (int dy = -reach; dy <= reach; dy++) {
+        int cy = gc.y + dy;
+        if (cy < 0 || cy >= g.gny) continue;
+        int x0 = max(gc.x - reach, 0), x1 = min(gc.x + reach, g.gnx - 1);
+        for (int cx = x0; cx <= x1; cx++) {
+            int2 r = a.cell_range[(long long)cy * g.gnx + cx];
+            for (int t = r.x; t < r.y; t++) {
+                if (!(a.s_info[t] & 1)) continue;
+                const int4 cj = a.s_coarse[t];
+                if (abs(cj.x - ci.z) > 1 || abs(cj.y - ci.w) > 1) continue;
+                const int tj = (int)a.idx[t];
+                const double2 pj = a.s_pos[t];
+                const double dx = __dadd_rn(pi.x, -pj.x), dyy = __dadd_rn(pi.y, -pj.y);
+                const double rr = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dyy, dyy)));
+                const double hij = __dmul_rn(0.5, __dadd_rn(hi, h64[tj]));
+                if (!(__ddiv_rn(rr, hij) <= 3.0)) continue;
+                const double inv_h = 1.0 / hij;
+                double w, gg;
+                sph_kernel<double, KID>(rr * inv_h, inv_h, 0.0, w, gg);
+                rho += m64[tj] * w;
+            }
+        }
+    }
+    rho_state[slot] = rho;
+    typedef decltype(Real2().x) Real;
+    Real2 rm = s_rm[s]; rm.x = (Real)rho; s_rm[s] = rm;
+    Real2 hp = s_hp[s]; hp.y = (Real)(p_state[slot] / (rho * rho)); s_hp[s] = hp;
+}
+
+template <typename Real2>
+static void launch_summation(osph_ctx *ctx, const PairArgs &a)
+{
+    int grid = div_up(a.n, 128);
+    Real2 *rm = (Real2 *)ctx->s_rm, *hp = (Real2 *)ctx->s_hp;
+    const double *h = ctx->f[OSPH_F_H], *m = ctx->f[OSPH_F_M], *p = ctx->f[OSPH_F_P];
+    double *rho = ctx->f[OSPH_F_RHO];
+    switch (ctx->cfg.kernel) {
+    case OSPH_KERNEL_CUBIC: k_summation_density<OSPH_KERNEL_CUBIC, Real2><<<grid, 128, 0, ctx->stream>>>(a, rm, hp, h, m, rho, p); break;
+    case OSPH_KERNEL_WENDLAND: k_summation_density<OSPH_KERNEL_WENDLAND, Real2><<<grid, 128, 0, ctx->stream>>>(a, rm, hp, h, m, rho, p); break;
+    default: k_summation_density<OSPH_KERNEL_GAUSSIAN, Real2><<<grid, 128, 0, ctx->stream>>>(a, rm, hp, h, m, rho, p); break;
+    }
+}
+
 template <typename Real, int KID, bool EXACT>
 static cudaError_t launch_one(const PairArgs &a, int grid, cudaStream_t stream)
 {
@@ -340,6 +406,11 @@ int osph_launch_pair(osph_ctx *ctx)
     a.lj_42 = (c.p1 == 4.0 && c.p2 == 2.0) ? 1 : 0;
     a.method_xsph = c.method_xsph; a.summation_density = c.summation_density;
     int grid = div_up(ctx->n + ctx->n_ghost, OSPH_PAIR_THREADS);
+    if (c.summation_density) {
+        if (ctx->n_ghost > 0) { ctx->err = "useSummationDensity is not supported in slab mode"; return OSPH_E_INVALID; }
+        if (c.precision == OSPH_FP64) launch_summation<double2>(ctx, a); else launch_summation<float2>(ctx, a);
+        OSPH_LAUNCH_CHECK();
+    }
     const bool timed = ctx->time_pair && ctx->pair_ev_used < OSPH_PAIR_EVENTS;
     if (timed) cudaEventRecord(ctx->pair_ev[2 * ctx->pair_ev_used], ctx->stream);
     int rc = c.precision == OSPH_FP64 ? launch_kid<double, true>(ctx, a, grid) : launch_kid<float, false>(ctx, a, grid);

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "step.cuh"
 #include "sort.cuh"
+#include "sph_math.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // K10: packed 154-byte records <-> SoA columns.  Doubles sit at byte offset 2 + 8k (2-byte aligned
@@ -654,6 +655,46 @@ __global__ void k_near_pos(NeighbourArgs a, double px, double py, double ph, lon
     *out_count = cnt;
 }
 
+// Batched SPH pressure probe (reference examples/IceBreak.py:252-285, called there once per ice node and step):
+// neighbours of the point by the reference predicate, W(r, h) with the PROBE's h, Shepard-normalised summation
+// density over the fluid neighbours (src/Equations/Shepard.py:5-12, SummationDensity.py:6-13), Tait EOS.
+template <int KID>
+__global__ void __launch_bounds__(64)
+k_probe_pressure(NeighbourArgs a, const double *__restrict__ m, const double *__restrict__ rho,
+                 const signed char *__restrict__ label, int npts, const double *__restrict__ px,
+                 const double *__restrict__ py, double ph, double rho0, double gamma, double B,
+                 double *__restrict__ out_rho, double *__restrict__ out_p)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npts) return;
+    const GridParams g = *a.gp;
+    const double x = px[k], y = py[k];
+    double rx = __dadd_rn(x, -g.xmin), ry = __dadd_rn(y, -g.ymin);
+    int qcx = (int)floor(__ddiv_rn(rx, g.cell_size)), qcy = (int)floor(__ddiv_rn(ry, g.cell_size));
+    int gx, gy, reach;
+    if (g.regime_a) { gx = qcx; gy = qcy; reach = 1; }
+    else {
+        gx = (int)floor(rx * g.ginv); gy = (int)floor(ry * g.ginv);
+        reach = (int)ceil(1.5 * (ph + g.hmax) * (1.0 + 1e-6) / g.gsize); if (reach < 1) reach = 1;
+    }
+    const double inv_h = 1.0 / ph;
+    double norm = 0.0, sum = 0.0;
+    walk_cells(g, a.cell_range, gx, gy, reach, [&](int t) {
+        int j = (int)a.idx[t];
+        double r, q, hij;
+        if (!ref_accept(x, y, ph, qcx, qcy, a.s_pos[t], a.h[j], a.s_coarse[t], &r, &q, &hij)) return;
+        if (label[j] != OSPH_FLUID) return;
+        double w, gg, qq = r * inv_h;
+        sph_kernel<double, KID>(qq, inv_h, 0.0, w, gg);
+        if (KID == OSPH_KERNEL_GAUSSIAN && !(qq <= 3.0)) w = 0.0;
+        if (rho[j] >= 1e-3) norm += w * m[j] / rho[j];
+        sum += m[j] * w;
+    });
+    double r_ = sum / norm;                 // sum_j m_j (w_j / w_tilde)
+    out_rho[k] = r_;
+    out_p[k] = (pow(r_ / rho0, gamma) - 1.0) * B;
+}
+
 __global__ void k_cells_to_active(const int4 *__restrict__ s_coarse, const unsigned int *__restrict__ idx,
                                   const int *__restrict__ act, int n, const GridParams *__restrict__ gp,
                                   long long *__restrict__ out)
@@ -922,6 +963,22 @@ int osph_launch_near_pos(osph_ctx *ctx, double x, double y, double h, long long 
 {
     NeighbourArgs a = neighbour_args(ctx);
     k_near_pos<<<1, 1, 0, ctx->stream>>>(a, x, y, h, cap, d_idx, d_r, d_q, d_h, d_count);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_launch_probe(osph_ctx *ctx, int npts, const double *d_x, const double *d_y, double h, double *d_rho, double *d_p)
+{
+    NeighbourArgs a = neighbour_args(ctx);
+    const osph_config &c = ctx->cfg;
+    const double *m = ctx->f[OSPH_F_M], *rho = ctx->f[OSPH_F_RHO];
+    int grid = div_up(npts, 64);
+    if (c.kernel == OSPH_KERNEL_CUBIC)
+        k_probe_pressure<OSPH_KERNEL_CUBIC><<<grid, 64, 0, ctx->stream>>>(a, m, rho, ctx->label, npts, d_x, d_y, h, c.rho0, c.gamma, c.B, d_rho, d_p);
+    else if (c.kernel == OSPH_KERNEL_WENDLAND)
+        k_probe_pressure<OSPH_KERNEL_WENDLAND><<<grid, 64, 0, ctx->stream>>>(a, m, rho, ctx->label, npts, d_x, d_y, h, c.rho0, c.gamma, c.B, d_rho, d_p);
+    else
+        k_probe_pressure<OSPH_KERNEL_GAUSSIAN><<<grid, 64, 0, ctx->stream>>>(a, m, rho, ctx->label, npts, d_x, d_y, h, c.rho0, c.gamma, c.B, d_rho, d_p);
     OSPH_LAUNCH_CHECK();
     return 0;
 }

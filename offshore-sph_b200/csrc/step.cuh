@@ -71,6 +71,7 @@ int osph_launch_neighbours(osph_ctx *ctx, int mode, long long *d_counts, const l
 int osph_launch_near_pos(osph_ctx *ctx, double x, double y, double h, long long cap, long long *d_idx, double *d_r,
                          double *d_q, double *d_h, long long *d_count);
 int osph_launch_cells(osph_ctx *ctx, long long *d_out);
+int osph_launch_probe(osph_ctx *ctx, int npts, const double *d_x, const double *d_y, double h, double *d_rho, double *d_p);
 int osph_launch_col_to_active(osph_ctx *ctx, int field, double *d_out);
 int osph_launch_col_from_active(osph_ctx *ctx, int field, const double *d_in);
 int osph_init_scalars(osph_ctx *ctx);

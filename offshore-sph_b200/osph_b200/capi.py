@@ -99,6 +99,7 @@ def lib():
         'osph_get_cells': (C.c_int, [ctx, dp, ip]),
         'osph_get_neighbours_csr': (C.c_int, [ctx, ip, ip, i64, ip]),
         'osph_near_pos': (C.c_int, [ctx, dbl, dbl, dbl, i64, ip, dp, dp, dp, ip]),
+        'osph_probe_pressure': (C.c_int, [ctx, i64, dp, dp, dbl, dp, dp]),
         'osph_get_timers': (C.c_int, [ctx, dp]),
         'osph_launch_count': (i64, [ctx]),
         'osph_stream': (C.c_uint64, [ctx]),
@@ -372,6 +373,14 @@ class Context:
         out = (C.c_int64 * 8)()
         self._L.osph_slab_last_counts(comm, out)
         return list(out)
+
+    def probe_pressure(self, x, y, h):
+        x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+        rho = np.empty_like(x); p = np.empty_like(x)
+        dp = C.POINTER(C.c_double)
+        self._ck(self._L.osph_probe_pressure(self._h, x.size, x.ctypes.data_as(dp), y.ctypes.data_as(dp), float(h),
+                                             rho.ctypes.data_as(dp), p.ctypes.data_as(dp)))
+        return rho, p
 
     def timers(self):
         out = (C.c_double * 6)()

@@ -295,6 +295,11 @@ class Solver:
         println('Solved {0} particles for {1:f} [s].'.format(self.num_particles, self.duration))
         println('Completed solve in {0:f} [s] and {1} steps'.format(self.timing_data['total'], t_step))
 
+    def probe_pressure(self, x, y, h):
+        """SPH-interpolated (rho, p) at the points (x[k], y[k]) in ONE device launch: the batched form of the
+        per-node `pressure_SPH` helper of examples/IceBreak.py:252-285 for coupling callbacks."""
+        return self._ctx.probe_pressure(x, y, h)
+
     def _store(self, t_step: int):
         if self._store_full:
             self._pull()

@@ -13,7 +13,7 @@ for p in (ROOT, PKG):
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 STEP_CASES = ['dambreak20_wendland', 'dambreak20_cubic', 'tank30_cubic_dynh',
-              'tank24_wendland_coupled', 'tank16_gaussian', 'block20_cubic_nobnd']
+              'tank24_wendland_coupled', 'tank16_gaussian', 'block20_cubic_nobnd', 'tank16_cubic_sumdens']
 
 
 def pytest_configure(config):

@@ -96,12 +96,12 @@ def run_loop(pA, kernel, method, nn):
     return ref._loop(pA, k.evaluate, k.gradient, method, nn)
 
 
-def make_case(name, case, kernel, useXSPH, damping, nsteps, strict=False, scale=2.0):
+def make_case(name, case, kernel, useXSPH, damping, nsteps, strict=False, scale=2.0, summation=False):
     pA0 = case['pA'].copy()
     c = case['consts']
     n = len(pA0)
     fixed_h = case['h']
-    method = ref.WCSPH(c['height'], c['r0'], c['rho0'], useXSPH, c['Pb'], False)
+    method = ref.WCSPH(c['height'], c['r0'], c['rho0'], useXSPH, c['Pb'], summation)
     assert method.co == c['co'] and method.B == c['B'] and method.D == c['D']
     integ = ref.PEC(useXSPH, strict)
     out = dict(aos=np.frombuffer(pA0.tobytes(), dtype=np.uint8).reshape(n, 154).copy())
@@ -144,7 +144,7 @@ def make_case(name, case, kernel, useXSPH, damping, nsteps, strict=False, scale=
     import numba
     out['meta'] = np.frombuffer(json.dumps(dict(
         name=name, kernel=kernel, useXSPH=bool(useXSPH), strict=bool(strict), damping=damping,
-        nsteps=nsteps, fixed_h=fixed_h, scale=scale, consts=c, n=n, n_fluid=nf,
+        nsteps=nsteps, fixed_h=fixed_h, scale=scale, consts=c, n=n, n_fluid=nf, summation=bool(summation),
         numba=numba.__version__, numpy=np.__version__)).encode(), dtype=np.uint8)
     path = os.path.join(HERE, name + '.npz')
     np.savez_compressed(path, **out)
@@ -195,9 +195,16 @@ def main():
     keep = blk['pA']['label'] == FLUID
     blk['pA'] = blk['pA'][keep]
     make_case('block20_cubic_nobnd', blk, 'cubic', True, 0.0, 2)
+    # optional summation-density branch of _loop (off in every shipped example)
+    make_case('tank16_cubic_sumdens', W.tank_case(16, h=1.3 / 16, useXSPH=True, seed=5), 'cubic', True, 0.0, 2,
+              summation=True)
     # the reference Solver end to end (settle -> gate removal -> time stepping)
     solver_run_case('solver_dambreak12_wendland', 12, 'wendland', 0.03, 6)
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'sumdens':      # regenerate only the newest case
+        make_case('tank16_cubic_sumdens', W.tank_case(16, h=1.3 / 16, useXSPH=True, seed=5), 'cubic', True, 0.0, 2,
+                  summation=True)
+    else:
+        main()

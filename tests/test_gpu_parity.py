@@ -19,7 +19,8 @@ STATE_FIELDS = ('x', 'y', 'vx', 'vy', 'rho', 'drho', 'ax', 'ay', 'xsphx', 'xsphy
 
 
 def _ctx(meta, precision=capi.FP64, keep_h=False, integrator='pec', kernel=None, reorder_every=0):
-    cfg = capi.make_config(meta['consts'] | {'useXSPH': meta['useXSPH']}, kernel or meta['kernel'], integrator,
+    cfg = capi.make_config(meta['consts'] | {'useXSPH': meta['useXSPH'], 'useSummationDensity': meta.get('summation', False)},
+                           kernel or meta['kernel'], integrator,
                            precision, meta['fixed_h'], strict=meta['strict'], keep_h=keep_h,
                            reorder_every=reorder_every)
     return capi.Context(cfg)
@@ -57,8 +58,14 @@ def test_loop_fields_vs_golden(name):
         for f in LOOP_FIELDS:
             assert field_err(out[f], g['loop_' + f]) <= TOL, f
         # columns the loop does not write come back bit-identical
-        for f in ('x', 'y', 'vx', 'vy', 'rho', 'm', 'h', 'x0', 'rho0'):
+        for f in ('x', 'y', 'vx', 'vy', 'm', 'h', 'x0', 'rho0') + (() if meta.get('summation') else ('rho',)):
             assert np.array_equal(out[f], pA[f]), f
+        if meta.get('summation'):        # the density written by the summation pass: against the oracle's _loop
+            P = O.Particles.from_aos(pA)
+            c = meta['consts']
+            O.loop(P, O.wcsph(c['height'], c['r0'], c['rho0'], meta['useXSPH'], c['Pb'], True), O.Grid(P, meta['scale']),
+                   meta['kernel'])
+            assert field_err(out['rho'], P.rho) <= TOL
         assert np.array_equal(out['label'], pA['label']) and np.array_equal(out['deleted'], pA['deleted'])
 
 

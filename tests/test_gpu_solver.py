@@ -134,3 +134,27 @@ def test_integrator_objects_standalone():
     pe = Euler().correct(dt, Euler().predict(dt, pe, 0), 0)
     for f in ('x', 'y', 'vx', 'vy', 'rho'):
         assert p3[f][0] == pytest.approx(pe[f][0])
+
+
+def test_batched_pressure_probe_matches_reference_recipe():
+    """osph_probe_pressure vs the IceBreak recipe evaluated with the oracle's nearPos and the leaf helpers."""
+    from osph_b200 import capi
+    from src.Equations.Shepard import Shepard
+    from src.Equations.SummationDensity import SummationDensity
+    g, meta, pA = load_golden('tank24_wendland_coupled')
+    c = meta['consts']
+    P = O.Particles.from_aos(pA)
+    og = O.Grid(P)
+    cfg = capi.make_config(c | {'useXSPH': True}, 'wendland', 'pec', capi.FP64, meta['fixed_h'], keep_h=True)
+    rng = np.random.default_rng(5)
+    xs = rng.uniform(0.05, 0.95, 40); ys = rng.uniform(0.05, 0.9, 40); h = 1.3 * c['r0']
+    with capi.Context(cfg) as ctx:
+        ctx.upload(pA); ctx.build_neighbours()
+        rho, p = ctx.probe_pressure(xs, ys, h)
+    for k in range(len(xs)):
+        hh, q, r, idx = og.near_pos(float(xs[k]), float(ys[k]), h)
+        w = O.kernel_evaluate('wendland', r, np.full_like(r, h))
+        wt = Shepard(w, pA['label'][idx], pA['m'][idx], pA['rho'][idx])
+        want = SummationDensity(pA['label'][idx], pA['m'][idx], wt)
+        assert rho[k] == pytest.approx(want, rel=1e-12)
+        assert p[k] == pytest.approx(((want / c['rho0']) ** 7 - 1) * c['B'], rel=1e-9, abs=1e-6)

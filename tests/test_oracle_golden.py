@@ -14,7 +14,7 @@ TOL = 1e-12
 
 def _wcsph(meta):
     c = meta['consts']
-    w = O.wcsph(c['height'], c['r0'], c['rho0'], meta['useXSPH'], c['Pb'], False)
+    w = O.wcsph(c['height'], c['r0'], c['rho0'], meta['useXSPH'], c['Pb'], meta.get('summation', False))
     assert w.co == c['co'] and w.B == c['B'] and w.D == c['D']
     return w
 
