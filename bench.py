@@ -247,7 +247,22 @@ def run_gpu(args):
                 "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "avg_launch_us": pair_us, "launches_timed": pair_n, "share_of_step": pair_us * 1e-6 * args.steps / t_dev,
                 "algorithmic_bytes_per_particle": 13 * F + 1,
-                "note": "pair kernel is FP-pipe bound (SURVEY 8d): ~70 flop/pair; see fp_pipe"}
+                "note": "k_pair is FP-pipe / latency bound, not HBM bound (DESIGN.md section 4); see fp_pipe"}
+    # FP-pipe view of the same kernel: SURVEY 8(d) flop model (70 flop per contributing pair, 10 per rejected
+    # candidate) against the FMA peak measured with tools/fp64_pipe.cu on this pool
+    try:
+        fp = json.load(open(os.path.join(ROOT, "profiles", "measured_fp_peaks.json")))
+        q = 3.0 if args.kernel == "gaussian" else 2.0
+        pairs = np.pi * (q * 1.6) ** 2                       # contributing neighbours per fluid particle at h = 1.6 r0
+        cand = 9.0 * (q * 1.6) ** 2                          # 3x3 cells of the pair radius
+        flops = (70.0 * pairs + 10.0 * (cand - pairs)) * int((pA['label'] == 0).sum())
+        peak = fp["fp64_tflops"] if prec == capi.FP64 else fp["fp32_tflops"]
+        ach = flops / (pair_us * 1e-6) / 1e12 if pair_us > 0 else 0.0
+        roofline["fp_pipe"] = {"achieved_tflops_model": ach, "peak_tflops_measured": peak, "frac": ach / peak,
+                               "pair_interactions_per_s": pairs * int((pA['label'] == 0).sum()) / (pair_us * 1e-6) if pair_us > 0 else 0.0,
+                               "model": "70 flop x %.1f contributing pairs + 10 flop x %.1f rejected candidates per fluid particle" % (pairs, cand - pairs)}
+    except Exception:
+        pass
     # ---- CPU baseline: oracle port on a bounded sample ----------------------------------------
     cpu = None
     if not args.no_cpu_baseline:

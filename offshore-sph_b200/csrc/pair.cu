@@ -363,14 +363,14 @@ static void launch_summation(osph_ctx *ctx, const PairArgs &a)
 }
 
 template <typename Real, int KID, bool EXACT>
-static cudaError_t launch_one(const PairArgs &a, int grid, cudaStream_t stream)
+static cudaError_t launch_one(const PairArgs &a, int grid, cudaStream_t stream, int device)
 {
-    static bool configured = false;
+    static unsigned long long configured = 0;           // one bit per device ordinal (the attribute is per device)
     constexpr size_t smem = pair_smem_bytes<Real, EXACT>();
-    if (!configured) {
+    if (!(configured >> (device & 63) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(k_pair<Real, KID, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured |= 1ull << (device & 63);
     }
     k_pair<Real, KID, EXACT><<<grid, OSPH_PAIR_THREADS, smem, stream>>>(a);
     return cudaSuccess;
@@ -381,9 +381,9 @@ static int launch_kid(osph_ctx *ctx, const PairArgs &a, int grid)
 {
     cudaError_t e;
     switch (ctx->cfg.kernel) {
-    case OSPH_KERNEL_CUBIC: e = launch_one<Real, OSPH_KERNEL_CUBIC, EXACT>(a, grid, ctx->stream); break;
-    case OSPH_KERNEL_WENDLAND: e = launch_one<Real, OSPH_KERNEL_WENDLAND, EXACT>(a, grid, ctx->stream); break;
-    default: e = launch_one<Real, OSPH_KERNEL_GAUSSIAN, EXACT>(a, grid, ctx->stream); break;
+    case OSPH_KERNEL_CUBIC: e = launch_one<Real, OSPH_KERNEL_CUBIC, EXACT>(a, grid, ctx->stream, ctx->device); break;
+    case OSPH_KERNEL_WENDLAND: e = launch_one<Real, OSPH_KERNEL_WENDLAND, EXACT>(a, grid, ctx->stream, ctx->device); break;
+    default: e = launch_one<Real, OSPH_KERNEL_GAUSSIAN, EXACT>(a, grid, ctx->stream, ctx->device); break;
     }
     if (e != cudaSuccess) { ctx->err = std::string("pair kernel configuration: ") + cudaGetErrorString(e); return OSPH_E_CUDA; }
     return 0;

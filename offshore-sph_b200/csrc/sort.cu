@@ -176,10 +176,10 @@ static int sort_pass(osph_ctx *ctx, int n, int nblocks, int shift, int cur, bool
 {
     constexpr int RADIX = 1 << BITS;
     constexpr size_t smem = sizeof(unsigned int) * (SORT_THREADS / 32 + 1) * RADIX;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;           // one bit per device ordinal
+    if (!(configured >> (ctx->device & 63) & 1ull)) {
         OSPH_CUDA(cudaFuncSetAttribute(k_sort_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= 1ull << (ctx->device & 63);
     }
     if (!have_hist) {
         k_sort_hist<BITS><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(ctx->key[cur], n, shift, nblocks, ctx->hist);
