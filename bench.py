@@ -120,23 +120,35 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampling in the background.  Started BEFORE the warm-up (the tool needs a few hundred ms to emit its
+    first line); samples are time-stamped and only those inside [mark_start, mark_end] -- the timed region -- count."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
+            time.sleep(0.5)
         except Exception:
             self.p = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.t1 = time.time()
+        time.sleep(0.1)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -145,18 +157,23 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].strip().lower().startswith("active"):
-                        reasons.add(nm)
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                parsed.append((ts, float(r[2]), float(r[3]), [nm for k, nm in enumerate(names)
+                                                             if r[6 + k].strip().lower().startswith("active")]))
             except Exception:
                 pass
+        inside = [q for q in parsed if self.t0 is not None and self.t0 - 0.02 <= q[0] <= self.t1 + 0.02]
+        use = inside if inside else parsed[-3:]
+        sm = [q[1] for q in use]; mx = [q[2] for q in use]
+        reasons = sorted({nm for q in use for nm in q[3]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(inside), "samples_total": len(parsed),
+                "window_s": (self.t1 - self.t0) if self.t0 is not None else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -200,13 +217,14 @@ def run_gpu(args):
         return e0.elapsed_time(e1) * 1e-3
 
     # ---- resident-in-HBM throughput -----------------------------------------------------------
+    clocks = ClockSampler(local)
     ctx.upload(pA)
     ctx.step(args.warmup, None, DAMPING)
     ctx.sync(); ctx.pair_kernel_time()
     l0 = ctx.launch_count
-    clocks = ClockSampler(local)
-    # osph_step enqueues asynchronously; keep the clock sampler running across the whole region
+    clocks.mark_start()
     t_dev = timed_region(lambda: ctx.step(1, None, DAMPING), args.steps)
+    clocks.mark_end()
     clk = clocks.stop()
     launches = ctx.launch_count - l0
     pair_us, pair_n = ctx.pair_kernel_time()

@@ -271,16 +271,20 @@ def bench_multi_gpu(args, rank, world, local):
     else:
         run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
 
+    clocks = B.ClockSampler(local) if rank == 0 else None
     run.step(args.warmup, None, B.DAMPING)
     ctx.sync(); ctx.pair_kernel_time()
     l0 = ctx.launch_count
-    clocks = B.ClockSampler(local) if rank == 0 else None
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    if clocks:
+        clocks.mark_start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     run.step(args.steps, None, B.DAMPING)
     e1.record(stream)
     e1.synchronize(); torch.cuda.synchronize()
+    if clocks:
+        clocks.mark_end()
     t_local = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device='cuda')
     dist.barrier()
     dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
