@@ -266,6 +266,9 @@ int osph_slab_comm_create(osph_ctx *ctx, const char *libnccl_path, const char un
 int osph_slab_comm_destroy(osph_ctx *ctx, osph_slab_comm *comm);
 /* Re-enter slab mode after osph_upload_aos replaced the particle set (host-buffer call pattern). */
 int osph_slab_comm_attach(osph_ctx *ctx, osph_slab_comm *comm);
+/* Move this rank's slab boundaries (load re-balancing; all ranks switch at the same step, the particles between the
+ * old and the new cut reach their new owner through the next step's migration). */
+int osph_slab_comm_set_bounds(osph_ctx *ctx, osph_slab_comm *comm, double x_lo, double x_hi);
 /* nsteps slab-decomposed steps: all_reduce(dt) -> predict -> pack -> all_gather(counts, bounds) -> send/recv
  * (migrants + halos) -> commit -> neighbours + pair kernel + correct. */
 int osph_slab_run(osph_ctx *ctx, osph_slab_comm *comm, int32_t nsteps, double fixed_dt, double damping);

@@ -146,6 +146,14 @@ extern "C" int osph_slab_comm_attach(osph_ctx *ctx, osph_slab_comm *s)
     return osph_slab_configure(ctx, s->x_lo, s->x_hi, s->d_ghost, s->ghost_cap);
 }
 
+// New slab boundaries (load re-balancing); every rank must switch at the same step.
+extern "C" int osph_slab_comm_set_bounds(osph_ctx *ctx, osph_slab_comm *s, double x_lo, double x_hi)
+{
+    if (!ctx || !s || !(x_lo < x_hi)) return OSPH_E_INVALID;
+    s->x_lo = x_lo; s->x_hi = x_hi;
+    return osph_slab_configure(ctx, x_lo, x_hi, s->d_ghost, s->ghost_cap);
+}
+
 extern "C" int osph_slab_run(osph_ctx *ctx, osph_slab_comm *s, int32_t nsteps, double fixed_dt, double damping)
 {
     if (!ctx || !s) return OSPH_E_INVALID;

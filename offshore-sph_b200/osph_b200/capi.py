@@ -120,6 +120,7 @@ def lib():
                                             C.POINTER(C.c_void_p)]),
         'osph_slab_comm_destroy': (C.c_int, [ctx, C.c_void_p]),
         'osph_slab_comm_attach': (C.c_int, [ctx, C.c_void_p]),
+        'osph_slab_comm_set_bounds': (C.c_int, [ctx, C.c_void_p, dbl, dbl]),
         'osph_slab_run': (C.c_int, [ctx, C.c_void_p, i32, dbl, dbl]),
         'osph_slab_last_counts': (C.c_int, [C.c_void_p, ip]),
         'osph_leaf_kernel': (C.c_int, [C.c_int, C.c_int, C.c_int, i64, dp, dp, dp, dp]),
@@ -365,6 +366,9 @@ class Context:
 
     def slab_comm_attach(self, comm):
         self._ck(self._L.osph_slab_comm_attach(self._h, comm))
+
+    def slab_comm_set_bounds(self, comm, x_lo, x_hi):
+        self._ck(self._L.osph_slab_comm_set_bounds(self._h, comm, x_lo, x_hi))
 
     def slab_run(self, comm, nsteps, fixed_dt=None, damping=0.0):
         self._ck(self._L.osph_slab_run(self._h, comm, nsteps, -1.0 if fixed_dt is None else fixed_dt, damping))

@@ -156,15 +156,18 @@ class SlabRun:
         self.last_counts = dict(mig_out=(out_l, out_r), halo_out=(halo_l, halo_r), mig_in=(in_mig_l, in_mig_r),
                                 halo_in=(in_halo_l, in_halo_r), ghosts=n_ghost, owned=ctx.num_active)
 
+    def export_device(self, fields):
+        """(ids, labels, [columns]) of the owned particles as tensors on the run's device."""
+        return _export_device(self.ctx, self.ghost.device, fields)
+
     def export(self, fields):
         """(ids, labels, {field: column}) of the owned particles, as host numpy arrays."""
-        n = self.ctx.num_active
-        dev = self.ghost.device
-        ids = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
-        lab = torch.zeros(max(n, 1), dtype=torch.int8, device=dev)
-        cols = [torch.zeros(max(n, 1), dtype=torch.float64, device=dev) for _ in fields]
-        self.ctx.slab_export(ids.data_ptr(), lab.data_ptr(), fields, [c.data_ptr() for c in cols])
-        return ids[:n].cpu().numpy(), lab[:n].cpu().numpy(), {f: c[:n].cpu().numpy() for f, c in zip(fields, cols)}
+        ids, lab, cols = self.export_device(fields)
+        return ids.cpu().numpy(), lab.cpu().numpy(), {f: c.cpu().numpy() for f, c in zip(fields, cols)}
+
+    def set_bounds(self, x_lo, x_hi):
+        self.x_lo, self.x_hi = float(x_lo), float(x_hi)
+        self.ctx.slab_configure(self.x_lo, self.x_hi, self.ghost.data_ptr(), self.ghost_cap)
 
 
 class NcclSlabRun:
@@ -206,18 +209,86 @@ class NcclSlabRun:
     def reattach(self):
         self.ctx.slab_comm_attach(self.comm)
 
+    def export_device(self, fields):
+        return _export_device(self.ctx, self.device, fields)
+
     def export(self, fields):
-        n = self.ctx.num_active
-        ids = torch.zeros(max(n, 1), dtype=torch.int32, device=self.device)
-        lab = torch.zeros(max(n, 1), dtype=torch.int8, device=self.device)
-        cols = [torch.zeros(max(n, 1), dtype=torch.float64, device=self.device) for _ in fields]
-        self.ctx.slab_export(ids.data_ptr(), lab.data_ptr(), fields, [c.data_ptr() for c in cols])
-        return ids[:n].cpu().numpy(), lab[:n].cpu().numpy(), {f: c[:n].cpu().numpy() for f, c in zip(fields, cols)}
+        ids, lab, cols = self.export_device(fields)
+        return ids.cpu().numpy(), lab.cpu().numpy(), {f: c.cpu().numpy() for f, c in zip(fields, cols)}
+
+    def set_bounds(self, x_lo, x_hi):
+        self.x_lo, self.x_hi = float(x_lo), float(x_hi)
+        self.ctx.slab_comm_set_bounds(self.comm, self.x_lo, self.x_hi)
 
     def close(self):
         if self.comm is not None:
             self.ctx.slab_comm_destroy(self.comm)
             self.comm = None
+
+
+def _export_device(ctx, device, fields):
+    n = ctx.num_active
+    ids = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
+    lab = torch.zeros(max(n, 1), dtype=torch.int8, device=device)
+    cols = [torch.zeros(max(n, 1), dtype=torch.float64, device=device) for _ in fields]
+    ctx.slab_export(ids.data_ptr(), lab.data_ptr(), fields, [c.data_ptr() for c in cols])
+    return ids[:n], lab[:n], [c[:n] for c in cols]
+
+
+def rebalance(run, group=None, bins=4096, max_move_frac=0.5):
+    """Re-cut the slabs so every rank owns the same number of fluid particles again (the fluid of a dam break
+    leaves the corner it started in; SURVEY.md section 7, hard part 7).
+
+    Collective: every rank must call it at the same step.  A histogram of the fluid x-coordinates over `bins`
+    columns is summed over the ranks (one all_reduce of `bins` doubles); the new cuts are its quantiles.  A cut
+    moves at most `max_move_frac` of the way into the neighbouring slab, so the particles between the old and the
+    new cut reach their new owner through the ordinary migration of the next step (migrants only ever travel to the
+    adjacent rank).  Returns the new list of cuts."""
+    world, rank = run.world, run.rank
+    _, lab, (x,) = run.export_device(['x'])
+    fx = x[lab == 0]
+    dev = x.device
+    big = 1e300
+    ext = torch.tensor([fx.min().item() if fx.numel() else big, -(fx.max().item() if fx.numel() else -big)],
+                       dtype=torch.float64, device=dev)
+    dist.all_reduce(ext, op=dist.ReduceOp.MIN, group=group)
+    lo, hi = float(ext[0]), float(-ext[1])
+    if not (hi > lo):
+        return None
+    hist = torch.histc(fx, bins=bins, min=lo, max=hi).to(torch.float64) if fx.numel() else \
+        torch.zeros(bins, dtype=torch.float64, device=dev)
+    # current inner cuts travel along so that every rank limits the moves identically
+    mine = torch.full((world + 1,), big, dtype=torch.float64, device=dev)
+    mine[rank] = run.x_lo if math.isfinite(run.x_lo) else -big
+    mine[rank + 1] = min(float(mine[rank + 1]), run.x_hi if math.isfinite(run.x_hi) else big)
+    payload = torch.cat((hist, mine))
+    red = payload.clone()
+    dist.all_reduce(red[:bins], op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(red[bins:], op=dist.ReduceOp.MIN, group=group)
+    hist = red[:bins].cpu().numpy()
+    old = red[bins:].cpu().numpy()
+    cdf = np.cumsum(hist)
+    total = cdf[-1]
+    if total <= 0:
+        return None
+    width = (hi - lo) / bins
+    cuts = [-math.inf]
+    for r in range(1, world):
+        target = total * r / world
+        b = int(np.searchsorted(cdf, target))
+        b = min(b, bins - 1)
+        before = cdf[b - 1] if b > 0 else 0.0
+        frac = (target - before) / hist[b] if hist[b] > 0 else 0.0
+        new = lo + (b + frac) * width
+        # stay inside the two slabs that meet at this cut
+        left_lo = old[r - 1] if r - 1 > 0 else lo
+        right_hi = old[r + 1] if r + 1 < world else hi
+        cur = old[r]
+        new = min(max(new, cur - max_move_frac * (cur - left_lo)), cur + max_move_frac * (right_hi - cur))
+        cuts.append(float(max(new, cuts[-1])))
+    cuts.append(math.inf)
+    run.set_bounds(cuts[rank], cuts[rank + 1])
+    return cuts
 
 
 def partition(pA, world, rank):

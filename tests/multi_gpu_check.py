@@ -55,9 +55,11 @@ def main():
         else:
             run = slabs.NcclSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cuda', local))
         moved = 0
-        for _ in range(a.steps):
+        for k in range(a.steps):
             run.step(1, FIXED_DT, 0.05)
             moved += sum(run.last_counts['mig_out'])
+            if k == a.steps // 2:
+                slabs.rebalance(run)                   # re-cut the slabs mid-run: results must not notice
         got, seen = slabs.gather_global(run, pA, FIELDS)
         dts = ctx.dt_log()
         status = ctx.sync()

@@ -105,6 +105,28 @@ def _particles(n=1500, seed=0):
     return pA
 
 
+def _worker_rebalance(rank, world, port, steps, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pA = _particles()
+        pA['label'] = 0
+        pA['vx'] = 0.04 * pA['x']                       # the cloud stretches to the right: static cuts would starve rank 0
+        cuts, local, ids = slabs.partition(pA, world, rank)
+        run = slabs.SlabRun(MockContext(), slabs.TorchComm(), cuts, local, ids, 'cubic', 0.01, HMAX,
+                            torch.device('cpu'), min_cap=4096)
+        hist = []
+        for k in range(steps):
+            run.step(1, None, 0.0)
+            if k % 2 == 1 and k < steps - 1:              # the step after a re-cut carries out its migration
+                slabs.rebalance(run, bins=512)
+            hist.append(run.ctx.num_active)
+        out, seen = slabs.gather_global(run, pA, ['x', 'ax'])
+        q.put((rank, hist, out['x'].copy(), out['ax'].copy(), seen, np.asarray([run.x_lo, run.x_hi])))
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, steps, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -180,3 +202,44 @@ def test_quantile_cuts_and_halo_width():
     assert slabs.halo_width('cubic', 0.5, 0.25) == pytest.approx(1.1)
     assert slabs.halo_width('gaussian', 0.5, 0.25) == pytest.approx(1.65)
     assert slabs.halo_width('cubic', 0.1, 1.0) == pytest.approx(0.33)          # Lennard-Jones range min(r0, 3h) wins
+
+
+def _spawn(target, world, steps):
+    import queue, time
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, steps, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res, t_end = [], time.time() + 180
+    while len(res) < world and time.time() < t_end:
+        try:
+            res.append(q.get(timeout=1.0))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    [p.join(30) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
+    assert len(res) == world and all(p.exitcode == 0 for p in procs)
+    return sorted(res, key=lambda t: t[0])
+
+
+def test_rebalance_keeps_the_load_even_and_the_physics_intact():
+    world, steps = 3, 13
+    res = _spawn(_worker_rebalance, world, steps)
+    pA = _particles(); pA['label'] = 0; pA['vx'] = 0.04 * pA['x']
+    n = len(pA)
+    final_counts = [r[1][-1] for r in res]
+    assert sum(final_counts) == n
+    # the cloud stretches by ~15 % over the run: static cuts would end near [435, 435, 630]; re-cut slabs stay even
+    assert max(final_counts) - min(final_counts) < 0.06 * n / world
+    for r in res:
+        assert np.array_equal(r[4], np.ones(n, dtype=np.int64))            # every particle owned exactly once
+    # slabs tile the line and the physics (neighbour counts through ghosts) is still the global brute force
+    edges = sorted(set(np.concatenate([r[5] for r in res]).tolist()))
+    assert edges[0] == -np.inf and edges[-1] == np.inf and len(edges) == world + 1
+    x = res[0][2]
+    d2 = (x[:, None] - x[None, :]) ** 2 + (pA['y'][:, None] - pA['y'][None, :]) ** 2
+    want = (d2 <= (R / 1.1) ** 2).sum(axis=1).astype(np.float64)
+    for r in res:
+        assert np.array_equal(r[3], want)
