@@ -158,3 +158,47 @@ def test_batched_pressure_probe_matches_reference_recipe():
         want = SummationDensity(pA['label'][idx], pA['m'][idx], wt)
         assert rho[k] == pytest.approx(want, rel=1e-12)
         assert p[k] == pytest.approx(((want / c['rho0']) ** 7 - 1) * c['B'], rel=1e-9, abs=1e-6)
+
+
+def test_solver_coupling_callback_path(monkeypatch):
+    """Coupled (ice-like) particles moved by a host-side NewmarkBeta integrator inside a coupling callback, the
+    IceBreak call pattern (examples/IceBreak.py:109-171): predict/correct of the coupled rows on the host mirror,
+    callback between compute and correct, batched device pressure probe inside the callback."""
+    monkeypatch.setenv("OSPH_QUIET", "1")
+    from src.Solver import Solver
+    from src.Methods.WCSPH import WCSPH
+    from src.Kernels.Wendland import Wendland
+    from src.Integrators.PEC import PEC
+    from src.Integrators.NewmarkBeta import NewmarkBeta
+    from src.Common import ParticleType
+    case = W.tank_case(16, h=1.3 / 16, useXSPH=True, seed=2, coupled_row=True, perturbed=False)
+    pA = case['pA']
+    nc = int((pA['label'] == ParticleType.Coupled).sum())
+    calls = []
+
+    def coupling(arr, solver):
+        c = arr['label'] == ParticleType.Coupled
+        rho, p = solver.probe_pressure(arr['x'][c], arr['y'][c] - 0.5 / 16, 1.3 / 16)
+        assert rho.shape == (nc,) and np.all(np.isfinite(p))
+        F = np.clip(p, -1e4, 1e4) * 1e-3
+        a = solver.couplingIntegrator.acceleration(solver.dt, F, arr['y'][c] - y0, arr['vy'][c])
+        arr['ay'][c] = a
+        calls.append(float(np.abs(a).max()))
+        return arr
+
+    y0 = pA['y'][pA['label'] == ParticleType.Coupled].copy()
+    nb = NewmarkBeta(0.25, 0.5, np.eye(nc) * 50.0, np.eye(nc) * 1e4, np.eye(nc) * 10.0)
+    method = WCSPH(height=1.0, r0=case['r0'], rho0=1000.0, useXSPH=True, Pb=0)
+    s = Solver(method, PEC(useXSPH=True, strict=False), Wendland(), 0.002, incrementalWriteout=False, h=1.3 / 16,
+               maxSettle=3, coupling=coupling, couplingIntegrator=nb, couplingProperties={}, exportProperties=['y'])
+    s.addParticles(pA)
+    s.setup()
+    s.run()
+    assert len(calls) == s.t_step and s.t >= 0.002
+    out = s.particleArray
+    assert np.all(np.isfinite(out['x'])) and np.all(np.isfinite(out['y']))
+    c = out['label'] == ParticleType.Coupled
+    assert np.any(out['y'][c] != y0)                         # the host integrator moved the coupled rows ...
+    f = out['label'] == 0
+    assert np.all(out['ay'][f] != 0)                          # ... and the device kept integrating the fluid
+    assert s.timing_data['coupling'] > 0
