@@ -119,13 +119,51 @@ __global__ void k_slab_append(SlabMoveArgs a, const double *__restrict__ rec, in
     else a.row[base + k] = (int)v;
 }
 
+// Small exchanges (the common case: a few dozen migrants per face and step) are committed by ONE CTA: mark, pick
+// fillers, move, append and install the all-reduced bounds, instead of two memsets and five launches.
+#define SLAB_SMALL 4096
+__global__ void __launch_bounds__(1024)
+k_slab_commit_small(SlabMoveArgs a, const int *__restrict__ mig_slots, int m, int n_new, int *__restrict__ tail_flag,
+                    int *__restrict__ holes, int *__restrict__ fillers, const double *__restrict__ rec, int n_in,
+                    StepScalars *sc, int set_bounds, double xmin, double nxmax, double ymin, double nymax, double hmin,
+                    double nhmax)
+{
+    __shared__ int nh, nf;
+    const int t = threadIdx.x, nt = blockDim.x;
+    if (t == 0) { nh = 0; nf = 0; }
+    for (int k = t; k < m; k += nt) tail_flag[k] = 0;
+    __syncthreads();
+    for (int k = t; k < m; k += nt) {
+        int h = mig_slots[k];
+        if (h >= n_new) tail_flag[h - n_new] = 1; else holes[atomicAdd(&nh, 1)] = h;
+    }
+    __syncthreads();
+    for (int k = t; k < m; k += nt) if (!tail_flag[k]) fillers[atomicAdd(&nf, 1)] = n_new + k;
+    __syncthreads();
+    const int W = OSPH_NUM_FIELDS + 2, pairs = nh;
+    for (int u = t; u < pairs * W; u += nt) {
+        int k = u / W, c = u % W, dst = holes[k], src = fillers[k];
+        if (c < OSPH_NUM_FIELDS) a.f[c][dst] = a.f[c][src];
+        else if (c == OSPH_NUM_FIELDS) a.label[dst] = a.label[src];
+        else a.row[dst] = a.row[src];
+    }
+    __syncthreads();
+    for (int u = t; u < n_in * W; u += nt) {
+        int k = u / W, c = u % W;
+        double v = rec[(size_t)k * OSPH_WIRE_FULL + c];
+        if (c < OSPH_NUM_FIELDS) a.f[c][n_new + k] = v;
+        else if (c == OSPH_NUM_FIELDS) a.label[n_new + k] = (signed char)v;
+        else a.row[n_new + k] = (int)v;
+    }
+    if (t == 0 && set_bounds) {
+        sc->xmin = enc_f64(xmin); sc->xmax = enc_f64(-nxmax); sc->ymin = enc_f64(ymin); sc->ymax = enc_f64(-nymax);
+        sc->hmin_all = enc_f64(hmin); sc->hmax_all = enc_f64(-nhmax);
+    }
+}
+
 __global__ void k_slab_dt_local(const StepScalars *sc, double *out)
 {
     out[0] = dec_f64(sc->hmin_fluid); out[1] = -dec_f64(sc->cmax_fluid); out[2] = -dec_f64(sc->a2max_fluid);
-}
-__global__ void k_slab_dt_set(StepScalars *sc, const double *in)
-{
-    sc->hmin_fluid = enc_f64(in[0]); sc->cmax_fluid = enc_f64(-in[1]); sc->a2max_fluid = enc_f64(-in[2]);
 }
 __global__ void k_slab_ids(const int *__restrict__ row, const signed char *__restrict__ label, int n,
                            int *__restrict__ ids, signed char *__restrict__ lab)
@@ -195,6 +233,18 @@ extern "C" int osph_slab_commit(osph_ctx *ctx, int64_t n_mig_out, const void *d_
         ctx->err = "osph_slab_commit: particle capacity exceeded (osph_reserve a larger capacity)"; return OSPH_E_CAPACITY;
     }
     int m = (int)n_mig_out;
+    if (m + n_mig_in <= SLAB_SMALL) {
+        const double z[6] = {0, 0, 0, 0, 0, 0};
+        const double *b = global_bounds ? global_bounds : z;
+        k_slab_commit_small<<<1, 1024, 0, ctx->stream>>>(move_args(ctx), ctx->d_mig_slots, m, (int)n_new, ctx->d_tail_flag,
+                                                         ctx->d_holes, ctx->d_fillers, (const double *)d_mig_in, (int)n_mig_in,
+                                                         ctx->d_sc, global_bounds ? 1 : 0, b[0], b[1], b[2], b[3], b[4], b[5]);
+        OSPH_LAUNCH_CHECK();
+        ctx->n = n_new + n_mig_in;
+        ctx->n_ghost = n_ghost;
+        ctx->prepared = true;
+        return 0;
+    }
     if (m > 0) {
         int *nh = ctx->d_slab_counters + 8, *nf = ctx->d_slab_counters + 9;
         OSPH_CUDA(cudaMemsetAsync(nh, 0, sizeof(int) * 2, ctx->stream));
@@ -240,8 +290,7 @@ extern "C" int osph_slab_step_begin(osph_ctx *ctx, const double *d_dt_reduced3, 
     CHECK_CTX();
     if (!ctx->slab) { ctx->err = "osph_slab_step_begin: context is not in slab mode"; return OSPH_E_INVALID; }
     int rc;
-    if (d_dt_reduced3) { k_slab_dt_set<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, d_dt_reduced3); OSPH_LAUNCH_CHECK(); }
-    if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true))) return rc;
+    if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true, d_dt_reduced3))) return rc;
     if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true))) return rc;
     ctx->neighbours_valid = false; ctx->reductions_valid = false;
     return 0;

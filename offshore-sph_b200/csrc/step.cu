@@ -504,8 +504,11 @@ template __global__ void k_correct<OSPH_INTEGRATOR_PEC, false>(CorrectArgs);
 
 // TimeStep.compute / courant / force (src/Equations/TimeStep.py:11-56), strict IEEE.
 __global__ void k_timestep(StepScalars *sc, double gamma_c, double gamma_f, double fixed_dt,
-                           double *dt_log, long long dt_log_cap, int reset_prepare)
+                           double *dt_log, long long dt_log_cap, int reset_prepare, const double *reduced3)
 {
+    if (reduced3) {           // slab mode: all-reduced {h_min, -c_max, -a2_max} replaces the local reduction
+        sc->hmin_fluid = enc_f64(reduced3[0]); sc->cmax_fluid = enc_f64(-reduced3[1]); sc->a2max_fluid = enc_f64(-reduced3[2]);
+    }
     if (reset_prepare) {      // folded k_reset_prepare_scalars: the predictor that follows reduces into these
         sc->xmin = ENC_POS_INF; sc->ymin = ENC_POS_INF; sc->xmax = ENC_NEG_INF; sc->ymax = ENC_NEG_INF;
         sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF;
@@ -921,10 +924,11 @@ int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, 
     return 0;
 }
 
-int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare)
+int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare, const double *d_reduced3)
 {
     k_timestep<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->cfg.cfl_courant, ctx->cfg.cfl_force, fixed_dt,
-                                         log ? ctx->d_dt_log : nullptr, (long long)ctx->dt_log_cap, reset_prepare ? 1 : 0);
+                                         log ? ctx->d_dt_log : nullptr, (long long)ctx->dt_log_cap, reset_prepare ? 1 : 0,
+                                         d_reduced3);
     OSPH_LAUNCH_CHECK();
     return 0;
 }

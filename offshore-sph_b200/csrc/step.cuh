@@ -64,7 +64,8 @@ int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids);
 int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
 int osph_launch_build(osph_ctx *ctx, bool reset_dt = false);   // grid params, keys, sort, (reorder), gather + cell table
 int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
-int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare = false);
+int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare = false,
+                         const double *d_reduced3 = nullptr);
 int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt = false);
 int osph_launch_ke(osph_ctx *ctx);
 int osph_launch_neighbours(osph_ctx *ctx, int mode, long long *d_counts, const long long *d_offsets, long long *d_out);
