@@ -320,9 +320,9 @@ def main():
     ap.add_argument("--total-side", action="store_true",
                     help="multi-GPU: --particles-per-side is the TOTAL problem (strong scaling) instead of per-GPU "
                          "N*sqrt(gpus) (weak scaling, default)")
-    ap.add_argument("--sequencer", default="nccl", choices=["nccl", "python"],
-                    help="multi-GPU: slab protocol sequenced inside the library with direct NCCL calls (default) or by "
-                         "osph_b200/slabs.py through torch.distributed")
+    ap.add_argument("--sequencer", default="p2p", choices=["p2p", "nccl", "python"],
+                    help="multi-GPU exchange: p2p = NVLink peer-memory windows + mailbox kernels (default, falls back to "
+                         "nccl), nccl = direct NCCL calls inside the library, python = osph_b200/slabs.py via torch.distributed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()

@@ -275,6 +275,23 @@ int osph_slab_run(osph_ctx *ctx, osph_slab_comm *comm, int32_t nsteps, double fi
 /* {mig_out l,r, halo_out l,r, mig_in l,r, halo_in l,r} of the last step */
 int osph_slab_last_counts(const osph_slab_comm *comm, int64_t out[8]);
 
+/*
+ * The same protocol over NVLink peer memory, no NCCL in the data path (csrc/slab_p2p.cu): every rank exports one
+ * HBM window with CUDA IPC; the pack kernel writes migrants and halos straight into the neighbours' windows, two
+ * mailbox all-gather kernels (store to every peer, system fence, sequence flag, spin on the own window) carry dt and
+ * counts + grid bounds.  All ranks must live on one NVLink / NVSwitch box.  The caller all-gathers the 64-byte
+ * handles (rank-major) between osph_slab_p2p_create and osph_slab_p2p_connect.
+ */
+typedef struct osph_slab_p2p osph_slab_p2p;
+int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x_lo, double x_hi, double r0, double hmax,
+                         int64_t mig_cap, int64_t halo_cap, osph_slab_p2p **out, char handle_out[64]);
+int osph_slab_p2p_connect(osph_ctx *ctx, osph_slab_p2p *p2p, const char *all_handles);
+int osph_slab_p2p_destroy(osph_ctx *ctx, osph_slab_p2p *p2p);
+int osph_slab_p2p_attach(osph_ctx *ctx, osph_slab_p2p *p2p);
+int osph_slab_p2p_set_bounds(osph_ctx *ctx, osph_slab_p2p *p2p, double x_lo, double x_hi);
+int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *p2p, int32_t nsteps, double fixed_dt, double damping);
+int osph_slab_p2p_last_counts(const osph_slab_p2p *p2p, int64_t out[8]);
+
 /* ---- stand-alone leaf functions on host arrays (context-free; `device` is a CUDA ordinal) ---------- */
 
 /* what == 0: kernel.evaluate(r, h); what == 1: kernel.gradient(x, r, h).

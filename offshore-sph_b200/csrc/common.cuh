@@ -33,6 +33,14 @@ struct GridParams {
     double pair_r2;        // square of the radius inside which a pair can contribute
 };
 
+// Ghost records live in up to three segments of the ghost buffer (slab mode): the rank's own migrants, the halo
+// received from the left neighbour and the one from the right.  NCCL receives pack them back to back (c0 = all);
+// peer-to-peer writes land in fixed regions of the rank's window (b1, b2 = region starts, in records).
+struct GhostMap {
+    int c0, c1;
+    long long b1, b2;
+};
+
 struct StepScalars {
     // order-preserving encodings (see enc_f64) so that atomicMin/atomicMax work on doubles
     unsigned long long xmin, xmax, ymin, ymax;   // bounds of active particles
@@ -96,6 +104,7 @@ struct osph_ctx {
     // slab mode: ghost particles as light wire records (OSPH_WIRE_HALO doubles each), appended after the owned ones
     double *d_ghost = nullptr;
     int64_t n_ghost = 0, ghost_cap = 0;
+    GhostMap gmap = {0, 0, 0, 0};
     bool ghost_external = false;
     unsigned int *scan_block = nullptr;   // block sums of the scan utility
     bool slab = false;
@@ -157,6 +166,12 @@ static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
 // device helpers
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ const double *ghost_record(const double *ghost, const GhostMap &gm, int g)
+{
+    long long slot = g < gm.c0 ? g : (g < gm.c0 + gm.c1 ? gm.b1 + (g - gm.c0) : gm.b2 + (g - gm.c0 - gm.c1));
+    return ghost + slot * OSPH_WIRE_HALO;
+}
 
 // Monotone map double -> uint64 so that unsigned atomicMin/atomicMax order doubles correctly.
 __device__ __forceinline__ unsigned long long enc_f64(double v)

@@ -124,8 +124,8 @@ __global__ void k_slab_append(SlabMoveArgs a, const double *__restrict__ rec, in
 #define SLAB_SMALL 4096
 __global__ void __launch_bounds__(1024)
 k_slab_commit_small(SlabMoveArgs a, const int *__restrict__ mig_slots, int m, int n_new, int *__restrict__ tail_flag,
-                    int *__restrict__ holes, int *__restrict__ fillers, const double *__restrict__ rec, int n_in,
-                    StepScalars *sc, int set_bounds, double xmin, double nxmax, double ymin, double nymax, double hmin,
+                    int *__restrict__ holes, int *__restrict__ fillers, const double *__restrict__ rec_l, int n_in_l,
+                    const double *__restrict__ rec_r, int n_in_r, StepScalars *sc, int set_bounds, double xmin, double nxmax, double ymin, double nymax, double hmin,
                     double nhmax)
 {
     __shared__ int nh, nf;
@@ -148,9 +148,10 @@ k_slab_commit_small(SlabMoveArgs a, const int *__restrict__ mig_slots, int m, in
         else a.row[dst] = a.row[src];
     }
     __syncthreads();
+    const int n_in = n_in_l + n_in_r;
     for (int u = t; u < n_in * W; u += nt) {
         int k = u / W, c = u % W;
-        double v = rec[(size_t)k * OSPH_WIRE_FULL + c];
+        double v = k < n_in_l ? rec_l[(size_t)k * OSPH_WIRE_FULL + c] : rec_r[(size_t)(k - n_in_l) * OSPH_WIRE_FULL + c];
         if (c < OSPH_NUM_FIELDS) a.f[c][n_new + k] = v;
         else if (c == OSPH_NUM_FIELDS) a.label[n_new + k] = (signed char)v;
         else a.row[n_new + k] = (int)v;
@@ -223,13 +224,13 @@ extern "C" int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left
     return 0;
 }
 
-extern "C" int osph_slab_commit(osph_ctx *ctx, int64_t n_mig_out, const void *d_mig_in, int64_t n_mig_in,
-                                int64_t n_ghost, const double global_bounds[6])
+int osph_slab_commit_impl(osph_ctx *ctx, int64_t n_mig_out, const double *d_in_l, int64_t n_in_l, const double *d_in_r,
+                          int64_t n_in_r, GhostMap gmap, int64_t n_ghost, const double global_bounds[6])
 {
-    CHECK_CTX();
     if (!ctx->slab) { ctx->err = "osph_slab_commit: context is not in slab mode"; return OSPH_E_INVALID; }
+    const int64_t n_mig_in = n_in_l + n_in_r;
     int64_t n_new = ctx->n - n_mig_out;
-    if (n_new < 0 || n_new + n_mig_in + n_ghost > ctx->cap || n_ghost > ctx->ghost_cap) {
+    if (n_new < 0 || n_new + n_mig_in + n_ghost > ctx->cap) {
         ctx->err = "osph_slab_commit: particle capacity exceeded (osph_reserve a larger capacity)"; return OSPH_E_CAPACITY;
     }
     int m = (int)n_mig_out;
@@ -237,40 +238,51 @@ extern "C" int osph_slab_commit(osph_ctx *ctx, int64_t n_mig_out, const void *d_
         const double z[6] = {0, 0, 0, 0, 0, 0};
         const double *b = global_bounds ? global_bounds : z;
         k_slab_commit_small<<<1, 1024, 0, ctx->stream>>>(move_args(ctx), ctx->d_mig_slots, m, (int)n_new, ctx->d_tail_flag,
-                                                         ctx->d_holes, ctx->d_fillers, (const double *)d_mig_in, (int)n_mig_in,
+                                                         ctx->d_holes, ctx->d_fillers, d_in_l, (int)n_in_l, d_in_r, (int)n_in_r,
                                                          ctx->d_sc, global_bounds ? 1 : 0, b[0], b[1], b[2], b[3], b[4], b[5]);
         OSPH_LAUNCH_CHECK();
-        ctx->n = n_new + n_mig_in;
-        ctx->n_ghost = n_ghost;
-        ctx->prepared = true;
-        return 0;
-    }
-    if (m > 0) {
-        int *nh = ctx->d_slab_counters + 8, *nf = ctx->d_slab_counters + 9;
-        OSPH_CUDA(cudaMemsetAsync(nh, 0, sizeof(int) * 2, ctx->stream));
-        OSPH_CUDA(cudaMemsetAsync(ctx->d_tail_flag, 0, sizeof(int) * m, ctx->stream));
-        k_slab_mark<<<div_up(m, 256), 256, 0, ctx->stream>>>(ctx->d_mig_slots, m, (int)n_new, ctx->d_tail_flag, ctx->d_holes, nh);
-        OSPH_LAUNCH_CHECK();
-        k_slab_fillers<<<div_up(m, 256), 256, 0, ctx->stream>>>(ctx->d_tail_flag, m, (int)n_new, ctx->d_fillers, nf);
-        OSPH_LAUNCH_CHECK();
-        k_slab_move<<<div_up((int64_t)m * (OSPH_NUM_FIELDS + 2), 256), 256, 0, ctx->stream>>>(move_args(ctx), ctx->d_holes,
-                                                                                            ctx->d_fillers, nh, m);
-        OSPH_LAUNCH_CHECK();
-    }
-    if (n_mig_in > 0) {
-        k_slab_append<<<div_up(n_mig_in * (OSPH_NUM_FIELDS + 2), 256), 256, 0, ctx->stream>>>(
-            move_args(ctx), (const double *)d_mig_in, (int)n_mig_in, (int)n_new);
-        OSPH_LAUNCH_CHECK();
+    } else {
+        if (m > 0) {
+            int *nh = ctx->d_slab_counters + 8, *nf = ctx->d_slab_counters + 9;
+            OSPH_CUDA(cudaMemsetAsync(nh, 0, sizeof(int) * 2, ctx->stream));
+            OSPH_CUDA(cudaMemsetAsync(ctx->d_tail_flag, 0, sizeof(int) * m, ctx->stream));
+            k_slab_mark<<<div_up(m, 256), 256, 0, ctx->stream>>>(ctx->d_mig_slots, m, (int)n_new, ctx->d_tail_flag, ctx->d_holes, nh);
+            OSPH_LAUNCH_CHECK();
+            k_slab_fillers<<<div_up(m, 256), 256, 0, ctx->stream>>>(ctx->d_tail_flag, m, (int)n_new, ctx->d_fillers, nf);
+            OSPH_LAUNCH_CHECK();
+            k_slab_move<<<div_up((int64_t)m * (OSPH_NUM_FIELDS + 2), 256), 256, 0, ctx->stream>>>(move_args(ctx), ctx->d_holes,
+                                                                                                ctx->d_fillers, nh, m);
+            OSPH_LAUNCH_CHECK();
+        }
+        if (n_in_l > 0) {
+            k_slab_append<<<div_up(n_in_l * (OSPH_NUM_FIELDS + 2), 256), 256, 0, ctx->stream>>>(move_args(ctx), d_in_l, (int)n_in_l, (int)n_new);
+            OSPH_LAUNCH_CHECK();
+        }
+        if (n_in_r > 0) {
+            k_slab_append<<<div_up(n_in_r * (OSPH_NUM_FIELDS + 2), 256), 256, 0, ctx->stream>>>(move_args(ctx), d_in_r, (int)n_in_r,
+                                                                                              (int)(n_new + n_in_l));
+            OSPH_LAUNCH_CHECK();
+        }
+        if (global_bounds) {
+            k_slab_set_bounds<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, global_bounds[0], global_bounds[1], global_bounds[2],
+                                                        global_bounds[3], global_bounds[4], global_bounds[5]);
+            OSPH_LAUNCH_CHECK();
+        }
     }
     ctx->n = n_new + n_mig_in;
     ctx->n_ghost = n_ghost;
-    if (global_bounds) {
-        k_slab_set_bounds<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, global_bounds[0], global_bounds[1], global_bounds[2],
-                                                    global_bounds[3], global_bounds[4], global_bounds[5]);
-        OSPH_LAUNCH_CHECK();
-    }
+    ctx->gmap = gmap;
     ctx->prepared = true;
     return 0;
+}
+
+extern "C" int osph_slab_commit(osph_ctx *ctx, int64_t n_mig_out, const void *d_mig_in, int64_t n_mig_in,
+                                int64_t n_ghost, const double global_bounds[6])
+{
+    CHECK_CTX();
+    if (n_ghost > ctx->ghost_cap) { ctx->err = "osph_slab_commit: ghost capacity exceeded"; return OSPH_E_CAPACITY; }
+    GhostMap gm = {(int)n_ghost, 0, 0, 0};                    // NCCL receives are packed back to back
+    return osph_slab_commit_impl(ctx, n_mig_out, (const double *)d_mig_in, n_mig_in, nullptr, 0, gm, n_ghost, global_bounds);
 }
 
 extern "C" int osph_slab_dt_local(osph_ctx *ctx, double *d_out3)

@@ -1,0 +1,219 @@
+// slab_p2p.cu -- the slab exchange over NVLink peer memory, without NCCL in the data path.
+//
+// Every rank owns one "window" in HBM, exported to the other ranks of the box with CUDA IPC.  Per step:
+//   * the pack kernel (slab.cu: k_slab_pack) writes this rank's migrants and halo particles DIRECTLY into the
+//     neighbours' windows -- packing and sending are one kernel, the records cross NVLink as they are produced;
+//   * two tiny "mailbox" all-gathers (k_mbox_allgather: every rank stores its payload into every peer's window,
+//     publishes a sequence number behind a system-scope fence, then spins on its own window) replace
+//     ncclAllReduce(dt) and ncclAllGather(counts + grid bounds).  The second one doubles as the "data has landed"
+//     signal: it is enqueued after the pack kernel on the same stream.
+// Received halos are used in place: k_keys / k_gather read ghost records from the window's regions (GhostMap).
+// A region is single-buffered: a neighbour can only start writing step k+1 after the dt mailbox of step k+1, to
+// which this rank contributes only after its step k has completed (stream order), so readers and writers of a
+// region never overlap.
+// NCCL (slab_nccl.cu) stays as the portable sequencer; this one needs all ranks on one NVLink/NVSwitch box.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "step.cuh"
+
+extern "C" {
+int osph_slab_configure(osph_ctx *ctx, double x_lo, double x_hi, void *d_ghost, int64_t ghost_capacity);
+int osph_slab_dt_local(osph_ctx *ctx, double *d_out3);
+int osph_slab_step_begin(osph_ctx *ctx, const double *d_dt_reduced3, double fixed_dt, double damping);
+int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
+                   void *d_halo_left, void *d_halo_right, int64_t halo_cap, double *d_meta);
+int osph_slab_step_end(osph_ctx *ctx, double damping);
+}
+
+#define P2P_MAX_WORLD 16
+#define MBOX_STRIDE 16            // doubles per (slot, sender) cell of a mailbox
+
+struct osph_slab_p2p {
+    int rank = 0, world = 1;
+    double x_lo = 0, x_hi = 0, r0 = 0, hmax = 0;
+    int kernel = 0;
+    int64_t mig_cap = 0, halo_cap = 0;
+    double *win = nullptr;                         // this rank's window
+    double *peer[P2P_MAX_WORLD] = {nullptr};       // every rank's window as mapped here (peer[rank] == win)
+    double **d_peer = nullptr;                     // the same table on the device
+    // window layout, offsets in doubles
+    size_t off_dt = 0, off_dt_flag = 0, off_meta = 0, off_meta_flag = 0;
+    size_t off_ghost = 0, off_halo_from_left = 0, off_halo_from_right = 0, off_mig_from_left = 0, off_mig_from_right = 0;
+    size_t win_doubles = 0;
+    double *d_meta = nullptr, *d_all_meta = nullptr, *d_dt3 = nullptr, *d_all_dt = nullptr, *h_all_meta = nullptr;
+    unsigned long long seq = 0;
+    int64_t last_counts[8] = {0};
+    int64_t steps = 0;
+};
+
+// One CTA, one warp per peer.  Warp r: store my payload into rank r's window, fence, publish `seq`; then wait until
+// rank r's payload for `seq` is in MY window and copy it out.  reduce_min != 0 appends the element-wise minimum.
+__global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int world, size_t off_data, size_t off_flag,
+                                 int slot, const double *__restrict__ payload, int n, unsigned long long seq,
+                                 double *__restrict__ out_all, int reduce_min)
+{
+    const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (r < world) {
+        double *dst = peers[r] + off_data + (size_t)(slot * world + me) * MBOX_STRIDE;
+        volatile unsigned long long *dflag = reinterpret_cast<volatile unsigned long long *>(peers[r] + off_flag) + slot * world + me;
+        if (lane < n) dst[lane] = payload[lane];
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) *dflag = seq;
+        const volatile double *src = peers[me] + off_data + (size_t)(slot * world + r) * MBOX_STRIDE;
+        volatile unsigned long long *sflag = reinterpret_cast<volatile unsigned long long *>(peers[me] + off_flag) + slot * world + r;
+        if (lane == 0) while (*sflag != seq) __nanosleep(64);
+        __syncwarp();
+        __threadfence_system();
+        if (lane < n) out_all[r * n + lane] = src[lane];
+    }
+    if (reduce_min) {
+        __syncthreads();
+        if (threadIdx.x < n) {
+            double m = out_all[threadIdx.x];
+            for (int q = 1; q < world; q++) m = fmin(m, out_all[q * n + threadIdx.x]);
+            out_all[world * n + threadIdx.x] = m;
+        }
+    }
+}
+
+extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x_lo, double x_hi, double r0, double hmax,
+                                    int64_t mig_cap, int64_t halo_cap, osph_slab_p2p **out, char handle_out[64])
+{
+    if (!ctx || !out || !handle_out || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return OSPH_E_INVALID;
+    OSPH_CUDA(cudaSetDevice(ctx->device));
+    osph_slab_p2p *s = new osph_slab_p2p();
+    s->rank = rank; s->world = world; s->x_lo = x_lo; s->x_hi = x_hi; s->r0 = r0; s->hmax = hmax;
+    s->kernel = ctx->cfg.kernel; s->mig_cap = mig_cap; s->halo_cap = halo_cap;
+    size_t o = 0;
+    auto take = [&](size_t doubles) { size_t at = o; o += (doubles + 15) / 16 * 16; return at; };
+    s->off_dt = take((size_t)2 * world * MBOX_STRIDE); s->off_dt_flag = take((size_t)2 * world);
+    s->off_meta = take((size_t)2 * world * MBOX_STRIDE); s->off_meta_flag = take((size_t)2 * world);
+    s->off_ghost = take((size_t)2 * mig_cap * OSPH_WIRE_HALO);                   // this rank's own migrants, kept as ghosts
+    s->off_halo_from_left = take((size_t)halo_cap * OSPH_WIRE_HALO);
+    s->off_halo_from_right = take((size_t)halo_cap * OSPH_WIRE_HALO);
+    s->off_mig_from_left = take((size_t)mig_cap * OSPH_WIRE_FULL);
+    s->off_mig_from_right = take((size_t)mig_cap * OSPH_WIRE_FULL);
+    s->win_doubles = o;
+    OSPH_CUDA(cudaMalloc(&s->win, sizeof(double) * o));
+    OSPH_CUDA(cudaMemset(s->win, 0, sizeof(double) * o));
+    OSPH_CUDA(cudaMalloc(&s->d_peer, sizeof(double *) * world));
+    OSPH_CUDA(cudaMalloc(&s->d_meta, sizeof(double) * MBOX_STRIDE));
+    OSPH_CUDA(cudaMalloc(&s->d_all_meta, sizeof(double) * MBOX_STRIDE * (world + 1)));
+    OSPH_CUDA(cudaMalloc(&s->d_dt3, sizeof(double) * 4));
+    OSPH_CUDA(cudaMalloc(&s->d_all_dt, sizeof(double) * 4 * (world + 1)));
+    OSPH_CUDA(cudaMallocHost(&s->h_all_meta, sizeof(double) * 12 * world));
+    cudaIpcMemHandle_t h;
+    OSPH_CUDA(cudaIpcGetMemHandle(&h, s->win));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, 64);
+    *out = s;
+    return 0;
+}
+
+// all_handles: world x 64 bytes, rank-major (all-gathered by the caller)
+extern "C" int osph_slab_p2p_connect(osph_ctx *ctx, osph_slab_p2p *s, const char *all_handles)
+{
+    if (!ctx || !s || !all_handles) return OSPH_E_INVALID;
+    OSPH_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < s->world; r++) {
+        if (r == s->rank) { s->peer[r] = s->win; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, all_handles + 64 * r, 64);
+        void *p = nullptr;
+        OSPH_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer[r] = (double *)p;
+    }
+    OSPH_CUDA(cudaMemcpy(s->d_peer, s->peer, sizeof(double *) * s->world, cudaMemcpyHostToDevice));
+    return osph_slab_configure(ctx, s->x_lo, s->x_hi, s->win + s->off_ghost, 2 * s->mig_cap);
+}
+
+extern "C" int osph_slab_p2p_destroy(osph_ctx *ctx, osph_slab_p2p *s)
+{
+    if (!s) return OSPH_E_INVALID;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); ctx->d_ghost = nullptr; ctx->n_ghost = 0; ctx->slab = false; }
+    for (int r = 0; r < s->world; r++) if (r != s->rank && s->peer[r]) cudaIpcCloseMemHandle(s->peer[r]);
+    cudaFree(s->win); cudaFree(s->d_peer); cudaFree(s->d_meta); cudaFree(s->d_all_meta); cudaFree(s->d_dt3); cudaFree(s->d_all_dt);
+    cudaFreeHost(s->h_all_meta);
+    delete s;
+    return 0;
+}
+
+extern "C" int osph_slab_p2p_attach(osph_ctx *ctx, osph_slab_p2p *s)
+{
+    if (!ctx || !s) return OSPH_E_INVALID;
+    return osph_slab_configure(ctx, s->x_lo, s->x_hi, s->win + s->off_ghost, 2 * s->mig_cap);
+}
+
+extern "C" int osph_slab_p2p_set_bounds(osph_ctx *ctx, osph_slab_p2p *s, double x_lo, double x_hi)
+{
+    if (!ctx || !s || !(x_lo < x_hi)) return OSPH_E_INVALID;
+    s->x_lo = x_lo; s->x_hi = x_hi;
+    return osph_slab_configure(ctx, x_lo, x_hi, s->win + s->off_ghost, 2 * s->mig_cap);
+}
+
+extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps, double fixed_dt, double damping)
+{
+    if (!ctx || !s) return OSPH_E_INVALID;
+    OSPH_CUDA(cudaSetDevice(ctx->device));
+    const int W = s->world, me = s->rank;
+    const int left = me > 0 ? me - 1 : -1, right = me < W - 1 ? me + 1 : -1;
+    const double q = s->kernel == OSPH_KERNEL_GAUSSIAN ? 3.0 : 2.0;
+    // where my outgoing records land: in the LEFT neighbour's "from right" regions and vice versa; without a
+    // neighbour nothing is ever written (the outer slabs are unbounded), any valid address will do
+    double *mig_l = left >= 0 ? s->peer[left] + s->off_mig_from_right : s->win + s->off_mig_from_left;
+    double *halo_l = left >= 0 ? s->peer[left] + s->off_halo_from_right : s->win + s->off_halo_from_left;
+    double *mig_r = right >= 0 ? s->peer[right] + s->off_mig_from_left : s->win + s->off_mig_from_right;
+    double *halo_r = right >= 0 ? s->peer[right] + s->off_halo_from_left : s->win + s->off_halo_from_right;
+    int rc;
+    for (int step = 0; step < nsteps; step++) {
+        s->seq++;
+        const int slot = (int)(s->seq & 1ull);
+        // ---- identical dt on every rank: mailbox all-gather + min ----
+        if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return rc;
+        k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, slot, s->d_dt3, 3, s->seq,
+                                                       s->d_all_dt, 1);
+        OSPH_LAUNCH_CHECK();
+        if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return rc;
+        // ---- classify + pack straight into the neighbours' windows; counts and bounds through the second mailbox ----
+        const double width = std::max(q * s->hmax, std::min(s->r0, 3.0 * s->hmax)) * 1.1;
+        if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return rc;
+        k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_meta, s->off_meta_flag, slot, s->d_meta, 12,
+                                                       s->seq, s->d_all_meta, 0);
+        OSPH_LAUNCH_CHECK();
+        OSPH_CUDA(cudaMemcpyAsync(s->h_all_meta, s->d_all_meta, sizeof(double) * 12 * W, cudaMemcpyDeviceToHost, ctx->stream));
+        OSPH_CUDA(cudaStreamSynchronize(ctx->stream));                  // the one host sync of the step
+        const double *M = s->h_all_meta;
+        double bounds[6];
+        for (int k = 0; k < 6; k++) { bounds[k] = M[4 + k]; for (int r = 1; r < W; r++) bounds[k] = std::min(bounds[k], M[12 * r + 4 + k]); }
+        for (int r = 0; r < W; r++)
+            if (M[12 * r + 10] != 0.0) { ctx->err = "slab exchange regions overflowed: raise the migrant / halo capacities"; return OSPH_E_CAPACITY; }
+        const double *mine = M + 12 * me;
+        const int64_t out_l = (int64_t)mine[0], out_r = (int64_t)mine[1], halo_out_l = (int64_t)mine[2], halo_out_r = (int64_t)mine[3];
+        const int64_t in_mig_l = left >= 0 ? (int64_t)M[12 * left + 1] : 0, in_halo_l = left >= 0 ? (int64_t)M[12 * left + 3] : 0;
+        const int64_t in_mig_r = right >= 0 ? (int64_t)M[12 * right + 0] : 0, in_halo_r = right >= 0 ? (int64_t)M[12 * right + 2] : 0;
+        s->hmax = -bounds[5];
+        GhostMap gm;
+        gm.c0 = (int)(out_l + out_r); gm.c1 = (int)in_halo_l;
+        gm.b1 = (long long)((s->off_halo_from_left - s->off_ghost) / OSPH_WIRE_HALO);
+        gm.b2 = (long long)((s->off_halo_from_right - s->off_ghost) / OSPH_WIRE_HALO);
+        const int64_t n_ghost = gm.c0 + in_halo_l + in_halo_r;
+        // ---- owned set update (migrants are already here), same grid everywhere, force evaluation, corrector ----
+        if ((rc = osph_slab_commit_impl(ctx, out_l + out_r, s->win + s->off_mig_from_left, in_mig_l,
+                                        s->win + s->off_mig_from_right, in_mig_r, gm, n_ghost, bounds))) return rc;
+        if ((rc = osph_slab_step_end(ctx, damping))) return rc;
+        const int64_t c[8] = {out_l, out_r, halo_out_l, halo_out_r, in_mig_l, in_mig_r, in_halo_l, in_halo_r};
+        memcpy(s->last_counts, c, sizeof(c));
+        s->steps++;
+    }
+    return 0;
+}
+
+extern "C" int osph_slab_p2p_last_counts(const osph_slab_p2p *s, int64_t out[8])
+{
+    if (!s) return OSPH_E_INVALID;
+    memcpy(out, s->last_counts, sizeof(s->last_counts));
+    return 0;
+}

@@ -335,7 +335,7 @@ __device__ __forceinline__ CellInfo cell_of(double x, double y, const GridParams
 template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, const double *__restrict__ ghost,
-       int n_all, const GridParams *__restrict__ gp, StepScalars *sc, unsigned int *__restrict__ key,
+       GhostMap gmap, int n_all, const GridParams *__restrict__ gp, StepScalars *sc, unsigned int *__restrict__ key,
        unsigned int *__restrict__ idx, int nblocks, unsigned int *__restrict__ hist)
 {
     constexpr int RADIX = 1 << BITS;
@@ -350,7 +350,7 @@ k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, 
         if (i >= n_all) continue;
         double px, py;
         if (i < n_owned) { px = x[i]; py = y[i]; }
-        else { const double *rec = ghost + (size_t)(i - n_owned) * OSPH_WIRE_HALO; px = rec[0]; py = rec[1]; }
+        else { const double *rec = ghost_record(ghost, gmap, i - n_owned); px = rec[0]; py = rec[1]; }
         CellInfo c = cell_of(px, py, g);
         unbinned |= !c.binned;
         key[i] = c.key; idx[i] = (unsigned int)i;
@@ -389,7 +389,7 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
         x = a.x[i]; y = a.y[i]; vx = a.vx[i]; vy = a.vy[i]; rho = a.rho[i]; m = a.m[i]; h = a.h[i];
         lab = a.label[i]; info = 2;                                   // bit1: owned = a target of the pair kernel
     } else {
-        const double *r = a.ghost + (size_t)(i - a.n_owned) * OSPH_WIRE_HALO;
+        const double *r = ghost_record(a.ghost, a.gmap, i - a.n_owned);
         x = r[0]; y = r[1]; vx = r[2]; vy = r[3]; rho = r[4]; m = r[5]; h = r[6]; lab = (int)r[7]; info = 0;
     }
     bool fluid = lab == OSPH_FLUID;
@@ -868,13 +868,13 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt)
         const int nblocks = div_up(n_all, SORT_TILE), db = osph_sort_digit_bits(ctx->key_bits);
         const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];
         if (db == 8)
-            k_keys<8><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, n_all, ctx->d_grid, ctx->d_sc,
+            k_keys<8><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid, ctx->d_sc,
                                                                  ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
         else if (db == 10)
-            k_keys<10><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, n_all, ctx->d_grid, ctx->d_sc,
+            k_keys<10><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid, ctx->d_sc,
                                                                   ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
         else
-            k_keys<11><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, n_all, ctx->d_grid, ctx->d_sc,
+            k_keys<11><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid, ctx->d_sc,
                                                                   ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
         OSPH_LAUNCH_CHECK();
     }
@@ -887,7 +887,7 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt)
     ctx->build_counter++;
 
     GatherArgs g;
-    g.n_owned = n; g.n_all = n_all; g.key = ctx->key[ctx->sorted_buf]; g.cell_range = ctx->cell_range; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label; g.ghost = ctx->d_ghost;
+    g.n_owned = n; g.n_all = n_all; g.key = ctx->key[ctx->sorted_buf]; g.cell_range = ctx->cell_range; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label; g.ghost = ctx->d_ghost; g.gmap = ctx->gmap;
     g.x = ctx->f[OSPH_F_X]; g.y = ctx->f[OSPH_F_Y]; g.vx = ctx->f[OSPH_F_VX]; g.vy = ctx->f[OSPH_F_VY];
     g.rho = ctx->f[OSPH_F_RHO]; g.m = ctx->f[OSPH_F_M]; g.h = ctx->f[OSPH_F_H]; g.p = ctx->f[OSPH_F_P];
     g.gp = ctx->d_grid;

@@ -30,6 +30,7 @@ struct GatherArgs {
     const unsigned int *idx;
     const signed char *label;
     const double *ghost;
+    GhostMap gmap;
     const double *x, *y, *vx, *vy, *rho, *m, *h;
     double *p;
     const GridParams *gp;
@@ -76,5 +77,8 @@ int osph_launch_probe(osph_ctx *ctx, int npts, const double *d_x, const double *
 int osph_launch_col_to_active(osph_ctx *ctx, int field, double *d_out);
 int osph_launch_col_from_active(osph_ctx *ctx, int field, const double *d_in);
 int osph_init_scalars(osph_ctx *ctx);
+// slab.cu: owned-set update after an exchange; migrants arrive in two buffers (from the left / right neighbour)
+int osph_slab_commit_impl(osph_ctx *ctx, int64_t n_mig_out, const double *d_in_l, int64_t n_in_l, const double *d_in_r,
+                          int64_t n_in_r, GhostMap gmap, int64_t n_ghost, const double global_bounds[6]);
 int osph_launch_fill(osph_ctx *ctx, double *d_col, double value);
 int osph_scan_exclusive(osph_ctx *ctx, unsigned int *d_data, int n);     // scan.cu, in place

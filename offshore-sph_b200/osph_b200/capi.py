@@ -123,6 +123,14 @@ def lib():
         'osph_slab_comm_set_bounds': (C.c_int, [ctx, C.c_void_p, dbl, dbl]),
         'osph_slab_run': (C.c_int, [ctx, C.c_void_p, i32, dbl, dbl]),
         'osph_slab_last_counts': (C.c_int, [C.c_void_p, ip]),
+        'osph_slab_p2p_create': (C.c_int, [ctx, C.c_int, C.c_int, dbl, dbl, dbl, dbl, i64, i64, C.POINTER(C.c_void_p),
+                                           C.c_char_p]),
+        'osph_slab_p2p_connect': (C.c_int, [ctx, C.c_void_p, C.c_char_p]),
+        'osph_slab_p2p_destroy': (C.c_int, [ctx, C.c_void_p]),
+        'osph_slab_p2p_attach': (C.c_int, [ctx, C.c_void_p]),
+        'osph_slab_p2p_set_bounds': (C.c_int, [ctx, C.c_void_p, dbl, dbl]),
+        'osph_slab_p2p_run': (C.c_int, [ctx, C.c_void_p, i32, dbl, dbl]),
+        'osph_slab_p2p_last_counts': (C.c_int, [C.c_void_p, ip]),
         'osph_leaf_kernel': (C.c_int, [C.c_int, C.c_int, C.c_int, i64, dp, dp, dp, dp]),
         'osph_leaf_tait_pressure': (C.c_int, [C.c_int, i64, dp, C.POINTER(C.c_int8), dbl, dbl, dbl, dbl, dp]),
         'osph_leaf_tait_height': (C.c_int, [C.c_int, i64, dp, dbl, dbl, dbl, dbl, dp]),
@@ -385,6 +393,32 @@ class Context:
         self._ck(self._L.osph_probe_pressure(self._h, x.size, x.ctypes.data_as(dp), y.ctypes.data_as(dp), float(h),
                                              rho.ctypes.data_as(dp), p.ctypes.data_as(dp)))
         return rho, p
+
+    # ---- slab decomposition over NVLink peer memory (CUDA IPC windows, mailbox kernels) ----
+    def slab_p2p_create(self, rank, world, x_lo, x_hi, r0, hmax, mig_cap, halo_cap):
+        h = C.c_void_p(); buf = C.create_string_buffer(64)
+        self._ck(self._L.osph_slab_p2p_create(self._h, rank, world, x_lo, x_hi, r0, hmax, mig_cap, halo_cap, C.byref(h), buf))
+        return h, buf.raw
+
+    def slab_p2p_connect(self, p2p, all_handles):
+        self._ck(self._L.osph_slab_p2p_connect(self._h, p2p, bytes(all_handles)))
+
+    def slab_p2p_destroy(self, p2p):
+        self._L.osph_slab_p2p_destroy(self._h, p2p)
+
+    def slab_p2p_attach(self, p2p):
+        self._ck(self._L.osph_slab_p2p_attach(self._h, p2p))
+
+    def slab_p2p_set_bounds(self, p2p, x_lo, x_hi):
+        self._ck(self._L.osph_slab_p2p_set_bounds(self._h, p2p, x_lo, x_hi))
+
+    def slab_p2p_run(self, p2p, nsteps, fixed_dt=None, damping=0.0):
+        self._ck(self._L.osph_slab_p2p_run(self._h, p2p, nsteps, -1.0 if fixed_dt is None else fixed_dt, damping))
+
+    def slab_p2p_last_counts(self, p2p):
+        out = (C.c_int64 * 8)()
+        self._L.osph_slab_p2p_last_counts(p2p, out)
+        return list(out)
 
     def timers(self):
         out = (C.c_double * 6)()

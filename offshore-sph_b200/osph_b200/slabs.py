@@ -13,6 +13,7 @@ The device work between the collectives is the C ABI's slab entry points (csrc/s
 sequences them.  `comm` is pluggable so the sequencing is unit-tested on CPU with gloo (tests/test_slabs_cpu.py).
 """
 import math
+import sys
 
 import numpy as np
 import torch
@@ -226,6 +227,57 @@ class NcclSlabRun:
             self.comm = None
 
 
+class P2PSlabRun(NcclSlabRun):
+    """Slab protocol over NVLink peer memory (osph_slab_p2p_run): IPC windows, the pack kernel writes into the
+    neighbours' HBM, mailbox kernels instead of NCCL collectives.  torch.distributed only all-gathers the 64-byte
+    IPC handles at start-up."""
+
+    def __init__(self, ctx, cuts, local_pA, local_ids, kernel, r0, hmax, device, group=None,
+                 mig_frac=0.02, ghost_frac=0.25, min_cap=4096):
+        self.ctx, self.kernel, self.r0 = ctx, kernel, r0
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.x_lo, self.x_hi = cuts[self.rank], cuts[self.rank + 1]
+        self.device = device
+        n = len(local_pA)
+        self.mig_cap = max(min_cap, int(n * mig_frac))
+        self.halo_cap = max(min_cap, int(n * ghost_frac))
+        self.ghost_cap = 2 * self.halo_cap + 2 * self.mig_cap
+        ctx.reserve(int(n * 1.3) + self.ghost_cap + 2 * self.mig_cap)
+        ctx.upload(local_pA)
+        ctx.set_row_ids(local_ids)
+        self.comm, handle = ctx.slab_p2p_create(self.rank, self.world, self.x_lo, self.x_hi, r0, float(hmax),
+                                                self.mig_cap, self.halo_cap)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device)
+        allh = torch.zeros(64 * self.world, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        ctx.slab_p2p_connect(self.comm, allh.cpu().numpy().tobytes())
+        dist.barrier(group=group)
+        self.steps = 0
+
+    def step(self, nsteps=1, fixed_dt=None, damping=0.0):
+        self.ctx.slab_p2p_run(self.comm, nsteps, fixed_dt, damping)
+        self.steps += nsteps
+
+    @property
+    def last_counts(self):
+        c = self.ctx.slab_p2p_last_counts(self.comm)
+        return dict(mig_out=(c[0], c[1]), halo_out=(c[2], c[3]), mig_in=(c[4], c[5]), halo_in=(c[6], c[7]),
+                    ghosts=c[0] + c[1] + c[6] + c[7], owned=self.ctx.num_active)
+
+    def reattach(self):
+        self.ctx.slab_p2p_attach(self.comm)
+
+    def set_bounds(self, x_lo, x_hi):
+        self.x_lo, self.x_hi = float(x_lo), float(x_hi)
+        self.ctx.slab_p2p_set_bounds(self.comm, self.x_lo, self.x_hi)
+
+    def close(self):
+        if self.comm is not None:
+            dist.barrier()                       # nobody may still be writing into a window that is about to go away
+            self.ctx.slab_p2p_destroy(self.comm)
+            self.comm = None
+
+
 def _export_device(ctx, device, fields):
     n = ctx.num_active
     ids = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
@@ -339,8 +391,25 @@ def bench_multi_gpu(args, rank, world, local):
     torch.cuda.set_stream(stream)
     if args.sequencer == 'python':
         run = SlabRun(ctx, TorchComm(), cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
-    else:
+    elif args.sequencer == 'nccl':
         run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+    else:
+        # default: NVLink peer-memory exchange; if CUDA IPC is not usable between the ranks (e.g. GPUs without peer
+        # access), every rank falls back to the NCCL sequencer together
+        run, err = None, None
+        try:
+            run = P2PSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+        except Exception as e:      # noqa: BLE001
+            err = e
+        ok = torch.tensor([1 if run is not None else 0], device='cuda')
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            if run is not None:
+                run.close()
+            if rank == 0:
+                print("bench: peer-memory sequencer unavailable (%s); using NCCL" % err, file=sys.stderr)
+            args.sequencer = 'nccl'
+            run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
 
     clocks = B.ClockSampler(local) if rank == 0 else None
     run.step(args.warmup, None, B.DAMPING)

@@ -34,6 +34,7 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok = True
     for kernel, prec, tol, seq in (('wendland', capi.FP64, 1e-11, 'nccl'), ('wendland', capi.FP64, 1e-11, 'python'),
+                                   ('wendland', capi.FP64, 1e-11, 'p2p'), ('cubic', capi.FP64, 1e-11, 'p2p'),
                                    ('cubic', capi.FP64, 1e-11, 'nccl'), ('gaussian', capi.FP32, 2e-3, 'nccl')):
         case = W.dam_break_case(a.side, seed=11)
         # give the fluid a push towards +x so particles cross the slab faces during the run
@@ -52,6 +53,8 @@ def main():
         if seq == 'python':
             run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'],
                                 torch.device('cuda', local))
+        elif seq == 'p2p':
+            run = slabs.P2PSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cuda', local))
         else:
             run = slabs.NcclSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cuda', local))
         moved = 0
