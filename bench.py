@@ -91,7 +91,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    case = build_case(args.particles_per_side)
+    # same workload as the GPU arm at this GPU count (weak scaling: N * sqrt(gpus) particles per side)
+    n_side = args.particles_per_side if (args.total_side or args.gpus <= 1) else \
+        int(round(args.particles_per_side * (args.gpus ** 0.5)))
+    case = build_case(n_side)
     n = len(case['pA'])
     from oracle import oracle as O
     O.build()
@@ -107,8 +110,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.particles_per_side, n, args.kernel, "FP64")},
+        "scaling": "strong" if args.total_side else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n_side, n, args.kernel, "FP64"), "particles": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -41,14 +41,14 @@ struct PhaseTimer {
 
 static void free_particles(osph_ctx *ctx)
 {
-    cudaFree(ctx->d_aos); cudaFree(ctx->d_row); cudaFree(ctx->d_act); cudaFree(ctx->d_slot_of_act);
+    cudaFree(ctx->d_aos); cudaFree(ctx->d_row); cudaFree(ctx->d_act);
     for (int k = 0; k < OSPH_NUM_FIELDS; k++) { cudaFree(ctx->f[k]); ctx->f[k] = nullptr; }
     cudaFree(ctx->label); cudaFree(ctx->scratch); cudaFree(ctx->d_stage);
     cudaFree(ctx->s_coarse); cudaFree(ctx->s_gcell); cudaFree(ctx->s_pos); cudaFree(ctx->s_vel);
     cudaFree(ctx->s_rm); cudaFree(ctx->s_hp); cudaFree(ctx->s_info);
     cudaFree(ctx->d_partial);
     osph_sort_free(ctx);
-    ctx->d_aos = nullptr; ctx->d_row = ctx->d_act = ctx->d_slot_of_act = nullptr; ctx->label = nullptr;
+    ctx->d_aos = nullptr; ctx->d_row = ctx->d_act = nullptr; ctx->label = nullptr;
     ctx->scratch = ctx->d_stage = nullptr; ctx->s_coarse = nullptr; ctx->s_gcell = nullptr; ctx->s_pos = nullptr;
     ctx->s_vel = ctx->s_rm = ctx->s_hp = nullptr; ctx->s_info = nullptr;
     ctx->d_partial = nullptr;
@@ -65,7 +65,6 @@ static int alloc_particles(osph_ctx *ctx, int64_t n_active, int64_t n_total, int
     OSPH_CUDA(cudaMalloc(&ctx->d_aos, std::max<size_t>(aos_bytes, 16)));
     OSPH_CUDA(cudaMalloc(&ctx->d_row, sizeof(int) * cap));
     OSPH_CUDA(cudaMalloc(&ctx->d_act, sizeof(int) * cap));
-    OSPH_CUDA(cudaMalloc(&ctx->d_slot_of_act, sizeof(int) * cap));
     for (int k = 0; k < OSPH_NUM_FIELDS; k++) OSPH_CUDA(cudaMalloc(&ctx->f[k], sizeof(double) * cap));
     OSPH_CUDA(cudaMalloc(&ctx->label, cap));
     OSPH_CUDA(cudaMalloc(&ctx->scratch, sizeof(double) * cap));
@@ -192,7 +191,7 @@ static int ingest(osph_ctx *ctx, const void *src, bool src_on_device, int64_t n,
     if (counters[0] != ctx->n) ctx->sized = false;
     ctx->n = counters[0]; ctx->n_fluid = counters[1];
     if (ctx->n > 0 && (rc = osph_launch_unpack(ctx))) return rc;
-    ctx->c_uniform = false; ctx->build_counter = 0; ctx->n_ghost = 0; ctx->slab = false; ctx->slot_of_act_valid = false;
+    ctx->c_uniform = false; ctx->build_counter = 0; ctx->n_ghost = 0; ctx->slab = false;
     invalidate_state(ctx);
     return 0;
 }

@@ -48,7 +48,7 @@ struct StepScalars {
     unsigned long long hmax_all;                 // max h over active, after refresh
     unsigned long long hmin_fluid, cmax_fluid, a2max_fluid;   // TimeStep.computeVars
     unsigned int status;                         // OSPH_S_* bits
-    unsigned int n_fluid_seen;
+    unsigned int reserved;
     double dt[3];                                // {dt, dt_c, dt_f} of the current step
     double ke;
     long long dt_log_count;
@@ -70,8 +70,6 @@ struct osph_ctx {
     unsigned char *d_aos = nullptr;  // n_total * stride bytes
     int *d_row = nullptr;            // storage slot -> row of the host array
     int *d_act = nullptr;            // storage slot -> index in the compacted active array
-    int *d_slot_of_act = nullptr;    // active index -> storage slot (rebuilt lazily)
-    bool slot_of_act_valid = false;
 
     // state, SoA, storage order (OSPH_NUM_FIELDS columns of doubles + label)
     double *f[OSPH_NUM_FIELDS] = {nullptr};

@@ -149,7 +149,6 @@ __global__ void k_reset_prepare_scalars(StepScalars *sc)
 __global__ void k_reset_dt_scalars(StepScalars *sc)
 {
     sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF;
-    sc->n_fluid_seen = 0;
 }
 __global__ void k_init_scalars(StepScalars *sc)
 {
@@ -255,8 +254,7 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
 {
     if (reset_dt) {           // folded k_reset_dt_scalars: the corrector of this step reduces into these
         sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF;
-        sc->n_fluid_seen = 0;
-    }
+        }
     double xmin = dec_f64(sc->xmin), xmax = dec_f64(sc->xmax), ymin = dec_f64(sc->ymin), ymax = dec_f64(sc->ymax);
     double hmin = dec_f64(sc->hmin_all), hmax = dec_f64(sc->hmax_all);
     g->xmin = xmin; g->xmax = xmax; g->ymin = ymin; g->ymax = ymax; g->hmax = hmax;
@@ -425,11 +423,6 @@ __global__ void k_iota(unsigned int *__restrict__ idx, int n)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) idx[s] = (unsigned int)s;
-}
-__global__ void k_invert_act(const int *__restrict__ act, int n, int *__restrict__ slot_of_act)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) slot_of_act[act[i]] = i;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -846,7 +839,6 @@ static int reorder_state(osph_ctx *ctx)
     OSPH_CUDA(cudaMemcpyAsync(ctx->d_row, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_act, perm, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
     OSPH_CUDA(cudaMemcpyAsync(ctx->d_act, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
-    ctx->slot_of_act_valid = false;
     return 0;
 }
 
