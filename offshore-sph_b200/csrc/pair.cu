@@ -131,12 +131,10 @@ k_pair(PairArgs a)
     }
     const int len0 = max(uhi0 - ulo0, 0), len1 = max(uhi1 - ulo1, 0), len2 = max(uhi2 - ulo2, 0);
 
-    const Real alpha_c = (Real)(a.alpha * a.c_half);      // alpha * 0.5 * c_i  (comp.c is never filled)
-    const Real beta = (Real)a.beta;
-    const Real r0 = (Real)a.r0, r0sq = r0 * r0;
-    const Real neg_eps = -(Real)a.eps;
+    // alpha_c = alpha * 0.5 * c_i (comp.c is never filled); all of these come straight from the constant bank
+#define PC(name) (sizeof(Real) == 8 ? (Real)a.name##_d : (Real)a.name##_f)
     const bool use_xsph = a.method_xsph != 0;
-    Real drho = 0, ax = 0, ay = 0, bx = 0, by = 0, xs = 0, ys = 0;
+    Real drho = 0, ax = 0, ay = 0, xs = 0, ys = 0;          // the wall force is accumulated into (ax, ay) as well
 
     // stage sorted particles [g0, g0 + cnt) into records [dst, dst + cnt)
     auto stage = [&](int g0, int cnt, int dst) {
@@ -173,7 +171,7 @@ k_pair(PairArgs a)
         // kernel support (q <= 2, or the q <= 3 cut of the Gaussian, which IS the set boundary: keep a band for the
         // exact test) and Lennard-Jones range
         const bool kern = r2 <= h2 * (KID == OSPH_KERNEL_GAUSSIAN ? Real(9.0 * (1.0 + 1e-6)) : Real(4));
-        const bool lj = !fluid_j && r2 <= r0sq;
+        const bool lj = !fluid_j && r2 <= PC(r0sq);
         bool ok = kern || lj;
         // membership in the reference neighbour set: q <= 3 (it can only fail for LJ pairs and at the Gaussian cut)
         if constexpr (EXACT) {
@@ -206,20 +204,20 @@ k_pair(PairArgs a)
         // artificial viscosity only for approaching pairs: min(dot, 0) makes it branch-free
         const Real dot = fmin(dvx * dx + dvy * dy, Real(0));
         const Real mu = hbar * dot * inv_den;
-        const Real PIij = mu * (beta * mu - alpha_c) * inv_rbar;
+        const Real PIij = mu * (PC(beta) * mu - PC(alpha_c)) * inv_rbar;
         const Real fac = mjf * (slf + hpj.y + PIij);
         ax -= fac * dwx; ay -= fac * dwy;
         if (use_xsph) {
-            const Real fx = neg_eps * mj * w * inv_rbar;
+            const Real fx = PC(neg_eps) * mj * w * inv_rbar;
             xs += fx * dvx; ys += fx * dvy;
         }
         if (lj && r2 > Real(1e-24)) {                              // wall / coupled particle inside r0
-            const Real frac = r0 * inv_rt;
+            const Real frac = PC(r0) * inv_rt;
             Real tmp;
             if (a.lj_42) { const Real f2 = frac * frac; tmp = f2 * f2 - f2; }
             else tmp = pow_gen(frac, (Real)a.p1) - pow_gen(frac, (Real)a.p2);
-            const Real fl = (Real)a.D * tmp * inv_rt * inv_rt;
-            bx += fl * dx; by += fl * dy;
+            const Real fl = PC(D) * tmp * inv_rt * inv_rt;
+            ax += fl * dx; ay += fl * dy;
         }
     };
 
@@ -285,8 +283,8 @@ k_pair(PairArgs a)
     if (fluid_i) {
         const int slot = (int)a.idx[s];
         a.drho[slot] = a.summation_density ? 0.0 : (double)drho;
-        a.ax[slot] = (double)ax + (double)bx;
-        a.ay[slot] = ((double)ay - a.gravity) + (double)by;
+        a.ax[slot] = (double)ax;
+        a.ay[slot] = (double)ay - a.gravity;
         if (a.method_xsph) {
             a.xsphx[slot] = a.vx[slot] + (double)xs;
             a.xsphy[slot] = a.vy[slot] + (double)ys;
@@ -404,6 +402,9 @@ int osph_launch_pair(osph_ctx *ctx)
     a.alpha = c.alpha; a.beta = c.beta; a.c_half = 0.5 * c.co; a.eps = c.epsilon;
     a.r0 = c.r0; a.D = c.D; a.p1 = c.p1; a.p2 = c.p2; a.gravity = c.gravity;
     a.lj_42 = (c.p1 == 4.0 && c.p2 == 2.0) ? 1 : 0;
+    a.alpha_c_d = c.alpha * 0.5 * c.co; a.beta_d = c.beta; a.r0_d = c.r0; a.r0sq_d = c.r0 * c.r0; a.neg_eps_d = -c.epsilon; a.D_d = c.D;
+    a.alpha_c_f = (float)a.alpha_c_d; a.beta_f = (float)c.beta; a.r0_f = (float)c.r0; a.r0sq_f = a.r0_f * a.r0_f;
+    a.neg_eps_f = (float)a.neg_eps_d; a.D_f = (float)c.D;
     a.method_xsph = c.method_xsph; a.summation_density = c.summation_density;
     int grid = div_up(ctx->n + ctx->n_ghost, OSPH_PAIR_THREADS);
     if (c.summation_density) {

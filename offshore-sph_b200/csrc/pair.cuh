@@ -16,4 +16,8 @@ struct PairArgs {
     double *drho, *ax, *ay, *xsphx, *xsphy;
     double alpha, beta, c_half, eps, r0, D, p1, p2, gravity;
     int lj_42, method_xsph, summation_density;
+    // loop constants precomputed on the host in both precisions: as kernel parameters they are constant-bank operands
+    // of the FP instructions and do not occupy registers in the pair loop
+    double alpha_c_d, beta_d, r0_d, r0sq_d, neg_eps_d, D_d;
+    float alpha_c_f, beta_f, r0_f, r0sq_f, neg_eps_f, D_f;
 };
