@@ -42,14 +42,26 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+WORKLOAD = "dam_break"      # set from --workload: dam_break (BASELINE configs[0,1,4]) | containment (configs[2]) | icebreak (configs[3])
+
+
 def build_case(n_side, seed=0):
+    """Synthetic particle block after Solver.setup() + deterministic jitter."""
     from osph_b200 import workloads as W
+    if WORKLOAD == "containment":          # closed tank, dynamic h = 1.3 sqrt(m/rho), XSPH off (examples/Containment.py)
+        return W.tank_case(n_side, h=None, useXSPH=False, seed=seed)
+    if WORKLOAD == "icebreak":             # tank with a floating row of Coupled particles (examples/IceBreak.py geometry)
+        return W.tank_case(n_side, width=60.0, height=10.0, h=1.3 * 60.0 / n_side, useXSPH=True, seed=seed, coupled_row=True)
     return W.dam_break_case(n_side, seed=seed)
 
 
 def workload_name(n_side, n, kernel, prec):
-    return "dam_break N=%d (%d particles), %s spline, PEC, XSPH, h=1.6 r0, %s" % (
-        n_side, n, {'cubic': 'cubic', 'wendland': 'Wendland', 'gaussian': 'Gaussian'}[kernel], prec)
+    k = {'cubic': 'cubic spline', 'wendland': 'Wendland', 'gaussian': 'Gaussian'}[kernel]
+    if WORKLOAD == "containment":
+        return "containment tank Nx=%d (%d particles), %s, PEC, no XSPH, dynamic h, %s" % (n_side, n, k, prec)
+    if WORKLOAD == "icebreak":
+        return "ice-break tank Nx=%d (%d particles incl. coupled ice row), %s, PEC, XSPH, %s" % (n_side, n, k, prec)
+    return "dam_break N=%d (%d particles), %s, PEC, XSPH, h=1.6 r0, %s" % (n_side, n, k, prec)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,6 +332,9 @@ def main():
     ap.add_argument("--kernel", default="cubic", choices=["cubic", "wendland", "gaussian"])
     ap.add_argument("--particles-per-side", type=int, default=1000,
                     help="N of the dam-break generator (N x N fluid particles); 1000 = BASELINE configs[1]")
+    ap.add_argument("--workload", default="dam_break", choices=["dam_break", "containment", "icebreak"],
+                    help="dam_break = BASELINE configs[0,1,4] (default, the metric's workload); containment = configs[2] "
+                         "(use --particles-per-side 2000 --precision fp32); icebreak = configs[3] (--particles-per-side 4900)")
     ap.add_argument("--total-side", action="store_true",
                     help="multi-GPU: --particles-per-side is the TOTAL problem (strong scaling) instead of per-GPU "
                          "N*sqrt(gpus) (weak scaling, default)")
@@ -329,6 +344,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -380,9 +380,11 @@ def bench_multi_gpu(args, rank, world, local):
     prec = capi.FP64 if args.precision == "fp64" else capi.FP32
     F = 8 if prec == capi.FP64 else 4
     n_side = args.particles_per_side if args.total_side else int(round(args.particles_per_side * math.sqrt(world)))
+    B.WORKLOAD = getattr(args, 'workload', 'dam_break')
     case = B.build_case(n_side)
     pA, c = case['pA'], case['consts']
     n_total = len(pA)
+    hmax0 = case['h'] if case['h'] is not None else float(pA['h'].max())
     cuts, local_pA, ids = partition(pA, world, rank)
     del pA
     cfg = capi.make_config(c, args.kernel, 'pec', prec, case['h'], device=local)
@@ -390,15 +392,15 @@ def bench_multi_gpu(args, rank, world, local):
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     torch.cuda.set_stream(stream)
     if args.sequencer == 'python':
-        run = SlabRun(ctx, TorchComm(), cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+        run = SlabRun(ctx, TorchComm(), cuts, local_pA, ids, args.kernel, case['r0'], hmax0, torch.device('cuda', local))
     elif args.sequencer == 'nccl':
-        run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+        run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], hmax0, torch.device('cuda', local))
     else:
         # default: NVLink peer-memory exchange; if CUDA IPC is not usable between the ranks (e.g. GPUs without peer
         # access), every rank falls back to the NCCL sequencer together
         run, err = None, None
         try:
-            run = P2PSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+            run = P2PSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], hmax0, torch.device('cuda', local))
         except Exception as e:      # noqa: BLE001
             err = e
         ok = torch.tensor([1 if run is not None else 0], device='cuda')
@@ -409,7 +411,7 @@ def bench_multi_gpu(args, rank, world, local):
             if rank == 0:
                 print("bench: peer-memory sequencer unavailable (%s); using NCCL" % err, file=sys.stderr)
             args.sequencer = 'nccl'
-            run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], case['h'], torch.device('cuda', local))
+            run = NcclSlabRun(ctx, cuts, local_pA, ids, args.kernel, case['r0'], hmax0, torch.device('cuda', local))
 
     clocks = B.ClockSampler(local) if rank == 0 else None
     run.step(args.warmup, None, B.DAMPING)
