@@ -12,6 +12,8 @@
 // which this rank contributes only after its step k has completed (stream order), so readers and writers of a
 // region never overlap.
 // NCCL (slab_nccl.cu) stays as the portable sequencer; this one needs all ranks on one NVLink/NVSwitch box.
+#include <stdio.h>
+
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -90,6 +92,7 @@ extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x
     s->kernel = ctx->cfg.kernel; s->mig_cap = mig_cap; s->halo_cap = halo_cap;
     size_t o = 0;
     auto take = [&](size_t doubles) { size_t at = o; o += (doubles + 15) / 16 * 16; return at; };
+    const size_t off_header = take(16);                                           // {world, mig_cap, halo_cap}: layout check
     s->off_dt = take((size_t)2 * world * MBOX_STRIDE); s->off_dt_flag = take((size_t)2 * world);
     s->off_meta = take((size_t)2 * world * MBOX_STRIDE); s->off_meta_flag = take((size_t)2 * world);
     s->off_ghost = take((size_t)2 * mig_cap * OSPH_WIRE_HALO);                   // this rank's own migrants, kept as ghosts
@@ -100,6 +103,8 @@ extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x
     s->win_doubles = o;
     OSPH_CUDA(cudaMalloc(&s->win, sizeof(double) * o));
     OSPH_CUDA(cudaMemset(s->win, 0, sizeof(double) * o));
+    const double header[3] = {(double)world, (double)mig_cap, (double)halo_cap};
+    OSPH_CUDA(cudaMemcpy(s->win + off_header, header, sizeof(header), cudaMemcpyHostToDevice));
     OSPH_CUDA(cudaMalloc(&s->d_peer, sizeof(double *) * world));
     OSPH_CUDA(cudaMalloc(&s->d_meta, sizeof(double) * MBOX_STRIDE));
     OSPH_CUDA(cudaMalloc(&s->d_all_meta, sizeof(double) * MBOX_STRIDE * (world + 1)));
@@ -125,6 +130,13 @@ extern "C" int osph_slab_p2p_connect(osph_ctx *ctx, osph_slab_p2p *s, const char
         void *p = nullptr;
         OSPH_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         s->peer[r] = (double *)p;
+        // every rank addresses its peers' windows with its own offsets: the layouts must be identical
+        double header[3] = {0, 0, 0};
+        OSPH_CUDA(cudaMemcpy(header, s->peer[r], sizeof(header), cudaMemcpyDeviceToHost));
+        if (header[0] != (double)s->world || header[1] != (double)s->mig_cap || header[2] != (double)s->halo_cap) {
+            ctx->err = "osph_slab_p2p_connect: ranks were created with different world size / region capacities";
+            return OSPH_E_INVALID;
+        }
     }
     OSPH_CUDA(cudaMemcpy(s->d_peer, s->peer, sizeof(double *) * s->world, cudaMemcpyHostToDevice));
     return osph_slab_configure(ctx, s->x_lo, s->x_hi, s->win + s->off_ghost, 2 * s->mig_cap);
@@ -189,7 +201,14 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         double bounds[6];
         for (int k = 0; k < 6; k++) { bounds[k] = M[4 + k]; for (int r = 1; r < W; r++) bounds[k] = std::min(bounds[k], M[12 * r + 4 + k]); }
         for (int r = 0; r < W; r++)
-            if (M[12 * r + 10] != 0.0) { ctx->err = "slab exchange regions overflowed: raise the migrant / halo capacities"; return OSPH_E_CAPACITY; }
+            if (M[12 * r + 10] != 0.0) {
+                char msg[320];
+                snprintf(msg, sizeof msg, "slab exchange regions overflowed on rank %d at step %lld: migrants %.0f/%.0f (cap %lld), "
+                         "halo %.0f/%.0f (cap %lld), flag %.3g, seq %llu", r, (long long)s->steps, M[12 * r], M[12 * r + 1],
+                         (long long)s->mig_cap, M[12 * r + 2], M[12 * r + 3], (long long)s->halo_cap, M[12 * r + 10], s->seq);
+                ctx->err = msg;
+                return OSPH_E_CAPACITY;
+            }
         const double *mine = M + 12 * me;
         const int64_t out_l = (int64_t)mine[0], out_r = (int64_t)mine[1], halo_out_l = (int64_t)mine[2], halo_out_r = (int64_t)mine[3];
         const int64_t in_mig_l = left >= 0 ? (int64_t)M[12 * left + 1] : 0, in_halo_l = left >= 0 ? (int64_t)M[12 * left + 3] : 0;

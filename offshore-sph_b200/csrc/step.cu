@@ -234,7 +234,10 @@ k_prepare(PrepareArgs a)
                 a.h[i] = h;
             }
         }
-        bx = x; Bx = x; by = y; By = y; hmx = h;
+        // a particle that has left the floating-point line must not define the grid (it is parked in the overflow cell)
+        if (isfinite(x) && isfinite(y)) { bx = x; Bx = x; by = y; By = y; }
+        else atomicOr(&a.sc->status, OSPH_S_NONFINITE);
+        hmx = h;
     }
     double v[6] = {bx, by, hmn, Bx, By, hmx};
     unsigned long long *const p[6] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all,
@@ -279,17 +282,23 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
     long long gnx, gny;
     if (regime_a) { gnx = ncx; gny = ncy; }
     else {
+        // cells of the pair radius; if the table cannot hold them (the domain grew since it was sized) coarsen in one
+        // shot to the cell size that fits, then nudge
+        const double ex = fmax(xmax - xmin, 0.0), ey = fmax(ymax - ymin, 0.0);
+        const double fit = sqrt((ex + gs) * (ey + gs) / (0.9 * (double)(cell_cap - 2)));
+        if (gs < fit) { gs = fit; atomicOr(&sc->status, OSPH_S_GRID_COARSE); }
         for (int it = 0; it < 64; it++) {
-            gnx = (long long)floor((xmax - xmin) / gs) + 1;
-            gny = (long long)floor((ymax - ymin) / gs) + 1;
+            gnx = (long long)floor(ex / gs) + 1;
+            gny = (long long)floor(ey / gs) + 1;
             if (gnx * gny + 1 <= cell_cap) break;
-            gs *= 1.25;                                // coarsen until the table fits
-            atomicOr(&sc->status, OSPH_S_GRID_COARSE);
+            gs *= 1.1;
         }
     }
-    if (gnx * gny + 1 > cell_cap) {                    // regime A cannot be coarsened
+    if (!(gnx >= 1 && gny >= 1 && gnx * gny + 1 <= cell_cap) || !isfinite(gs)) {
+        // regime A cannot be coarsened (it IS the reference grid), or the bounds are unusable
         atomicOr(&sc->status, 0x80000000u);
-        gnx = 1; gny = 1; gs = fmax(xmax - xmin, ymax - ymin) + 1.0; regime_a = 0;
+        gnx = 1; gny = 1; gs = fmax(fmax(xmax - xmin, ymax - ymin), 0.0) + 1.0; regime_a = 0;
+        if (!isfinite(gs)) gs = 1.0;
     }
     g->regime_a = regime_a; g->gsize = gs; g->ginv = 1.0 / gs; g->gnx = (int)gnx; g->gny = (int)gny;
     double rs = 3.0 * hmax * (1.0 + 1e-6);
@@ -316,6 +325,12 @@ __device__ __forceinline__ CellInfo cell_of(double x, double y, const GridParams
     c.coarse.x = c.binned ? (int)(flat % g.ncx) : -1000000;
     c.coarse.y = c.binned ? (int)(flat / g.ncx) : -1000000;
     c.coarse.z = (int)cx; c.coarse.w = (int)cy;
+    if (!(isfinite(x) && isfinite(y))) {                                        // parked: never found, finds nothing
+        c.binned = false; c.coarse = make_int4(-1000000, -1000000, -1000000, -1000000);
+        c.gcell = make_int2(-1000000, -1000000);
+        c.key = (unsigned int)g.gnx * (unsigned int)g.gny;                      // the extra cell behind the table
+        return c;
+    }
     if (g.regime_a) {
         c.gcell = make_int2((int)cx, (int)cy);                                  // query cell: raw reference ids
         c.key = c.binned ? (unsigned int)flat : (unsigned int)g.n_cells;        // bin cell: the reference's flat id

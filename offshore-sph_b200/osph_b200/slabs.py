@@ -241,6 +241,10 @@ class P2PSlabRun(NcclSlabRun):
         n = len(local_pA)
         self.mig_cap = max(min_cap, int(n * mig_frac))
         self.halo_cap = max(min_cap, int(n * ghost_frac))
+        # every rank addresses its neighbours' windows with its OWN layout, so the region capacities must be identical
+        caps = torch.tensor([self.mig_cap, self.halo_cap], dtype=torch.int64, device=device)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)
+        self.mig_cap, self.halo_cap = int(caps[0]), int(caps[1])
         self.ghost_cap = 2 * self.halo_cap + 2 * self.mig_cap
         ctx.reserve(int(n * 1.3) + self.ghost_cap + 2 * self.mig_cap)
         ctx.upload(local_pA)

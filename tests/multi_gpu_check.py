@@ -54,7 +54,9 @@ def main():
             run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'],
                                 torch.device('cuda', local))
         elif seq == 'p2p':
-            run = slabs.P2PSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cuda', local))
+            # capacities derived from the (rank-dependent) local counts: the ranks must agree on one window layout
+            run = slabs.P2PSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cuda', local),
+                                   mig_frac=0.2, ghost_frac=0.5, min_cap=256)
         else:
             run = slabs.NcclSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cuda', local))
         moved = 0
