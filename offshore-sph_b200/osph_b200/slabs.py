@@ -492,8 +492,9 @@ def bench_multi_gpu(args, rank, world, local):
                        "particles": n_total, "particles_per_gpu": [int(v) for v in per[:, 0]],
                        "ghosts_per_gpu": [int(v) for v in per[:, 1]], "damping": B.DAMPING, "dt": "dynamic",
                        "l2": "per-GPU working set exceeds the 126 MB L2",
-                       "parallelism": "1-D slabs along x, %d ranks, NCCL halo + migration (%s sequencer), fluid-quantile cuts"
-                                      % (world, args.sequencer)},
+                       "parallelism": "1-D slabs along x, %d ranks, halo + migration over %s, fluid-quantile cuts" % (
+                           world, {"p2p": "NVLink peer-memory windows (mailbox kernels, pack kernel writes into peers)",
+                                   "nccl": "NCCL send/recv sequenced in C++", "python": "NCCL via torch.distributed"}[args.sequencer])},
             "clocks": clk, "gpu_launches": int(per[:, 2].sum()),
             "e2e": {"value": n_total * e2e_steps / float(t_e2e.item()), "unit": B.UNIT,
                     "h2d_bytes_per_step": int(mv.item()), "d2h_bytes_per_step": int(mv.item()), "steps": e2e_steps,
