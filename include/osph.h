@@ -136,6 +136,18 @@ int osph_export_device_aos(osph_ctx *ctx, void *d_pA, int64_t n, int64_t stride)
 int osph_download_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, double *const *cols);
 /* Overwrite columns of the active particles from host arrays in active order (coupling write-back). */
 int osph_upload_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, const double *const *cols);
+/*
+ * Asynchronous, double-buffered form of osph_download_fields.  osph_export_begin snapshots the columns in stream
+ * order (later steps may change the state) and starts their device->host copy on a separate copy stream into
+ * pinned memory owned by the library; it returns at once with a ticket.  osph_export_end(ticket) waits for that
+ * copy only and writes cols[k][0..n).  row_space == 0: active particles in active order, n = osph_num_active at the
+ * time of the begin (as osph_download_fields).  row_space != 0: one value per ROW of the uploaded array in host row
+ * order, n = rows uploaded; deleted rows carry the uploaded value -- exactly the array Solver._store appends, with no
+ * host-side merge.  Two tickets may be in flight; a third begin returns OSPH_E_CAPACITY until the oldest is ended.
+ * replaces: the blocking per-step copy of Solver._store (src/Solver.py:477-486) -- SURVEY section 8(f) rank 2.
+ */
+int osph_export_begin(osph_ctx *ctx, int32_t nfields, const int32_t *fields, int32_t row_space, int64_t *ticket);
+int osph_export_end(osph_ctx *ctx, int64_t ticket, int32_t nfields, double *const *cols, int64_t n);
 int64_t osph_num_active(const osph_ctx *ctx);
 int64_t osph_num_fluid(const osph_ctx *ctx);
 

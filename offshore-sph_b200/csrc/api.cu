@@ -149,6 +149,7 @@ extern "C" int osph_destroy(osph_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     PhaseTimer::drain(ctx);
+    osph_export_free(ctx);
     free_particles(ctx);
     cudaFree(ctx->cell_range); cudaFree(ctx->d_grid); cudaFree(ctx->d_sc); cudaFree(ctx->d_dt_log);
     cudaFree(ctx->scan_block); cudaFree(ctx->d_slab_counters); cudaFree(ctx->d_mig_slots); cudaFree(ctx->d_tail_flag);

@@ -54,6 +54,8 @@ struct StepScalars {
     long long dt_log_count;
 };
 
+struct osph_export_ring;          // export.cu
+
 struct osph_ctx {
     osph_config cfg;
     int device = 0;
@@ -137,7 +139,11 @@ struct osph_ctx {
     // pinned staging for transfers
     unsigned char *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
+
+    osph_export_ring *xring = nullptr;   // asynchronous column export (export.cu), created on first use
 };
+
+void osph_export_free(osph_ctx *ctx);
 
 #define OSPH_CUDA(call)                                                                    \
     do {                                                                                   \
@@ -219,3 +225,21 @@ int osph_sort_pairs(osph_ctx *ctx, int64_t n, int bits, bool first_hist_done);  
 int osph_sort_alloc(osph_ctx *ctx, int64_t cap);
 void osph_sort_free(osph_ctx *ctx);
 int osph_launch_pair(osph_ctx *ctx);                                      // pair.cu
+
+#ifdef __CUDACC__
+// The reference record is packed (154 bytes, src/Common.py:26-57): its doubles sit at 2-byte alignment only.
+__device__ __forceinline__ double load_f64_unaligned(const unsigned char *p)
+{
+    const unsigned short *s = reinterpret_cast<const unsigned short *>(p);
+    unsigned long long u = (unsigned long long)s[0] | ((unsigned long long)s[1] << 16) |
+                           ((unsigned long long)s[2] << 32) | ((unsigned long long)s[3] << 48);
+    return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ void store_f64_unaligned(unsigned char *p, double v)
+{
+    unsigned short *s = reinterpret_cast<unsigned short *>(p);
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    s[0] = (unsigned short)u; s[1] = (unsigned short)(u >> 16);
+    s[2] = (unsigned short)(u >> 32); s[3] = (unsigned short)(u >> 48);
+}
+#endif

@@ -14,20 +14,6 @@
 // K10: packed 154-byte records <-> SoA columns.  Doubles sit at byte offset 2 + 8k (2-byte aligned
 // only), so they are moved as four 16-bit words.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double load_f64_unaligned(const unsigned char *p)
-{
-    const unsigned short *s = reinterpret_cast<const unsigned short *>(p);
-    unsigned long long u = (unsigned long long)s[0] | ((unsigned long long)s[1] << 16) |
-                           ((unsigned long long)s[2] << 32) | ((unsigned long long)s[3] << 48);
-    return __longlong_as_double((long long)u);
-}
-__device__ __forceinline__ void store_f64_unaligned(unsigned char *p, double v)
-{
-    unsigned short *s = reinterpret_cast<unsigned short *>(p);
-    unsigned long long u = (unsigned long long)__double_as_longlong(v);
-    s[0] = (unsigned short)u; s[1] = (unsigned short)(u >> 16);
-    s[2] = (unsigned short)(u >> 32); s[3] = (unsigned short)(u >> 48);
-}
 
 struct Columns { double *f[OSPH_NUM_FIELDS]; };
 

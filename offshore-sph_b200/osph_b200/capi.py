@@ -84,6 +84,8 @@ def lib():
         'osph_export_device_aos': (C.c_int, [ctx, C.c_void_p, i64, i64]),
         'osph_download_fields': (C.c_int, [ctx, i32, C.POINTER(i32), C.POINTER(dp)]),
         'osph_upload_fields': (C.c_int, [ctx, i32, C.POINTER(i32), C.POINTER(dp)]),
+        'osph_export_begin': (C.c_int, [ctx, i32, C.POINTER(i32), i32, ip]),
+        'osph_export_end': (C.c_int, [ctx, i64, i32, C.POINTER(dp), i64]),
         'osph_num_active': (i64, [ctx]),
         'osph_num_fluid': (i64, [ctx]),
         'osph_initialize': (C.c_int, [ctx]),
@@ -230,6 +232,21 @@ class Context:
         ids = (C.c_int32 * len(names))(*[FIELD_ID[f] for f in names])
         ptrs = (C.POINTER(C.c_double) * len(names))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
         self._ck(self._L.osph_download_fields(self._h, len(names), ids, ptrs))
+        return dict(zip(names, cols))
+
+    def export_begin(self, names, rows=False):
+        """Start an asynchronous export of the named columns; returns a ticket for export_end.
+        rows=True: one value per row of the uploaded array (deleted rows keep their uploaded value)."""
+        ids = (C.c_int32 * len(names))(*[FIELD_ID[f] for f in names])
+        t = C.c_int64(-1)
+        self._ck(self._L.osph_export_begin(self._h, len(names), ids, 1 if rows else 0, C.byref(t)))
+        return (int(t.value), tuple(names), self._shape[0] if rows else self.num_active)
+
+    def export_end(self, ticket):
+        t, names, n = ticket
+        cols = [np.empty(n, dtype=np.float64) for _ in names]
+        ptrs = (C.POINTER(C.c_double) * len(names))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
+        self._ck(self._L.osph_export_end(self._h, t, len(names), ptrs, n))
         return dict(zip(names, cols))
 
     def upload_fields(self, cols):

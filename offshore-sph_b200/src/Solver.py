@@ -8,12 +8,14 @@ Per step (same order as reference src/Solver.py:366-465):
     osph_compute                  <- _loop(pA[indexes], kernel..., method, nn)      (:254)
     [coupling callback on a downloaded host copy]                                   (:389-392)
     osph_correct                  <- integrator.correct(...)                        (:396)
-    _store: only the exportProperties columns are downloaded                        (:477-486)
+    _store: only the exportProperties columns are downloaded, asynchronously        (:477-486)
 
 `solver.particleArray` stays a plain numpy array; it is refreshed from the device when the run ends, when the
 settling phase ends, around coupling callbacks and on save().  Backend knobs come from the environment so
 that example scripts run unedited: OSPH_PRECISION=fp64|fp32, OSPH_DEVICE=<ordinal>, OSPH_STORE_FULL=1
-(keep the reference's per-step full copies in `solver.data`).
+(keep the reference's per-step full copies in `solver.data`), OSPH_SYNC_EXPORT=1 (blocking per-step export; by
+default the exported columns of step k cross PCIe while step k+1 is computed and appear in `solver.export` one
+step later -- always complete when run() returns or save() is called).
 """
 import os
 from time import perf_counter
@@ -94,6 +96,10 @@ class Solver:
         self._ctx = None
         self._host_dirty = False      # device state is newer than self.particleArray
         self._store_full = bool(os.environ.get("OSPH_STORE_FULL"))
+        # export columns cross PCIe on a copy stream while the next step runs (osph_export_begin / _end);
+        # OSPH_SYNC_EXPORT=1 restores the blocking per-step download
+        self._async_export = not os.environ.get("OSPH_SYNC_EXPORT")
+        self._export_pending = []
 
     # ------------------------------------------------------------------------------------------
     def load(self, file: str):
@@ -285,6 +291,7 @@ class Solver:
                 tbar.update(self.dt)
 
         tbar.close()
+        self._export_drain()
         self._pull()
         status = ctx.sync()
         if status & capi.S_NONFINITE:
@@ -305,13 +312,30 @@ class Solver:
             self._pull()
             self.data.append(np.copy(self.particleArray))
         if self.exportProperties:
-            cols = self._ctx.download_fields(self.exportProperties)
-            for key in self.exportProperties:
-                full = np.copy(self.particleArray[key])
-                full[self.indexes] = cols[key]
-                self.export[key].append(full)
+            if self._async_export:
+                # step k's columns travel while step k+1 is computed; step k-1's are merged into the lists now
+                self._export_pending.append(self._ctx.export_begin(self.exportProperties, rows=True))
+                while len(self._export_pending) > 1:
+                    self._export_finish()
+            else:
+                self._export_merge(self._ctx.download_fields(self.exportProperties), self.indexes)
         if self.incrementalWriteout and t_step % self.incrementalFreq == 0:
             self.save('{0}-{1}.hdf5'.format(self.incrementalFile, t_step), printLocation=False)
+
+    def _export_merge(self, cols, indexes):
+        for key in cols:
+            full = np.copy(self.particleArray[key])
+            full[indexes] = cols[key]
+            self.export[key].append(full)
+
+    def _export_finish(self):
+        # row-space columns: already the full per-row arrays (deleted rows keep their uploaded values)
+        for key, col in self._ctx.export_end(self._export_pending.pop(0)).items():
+            self.export[key].append(col)
+
+    def _export_drain(self):
+        while self._export_pending:
+            self._export_finish()
 
     # ------------------------------------------------------------------------------------------
     def timing(self):
@@ -327,6 +351,7 @@ class Solver:
 
     def save(self, location: str, printLocation: bool = True, extraProperties: dict = None):
         """gzip HDF5 like the reference (:497-531) when h5py is importable, else the same datasets as .npz."""
+        self._export_drain()
         println('Starting file export.')
         self._pull()
         datasets = dict(particleArray=self.particleArray, dt_a=np.asarray(self.dt_a), dt_c=np.asarray(self.dt_c),

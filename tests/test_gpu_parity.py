@@ -242,6 +242,50 @@ def test_kinetic_energy_and_timestep_edges():
             ctx.compute()
 
 
+def test_async_export_snapshots_in_stream_order():
+    """osph_export_begin/_end: the columns are those of the moment of the begin, two tickets in flight, the copy
+    overlaps later steps (include/osph.h; replaces the blocking copies of src/Solver.py:477-486)."""
+    g, meta, pA = load_golden('dambreak20_cubic')
+    names = ['x', 'y', 'p', 'c']
+    with _ctx(meta) as ctx:
+        ctx.upload(pA)
+        ctx.step(2)
+        want0 = ctx.download_fields(names)
+        t0 = ctx.export_begin(names)
+        ctx.step(3)                                   # state moves on while ticket 0 is in flight
+        want1 = ctx.download_fields(names[:2])
+        t1 = ctx.export_begin(names[:2])
+        with pytest.raises(capi.OsphError):           # ring of two
+            ctx.export_begin(names)
+        ctx.step(1)
+        got0 = ctx.export_end(t0)
+        got1 = ctx.export_end(t1)
+        with pytest.raises(capi.OsphError):           # a ticket can be ended once
+            ctx.export_end(t0)
+        for f in names:
+            assert np.array_equal(got0[f], want0[f]), f
+        for f in names[:2]:
+            assert np.array_equal(got1[f], want1[f]), f
+        assert not np.array_equal(want0['x'], want1['x'])
+        t2 = ctx.export_begin(['rho'])                # slots are reusable, with a different column count
+        assert np.array_equal(ctx.export_end(t2)['rho'], ctx.download_fields(['rho'])['rho'])
+    # row space: one value per uploaded row, deleted rows keep what the host uploaded (what Solver._store appends)
+    pB = pA.copy()
+    dead = np.zeros(len(pB), dtype=bool)
+    dead[5::7] = True
+    pB['deleted'] = dead
+    pB['p'][dead] = -1e15
+    with _ctx(meta) as ctx:
+        ctx.upload(pB)
+        ctx.step(2)
+        act = ctx.download_fields(['x', 'p', 'c'])
+        rows = ctx.export_end(ctx.export_begin(['x', 'p', 'c'], rows=True))
+        for f in ('x', 'p', 'c'):
+            assert len(rows[f]) == len(pB)
+            assert np.array_equal(rows[f][~dead], act[f]), f
+            assert np.array_equal(rows[f][dead], pB[f][dead]), f
+
+
 def test_upload_fields_roundtrip_and_single_particle():
     g, meta, pA = load_golden('block20_cubic_nobnd')
     with _ctx(meta) as ctx:

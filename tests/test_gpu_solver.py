@@ -40,6 +40,36 @@ def test_solver_run_matches_reference_solver(monkeypatch):
     assert s.timing_data['total'] > 0 and set(s.timing_data) >= {'compute', 'neighbour_hood', 'time_step'}
 
 
+def test_async_export_equals_blocking_export(monkeypatch):
+    """The double-buffered export path fills solver.export with the same arrays as the blocking one."""
+    monkeypatch.setenv("OSPH_QUIET", "1")
+    from src.Solver import Solver
+    from src.Methods.WCSPH import WCSPH
+    from src.Kernels.CubicSpline import CubicSpline
+    from src.Integrators.PEC import PEC
+    runs = []
+    for sync in ("1", ""):
+        if sync:
+            monkeypatch.setenv("OSPH_SYNC_EXPORT", sync)
+        else:
+            monkeypatch.delenv("OSPH_SYNC_EXPORT", raising=False)
+        r0, pA = W.dam_break(10)
+        method = WCSPH(height=25.0, r0=r0, rho0=1000.0, useXSPH=True, Pb=0, useSummationDensity=False)
+        s = Solver(method, PEC(useXSPH=True, strict=False), CubicSpline(), 0.02, incrementalWriteout=False,
+                   h=1.6 * r0, maxSettle=4, exportProperties=['x', 'y', 'p', 'vx'])
+        s.addParticles(pA)
+        s.setup()
+        s.run()
+        assert s._async_export == (not sync) and not s._export_pending
+        runs.append(s)
+    a, b = runs
+    assert a.t_step == b.t_step
+    for key in ('x', 'y', 'p', 'vx'):
+        assert len(a.export[key]) == len(b.export[key]) == a.t_step
+        for u, v in zip(a.export[key], b.export[key]):
+            assert np.array_equal(u, v, equal_nan=True), key
+
+
 def test_containment_example_runs(monkeypatch):
     """Dynamic h, XSPH off, WCSPH() without useSummationDensity: the shipped Containment call pattern."""
     monkeypatch.setenv("OSPH_QUIET", "1")
