@@ -148,6 +148,16 @@ int osph_upload_fields(osph_ctx *ctx, int32_t nfields, const int32_t *fields, co
  */
 int osph_export_begin(osph_ctx *ctx, int32_t nfields, const int32_t *fields, int32_t row_space, int64_t *ticket);
 int osph_export_end(osph_ctx *ctx, int64_t ticket, int32_t nfields, double *const *cols, int64_t n);
+/*
+ * Transfers of a FEW rows: the records of host rows rows[0..nrows) are written to / read from the caller's array
+ * at pA + rows[k] * stride (same array convention as osph_download_aos); every row must be active.  Upload
+ * overwrites the 19 doubles of those rows (label / deleted are ignored) and invalidates the neighbour structure.
+ * replaces: the whole-array copies around the Coupled rows of a structure, `pA[c_indexes] =
+ * couplingIntegrator.predict(...)` / `.correct(...)` and the coupling callback (src/Solver.py:381-398) --
+ * SURVEY section 8(f) rank 1.
+ */
+int osph_download_rows(osph_ctx *ctx, int64_t nrows, const int64_t *rows, void *pA, int64_t stride);
+int osph_upload_rows(osph_ctx *ctx, int64_t nrows, const int64_t *rows, const void *pA, int64_t stride);
 int64_t osph_num_active(const osph_ctx *ctx);
 int64_t osph_num_fluid(const osph_ctx *ctx);
 

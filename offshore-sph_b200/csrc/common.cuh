@@ -141,6 +141,8 @@ struct osph_ctx {
     size_t h_pinned_bytes = 0;
 
     osph_export_ring *xring = nullptr;   // asynchronous column export (export.cu), created on first use
+    unsigned char *d_rows_buf = nullptr; // workspace of the row transfers (export.cu)
+    size_t rows_bytes = 0;
 };
 
 void osph_export_free(osph_ctx *ctx);

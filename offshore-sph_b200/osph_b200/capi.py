@@ -86,6 +86,8 @@ def lib():
         'osph_upload_fields': (C.c_int, [ctx, i32, C.POINTER(i32), C.POINTER(dp)]),
         'osph_export_begin': (C.c_int, [ctx, i32, C.POINTER(i32), i32, ip]),
         'osph_export_end': (C.c_int, [ctx, i64, i32, C.POINTER(dp), i64]),
+        'osph_download_rows': (C.c_int, [ctx, i64, ip, C.c_void_p, i64]),
+        'osph_upload_rows': (C.c_int, [ctx, i64, ip, C.c_void_p, i64]),
         'osph_num_active': (i64, [ctx]),
         'osph_num_fluid': (i64, [ctx]),
         'osph_initialize': (C.c_int, [ctx]),
@@ -248,6 +250,21 @@ class Context:
         ptrs = (C.POINTER(C.c_double) * len(names))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
         self._ck(self._L.osph_export_end(self._h, t, len(names), ptrs, n))
         return dict(zip(names, cols))
+
+    def download_rows(self, rows, pA):
+        """Refresh the records pA[rows] (host row numbers of active rows) from the device; the rest of pA is untouched."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        assert pA.flags['C_CONTIGUOUS'] and (len(pA), pA.dtype.itemsize) == self._shape
+        self._ck(self._L.osph_download_rows(self._h, len(rows), rows.ctypes.data_as(C.POINTER(C.c_int64)), pA.ctypes.data,
+                                            pA.dtype.itemsize))
+        return pA
+
+    def upload_rows(self, rows, pA):
+        """Overwrite the device state of the active rows `rows` from pA[rows]."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        assert pA.flags['C_CONTIGUOUS'] and (len(pA), pA.dtype.itemsize) == self._shape
+        self._ck(self._L.osph_upload_rows(self._h, len(rows), rows.ctypes.data_as(C.POINTER(C.c_int64)), pA.ctypes.data,
+                                          pA.dtype.itemsize))
 
     def upload_fields(self, cols):
         names = list(cols)

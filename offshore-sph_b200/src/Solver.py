@@ -56,7 +56,7 @@ class Solver:
                  incrementalWriteout: bool = True, incrementalFile: str = "export", incrementalFreq: int = 1000,
                  exportProperties: List[str] = ['x', 'y', 'p'], kE: float = 0.8, maxSettle: int = 500,
                  timeStep: float = None, h: float = None, coupling=None, couplingIntegrator=None,
-                 couplingProperties=None, customSettle=None, damping: float = 0.05):
+                 couplingProperties=None, customSettle=None, damping: float = 0.05, couplingRowsOnly: bool = None):
         self.method = method
         self.integrator = integrator
         self.kernel = kernel
@@ -74,6 +74,13 @@ class Solver:
         self.coupling = coupling
         self.couplingIntegrator = couplingIntegrator
         self.couplingProperties = couplingProperties
+        # True: only the Coupled rows travel between host and device around couplingIntegrator.predict / .correct and
+        # the coupling callback (osph_download_rows / osph_upload_rows); the callback then sees stale fluid rows in
+        # the array it is handed and should query the fluid through solver.probe_pressure().  Default (reference
+        # behaviour): the whole array is refreshed and re-uploaded.
+        if couplingRowsOnly is None:
+            couplingRowsOnly = bool(os.environ.get("OSPH_COUPLING_ROWS"))
+        self.couplingRowsOnly = bool(couplingRowsOnly)
         self.customSettle = customSettle
 
         self.incrementalWriteout = incrementalWriteout
@@ -143,6 +150,7 @@ class Solver:
         self.f_indexes = (pa['label'] == ParticleType.Fluid) & (pa['deleted'] == False)      # noqa: E712
         self.c_indexes = (pa['label'] == ParticleType.Coupled) & (pa['deleted'] == False)    # noqa: E712
         self.fluid_count = int(np.sum(self.f_indexes))
+        self._c_rows = np.flatnonzero(self.c_indexes).astype(np.int64)
 
     def _pull(self):
         """Refresh the host mirror from the device."""
@@ -197,7 +205,12 @@ class Solver:
         self.timing_data['compute'] += perf_counter() - start
 
     def _host_rows(self, mask, fn, *args):
-        """Run a host-side integrator on the rows `mask` of the mirror and push the result."""
+        if self.couplingRowsOnly and mask is self.c_indexes:
+            rows = self._c_rows
+            self._ctx.download_rows(rows, self.particleArray)
+            self.particleArray[rows] = fn(*args[:1], self.particleArray[rows], *args[1:])
+            self._ctx.upload_rows(rows, self.particleArray)
+            return
         self._pull()
         self.particleArray[mask] = fn(*args[:1], self.particleArray[mask], *args[1:])
         self._push()
@@ -237,9 +250,14 @@ class Solver:
 
             if self.coupling is not None:
                 start = perf_counter()
-                self._pull()
-                self.particleArray = self.coupling(self.particleArray, self)
-                self._push()
+                if self.couplingRowsOnly:
+                    ctx.download_rows(self._c_rows, self.particleArray)
+                    self.particleArray = self.coupling(self.particleArray, self)
+                    ctx.upload_rows(self._c_rows, self.particleArray)
+                else:
+                    self._pull()
+                    self.particleArray = self.coupling(self.particleArray, self)
+                    self._push()
                 self.timing_data['coupling'] += perf_counter() - start
 
             start = perf_counter()

@@ -286,6 +286,41 @@ def test_async_export_snapshots_in_stream_order():
             assert np.array_equal(rows[f][dead], pB[f][dead]), f
 
 
+def test_row_transfers():
+    """osph_download_rows / osph_upload_rows: a few host rows by number, across a physical reorder of the device
+    storage, with deleted rows in between (src/Solver.py:381-398 moves the Coupled rows this way)."""
+    g, meta, pA = load_golden('tank24_wendland_coupled')
+    pB = pA.copy()
+    dead = np.zeros(len(pB), dtype=bool)
+    dead[3::11] = True
+    pB['deleted'] = dead
+    live = np.flatnonzero(~dead)
+    rows = live[::5][:40].astype(np.int64)[::-1].copy()            # unordered on purpose
+    with _ctx(meta) as ctx:
+        ctx.upload(pB)
+        ctx.step(3)                                                # build #2 reorders the storage physically
+        full = ctx.download(pB.copy())
+        part = pB.copy()
+        ctx.download_rows(rows, part)
+        assert part[rows].tobytes() == full[rows].tobytes()
+        untouched = np.setdiff1d(np.arange(len(pB)), rows)
+        assert part[untouched].tobytes() == pB[untouched].tobytes()
+        # write the rows back shifted, everything else must stay as it was
+        edit = full.copy()
+        edit['y'][rows] += 0.125
+        edit['vx'][rows] = -3.0
+        edit['c'][rows] = 7.0
+        ctx.upload_rows(rows, edit)
+        after = ctx.download(pB.copy())
+        assert after[live].tobytes() == edit[live].tobytes()
+        with pytest.raises(capi.OsphError):                        # deleted rows have no device state
+            ctx.download_rows(np.array([np.flatnonzero(dead)[0]], dtype=np.int64), part)
+        with pytest.raises(capi.OsphError):
+            ctx.download_rows(np.array([len(pB)], dtype=np.int64), part)
+        ctx.step(1)                                                # the neighbour structure is rebuilt after the upload
+        assert np.all(np.isfinite(ctx.download(pB.copy())['ax'][live]))
+
+
 def test_upload_fields_roundtrip_and_single_particle():
     g, meta, pA = load_golden('block20_cubic_nobnd')
     with _ctx(meta) as ctx:

@@ -190,11 +190,7 @@ def test_batched_pressure_probe_matches_reference_recipe():
         assert p[k] == pytest.approx(((want / c['rho0']) ** 7 - 1) * c['B'], rel=1e-9, abs=1e-6)
 
 
-def test_solver_coupling_callback_path(monkeypatch):
-    """Coupled (ice-like) particles moved by a host-side NewmarkBeta integrator inside a coupling callback, the
-    IceBreak call pattern (examples/IceBreak.py:109-171): predict/correct of the coupled rows on the host mirror,
-    callback between compute and correct, batched device pressure probe inside the callback."""
-    monkeypatch.setenv("OSPH_QUIET", "1")
+def _run_coupled(rows_only):
     from src.Solver import Solver
     from src.Methods.WCSPH import WCSPH
     from src.Kernels.Wendland import Wendland
@@ -220,15 +216,38 @@ def test_solver_coupling_callback_path(monkeypatch):
     nb = NewmarkBeta(0.25, 0.5, np.eye(nc) * 50.0, np.eye(nc) * 1e4, np.eye(nc) * 10.0)
     method = WCSPH(height=1.0, r0=case['r0'], rho0=1000.0, useXSPH=True, Pb=0)
     s = Solver(method, PEC(useXSPH=True, strict=False), Wendland(), 0.002, incrementalWriteout=False, h=1.3 / 16,
-               maxSettle=3, coupling=coupling, couplingIntegrator=nb, couplingProperties={}, exportProperties=['y'])
+               maxSettle=3, coupling=coupling, couplingIntegrator=nb, couplingProperties={}, exportProperties=['y'],
+               couplingRowsOnly=rows_only)
     s.addParticles(pA)
     s.setup()
     s.run()
-    assert len(calls) == s.t_step and s.t >= 0.002
-    out = s.particleArray
-    assert np.all(np.isfinite(out['x'])) and np.all(np.isfinite(out['y']))
-    c = out['label'] == ParticleType.Coupled
-    assert np.any(out['y'][c] != y0)                         # the host integrator moved the coupled rows ...
-    f = out['label'] == 0
-    assert np.all(out['ay'][f] != 0)                          # ... and the device kept integrating the fluid
-    assert s.timing_data['coupling'] > 0
+    return s, calls, y0
+
+
+def test_solver_coupling_callback_path(monkeypatch):
+    """Coupled (ice-like) particles moved by a host-side NewmarkBeta integrator inside a coupling callback, the
+    IceBreak call pattern (examples/IceBreak.py:109-171): predict/correct of the coupled rows on the host mirror,
+    callback between compute and correct, batched device pressure probe inside the callback.  Run twice: with the
+    reference's whole-array round trips, and with only the Coupled rows crossing PCIe (osph_download_rows /
+    osph_upload_rows); both must give the same simulation."""
+    monkeypatch.setenv("OSPH_QUIET", "1")
+    from src.Common import ParticleType
+    runs = []
+    for rows_only in (False, True):
+        s, calls, y0 = _run_coupled(rows_only)
+        assert s.couplingRowsOnly == rows_only
+        assert len(calls) == s.t_step and s.t >= 0.002
+        out = s.particleArray
+        assert np.all(np.isfinite(out['x'])) and np.all(np.isfinite(out['y']))
+        c = out['label'] == ParticleType.Coupled
+        assert np.any(out['y'][c] != y0)                         # the host integrator moved the coupled rows ...
+        f = out['label'] == 0
+        assert np.all(out['ay'][f] != 0)                          # ... and the device kept integrating the fluid
+        assert s.timing_data['coupling'] > 0
+        runs.append((s, calls))
+    (a, ca), (b, cb) = runs
+    assert a.t_step == b.t_step and np.allclose(a.dt_a, b.dt_a, rtol=1e-10, atol=0)
+    assert np.allclose(ca, cb, rtol=1e-8, atol=1e-12)
+    for f in ('x', 'y', 'vx', 'vy', 'rho', 'p', 'ax', 'ay'):      # storage order differs between the modes: summation order only
+        assert field_err(a.particleArray[f], b.particleArray[f]) <= 1e-9, f
+    assert len(a.export['y']) == len(b.export['y']) == a.t_step
