@@ -41,6 +41,15 @@
 #ifndef PAIR_SCAN_ILP
 #define PAIR_SCAN_ILP 1       // 1: the PAIR_SCAN loads and distance tests of one round are independent of each other
 #endif
+#ifndef PAIR_SCAN_F32
+#define PAIR_SCAN_F32 1       // double instantiation: scan on float copies of the positions with a conservative radius
+#endif
+#ifndef PAIR_NO_FMAX
+#define PAIR_NO_FMAX 1        // no clamp in front of the rsqrt: the r = 0 lanes are removed by the selects that follow
+#endif
+#ifndef PAIR_PREFETCH_IDX
+#define PAIR_PREFETCH_IDX 1   // heavy loop: fetch the next list entry while the current pair is evaluated
+#endif
 #ifndef PAIR_CAP
 #define PAIR_CAP 1024         // candidate records resident in shared memory at once
 #endif
@@ -55,7 +64,7 @@ template <typename Real, bool EXACT>
 constexpr size_t pair_smem_bytes()
 {
     return sizeof(Rec<Real, EXACT>) * PAIR_CAP + sizeof(unsigned short) * (sizeof(Real) == 8 ? PAIR_LIST64 : PAIR_LIST32) * OSPH_PAIR_THREADS +
-           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6;
+           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6 + ((EXACT && PAIR_SCAN_F32) ? sizeof(float2) * PAIR_CAP : 0);
 }
 
 template <typename Real, int KID, bool EXACT>
@@ -71,6 +80,9 @@ k_pair(PairArgs a)
     RecT *sh_rec = reinterpret_cast<RecT *>(smem_raw);
     unsigned short *sh_list = reinterpret_cast<unsigned short *>(smem_raw + sizeof(RecT) * CAP);
     int(*sh_red)[6] = reinterpret_cast<int(*)[6]>(smem_raw + sizeof(RecT) * CAP + sizeof(unsigned short) * PAIR_LIST * NT);
+    constexpr bool SCANF = EXACT && PAIR_SCAN_F32;
+    float2 *sh_pf = reinterpret_cast<float2 *>(smem_raw + sizeof(RecT) * CAP + sizeof(unsigned short) * PAIR_LIST * NT +
+                                               sizeof(int) * (NT / 32) * 6);
 
     const Real2 *__restrict__ g_vel = reinterpret_cast<const Real2 *>(a.s_vel);
     const Real2 *__restrict__ g_rm = reinterpret_cast<const Real2 *>(a.s_rm);
@@ -86,6 +98,16 @@ k_pair(PairArgs a)
 
     // anchor for relative coordinates (FP32 mode): first particle of the CTA
     const double2 anchor = EXACT ? make_double2(0.0, 0.0) : a.s_pos[s0];
+    // float scan of the double instantiation: positions relative to the CTA's first particle; every coordinate is
+    // off by at most 2^-24 of the domain extent, so a radius enlarged by four such errors cannot lose a pair (a
+    // candidate accepted in excess is rejected by the exact tests of the heavy body)
+    const double2 anchor_f = SCANF ? a.s_pos[s0] : make_double2(0.0, 0.0);
+    float xf = 0.f, yf = 0.f, thr_f = 0.f;
+    if constexpr (SCANF) {
+        const double ext = fmax(gp->xmax - gp->xmin, gp->ymax - gp->ymin);
+        const double rad = sqrt(gp->pair_r2) + 4.0 * 5.97e-8 * ext;
+        thr_f = __double2float_ru(rad * rad * (1.0 + 1e-6));
+    }
 
     Real xi = 0, yi = 0, vxi = 0, vyi = 0, rhoi = 1, hi = 0, slf = 0;
     int qcx = 0, qcy = 0;
@@ -94,6 +116,7 @@ k_pair(PairArgs a)
     if (valid) {
         double2 p = a.s_pos[s];
         xi = (Real)(p.x - anchor.x); yi = (Real)(p.y - anchor.y);
+        if constexpr (SCANF) { xf = (float)(p.x - anchor_f.x); yf = (float)(p.y - anchor_f.y); }
         Real2 v = g_vel[s]; vxi = v.x; vyi = v.y;
         Real2 rm = g_rm[s]; rhoi = rm.x;
         Real2 hp = g_hp[s]; hi = hp.x; slf = hp.y;
@@ -148,6 +171,7 @@ k_pair(PairArgs a)
             RecT rec;
             double2 p = a.s_pos[g];
             rec.pos.x = (Real)(p.x - anchor.x); rec.pos.y = (Real)(p.y - anchor.y);
+            if constexpr (SCANF) sh_pf[dst + t] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
             rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
             if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
             rec.pad = 0;
@@ -189,7 +213,11 @@ k_pair(PairArgs a)
             ok = ok && r2 <= h2 * Real(9);
         }
         if (!ok) return;
+#if PAIR_NO_FMAX
+        const Real rs = rsqrt_fast(r2);                            // r2 == 0: inf / NaN, discarded by the two selects below
+#else
         const Real rs = rsqrt_fast(fmax(r2, Real(1e-30)));
+#endif
         const Real inv_h = rcp_fast(hij);
         const Real rbar = Real(0.5) * (rhoi + rmj.x);
         const Real inv_rbar = rcp_fast(rbar);
@@ -232,8 +260,18 @@ k_pair(PairArgs a)
     // of the ~35-45% a fused test-and-evaluate loop achieves (profiles/r01).
     int nl = 0;
     auto flush = [&]() {
+#if PAIR_PREFETCH_IDX
+        int jn = nl > 0 ? (int)sh_list[tid] : 0;
+#pragma unroll 1
+        for (int k = 0; k < nl; k++) {
+            const int j = jn;
+            jn = (int)sh_list[min(k + 1, PAIR_LIST - 1) * NT + tid];      // next index while this pair is evaluated
+            interact(j);
+        }
+#else
 #pragma unroll 1
         for (int k = 0; k < nl; k++) interact((int)sh_list[k * NT + tid]);
+#endif
         nl = 0;
     };
     auto scan = [&](int j, const int j1) {          // all 32 lanes of a warp call this together
@@ -245,16 +283,29 @@ k_pair(PairArgs a)
             // candidate past the end is discarded), then the independent distance tests, then the appends.  The
             // serial form (load, test, append, next) left the warp waiting on one shared-memory load and one
             // dependent FP chain at a time: 48 % of the kernel's stall samples on 25 % of its instructions.
-            Real d2[PAIR_SCAN];
+            if constexpr (SCANF) {
+                float d2[PAIR_SCAN];
 #pragma unroll
-            for (int u = 0; u < PAIR_SCAN; u++) {
-                const Real2 pj = sh_rec[min(j + u, CAP - 1)].pos;
-                const Real dx = xi - pj.x, dy = yi - pj.y;
-                d2[u] = dx * dx + dy * dy;
+                for (int u = 0; u < PAIR_SCAN; u++) {
+                    const float2 pj = sh_pf[min(j + u, CAP - 1)];
+                    const float dx = xf - pj.x, dy = yf - pj.y;
+                    d2[u] = dx * dx + dy * dy;
+                }
+#pragma unroll
+                for (int u = 0; u < PAIR_SCAN; u++)
+                    if (j + u < j1 && d2[u] <= thr_f) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
+            } else {
+                Real d2[PAIR_SCAN];
+#pragma unroll
+                for (int u = 0; u < PAIR_SCAN; u++) {
+                    const Real2 pj = sh_rec[min(j + u, CAP - 1)].pos;
+                    const Real dx = xi - pj.x, dy = yi - pj.y;
+                    d2[u] = dx * dx + dy * dy;
+                }
+#pragma unroll
+                for (int u = 0; u < PAIR_SCAN; u++)
+                    if (j + u < j1 && d2[u] <= pair_r2) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
             }
-#pragma unroll
-            for (int u = 0; u < PAIR_SCAN; u++)
-                if (j + u < j1 && d2[u] <= pair_r2) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
             j += PAIR_SCAN;
 #else
 #pragma unroll
