@@ -110,8 +110,9 @@ k_pair(PairArgs a)
     }
 
     Real xi = 0, yi = 0, vxi = 0, vyi = 0, rhoi = 1, hi = 0, slf = 0;
-    int qcx = 0, qcy = 0;
+    int qcx = 0, qcy = 0, info_i = 0;
     bool fluid_i = false;
+    const bool need_adj = gp->regime_a != 0;
     int ra0 = 0x7fffffff, ra1 = 0x7fffffff, ra2 = 0x7fffffff, rb0 = 0, rb1 = 0, rb2 = 0;
     if (valid) {
         double2 p = a.s_pos[s];
@@ -120,7 +121,8 @@ k_pair(PairArgs a)
         Real2 v = g_vel[s]; vxi = v.x; vyi = v.y;
         Real2 rm = g_rm[s]; rhoi = rm.x;
         Real2 hp = g_hp[s]; hi = hp.x; slf = hp.y;
-        fluid_i = (a.s_info[s] & 3) == 3;          // fluid AND owned (ghosts of a slab are sources only)
+        info_i = a.s_info[s];
+        fluid_i = (info_i & 3) == 3;               // fluid AND owned (ghosts of a slab are sources only)
         if constexpr (EXACT) { int4 c = a.s_coarse[s]; qcx = c.z; qcy = c.w; }
         if (fluid_i) {
             int2 gc = a.s_gcell[s];
@@ -202,15 +204,22 @@ k_pair(PairArgs a)
         const bool kern = r2 <= h2 * (KID == OSPH_KERNEL_GAUSSIAN ? Real(9.0 * (1.0 + 1e-6)) : Real(4));
         const bool lj = !fluid_j && r2 <= PC(r0sq);
         bool ok = kern || lj;
-        // membership in the reference neighbour set: q <= 3 (it can only fail for LJ pairs and at the Gaussian cut)
+        // Membership in the reference neighbour set = adjacent reference cells AND q <= 3.
+        //  * cells: where the acceleration grid is finer than the reference grid (regime B) two particles within the
+        //    pair radius sit in adjacent reference cells by construction, unless the reference bins one of them
+        //    irregularly (info bit 2); only then, and in regime A, the stored cell ids are compared;
+        //  * q <= 3 can only bind for wall pairs outside the kernel support and at the cut of the Gaussian.
         if constexpr (EXACT) {
-            ok = ok && abs(cbx - qcx) <= 1 && abs(cby - qcy) <= 1 && r2 <= h2 * (9.0 * (1.0 + 1e-13));
-            if (ok && r2 > h2 * (9.0 * (1.0 - 1e-13))) {          // within 1e-13 of the threshold: decide in strict IEEE
-                double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
-                ok = __ddiv_rn(rr, (double)hij) <= 3.0;
+            if (need_adj || ((info_j | info_i) & 4)) ok = ok && abs(cbx - qcx) <= 1 && abs(cby - qcy) <= 1;
+            if (KID == OSPH_KERNEL_GAUSSIAN || !kern) {
+                ok = ok && r2 <= h2 * (9.0 * (1.0 + 1e-13));
+                if (ok && r2 > h2 * (9.0 * (1.0 - 1e-13))) {      // within 1e-13 of the threshold: decide in strict IEEE
+                    double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+                    ok = __ddiv_rn(rr, (double)hij) <= 3.0;
+                }
             }
         } else {
-            ok = ok && r2 <= h2 * Real(9);
+            if (KID == OSPH_KERNEL_GAUSSIAN || !kern) ok = ok && r2 <= h2 * Real(9);
         }
         if (!ok) return;
 #if PAIR_NO_FMAX

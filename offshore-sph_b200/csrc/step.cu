@@ -401,8 +401,11 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
     Real2 v; v.x = (Real)vx; v.y = (Real)vy; s_vel[s] = v;
     Real2 rm; rm.x = (Real)rho; rm.y = (Real)m; s_rm[s] = rm;
     Real2 hp; hp.x = (Real)h; hp.y = (Real)pr2; s_hp[s] = hp;
-    a.s_info[s] = info | (fluid ? 1 : 0);
     CellInfo c = cell_of(x, y, *a.gp);
+    // bit2: the reference bins this particle in a cell other than the one it queries from (wrapped last column,
+    // unbinned, non-finite): cell adjacency then does not follow from distance and the pair kernel tests it
+    const bool irregular = c.coarse.x != c.coarse.z || c.coarse.y != c.coarse.w || !c.binned;
+    a.s_info[s] = info | (fluid ? 1 : 0) | (irregular ? 4 : 0);
     a.s_coarse[s] = c.coarse;
     a.s_gcell[s] = c.gcell;
 }
