@@ -115,31 +115,37 @@ k_pair(PairArgs a)
     const bool need_adj = gp->regime_a != 0;
     int ra0 = 0x7fffffff, ra1 = 0x7fffffff, ra2 = 0x7fffffff, rb0 = 0, rb1 = 0, rb2 = 0;
     if (valid) {
-        double2 p = a.s_pos[s];
+        // every load of the prologue is issued before the first use: two global round trips (state + cell id, then
+        // the nine cell ranges) instead of the four a test-then-load order costs
+        const double2 p = a.s_pos[s];
+        const Real2 v = g_vel[s], rm = g_rm[s], hp = g_hp[s];
+        info_i = a.s_info[s];
+        const int2 gc = a.s_gcell[s];
+        if constexpr (EXACT) { int4 c = a.s_coarse[s]; qcx = c.z; qcy = c.w; }
         xi = (Real)(p.x - anchor.x); yi = (Real)(p.y - anchor.y);
         if constexpr (SCANF) { xf = (float)(p.x - anchor_f.x); yf = (float)(p.y - anchor_f.y); }
-        Real2 v = g_vel[s]; vxi = v.x; vyi = v.y;
-        Real2 rm = g_rm[s]; rhoi = rm.x;
-        Real2 hp = g_hp[s]; hi = hp.x; slf = hp.y;
-        info_i = a.s_info[s];
+        vxi = v.x; vyi = v.y; rhoi = rm.x; hi = hp.x; slf = hp.y;
         fluid_i = (info_i & 3) == 3;               // fluid AND owned (ghosts of a slab are sources only)
-        if constexpr (EXACT) { int4 c = a.s_coarse[s]; qcx = c.z; qcy = c.w; }
-        if (fluid_i) {
-            int2 gc = a.s_gcell[s];
-            int x0 = max(gc.x - 1, 0), x1 = min(gc.x + 1, gnx - 1);
+        const int x0 = max(gc.x - 1, 0), x1 = min(gc.x + 1, gnx - 1);
+        int2 cr[9];
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                int cy = gc.y + d - 1;
-                int lo = 0x7fffffff, hiE = 0;
-                if (cy >= 0 && cy < gny && x0 <= x1) {
-                    const int2 *row = a.cell_range + (long long)cy * gnx;
-                    for (int cx = x0; cx <= x1; cx++) {
-                        int2 r = row[cx];
-                        if (r.y > r.x) { lo = min(lo, r.x); hiE = max(hiE, r.y); }
-                    }
-                }
-                if (d == 0) { ra0 = lo; rb0 = hiE; } else if (d == 1) { ra1 = lo; rb1 = hiE; } else { ra2 = lo; rb2 = hiE; }
+        for (int d = 0; d < 3; d++) {
+            const int cyc = min(max(gc.y + d - 1, 0), gny - 1);
+            const int2 *row = a.cell_range + (long long)cyc * gnx;
+#pragma unroll
+            for (int e = 0; e < 3; e++) cr[3 * d + e] = row[min(max(x0 + e, 0), gnx - 1)];
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int cy = gc.y + d - 1;
+            const bool rowok = fluid_i && cy >= 0 && cy < gny;
+            int lo = 0x7fffffff, hiE = 0;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const int2 r = cr[3 * d + e];
+                if (rowok && x0 + e <= x1 && r.y > r.x) { lo = min(lo, r.x); hiE = max(hiE, r.y); }
             }
+            if (d == 0) { ra0 = lo; rb0 = hiE; } else if (d == 1) { ra1 = lo; rb1 = hiE; } else { ra2 = lo; rb2 = hiE; }
         }
     }
     // CTA-wide union of the runs, per row offset
@@ -167,18 +173,18 @@ k_pair(PairArgs a)
     Real drho = 0, ax = 0, ay = 0, xs = 0, ys = 0;          // the wall force is accumulated into (ax, ay) as well
 
     // stage sorted particles [g0, g0 + cnt) into records [dst, dst + cnt)
+    auto stage_one = [&](const int g, const int dst) {
+        RecT rec;
+        double2 p = a.s_pos[g];
+        rec.pos.x = (Real)(p.x - anchor.x); rec.pos.y = (Real)(p.y - anchor.y);
+        if constexpr (SCANF) sh_pf[dst] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
+        rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
+        if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
+        rec.pad = 0;
+        sh_rec[dst] = rec;
+    };
     auto stage = [&](int g0, int cnt, int dst) {
-        for (int t = tid; t < cnt; t += NT) {
-            const int g = g0 + t;
-            RecT rec;
-            double2 p = a.s_pos[g];
-            rec.pos.x = (Real)(p.x - anchor.x); rec.pos.y = (Real)(p.y - anchor.y);
-            if constexpr (SCANF) sh_pf[dst + t] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
-            rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
-            if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
-            rec.pad = 0;
-            sh_rec[dst + t] = rec;
-        }
+        for (int t = tid; t < cnt; t += NT) stage_one(g0 + t, dst + t);
     };
 
     // One listed candidate: everything the reference evaluates per neighbour, fused.  Written as one straight
@@ -267,7 +273,9 @@ k_pair(PairArgs a)
     // the staged records, accepted candidates appended to a per-thread list.  (2) flush: when any lane's list
     // is nearly full every lane evaluates its list.  The heavy body then runs with most lanes active instead
     // of the ~35-45% a fused test-and-evaluate loop achieves (profiles/r01).
-    int nl = 0;
+    int nl = 0, slot = -1;
+    double vx_st = 0.0, vy_st = 0.0;
+    bool have_v = false;
     auto flush = [&]() {
 #if PAIR_PREFETCH_IDX
         int jn = nl > 0 ? (int)sh_list[tid] : 0;
@@ -335,14 +343,19 @@ k_pair(PairArgs a)
     if (len0 + len1 + len2 <= CAP) {
         // common case: the three runs of the CTA fit in shared memory together; one staging pass, the
         // candidate list persists across the rows and is flushed only when full and once at the end
-        const int o1 = len0, o2 = len0 + len1;
-        stage(ulo0, len0, 0); stage(ulo1, len1, o1); stage(ulo2, len2, o2);
+        const int o1 = len0, o2 = len0 + len1, total = o2 + len2;
+        // one loop over the three runs: all of a thread's loads are in flight together
+#pragma unroll 4
+        for (int t = tid; t < total; t += NT)
+            stage_one(t < o1 ? ulo0 + t : (t < o2 ? ulo1 + (t - o1) : ulo2 + (t - o2)), t);
         __syncthreads();
         // (an empty run is ra = INT_MAX, rb = 0: test it before doing index arithmetic on it)
         const bool h0 = fluid_i && rb0 > ra0, h1 = fluid_i && rb1 > ra1, h2 = fluid_i && rb2 > ra2;
         scan(h0 ? ra0 - ulo0 : 0, h0 ? rb0 - ulo0 : 0);
         scan(h1 ? ra1 - ulo1 + o1 : 0, h1 ? rb1 - ulo1 + o1 : 0);
+        if (fluid_i) slot = (int)a.idx[s];                       // the epilogue's loads travel under the remaining work
         scan(h2 ? ra2 - ulo2 + o2 : 0, h2 ? rb2 - ulo2 + o2 : 0);
+        if constexpr (!EXACT) { if (fluid_i && a.method_xsph) { vx_st = a.vx[slot]; vy_st = a.vy[slot]; have_v = true; } }
         flush();
     } else {
         // rare: a run longer than the buffer (very dense cells or sparse rows spanning the domain): batches
@@ -364,13 +377,16 @@ k_pair(PairArgs a)
     }
 
     if (fluid_i) {
-        const int slot = (int)a.idx[s];
+        if (slot < 0) slot = (int)a.idx[s];
         a.drho[slot] = a.summation_density ? 0.0 : (double)drho;
         a.ax[slot] = (double)ax;
         a.ay[slot] = (double)ay - a.gravity;
         if (a.method_xsph) {
-            a.xsphx[slot] = a.vx[slot] + (double)xs;
-            a.xsphy[slot] = a.vy[slot] + (double)ys;
+            // xsph = v + correction (WCSPH.py:171-189).  Double instantiation: the sorted copy of v IS the state's v
+            if constexpr (EXACT) { vx_st = (double)vxi; vy_st = (double)vyi; }
+            else if (!have_v) { vx_st = a.vx[slot]; vy_st = a.vy[slot]; }
+            a.xsphx[slot] = vx_st + (double)xs;
+            a.xsphy[slot] = vy_st + (double)ys;
         } else {
             a.xsphx[slot] = 0.0; a.xsphy[slot] = 0.0;
         }
