@@ -109,7 +109,7 @@ k_pair(PairArgs a)
         thr_f = __double2float_ru(rad * rad * (1.0 + 1e-6));
     }
 
-    Real xi = 0, yi = 0, vxi = 0, vyi = 0, rhoi = 1, hi = 0, slf = 0;
+    Real xi = 0, yi = 0, vxi = 0, vyi = 0, rhoi = 1, hi = 0, slf = 0, hi_half = 0, rhoi_half = Real(0.5);
     int qcx = 0, qcy = 0, info_i = 0;
     bool fluid_i = false;
     const bool need_adj = gp->regime_a != 0;
@@ -125,6 +125,7 @@ k_pair(PairArgs a)
         xi = (Real)(p.x - anchor.x); yi = (Real)(p.y - anchor.y);
         if constexpr (SCANF) { xf = (float)(p.x - anchor_f.x); yf = (float)(p.y - anchor_f.y); }
         vxi = v.x; vyi = v.y; rhoi = rm.x; hi = hp.x; slf = hp.y;
+        hi_half = Real(0.5) * hi; rhoi_half = Real(0.5) * rhoi;
         fluid_i = (info_i & 3) == 3;               // fluid AND owned (ghosts of a slab are sources only)
         const int x0 = max(gc.x - 1, 0), x1 = min(gc.x + 1, gnx - 1);
         int2 cr[9];
@@ -179,6 +180,7 @@ k_pair(PairArgs a)
         rec.pos.x = (Real)(p.x - anchor.x); rec.pos.y = (Real)(p.y - anchor.y);
         if constexpr (SCANF) sh_pf[dst] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
         rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
+        rec.rm.x *= Real(0.5); rec.hp.x *= Real(0.5);       // staged as rho_j / 2 and h_j / 2: the pair means are one add
         if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
         rec.pad = 0;
         sh_rec[dst] = rec;
@@ -202,7 +204,7 @@ k_pair(PairArgs a)
         if constexpr (EXACT) { cbx = rj->cbx; cby = rj->cby; }
         const Real dx = xi - pj.x, dy = yi - pj.y;
         const Real r2 = dx * dx + dy * dy;
-        const Real hij = Real(0.5) * (hi + hpj.x);
+        const Real hij = hi_half + hpj.x;                          // == 0.5 * (h_i + h_j) bit for bit
         const Real h2 = hij * hij;
         const bool fluid_j = (info_j & 1) != 0;
         // kernel support (q <= 2, or the q <= 3 cut of the Gaussian, which IS the set boundary: keep a band for the
@@ -234,16 +236,17 @@ k_pair(PairArgs a)
         const Real rs = rsqrt_fast(fmax(r2, Real(1e-30)));
 #endif
         const Real inv_h = rcp_fast(hij);
-        const Real rbar = Real(0.5) * (rhoi + rmj.x);
+        const Real rbar = rhoi_half + rmj.x;                       // == 0.5 * (rho_i + rho_j)
         const Real inv_rbar = rcp_fast(rbar);
-        const Real hbar = Real(0.5) * (hi + hij);                 // h averaged twice (Momentum.py:43)
+        const Real hbar = fma(Real(0.5), hij, hi_half);            // h averaged twice (Momentum.py:43)
         const Real inv_den = rcp_fast(r2 + Real(0.01) * hbar * hbar);
         const Real inv_rt = r2 > Real(1e-24) ? rs : Real(0);       // LJ guard: r > 1e-12
         const Real inv_r = r2 > Real(1e-20) ? rs : Real(0);        // gradient guard: r >= 1e-10
         const Real r = r2 * inv_rt;
         const Real q = r * inv_h;
         Real w, g;
-        sph_kernel<Real, KID>(q, inv_h, inv_r, w, g);
+        if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair<Real>(q, inv_h, inv_r, w, g);
+        else sph_kernel<Real, KID>(q, inv_h, inv_r, w, g);
         const Real dwx = g * dx, dwy = g * dy;
         const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
         const Real mj = rmj.y;
@@ -256,7 +259,7 @@ k_pair(PairArgs a)
         const Real fac = mjf * (slf + hpj.y + PIij);
         ax -= fac * dwx; ay -= fac * dwy;
         if (use_xsph) {
-            const Real fx = PC(neg_eps) * mj * w * inv_rbar;
+            const Real fx = mj * w * inv_rbar;                     // -epsilon is applied once, to the sums
             xs += fx * dvx; ys += fx * dvy;
         }
         if (lj && r2 > Real(1e-24)) {                              // wall / coupled particle inside r0
@@ -385,8 +388,8 @@ k_pair(PairArgs a)
             // xsph = v + correction (WCSPH.py:171-189).  Double instantiation: the sorted copy of v IS the state's v
             if constexpr (EXACT) { vx_st = (double)vxi; vy_st = (double)vyi; }
             else if (!have_v) { vx_st = a.vx[slot]; vy_st = a.vy[slot]; }
-            a.xsphx[slot] = vx_st + (double)xs;
-            a.xsphy[slot] = vy_st + (double)ys;
+            a.xsphx[slot] = vx_st + (double)(PC(neg_eps) * xs);
+            a.xsphy[slot] = vy_st + (double)(PC(neg_eps) * ys);
         } else {
             a.xsphx[slot] = 0.0; a.xsphy[slot] = 0.0;
         }

@@ -80,3 +80,19 @@ __device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real 
     }
 }
 
+// Cubic spline of the fused pair kernel: the same piecewise polynomial written with clamped terms,
+//   W/alpha = (2-q)+^3 / 4 - (1-q)+^3,   W'/alpha = -3/4 (2-q)+^2 + 3 (1-q)+^2,
+// identical to CubicSpline.py:10-70 on every branch (q <= 1, 1 < q <= 2, q > 2) up to rounding of O(1e-16) terms, without
+// evaluating both branches and selecting.
+template <typename Real>
+__device__ __forceinline__ void cubic_pair(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
+{
+    const Real alpha = Real(10.0 / (7.0 * PI_D)) * inv_h * inv_h;
+    const Real t2 = fmax(Real(2) - q, Real(0)), t1 = fmax(Real(1) - q, Real(0));
+    const Real s2 = t2 * t2, s1 = t1 * t1;
+    const Real wv = fma(-s1, t1, Real(0.25) * s2 * t2);
+    const Real gv = fma(Real(3), s1, Real(-0.75) * s2);
+    w = alpha * wv;
+    g = alpha * gv * inv_h * inv_r;
+}
+
