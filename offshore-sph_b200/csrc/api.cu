@@ -414,17 +414,30 @@ extern "C" int osph_step(osph_ctx *ctx, int32_t nsteps, double fixed_dt, double 
     CHECK_CTX(); NEED_PARTICLES();
     if (ctx->n_fluid == 0 && !(fixed_dt > 0)) { ctx->err = "osph_step: no fluid particles"; return OSPH_E_NO_FLUID; }
     int rc;
+    // PEC, several steps in one call: the corrector of step k and the predictor of step k+1 are one pass over the state
+    // (k_prepare<.., FUSED>).  What TimeStep needs for step k+1 is reduced on the way: min h by the predictor of
+    // step k (h is final after its refresh), max |a|^2 by the pair kernel of step k, c_max = co.  The last step of the
+    // call ends with the plain corrector, so the state and the reductions are complete when the call returns.
+    const bool fuse = nsteps > 1 && ctx->cfg.integrator == OSPH_INTEGRATOR_PEC && !ctx->slab && ctx->n_fluid > 0 &&
+                      !ctx->cfg.summation_density;
     for (int s = 0; s < nsteps; s++) {
-        if ((rc = ensure_reductions(ctx))) return rc;
-        // the two scalar resets ride along in k_timestep / k_grid_params on this fused path
-        if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true))) return rc;
-        if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true))) return rc;
+        const bool fused_step = fuse && s > 0;
+        if (!fused_step && (rc = ensure_reductions(ctx))) return rc;
+        // the scalar resets ride along in k_timestep / k_grid_params
+        if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true, nullptr, fuse ? (fused_step ? 2 : 1) : 0)))
+            return rc;
+        if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true, fuse ? (fused_step ? 2 : 1) : 0))) return rc;
         ctx->prepared = true;
         if ((rc = osph_size_cell_table(ctx))) return rc;
-        if ((rc = osph_launch_build(ctx, true))) return rc;
-        if ((rc = osph_launch_pair(ctx))) return rc;
+        if ((rc = osph_launch_build(ctx, !fuse))) return rc;
+        ctx->pair_reduce_a2 = fuse;
+        rc = osph_launch_pair(ctx);
+        ctx->pair_reduce_a2 = false;
+        if (rc) return rc;
         ctx->c_uniform = true;
-        if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true, true))) return rc;
+        if (!fuse || s == nsteps - 1) {
+            if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true, true))) return rc;
+        }
         invalidate_state(ctx);
         ctx->reductions_valid = true;
         ctx->step_counter++;

@@ -52,6 +52,7 @@ struct StepScalars {
     double dt[3];                                // {dt, dt_c, dt_f} of the current step
     double ke;
     long long dt_log_count;
+    double dt_prev;                              // dt of the step before (fused corrector + predictor, step.cu)
 };
 
 struct osph_export_ring;          // export.cu
@@ -135,6 +136,7 @@ struct osph_ctx {
     cudaEvent_t pair_ev[2 * OSPH_PAIR_EVENTS] = {nullptr};   // (start, stop) per pair-kernel launch
     int pair_ev_used = 0;
     bool time_pair = true;
+    bool pair_reduce_a2 = false;     // osph_step's fused loop: the pair kernel reduces max |a|^2 for the next dt
 
     // pinned staging for transfers
     unsigned char *h_pinned = nullptr;

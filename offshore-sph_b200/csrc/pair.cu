@@ -379,6 +379,18 @@ k_pair(PairArgs a)
         }
     }
 
+    if (a.a2max) {
+        // fused step loop: the force criterion of the NEXT time step is reduced here, from the values stored below
+        // (same operations as k_correct), so that no pass over the state is needed between two steps
+        double a2 = -INFINITY;
+        if (fluid_i) {
+            const double axd = (double)ax, ayd = (double)ay - a.gravity;
+            a2 = __dadd_rn(__dmul_rn(axd, axd), __dmul_rn(ayd, ayd));
+            if (!(a2 == a2)) a2 = INFINITY;
+        }
+        a2 = warp_max(a2);
+        if ((tid & 31) == 0 && a2 > -INFINITY) atomicMax(a.a2max, enc_f64(a2));
+    }
     if (fluid_i) {
         if (slot < 0) slot = (int)a.idx[s];
         a.drho[slot] = a.summation_density ? 0.0 : (double)drho;
@@ -497,6 +509,7 @@ int osph_launch_pair(osph_ctx *ctx)
     a.s_pos = ctx->s_pos; a.s_vel = ctx->s_vel; a.s_rm = ctx->s_rm; a.s_hp = ctx->s_hp;
     a.s_info = ctx->s_info; a.s_coarse = ctx->s_coarse; a.s_gcell = ctx->s_gcell;
     a.cell_range = ctx->cell_range; a.gp = ctx->d_grid;
+    a.a2max = ctx->pair_reduce_a2 ? &ctx->d_sc->a2max_fluid : nullptr;
     a.vx = ctx->f[OSPH_F_VX]; a.vy = ctx->f[OSPH_F_VY];
     a.drho = ctx->f[OSPH_F_DRHO]; a.ax = ctx->f[OSPH_F_AX]; a.ay = ctx->f[OSPH_F_AY];
     a.xsphx = ctx->f[OSPH_F_XSPHX]; a.xsphy = ctx->f[OSPH_F_XSPHY];

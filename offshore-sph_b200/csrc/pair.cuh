@@ -12,6 +12,7 @@ struct PairArgs {
     const int2 *s_gcell;
     const int2 *cell_range;
     const GridParams *gp;
+    unsigned long long *a2max;        // optional: order-preserving encoding of max |a|^2 over the fluid rows (TimeStep.py:58-91)
     const double *vx, *vy;            // state columns (storage order), for xsph = v + correction
     double *drho, *ax, *ay, *xsphx, *xsphy;
     double alpha, beta, c_half, eps, r0, D, p1, p2, gravity;

@@ -174,22 +174,49 @@ __device__ __forceinline__ void block_minmax_atomic(double (&vmin)[NV], unsigned
 // Solver._compute (src/Solver.py:242-246, computeH SolverTools.py:106-118).
 // dt is read from device memory so a multi-step loop needs no host round trip.
 // ---------------------------------------------------------------------------------------------
-template <int INTEG, bool PREDICT>
+// FUSED (PEC only, osph_step's multi-step loop): the corrector of the PREVIOUS step (same arithmetic as k_correct, with
+// sc->dt_prev) is applied in registers first, so the corrected state is never written and re-read between two steps:
+// one pass over the state per step boundary instead of two.
+template <int INTEG, bool PREDICT, bool FUSED>
 __global__ void __launch_bounds__(256)
 k_prepare(PrepareArgs a)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double bx = INFINITY, by = INFINITY, hmn = INFINITY, Bx = -INFINITY, By = -INFINITY, hmx = -INFINITY;
+    double bx = INFINITY, by = INFINITY, hmn = INFINITY, Bx = -INFINITY, By = -INFINITY, hmx = -INFINITY, hfl = INFINITY;
     if (i < a.n) {
         bool fluid = a.label[i] == OSPH_FLUID;
-        double x = a.x[i], y = a.y[i], h = a.h[i];
+        double x, y, h = a.h[i];
+        if (!(FUSED && fluid)) { x = a.x[i]; y = a.y[i]; }
         hmn = h;
         if (fluid) {
-            double rho = a.rho[i];
+            double rho, vx, vy;
+            if (FUSED) {
+                // corrector of the step before: PEC.py:62-88, identical operation order to k_correct
+                const double hdtp = __dmul_rn(0.5, a.sc->dt_prev);
+                const double x0 = a.x0[i], y0 = a.y0[i], vx0 = a.vx0[i], vy0 = a.vy0[i], rho0 = a.rho0[i];
+                double ux, uy;
+                if (a.integ_xsph) { ux = a.xsphx[i]; uy = a.xsphy[i]; } else { ux = a.vx[i]; uy = a.vy[i]; }
+                const double mx = __dadd_rn(x0, __dmul_rn(hdtp, ux));
+                const double my = __dadd_rn(y0, __dmul_rn(hdtp, uy));
+                const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
+                const double mvx = __ddiv_rn(__dadd_rn(vx0, __dmul_rn(hdtp, a.ax[i])), den);
+                const double mvy = __ddiv_rn(__dadd_rn(vy0, __dmul_rn(hdtp, a.ay[i])), den);
+                x = __dadd_rn(__dmul_rn(2.0, mx), -x0);
+                y = __dadd_rn(__dmul_rn(2.0, my), -y0);
+                vx = __dadd_rn(__dmul_rn(2.0, mvx), -vx0);
+                vy = __dadd_rn(__dmul_rn(2.0, mvy), -vy0);
+                const double mrho = __dadd_rn(rho0, __dmul_rn(hdtp, a.drho[i]));
+                rho = __dadd_rn(__dmul_rn(2.0, mrho), -rho0);
+                if (a.strict && rho < 0.0) rho = 0.0;
+                if (!(isfinite(x) && isfinite(y) && isfinite(vx) && isfinite(vy) && isfinite(rho)))
+                    atomicOr(&a.sc->status, OSPH_S_NONFINITE);
+            } else {
+                rho = a.rho[i];
+                if (PREDICT) { vx = a.vx[i]; vy = a.vy[i]; }
+            }
             if (PREDICT) {
                 const double dt = a.use_dev_dt ? a.sc->dt[0] : a.dt;
                 const double hdt = __dmul_rn(0.5, dt);
-                double vx = a.vx[i], vy = a.vy[i];
                 if (INTEG == OSPH_INTEGRATOR_PEC) {
                     a.x0[i] = x; a.y0[i] = y; a.vx0[i] = vx; a.vy0[i] = vy;
                     double ux = vx, uy = vy;
@@ -224,16 +251,25 @@ k_prepare(PrepareArgs a)
         if (isfinite(x) && isfinite(y)) { bx = x; Bx = x; by = y; By = y; }
         else atomicOr(&a.sc->status, OSPH_S_NONFINITE);
         hmx = h;
+        if (fluid) hfl = h;
     }
-    double v[6] = {bx, by, hmn, Bx, By, hmx};
-    unsigned long long *const p[6] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all,
-                                      &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all};
-    block_minmax_atomic<6>(v, p, 3);
+    if (a.reduce_hmin_fluid) {
+        double v[7] = {bx, by, hmn, hfl, Bx, By, hmx};
+        unsigned long long *const p[7] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all, &a.sc->hmin_fluid,
+                                          &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all};
+        block_minmax_atomic<7>(v, p, 4);
+    } else {
+        double v[6] = {bx, by, hmn, Bx, By, hmx};
+        unsigned long long *const p[6] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all,
+                                          &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all};
+        block_minmax_atomic<6>(v, p, 3);
+    }
 }
 
-template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, true>(PrepareArgs);
-template __global__ void k_prepare<OSPH_INTEGRATOR_VERLET, true>(PrepareArgs);
-template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, false>(PrepareArgs);
+template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, true, false>(PrepareArgs);
+template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, true, true>(PrepareArgs);
+template __global__ void k_prepare<OSPH_INTEGRATOR_VERLET, true, false>(PrepareArgs);
+template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, false, false>(PrepareArgs);
 
 // ---------------------------------------------------------------------------------------------
 // Grid parameters: the reference grid (NNLinkedList.py:86-127) and the acceleration grid.
@@ -500,8 +536,10 @@ template __global__ void k_correct<OSPH_INTEGRATOR_VERLET, true>(CorrectArgs);
 template __global__ void k_correct<OSPH_INTEGRATOR_PEC, false>(CorrectArgs);
 
 // TimeStep.compute / courant / force (src/Equations/TimeStep.py:11-56), strict IEEE.
+// fused (osph_step's multi-step loop): 1 = the dt scalars are reset here, right after use (the predictor and the pair
+// kernel of this step reduce the next ones); 2 = additionally c_max is the uniform co (no corrector pass reduced it).
 __global__ void k_timestep(StepScalars *sc, double gamma_c, double gamma_f, double fixed_dt,
-                           double *dt_log, long long dt_log_cap, int reset_prepare, const double *reduced3)
+                           double *dt_log, long long dt_log_cap, int reset_prepare, const double *reduced3, int fused, double co)
 {
     if (reduced3) {           // slab mode: all-reduced {h_min, -c_max, -a2_max} replaces the local reduction
         sc->hmin_fluid = enc_f64(reduced3[0]); sc->cmax_fluid = enc_f64(-reduced3[1]); sc->a2max_fluid = enc_f64(-reduced3[2]);
@@ -513,12 +551,14 @@ __global__ void k_timestep(StepScalars *sc, double gamma_c, double gamma_f, doub
     double out0, c = 0.0, f = 0.0;
     if (fixed_dt > 0.0) { out0 = fixed_dt; }
     else {
-        double hmin = dec_f64(sc->hmin_fluid), cmax = dec_f64(sc->cmax_fluid), a2 = dec_f64(sc->a2max_fluid);
+        double hmin = dec_f64(sc->hmin_fluid), cmax = fused == 2 ? co : dec_f64(sc->cmax_fluid), a2 = dec_f64(sc->a2max_fluid);
         c = __ddiv_rn(__dmul_rn(gamma_c, hmin), cmax);
         f = (a2 < 1e-12) ? 1e10 : __dmul_rn(gamma_f, __dsqrt_rn(__ddiv_rn(hmin, a2)));
         out0 = c < f ? c : f;
         if (out0 < 1e-6) atomicOr(&sc->status, OSPH_S_SMALL_DT);
     }
+    if (fused) { sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF; }
+    sc->dt_prev = sc->dt[0];
     sc->dt[0] = out0; sc->dt[1] = c; sc->dt[2] = f;
     if (dt_log) {
         long long k = sc->dt_log_count;
@@ -776,7 +816,7 @@ int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids)
     return 0;
 }
 
-int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset)
+int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset, int fused)
 {
     PrepareArgs a;
     a.n = (int)ctx->n; a.label = ctx->label;
@@ -789,12 +829,17 @@ int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, 
     a.sc = ctx->d_sc; a.dt = dt; a.damping = damping; a.fixed_h = ctx->cfg.fixed_h; a.h_sigma = ctx->cfg.h_sigma;
     a.use_dev_dt = use_dev_dt ? 1 : 0; a.integ_xsph = ctx->cfg.integrator_xsph; a.strict = ctx->cfg.strict;
     a.dynamic_h = ctx->cfg.dynamic_h;
+    a.reduce_hmin_fluid = fused ? 1 : 0;
     if (!skip_reset) { k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
     int grid = div_up(ctx->n, 256);
     int integ = ctx->cfg.integrator;
-    if (predict && integ == OSPH_INTEGRATOR_PEC) k_prepare<OSPH_INTEGRATOR_PEC, true><<<grid, 256, 0, ctx->stream>>>(a);
-    else if (predict && integ == OSPH_INTEGRATOR_VERLET) k_prepare<OSPH_INTEGRATOR_VERLET, true><<<grid, 256, 0, ctx->stream>>>(a);
-    else k_prepare<OSPH_INTEGRATOR_PEC, false><<<grid, 256, 0, ctx->stream>>>(a);
+    if (fused == 2) {
+        if (!(predict && integ == OSPH_INTEGRATOR_PEC)) { ctx->err = "fused corrector + predictor exists for PEC only"; return OSPH_E_INVALID; }
+        k_prepare<OSPH_INTEGRATOR_PEC, true, true><<<grid, 256, 0, ctx->stream>>>(a);
+    }
+    else if (predict && integ == OSPH_INTEGRATOR_PEC) k_prepare<OSPH_INTEGRATOR_PEC, true, false><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (predict && integ == OSPH_INTEGRATOR_VERLET) k_prepare<OSPH_INTEGRATOR_VERLET, true, false><<<grid, 256, 0, ctx->stream>>>(a);
+    else k_prepare<OSPH_INTEGRATOR_PEC, false, false><<<grid, 256, 0, ctx->stream>>>(a);
     OSPH_LAUNCH_CHECK();
     return 0;
 }
@@ -920,11 +965,11 @@ int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, 
     return 0;
 }
 
-int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare, const double *d_reduced3)
+int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare, const double *d_reduced3, int fused)
 {
     k_timestep<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->cfg.cfl_courant, ctx->cfg.cfl_force, fixed_dt,
                                          log ? ctx->d_dt_log : nullptr, (long long)ctx->dt_log_cap, reset_prepare ? 1 : 0,
-                                         d_reduced3);
+                                         d_reduced3, fused, ctx->cfg.co);
     OSPH_LAUNCH_CHECK();
     return 0;
 }

@@ -11,6 +11,7 @@ struct PrepareArgs {
     StepScalars *sc;
     double dt, damping, fixed_h, h_sigma;
     int use_dev_dt, integ_xsph, strict, dynamic_h;
+    int reduce_hmin_fluid;            // fused loop: min h over the fluid rows (TimeStep of the next step) is taken here
 };
 
 struct CorrectArgs {
@@ -62,11 +63,12 @@ int osph_launch_unpack(osph_ctx *ctx);
 int osph_launch_active_list(osph_ctx *ctx, int n_total, int *d_counters);
 int osph_launch_pack(osph_ctx *ctx);
 int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids);
-int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
+int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset = false,
+                        int fused = 0);   // fused 1: reduce fluid h_min too; 2: also apply the previous step's corrector first
 int osph_launch_build(osph_ctx *ctx, bool reset_dt = false);   // grid params, keys, sort, (reorder), gather + cell table
 int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
 int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare = false,
-                         const double *d_reduced3 = nullptr);
+                         const double *d_reduced3 = nullptr, int fused = 0);   // fused 1: reset the dt scalars after use; 2: c_max = co too
 int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt = false);
 int osph_launch_ke(osph_ctx *ctx);
 int osph_launch_neighbours(osph_ctx *ctx, int mode, long long *d_counts, const long long *d_offsets, long long *d_out);

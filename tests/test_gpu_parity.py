@@ -103,6 +103,25 @@ def test_fused_loop_equals_explicit_calls(name):
         assert np.array_equal(b.dt_log(), np.asarray(dts))
 
 
+@pytest.mark.parametrize("fixed_dt", [None, 2e-4])
+def test_multi_step_call_equals_single_step_calls(fixed_dt):
+    """osph_step(n) fuses the corrector of step k with the predictor of step k+1 and takes the dt reductions from the
+    predictor / pair kernel; the result must be the bytes of n separate osph_step(1) calls, however the calls are cut."""
+    g, meta, pA = load_golden('tank30_cubic_dynh')
+    with _ctx(meta) as a, _ctx(meta) as b, _ctx(meta) as c:
+        for ctx in (a, b, c):
+            ctx.upload(pA)
+        for _ in range(6):
+            a.step(1, fixed_dt, 0.05)
+        b.step(6, fixed_dt, 0.05)
+        c.step(2, fixed_dt, 0.05); c.step(1, fixed_dt, 0.05); c.step(3, fixed_dt, 0.05)
+        A, B, C = (ctx.download(pA.copy()) for ctx in (a, b, c))
+        assert A.tobytes() == B.tobytes() == C.tobytes()
+        la, lb, lc = a.dt_log(), b.dt_log(), c.dt_log()
+        assert np.array_equal(la, lb) and np.array_equal(la, lc) and len(la) == 6
+        assert a.timestep() == b.timestep() == c.timestep()            # the reductions left behind agree too
+
+
 @pytest.mark.parametrize("integrator", ['euler', 'verlet'])
 def test_other_integrators_vs_oracle(integrator):
     g, meta, pA = load_golden('dambreak20_cubic')
