@@ -389,7 +389,10 @@ k_pair(PairArgs a)
             if (!(a2 == a2)) a2 = INFINITY;
         }
         a2 = warp_max(a2);
-        if ((tid & 31) == 0 && a2 > -INFINITY) atomicMax(a.a2max, enc_f64(a2));
+        if ((tid & 31) == 0 && a2 > -INFINITY) {
+            const unsigned long long e = enc_f64(a2);
+            if (e > *reinterpret_cast<volatile unsigned long long *>(a.a2max)) atomicMax(a.a2max, e);
+        }
     }
     if (fluid_i) {
         if (slot < 0) slot = (int)a.idx[s];

@@ -160,8 +160,10 @@ __device__ __forceinline__ void block_minmax_atomic(double (&vmin)[NV], unsigned
             double v = lane < nw ? sh[k][lane] : (k < nmin ? INFINITY : -INFINITY);
             v = k < nmin ? warp_min(v) : warp_max(v);
             if (lane == 0) {
-                if (k < nmin) { if (v < INFINITY) atomicMin(pmin[k], enc_f64(v)); }
-                else { if (v > -INFINITY) atomicMax(pmin[k], enc_f64(v)); }
+                // look before the atomic: thousands of CTAs hit the same few words and almost none improves them
+                const unsigned long long e = enc_f64(v), cur = *reinterpret_cast<volatile unsigned long long *>(pmin[k]);
+                if (k < nmin) { if (v < INFINITY && e < cur) atomicMin(pmin[k], e); }
+                else { if (v > -INFINITY && e > cur) atomicMax(pmin[k], e); }
             }
         }
     }
