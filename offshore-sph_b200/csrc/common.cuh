@@ -22,6 +22,7 @@
 struct GridParams {
     // reference grid (NNLinkedList._init, reference src/Tools/NNLinkedList.py:86-127)
     double xmin, xmax, ymin, ymax, cell_size;
+    double rcell;          // RN(1 / cell_size) for the constant-divisor division of cell_of (step.cu: div_den), 0: divide
     long long ncx, ncy, n_cells;
     // acceleration grid used on the device (regime A: identical to the reference grid;
     // regime B: cells of the pair-interaction radius)

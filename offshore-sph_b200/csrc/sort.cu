@@ -22,7 +22,8 @@ k_sort_hist(const unsigned int *__restrict__ key, int n, int shift, int nblocks,
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; r++) {
         int i = base + r * SORT_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&cnt[(key[i] >> shift) & (RADIX - 1)], 1u);
+        const bool ok = i < n;
+        warp_hist_add(cnt, ok ? ((key[i] >> shift) & (RADIX - 1)) : 0u, ok);
     }
     __syncthreads();
     for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = cnt[d];

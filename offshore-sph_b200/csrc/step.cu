@@ -169,6 +169,29 @@ __device__ __forceinline__ void block_minmax_atomic(double (&vmin)[NV], unsigned
     }
 }
 
+// v / den for the loop-invariant den = 1 + damping / 2 (PEC.py:44-45, 72-73).  With rden = RN(1 / den), one
+// correction step on q = RN(v * rden) -- r = v - q * den exactly (fma), q' = RN(q + r * rden) -- gives the correctly
+// rounded quotient (Markstein), i.e. the bits of the division the reference performs, for 3 instructions instead of
+// the division subroutine; checked against v / den on 6.6e8 random operands.  rden == 0 (set on
+// the host when den's significand is all ones, the one case the theorem excludes) selects the plain division.
+__device__ __forceinline__ double div_den(double v, double den, double rden)
+{
+    if (rden == 0.0) return __ddiv_rn(v, den);
+    const double q = __dmul_rn(v, rden);
+    const double r = __fma_rn(-q, den, v);
+    return __fma_rn(r, rden, q);
+}
+
+static double rden_for(double damping)
+{
+    const double den = 1.0 + 0.5 * damping;
+    unsigned long long bits;
+    memcpy(&bits, &den, 8);
+    if (!(den > 0.0) || !std::isfinite(den) || (bits & 0xfffffffffffffULL) == 0xfffffffffffffULL) return 0.0;
+    const double r = 1.0 / den;
+    return std::isfinite(r) ? r : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1 + K2: predictor (PEC: reference src/Integrators/PEC.py:32-60, Verlet.py:28-36, Euler: identity)
 // fused with the reductions NNLinkedList._init needs (bounds of ALL active particles,
@@ -201,8 +224,8 @@ k_prepare(PrepareArgs a)
                 const double mx = __dadd_rn(x0, __dmul_rn(hdtp, ux));
                 const double my = __dadd_rn(y0, __dmul_rn(hdtp, uy));
                 const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
-                const double mvx = __ddiv_rn(__dadd_rn(vx0, __dmul_rn(hdtp, a.ax[i])), den);
-                const double mvy = __ddiv_rn(__dadd_rn(vy0, __dmul_rn(hdtp, a.ay[i])), den);
+                const double mvx = div_den(__dadd_rn(vx0, __dmul_rn(hdtp, a.ax[i])), den, a.rden);
+                const double mvy = div_den(__dadd_rn(vy0, __dmul_rn(hdtp, a.ay[i])), den, a.rden);
                 x = __dadd_rn(__dmul_rn(2.0, mx), -x0);
                 y = __dadd_rn(__dmul_rn(2.0, my), -y0);
                 vx = __dadd_rn(__dmul_rn(2.0, mvx), -vx0);
@@ -226,8 +249,8 @@ k_prepare(PrepareArgs a)
                     x = __dadd_rn(x, __dmul_rn(hdt, ux));
                     y = __dadd_rn(y, __dmul_rn(hdt, uy));
                     const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
-                    a.vx[i] = __ddiv_rn(__dadd_rn(vx, __dmul_rn(hdt, a.ax[i])), den);
-                    a.vy[i] = __ddiv_rn(__dadd_rn(vy, __dmul_rn(hdt, a.ay[i])), den);
+                    a.vx[i] = div_den(__dadd_rn(vx, __dmul_rn(hdt, a.ax[i])), den, a.rden);
+                    a.vy[i] = div_den(__dadd_rn(vy, __dmul_rn(hdt, a.ay[i])), den, a.rden);
                     a.rho0[i] = rho;
                     rho = __dadd_rn(rho, __dmul_rn(hdt, a.drho[i]));
                     if (a.strict && rho < 0.0) rho = 0.0;
@@ -289,6 +312,7 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
     if (cs < 1e-6) cs = 1.0;                          // :107-108
     g->cell_size = cs;
     double inv = __ddiv_rn(1.0, cs);                  // :113
+    g->rcell = ((unsigned long long)__double_as_longlong(cs) & 0xfffffffffffffULL) == 0xfffffffffffffULL || !isfinite(inv) ? 0.0 : inv;
     long long ncx = (long long)ceil(__dmul_rn(inv, __dadd_rn(xmax, -xmin)));
     long long ncy = (long long)ceil(__dmul_rn(inv, __dadd_rn(ymax, -ymin)));
     if (ncx < 1) ncx = 1;
@@ -342,8 +366,8 @@ __device__ __forceinline__ CellInfo cell_of(double x, double y, const GridParams
 {
     CellInfo c;
     double rx = __dadd_rn(x, -g.xmin), ry = __dadd_rn(y, -g.ymin);
-    long long cx = (long long)floor(__ddiv_rn(rx, g.cell_size));
-    long long cy = (long long)floor(__ddiv_rn(ry, g.cell_size));
+    long long cx = (long long)floor(div_den(rx, g.cell_size, g.rcell));       // == rx / cell_size, correctly rounded
+    long long cy = (long long)floor(div_den(ry, g.cell_size, g.rcell));
     long long flat = cx + g.ncx * cy;
     c.binned = flat >= 0 && flat < g.n_cells;
     c.coarse.x = c.binned ? (int)(flat % g.ncx) : -1000000;
@@ -384,14 +408,18 @@ k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, 
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; r++) {
         int i = blockIdx.x * SORT_TILE + r * SORT_THREADS + threadIdx.x;
-        if (i >= n_all) continue;
-        double px, py;
-        if (i < n_owned) { px = x[i]; py = y[i]; }
-        else { const double *rec = ghost_record(ghost, gmap, i - n_owned); px = rec[0]; py = rec[1]; }
-        CellInfo c = cell_of(px, py, g);
-        unbinned |= !c.binned;
-        key[i] = c.key; idx[i] = (unsigned int)i;
-        atomicAdd(&cnt[c.key & (RADIX - 1)], 1u);
+        const bool ok = i < n_all;
+        unsigned int digit = 0;
+        if (ok) {
+            double px, py;
+            if (i < n_owned) { px = x[i]; py = y[i]; }
+            else { const double *rec = ghost_record(ghost, gmap, i - n_owned); px = rec[0]; py = rec[1]; }
+            CellInfo c = cell_of(px, py, g);
+            unbinned |= !c.binned;
+            key[i] = c.key; idx[i] = (unsigned int)i;
+            digit = c.key & (RADIX - 1);
+        }
+        warp_hist_add(cnt, digit, ok);
     }
     if (unbinned) atomicOr(&sc->status, OSPH_S_UNBINNED);
     __syncthreads();
@@ -492,8 +520,8 @@ k_correct(CorrectArgs a)
                 double mx = __dadd_rn(x0, __dmul_rn(hdt, ux));
                 double my = __dadd_rn(y0, __dmul_rn(hdt, uy));
                 const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
-                double mvx = __ddiv_rn(__dadd_rn(vx0, __dmul_rn(hdt, ax)), den);
-                double mvy = __ddiv_rn(__dadd_rn(vy0, __dmul_rn(hdt, ay)), den);
+                double mvx = div_den(__dadd_rn(vx0, __dmul_rn(hdt, ax)), den, a.rden);
+                double mvy = div_den(__dadd_rn(vy0, __dmul_rn(hdt, ay)), den, a.rden);
                 x = __dadd_rn(__dmul_rn(2.0, mx), -x0);
                 y = __dadd_rn(__dmul_rn(2.0, my), -y0);
                 vx = __dadd_rn(__dmul_rn(2.0, mvx), -vx0);
@@ -832,6 +860,7 @@ int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, 
     a.use_dev_dt = use_dev_dt ? 1 : 0; a.integ_xsph = ctx->cfg.integrator_xsph; a.strict = ctx->cfg.strict;
     a.dynamic_h = ctx->cfg.dynamic_h;
     a.reduce_hmin_fluid = fused ? 1 : 0;
+    a.rden = rden_for(damping);
     if (!skip_reset) { k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
     int grid = div_up(ctx->n, 256);
     int integ = ctx->cfg.integrator;
@@ -957,6 +986,7 @@ int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, 
     a.sc = ctx->d_sc; a.dt = dt; a.damping = damping; a.co = ctx->cfg.co;
     a.use_dev_dt = use_dev_dt ? 1 : 0; a.integ_xsph = ctx->cfg.integrator_xsph; a.strict = ctx->cfg.strict;
     a.c_uniform = ctx->c_uniform ? 1 : 0;
+    a.rden = rden_for(damping);
     if (!skip_reset) { k_reset_dt_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
     int grid = div_up(ctx->n, 256);
     if (!correct) k_correct<OSPH_INTEGRATOR_PEC, false><<<grid, 256, 0, ctx->stream>>>(a);

@@ -12,6 +12,7 @@ struct PrepareArgs {
     double dt, damping, fixed_h, h_sigma;
     int use_dev_dt, integ_xsph, strict, dynamic_h;
     int reduce_hmin_fluid;            // fused loop: min h over the fluid rows (TimeStep of the next step) is taken here
+    double rden;                      // RN(1 / (1 + damping / 2)) for div_den, 0: divide
 };
 
 struct CorrectArgs {
@@ -21,6 +22,7 @@ struct CorrectArgs {
     const double *h, *c, *ax, *ay, *drho, *xsphx, *xsphy, *x0, *y0, *vx0, *vy0, *rho0;
     StepScalars *sc;
     double dt, damping, co;
+    double rden;                      // as PrepareArgs::rden
     int use_dev_dt, integ_xsph, strict, c_uniform;
 };
 
