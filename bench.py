@@ -9,7 +9,8 @@ neighbour structure, fused pair kernel, PEC correct) over the synthetic dam-brea
 SURVEY.md section 8(d): the reference's DamBreak generator scaled to N x N fluid particles, setup as
 Solver.setup() does, jittered deterministically so pair forces do not vanish.
 
-  value          particle-steps/s with the state resident in HBM (osph_step, no host round trip)
+  value          particle-steps/s with the state resident in HBM: ONE osph_step(K) call for the K timed steps, no host
+                 round trip inside (the library applies the corrector of step k in the predictor pass of step k+1)
   e2e            the same through the plugin boundary with HOST buffers: every step uploads the packed
                  particle_dtype array from pinned memory, runs one step, downloads it again
   roofline       the fused pair kernel against the measured HBM peak (algorithmic bytes 13F+1 per particle)
