@@ -179,6 +179,34 @@ def solver_run_case(name, N, kernel, duration, maxSettle):
                                                             os.path.getsize(path) / 1e3))
 
 
+def verlet_case(name='verlet_leaf'):
+    """The reference's Verlet integrator (src/Integrators/Verlet.py:28-55) on a random fluid block: state after
+    predict and after correct, with and without XSPH.  Pins the oracle's Verlet (the GPU path is checked against it)."""
+    rng = np.random.default_rng(11)
+    n = 96
+    pA = np.zeros(n, dtype=ref.particle_dtype)
+    for f in ('x', 'y', 'vx', 'vy', 'ax', 'ay', 'xsphx', 'xsphy', 'drho'):
+        pA[f] = rng.normal(size=n) * {'ax': 9.0, 'ay': 9.0, 'drho': 40.0}.get(f, 1.5)
+    pA['rho'] = 1000.0 + rng.normal(size=n)
+    pA['m'] = 1.0
+    dt, damping = 3.7e-4, 0.05
+    out = dict(aos=np.frombuffer(pA.tobytes(), dtype=np.uint8).reshape(n, 154).copy(), dt=np.float64(dt))
+    for useXSPH in (True, False):
+        integ = ref.Verlet(useXSPH)
+        assert integ.isMultiStage() is False
+        q = integ.predict(dt, pA.copy(), damping)
+        tag = 'xsph' if useXSPH else 'raw'
+        out['pred_%s' % tag] = np.frombuffer(q.tobytes(), dtype=np.uint8).reshape(n, 154).copy()
+        q = integ.correct(dt, q, damping)
+        out['corr_%s' % tag] = np.frombuffer(q.tobytes(), dtype=np.uint8).reshape(n, 154).copy()
+    import numba
+    out['meta'] = np.frombuffer(json.dumps(dict(name=name, n=n, dt=dt, damping=damping, numba=numba.__version__,
+                                                numpy=np.__version__)).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print('%-28s n=%d -> %.0f kB' % (name, n, os.path.getsize(path) / 1e3))
+
+
 def main():
     # regime A: 3h > reference cell (1.0): the 3x3 coarse walk truncates the neighbourhood
     make_case('dambreak20_wendland', W.dam_break_case(20), 'wendland', True, 0.05, 3)
@@ -200,11 +228,14 @@ def main():
               summation=True)
     # the reference Solver end to end (settle -> gate removal -> time stepping)
     solver_run_case('solver_dambreak12_wendland', 12, 'wendland', 0.03, 6)
+    verlet_case()
 
 
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'sumdens':      # regenerate only the newest case
         make_case('tank16_cubic_sumdens', W.tank_case(16, h=1.3 / 16, useXSPH=True, seed=5), 'cubic', True, 0.0, 2,
                   summation=True)
+    elif len(sys.argv) > 1 and sys.argv[1] == 'verlet':
+        verlet_case()
     else:
         main()

@@ -127,6 +127,38 @@ def test_pec_equals_euler_with_frozen_forces():
         assert getattr(A, f)[0] == pytest.approx(getattr(B, f)[0])
 
 
+def test_euler_known_answer():
+    """reference test/test_integrators_euler.py:30-38 (the fluid half; the class itself no longer builds under numba
+    >= 0.59, the boundary half of that test contradicts Euler.py:17-26 and is stale)."""
+    P = O.Particles(1)
+    P.vx[0] = 1.0; P.vy[0] = 3.0; P.ax[0] = 5.0; P.drho[0] = 10.0
+    dt = 2.0
+    O.euler_correct(P, np.ones(1, dtype=np.uint8), dt)
+    assert P.x[0] == 1.0 * dt + 0.5 * 5.0 * dt * dt and P.y[0] == 3.0 * dt and P.rho[0] == 10 * dt
+    assert (P.vx[0], P.vy[0]) == (1.0 + dt * 5.0, 3.0)
+
+
+def test_verlet_matches_reference_verlet():
+    """Golden `verlet_leaf` = the reference's own Verlet.predict / .correct (src/Integrators/Verlet.py:28-55, run
+    under numba by tests/golden/make_golden.py), with and without XSPH.  No density update, no damping: as shipped."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'verlet_leaf.npz'))
+    pA = np.frombuffer(g['aos'].tobytes(), dtype=O.particle_dtype)
+    dt = float(g['dt'])
+    mask = np.ones(len(pA), dtype=np.uint8)
+    for tag, xs in (('xsph', True), ('raw', False)):
+        P = O.Particles.from_aos(pA)
+        O.verlet_predict(P, mask, dt)
+        want = np.frombuffer(g['pred_' + tag].tobytes(), dtype=O.particle_dtype)
+        for f in ('x', 'y', 'vx', 'vy', 'rho'):
+            assert np.array_equal(getattr(P, f), want[f]), (tag, 'predict', f)
+        O.verlet_correct(P, mask, dt, useXSPH=xs)
+        want = np.frombuffer(g['corr_' + tag].tobytes(), dtype=O.particle_dtype)
+        for f in ('x', 'y', 'vx', 'vy', 'rho'):
+            assert field_err(getattr(P, f), want[f]) <= 1e-15, (tag, 'correct', f)
+        assert np.array_equal(P.rho, pA['rho'])
+
+
 def test_linked_list_known_answer():
     """reference test/test_linked_list.py:56-79: 26x26 unit lattice, h = 1, scale = 3."""
     xv = np.linspace(0, 25, 26)
