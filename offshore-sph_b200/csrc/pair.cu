@@ -9,15 +9,18 @@
 // Mapping.  Particles are sorted by acceleration-grid cell (row-major), so the candidates of a particle
 // are three contiguous runs of the sorted arrays (cells cx-1..cx+1 of rows cy-1, cy, cy+1).  A CTA owns
 // 256 CONSECUTIVE sorted particles; per row offset the union of its threads' runs is again one contiguous
-// interval, which the CTA stages through shared memory in batches of OSPH_CAP_STAGE candidates with
-// coalesced 16-byte loads.  Each thread then walks only its own sub-interval of the staged batch; threads
-// of one cell read the same shared-memory address (broadcast).  Outputs are scattered to the storage-order
-// state columns.  No atomics, no neighbour list in memory, deterministic summation order.
+// interval.  The three intervals are staged ONCE into shared memory as array-of-structure records (PAIR_CAP of
+// them; longer runs fall back to batches) with coalesced 16-byte loads.  Each thread then walks only its own
+// sub-intervals in two phases, warp-synchronously: a cheap scan that appends accepted record indices to a
+// per-thread list, and a flush that evaluates the listed pairs with (almost) all lanes active.  Threads of one
+// cell read the same shared-memory address (broadcast).  Outputs are scattered to the storage-order state
+// columns.  No atomics on the sums, no neighbour list in memory, deterministic summation order.
 //
 // FP64 instantiation = validation mode: membership of a pair in the reference neighbour set is decided
-// exactly (reference-cell adjacency on stored integer cell ids; r/h_ij <= 3.0 re-evaluated in strict IEEE
-// when the cheap test is within 1e-13 of the threshold).  FP32 instantiation = performance mode: positions
-// are staged relative to a per-CTA anchor (subtracted in double, then rounded), arithmetic in float.
+// exactly (reference-cell adjacency on stored integer cell ids wherever distance does not already imply it;
+// r/h_ij <= 3.0 re-evaluated in strict IEEE when the cheap test is within 1e-13 of the threshold).  FP32
+// instantiation = performance mode: positions are staged relative to a per-CTA anchor (subtracted in double,
+// then rounded), arithmetic in float.
 #include "common.cuh"
 #include "pair.cuh"
 
