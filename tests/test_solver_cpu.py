@@ -131,3 +131,24 @@ def test_coupling_rows_only_moves_only_the_coupled_rows(oracle_backend):
     for f in ('x', 'y', 'vx', 'vy', 'rho', 'ax', 'ay'):
         assert np.array_equal(a.particleArray[f], b.particleArray[f]), f
     assert np.any(a.particleArray['y'][a.particleArray['label'] == ParticleType.Coupled] != 0)
+
+
+@pytest.mark.parametrize("example, args", [("containment", ['--nx', '12', '--duration', '0.002', '--max-settle', '3']),
+                                            ("dam_break", ['--n', '10', '--duration', '0.002', '--max-settle', '3'])])
+def test_shipped_examples_run_on_the_oracle_backend(oracle_backend, example, args, tmp_path):
+    """The package's own example scripts (Containment: dynamic h, XSPH off, `Solver(h=None)`; both call timing() and
+    save()) drive the Solver end to end on CPU."""
+    import importlib.util
+    import os
+    from conftest import PKG
+    spec = importlib.util.spec_from_file_location("ex_" + example, os.path.join(PKG, "examples", example + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    s = mod.main(args + ['--out', str(tmp_path / "run")])
+    pa = s.particleArray
+    assert s.t >= 0.002 and s.t_step > 0 and np.all(np.isfinite(pa['x'])) and np.all(np.isfinite(pa['rho']))
+    fluid = (pa['label'] == 0) & ~pa['deleted']
+    assert np.all(pa['h'][fluid] > 0)
+    for key in s.exportProperties:
+        assert len(s.export[key]) == s.t_step
+    assert any(f.startswith("run") for f in os.listdir(tmp_path))          # save(): .hdf5 with h5py, else .npz
