@@ -21,6 +21,14 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    if os.environ.get("OSPH_EMU") == "1":
+        # manual mode: run the GPU-marked tests against the SIMT-emulated build of the kernel sources (tests/emu);
+        # `OSPH_EMU=1 pytest tests/test_gpu_parity.py -m gpu`.  The default CPU run uses tests/test_emu_kernels.py.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build as emu_build
+        from osph_b200 import capi
+        capi.LIB_PATH, capi._lib = emu_build.build(), None
+        return
     import torch
     if torch.cuda.is_available():
         return

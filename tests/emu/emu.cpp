@@ -1,0 +1,296 @@
+// emu.cpp -- fiber scheduler of the SIMT emulator and a stand-in for the handful of CUDA runtime calls the library
+// makes (device memory = host memory, one in-order "stream").  TEST INFRASTRUCTURE ONLY, see emu.h.
+#include "emu.h"
+
+#include <stdio.h>
+#include <sys/mman.h>
+
+#include <vector>
+
+namespace emu {
+
+ThreadCtx *cur = nullptr;
+unsigned char *dyn_smem_ptr = nullptr;
+
+// ---- context switch ---------------------------------------------------------------------------------------------------
+#if defined(__x86_64__)
+extern "C" void emu_switch(void **from_sp, void *to_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#else
+#error "the SIMT emulator's context switch is written for x86-64"
+#endif
+
+enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
+
+struct Fiber {
+    void *sp = nullptr;
+    State state = DONE;
+    ThreadCtx tc;
+};
+
+struct Warp {
+    unsigned arrived = 0, alive = 0, mask = 0;
+    Op op = OP_SYNC;
+    int width = 32;
+    uint64_t val[32];
+    int param[32];
+    uint64_t res[32];
+};
+
+static const size_t STACK_BYTES = 256 * 1024;
+static std::vector<Fiber> fibers;
+static std::vector<Warp> warps;
+static unsigned char *stack_pool = nullptr;
+static size_t stack_pool_threads = 0;
+static void *sched_sp = nullptr;
+static const std::function<void()> *body_fn = nullptr;
+static int barrier_waiting = 0, alive_threads = 0;
+static Fiber *running = nullptr;
+
+static void yield_to_scheduler()
+{
+    Fiber *f = running;
+    emu_switch(&f->sp, sched_sp);
+}
+
+static void fiber_entry()
+{
+    (*body_fn)();
+    running->state = DONE;
+    yield_to_scheduler();
+    abort();      // a finished fiber is never resumed
+}
+
+static void prepare_fiber(Fiber &f, int slot)
+{
+    unsigned char *top = stack_pool + (size_t)(slot + 1) * STACK_BYTES;
+    void **sp = reinterpret_cast<void **>(top);
+    *--sp = nullptr;                                      // fake return address of fiber_entry: keeps rsp = 8 mod 16
+    *--sp = reinterpret_cast<void *>(&fiber_entry);       // popped by emu_switch's ret
+    for (int k = 0; k < 6; k++) *--sp = nullptr;          // rbp rbx r12 r13 r14 r15
+    f.sp = sp;
+    f.state = READY;
+}
+
+void block_barrier()
+{
+    running->state = WAIT_BLOCK;
+    barrier_waiting++;
+    yield_to_scheduler();
+}
+
+uint64_t warp_collective(Op op, unsigned mask, uint64_t value, int param, int width)
+{
+    Fiber *f = running;
+    Warp &w = warps[f->tc.warp];
+    const int lane = f->tc.lane;
+    if (w.arrived == 0) { w.op = op; w.mask = mask; w.width = width; }
+    else if (w.op != op) { fprintf(stderr, "emu: lanes of one warp reached different collectives (%d vs %d)\n", (int)w.op, (int)op); abort(); }
+    w.val[lane] = value; w.param[lane] = param;
+    w.arrived |= 1u << lane;
+    f->state = WAIT_WARP;
+    yield_to_scheduler();
+    return w.res[lane];
+}
+
+static void complete_warp(Warp &w, int warp_index, int nthreads)
+{
+    const unsigned part = w.arrived;            // participating lanes
+    for (int l = 0; l < 32; l++) {
+        if (!(part >> l & 1)) continue;
+        uint64_t r = 0;
+        switch (w.op) {
+        case OP_SHFL_IDX: case OP_SHFL_XOR: case OP_SHFL_UP: case OP_SHFL_DOWN: {
+            const int wd = w.width, seg = l & ~(wd - 1);
+            int src;
+            if (w.op == OP_SHFL_IDX) src = seg + (w.param[l] & (wd - 1));
+            else if (w.op == OP_SHFL_XOR) src = l ^ w.param[l];
+            else if (w.op == OP_SHFL_UP) src = l - w.param[l];
+            else src = l + w.param[l];
+            bool ok = src >= seg && src < seg + wd && (part >> src & 1);
+            if (w.op == OP_SHFL_XOR) ok = src >= 0 && src < 32 && (src & ~(wd - 1)) == seg && (part >> src & 1);
+            r = ok ? w.val[src] : w.val[l];
+            break;
+        }
+        case OP_BALLOT: {
+            unsigned b = 0;
+            for (int k = 0; k < 32; k++) if ((part >> k & 1) && w.val[k]) b |= 1u << k;
+            r = b & w.mask;
+            break;
+        }
+        case OP_MATCH: {
+            unsigned b = 0;
+            for (int k = 0; k < 32; k++) if ((part >> k & 1) && w.val[k] == w.val[l]) b |= 1u << k;
+            r = b;
+            break;
+        }
+        case OP_SYNC: break;
+        }
+        w.res[l] = r;
+    }
+    for (int l = 0; l < 32; l++)
+        if (part >> l & 1) {
+            int t = warp_index * 32 + l;
+            if (t < nthreads) fibers[t].state = READY;
+        }
+    w.arrived = 0;
+}
+
+static void run_block(dim3 grid, dim3 block, uint3 bid)
+{
+    const int nthreads = (int)(block.x * block.y * block.z);
+    const int nwarps = (nthreads + 31) / 32;
+    fibers.resize(nthreads);
+    warps.assign(nwarps, Warp());
+    for (int t = 0; t < nthreads; t++) {
+        Fiber &f = fibers[t];
+        prepare_fiber(f, t);
+        f.tc.tid.x = t % block.x; f.tc.tid.y = (t / block.x) % block.y; f.tc.tid.z = t / (block.x * block.y);
+        f.tc.bid = bid; f.tc.bdim = block; f.tc.gdim = grid;
+        f.tc.linear = t; f.tc.lane = t & 31; f.tc.warp = t >> 5;
+        warps[t >> 5].alive |= 1u << (t & 31);
+    }
+    alive_threads = nthreads;
+    barrier_waiting = 0;
+    while (alive_threads > 0) {
+        bool progressed = false;
+        for (int t = 0; t < nthreads; t++) {
+            Fiber &f = fibers[t];
+            if (f.state != READY) continue;
+            running = &f; cur = &f.tc;
+            emu_switch(&sched_sp, f.sp);
+            progressed = true;
+            if (f.state == DONE) { alive_threads--; warps[t >> 5].alive &= ~(1u << (t & 31)); }
+        }
+        for (int wi = 0; wi < nwarps; wi++) {
+            Warp &w = warps[wi];
+            // every live lane named by the mask has arrived (exited lanes count as arrived)
+            if (w.arrived && (w.arrived & w.mask) == (w.alive & w.mask)) { complete_warp(w, wi, nthreads); progressed = true; }
+        }
+        if (barrier_waiting > 0 && barrier_waiting == alive_threads) {
+            for (int t = 0; t < nthreads; t++) if (fibers[t].state == WAIT_BLOCK) fibers[t].state = READY;
+            barrier_waiting = 0;
+            progressed = true;
+        }
+        if (!progressed) {
+            fprintf(stderr, "emu: deadlock in block (%u,%u,%u): %d threads alive, %d at __syncthreads\n", bid.x, bid.y, bid.z,
+                    alive_threads, barrier_waiting);
+            abort();
+        }
+    }
+    running = nullptr; cur = nullptr;
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
+{
+    const size_t nthreads = (size_t)block.x * block.y * block.z;
+    if (nthreads == 0 || nthreads > 1024 || (size_t)grid.x * grid.y * grid.z == 0) return;
+    if (running) { fprintf(stderr, "emu: nested launch\n"); abort(); }
+    if (nthreads > stack_pool_threads) {
+        if (stack_pool) munmap(stack_pool, stack_pool_threads * STACK_BYTES);
+        stack_pool_threads = std::max<size_t>(nthreads, 256);
+        stack_pool = (unsigned char *)mmap(nullptr, stack_pool_threads * STACK_BYTES, PROT_READ | PROT_WRITE,
+                                           MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (stack_pool == MAP_FAILED) { perror("emu: mmap"); abort(); }
+    }
+    std::vector<unsigned char> dyn(smem + 64);
+    unsigned char *aligned = dyn.data() + ((64 - (reinterpret_cast<uintptr_t>(dyn.data()) & 63)) & 63);
+    memset(dyn.data(), 0xA5, dyn.size());
+    dyn_smem_ptr = aligned;
+    body_fn = &body;
+    for (unsigned z = 0; z < grid.z; z++)
+        for (unsigned y = 0; y < grid.y; y++)
+            for (unsigned x = 0; x < grid.x; x++) {
+                uint3 bid; bid.x = x; bid.y = y; bid.z = z;
+                run_block(grid, block, bid);
+            }
+    body_fn = nullptr; dyn_smem_ptr = nullptr;
+}
+
+// MUFU.RCP64H / MUFU.RSQ64H model: a seed whose lower 32 mantissa bits are zero (about 2^-20 relative error); the
+// Newton steps of sph_math.cuh have to recover the rest, which is what the emulated runs then check.
+static double chop32(double v)
+{
+    uint64_t u; memcpy(&u, &v, 8); u &= 0xffffffff00000000ull; memcpy(&v, &u, 8); return v;
+}
+double rcp_approx_f64(double x) { return chop32(1.0 / x); }
+double rsqrt_approx_f64(double x) { return chop32(1.0 / std::sqrt(x)); }
+
+}  // namespace emu
+
+// =====================================================================================================================
+// CUDA runtime stand-in: just what libosph_b200 calls.  "Device" memory is host memory filled with a garbage pattern.
+// =====================================================================================================================
+static cudaError_t g_last = cudaSuccess;
+
+extern "C" {
+
+cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { cudaError_t e = g_last; g_last = cudaSuccess; return e; }
+const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+
+cudaError_t cudaMalloc(void **p, size_t bytes)
+{
+    size_t b = (bytes + 255) & ~(size_t)255;
+    if (b == 0) b = 256;
+    void *q = aligned_alloc(256, b);
+    if (!q) return cudaErrorMemoryAllocation;
+    memset(q, 0xA5, b);
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned int) { return cudaMallocHost(p, bytes); }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
+
+cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = reinterpret_cast<cudaStream_t>(malloc(8)); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int) { return cudaStreamCreate(s); }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = reinterpret_cast<cudaEvent_t>(malloc(8)); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned int) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.001f; return cudaSuccess; }
+
+cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
+
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 0; return cudaSuccess; }
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned int) { return cudaErrorNotSupported; }
+
+}  // extern "C"

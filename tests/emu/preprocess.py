@@ -1,0 +1,119 @@
+"""Rewrites the three CUDA constructs g++ cannot parse so that the kernel sources compile against tests/emu/emu.h:
+
+  kernel<T...><<<grid, block, smem, stream>>>(args)   ->  emu::launch_k(grid, block, smem, kernel<T...>, args)
+  extern __shared__ [__align__(n)] T name[];          ->  T *name = (T *)emu::dyn_smem();
+  asm("rcp.approx.ftz.f64 ..." / "rsqrt.approx.ftz.f64 ...")  ->  emu::rcp_approx_f64 / emu::rsqrt_approx_f64
+
+Everything else (kernel bodies, launch logic, the C ABI) is compiled as written.  TEST INFRASTRUCTURE ONLY.
+"""
+import os
+import re
+import sys
+
+
+def _match_forward(s, i, open_c, close_c):
+    """s[i] == open_c; returns the index of the matching close_c."""
+    depth = 0
+    k = i
+    while k < len(s):
+        c = s[k]
+        if c == open_c:
+            depth += 1
+        elif c == close_c:
+            depth -= 1
+            if depth == 0:
+                return k
+        k += 1
+    raise ValueError("unbalanced %s%s" % (open_c, close_c))
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, []
+    for c in s:
+        if c in "([{":
+            depth += 1
+        elif c in ")]}":
+            depth -= 1
+        if c == "," and depth == 0:
+            out.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(c)
+    out.append("".join(cur).strip())
+    return out
+
+
+def rewrite_launches(src):
+    out = []
+    pos = 0
+    while True:
+        i = src.find("<<<", pos)
+        if i < 0:
+            out.append(src[pos:])
+            break
+        # kernel expression, backwards: optional template argument list, then the (qualified) identifier
+        k = i
+        while k > 0 and src[k - 1].isspace():
+            k -= 1
+        if src[k - 1] == ">":
+            depth = 0
+            while k > 0:
+                k -= 1
+                if src[k] == ">":
+                    depth += 1
+                elif src[k] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+        while k > 0 and (src[k - 1].isalnum() or src[k - 1] in "_:"):
+            k -= 1
+        name = src[k:i].strip()
+        j = src.index(">>>", i)
+        cfg = _split_top(src[i + 3:j])
+        while len(cfg) < 3:
+            cfg.append("0")
+        p = j + 3
+        while src[p].isspace():
+            p += 1
+        assert src[p] == "(", "launch without argument list near: " + src[i - 40:i + 40]
+        q = _match_forward(src, p, "(", ")")
+        args = src[p + 1:q].strip()
+        out.append(src[pos:k])
+        out.append("emu::launch_k(%s, %s, %s, %s%s)" % (cfg[0], cfg[1], cfg[2], name, (", " + args) if args else ""))
+        pos = q + 1
+    return "".join(out)
+
+
+_EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w\s]+?)\s+(\w+)\s*\[\s*\]\s*;")
+_ASM_RCP = re.compile(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;"\s*:\s*"=d"\((\w+)\)\s*:\s*"d"\((\w+)\)\);')
+_ASM_RSQ = re.compile(r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;"\s*:\s*"=d"\((\w+)\)\s*:\s*"d"\((\w+)\)\);')
+
+
+def transform(src):
+    src = rewrite_launches(src)
+    src = _EXTERN_SHARED.sub(lambda m: "%s *%s = (%s *)emu::dyn_smem();" % (m.group(1), m.group(2), m.group(1)), src)
+    src = _ASM_RCP.sub(lambda m: "%s = emu::rcp_approx_f64(%s);" % (m.group(1), m.group(2)), src)
+    src = _ASM_RSQ.sub(lambda m: "%s = emu::rsqrt_approx_f64(%s);" % (m.group(1), m.group(2)), src)
+    if "asm(" in src or "asm volatile" in src:
+        raise ValueError("inline PTX the emulator has no model for")
+    return src
+
+
+def main(csrc, gen):
+    os.makedirs(gen, exist_ok=True)
+    made = []
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cu", ".cuh")):
+            continue
+        text = open(os.path.join(csrc, f)).read()
+        dst = os.path.join(gen, f[:-3] + ".cpp" if f.endswith(".cu") else f)
+        new = '#include "emu.h"\n' + transform(text)
+        if not os.path.exists(dst) or open(dst).read() != new:
+            with open(dst, "w") as o:
+                o.write(new)
+        made.append(dst)
+    return made
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])

@@ -1,0 +1,36 @@
+"""CPU: the kernel SOURCES of offshore-sph_b200/csrc executed under the SIMT emulator of tests/emu (g++ build of the
+same .cu files: fibers for CUDA threads, __syncthreads / warp collectives as switch points) and held to the same
+parity tests as the GPU build -- cell ids and neighbour sets bit-exact, FP64 fields within 1e-10 of the golden
+vectors and the oracle, fused step loop identical to the explicit calls, and so on.
+
+This is test infrastructure: it checks the kernels' logic (indexing, staging, warp-synchronous control flow, edge
+paths) in a container without a GPU.  It is NOT a product path -- nothing under offshore-sph_b200/ knows about the
+emulated library, and the GPU tests (-m gpu) remain the parity gate on the real hardware.
+"""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import build as emu_build  # noqa: E402
+
+if not emu_build.available():
+    pytest.skip("g++ or the CUDA headers are missing: cannot build the emulated library", allow_module_level=True)
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _emulated_library():
+    from osph_b200 import capi
+    path = emu_build.build()
+    saved = (capi.LIB_PATH, capi._lib)
+    capi.LIB_PATH, capi._lib = path, None
+    yield
+    capi.LIB_PATH, capi._lib = saved
+
+
+# the GPU parity tests, re-collected here without their `gpu` mark (it is attached to the modules, not the functions)
+from test_gpu_parity import *  # noqa: F401,F403,E402
+from test_gpu_solver import *  # noqa: F401,F403,E402
+
+pytestmark = []          # the star imports brought the modules' `gpu` mark along: these run on the CPU
