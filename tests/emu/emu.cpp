@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <sys/mman.h>
 
+#include <map>
 #include <vector>
 
 namespace emu {
@@ -244,6 +245,15 @@ double rsqrt_approx_f64(double x) { return chop32(1.0 / std::sqrt(x)); }
 // =====================================================================================================================
 static cudaError_t g_last = cudaSuccess;
 
+// OSPH_EMU_GUARD=1: every device allocation ends right in front of an inaccessible page (and starts right behind one),
+// so a kernel that reads or writes past its buffer faults at the offending instruction -- a poor man's
+// compute-sanitizer memcheck.  OSPH_EMU_FILL=<byte> changes the garbage pattern fresh allocations are filled with
+// (two runs with different patterns that agree bit for bit do not depend on uninitialised device memory).
+static std::map<void *, std::pair<void *, size_t>> g_guarded;      // user pointer -> (mapping, mapped bytes)
+static bool guard_mode() { static int g = -1; if (g < 0) { const char *e = getenv("OSPH_EMU_GUARD"); g = e && *e == '1'; } return g == 1; }
+static int fill_byte() { static int f = -1; if (f < 0) { const char *e = getenv("OSPH_EMU_FILL"); f = e ? (int)strtol(e, nullptr, 0) & 255 : 0xA5; } return f; }
+
+
 extern "C" {
 
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
@@ -253,15 +263,35 @@ const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no er
 
 cudaError_t cudaMalloc(void **p, size_t bytes)
 {
+    if (guard_mode()) {
+        const size_t page = 4096, user = (bytes + 15) & ~(size_t)15;          // 16-byte vector loads stay aligned
+        const size_t body = (user + page - 1) / page * page, total = body + 2 * page;
+        unsigned char *m = (unsigned char *)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+        memset(m, fill_byte(), total);
+        mprotect(m, page, PROT_NONE);
+        mprotect(m + page + body, page, PROT_NONE);
+        unsigned char *u = m + page + body - user;
+        g_guarded[u] = std::make_pair((void *)m, total);
+        *p = u;
+        return cudaSuccess;
+    }
     size_t b = (bytes + 255) & ~(size_t)255;
     if (b == 0) b = 256;
     void *q = aligned_alloc(256, b);
     if (!q) return cudaErrorMemoryAllocation;
-    memset(q, 0xA5, b);
+    memset(q, fill_byte(), b);
     *p = q;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p)
+{
+    if (!p) return cudaSuccess;
+    auto it = g_guarded.find(p);
+    if (it != g_guarded.end()) { munmap(it->second.first, it->second.second); g_guarded.erase(it); return cudaSuccess; }
+    free(p);
+    return cudaSuccess;
+}
 cudaError_t cudaMallocHost(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned int) { return cudaMallocHost(p, bytes); }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }

@@ -1,0 +1,100 @@
+"""CPU (gloo, world_size 2 and 3): the slab-decomposed step with the REAL device code of csrc/slab.cu, step.cu and
+pair.cu executed under the SIMT emulator (tests/emu), sequenced by osph_b200.slabs.SlabRun over torch.distributed.
+
+Same assertions as tests/multi_gpu_check.py makes on the GPUs: after a run with migration across the slab faces and
+a mid-run re-cut of the slabs, the gathered result equals the single-rank run to summation order, every particle is
+owned exactly once, and dt is identical on every rank.  Test infrastructure only (see tests/emu/emu.h).
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+import build as emu_build  # noqa: E402
+
+if not emu_build.available():
+    pytest.skip("g++ or the CUDA headers are missing: cannot build the emulated library", allow_module_level=True)
+
+FIXED_DT = 2e-4
+FIELDS = ['x', 'y', 'vx', 'vy', 'rho', 'p', 'drho', 'ax', 'ay', 'xsphx', 'xsphy', 'h', 'x0', 'y0', 'vx0', 'vy0', 'rho0', 'm', 'c']
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, lib, side, steps, kernel, q):
+    os.environ["OSPH_LIB"] = lib                     # read by osph_b200.capi at import: this process binds the emulated build
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    root = os.path.dirname(HERE)
+    for p in (root, os.path.join(root, "offshore-sph_b200"), HERE):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from conftest import field_err
+    from osph_b200 import capi, slabs, workloads as W
+    assert capi.LIB_PATH == lib
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = W.dam_break_case(side, seed=11)
+    f = case['pA']['label'] == 0
+    case['pA']['vx'][f] += 100.0                     # push the fluid across the slab faces
+    pA, c = case['pA'], case['consts']
+    cfg = capi.make_config(c, kernel, 'pec', capi.FP64, case['h'], reorder_every=3)
+    with capi.Context(cfg) as single:
+        single.upload(pA)
+        single.step(steps, FIXED_DT, 0.05)
+        ref = single.download(pA.copy())
+        ref_dt = single.dt_log()
+    ctx = capi.Context(cfg)
+    cuts, local_pA, ids = slabs.partition(pA, world, rank)
+    run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
+                        mig_frac=0.2, ghost_frac=0.5, min_cap=256)
+    moved = 0
+    for k in range(steps):
+        run.step(1, FIXED_DT, 0.05)
+        moved += sum(run.last_counts['mig_out'])
+        if k == steps // 2:
+            slabs.rebalance(run)
+    got, seen = slabs.gather_global(run, pA, FIELDS)
+    dts = ctx.dt_log()
+    status = ctx.sync()
+    errs = {f_: field_err(got[f_], ref[f_]) for f_ in FIELDS}
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, errs, bool(np.all(seen == 1)), int(status), bool(np.array_equal(dts, ref_dt)), moved, len(pA)))
+
+
+@pytest.mark.parametrize("world,kernel", [(2, 'wendland'), (3, 'cubic')])
+def test_emulated_slab_run_reproduces_single_rank_run(world, kernel):
+    import queue
+    import time
+    lib = emu_build.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, lib, 60, 14, kernel, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res, t_end = [], time.time() + 300
+    while len(res) < world and time.time() < t_end:
+        try:
+            res.append(q.get(timeout=1.0))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    [p.join(30) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
+    assert len(res) == world and all(p.exitcode == 0 for p in procs)
+    for rank, errs, owned_once, status, dt_equal, moved, n in res:
+        assert owned_once, "a particle is owned by no rank or by two"
+        assert status == 0
+        assert dt_equal, "dt differs from the single-rank run"
+        worst = max(errs, key=errs.get)
+        assert errs[worst] <= 1e-11, (worst, errs[worst])
+    assert sum(r[5] for r in res) > 0, "no particle migrated: the test did not exercise the exchange"
