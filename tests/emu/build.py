@@ -32,8 +32,11 @@ def available():
     return shutil.which("g++") is not None and cuda_include() is not None
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=""):
+    """defines/tag: a variant build (e.g. a tiny PAIR_CAP to force the pair kernel's batched staging path) -> libosph_emu<tag>.so"""
     import preprocess
+    LIB = os.path.join(HERE, "libosph_emu%s.so" % tag)
+    GEN = os.path.join(HERE, "gen" + tag)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     srcs += [os.path.join(HERE, f) for f in ("emu.h", "emu.cpp", "preprocess.py", "build.py")]
     srcs.append(os.path.join(ROOT, "include", "osph.h"))
@@ -43,6 +46,7 @@ def build(force=False, verbose=False):
     units = [g for g in gen if g.endswith(".cpp")] + [os.path.join(HERE, "emu.cpp")]
     flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas",
              "-Wno-attributes", "-Wno-deprecated-declarations", "-I", HERE, "-I", CSRC, "-I", cuda_include()]
+    flags += ["-D" + d for d in defines]
     objs = []
 
     def compile_one(u):

@@ -32,5 +32,25 @@ def _emulated_library():
 # the GPU parity tests, re-collected here without their `gpu` mark (it is attached to the modules, not the functions)
 from test_gpu_parity import *  # noqa: F401,F403,E402
 from test_gpu_solver import *  # noqa: F401,F403,E402
+from test_gpu_edges import *  # noqa: F401,F403,E402
+import test_gpu_edges as _edges  # noqa: E402
+import test_gpu_parity as _parity  # noqa: E402
+
+
+def test_pair_kernel_batched_staging_path():
+    """A build with PAIR_CAP = 96 staged records: the candidate runs of a CTA never fit in shared memory together, so
+    every CTA takes the batched path that production sizes only reach with very dense cells or domain-spanning rows."""
+    from osph_b200 import capi
+    path = emu_build.build(defines=("PAIR_CAP=96",), tag="_cap96")
+    saved = (capi.LIB_PATH, capi._lib)
+    capi.LIB_PATH, capi._lib = path, None
+    try:
+        _parity.test_dam_break_vs_oracle(60, 'wendland')
+        _parity.test_dam_break_vs_oracle(150, 'gaussian')
+        _parity.test_whole_steps_vs_golden('tank30_cubic_dynh')
+        _edges.test_cluster_denser_than_the_candidate_list()
+        _edges.test_coincident_particles_follow_the_reference_guards()
+    finally:
+        capi.LIB_PATH, capi._lib = saved
 
 pytestmark = []          # the star imports brought the modules' `gpu` mark along: these run on the CPU
