@@ -200,26 +200,26 @@ __host__ __device__ __forceinline__ double dec_f64(unsigned long long u)
 #define ENC_POS_INF 0xfff0000000000000ULL   // enc(+inf)
 #define ENC_NEG_INF 0x000fffffffffffffULL   // enc(-inf)
 
-__device__ __forceinline__ double warp_min(double v)
+// Warp-wide max / min of 64-bit keys with the redux unit: two 32-bit reductions (high words, then the low words of the
+// lanes that hold the winning high word) instead of five shuffle rounds with a 64-bit compare-and-select each.  Doubles go
+// through enc_f64, so the result is the same value a chain of fmin / fmax would return.  All 32 lanes must call.
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long e)
 {
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    const unsigned int hi = (unsigned int)(e >> 32), lo = (unsigned int)e;
+    const unsigned int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned int mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return ((unsigned long long)mhi << 32) | mlo;
 }
-__device__ __forceinline__ double warp_max(double v)
-{
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ int warp_min_i(int v)
-{
-    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ int warp_max_i(int v)
-{
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long e) { return ~warp_max_u64(~e); }
+
+// NaN is skipped, as fmin / fmax would: it maps to the identity of the reduction.
+__device__ __forceinline__ unsigned long long enc_for_min(double v) { return v == v ? enc_f64(v) : ENC_POS_INF; }
+__device__ __forceinline__ unsigned long long enc_for_max(double v) { return v == v ? enc_f64(v) : ENC_NEG_INF; }
+
+__device__ __forceinline__ double warp_min(double v) { return dec_f64(warp_min_u64(enc_for_min(v))); }
+__device__ __forceinline__ double warp_max(double v) { return dec_f64(warp_max_u64(enc_for_max(v))); }
+__device__ __forceinline__ int warp_min_i(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
 #endif  // __CUDACC__
 

@@ -95,6 +95,22 @@ inline unsigned __ballot_sync(unsigned m, int pred) { return (unsigned)emu::warp
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
 template <typename T> inline unsigned __match_any_sync(unsigned m, T v) { return (unsigned)emu::warp_collective(emu::OP_MATCH, m, emu::to_bits(v), 0, 32); }
+// redux.sync: same result as a butterfly of shuffles (full or partial masks whose lanes all arrive)
+#define EMU_REDUX(name, T, expr)                                                                                        \
+    inline T name(unsigned m, T v)                                                                                      \
+    {                                                                                                                   \
+        for (int o = 16; o > 0; o >>= 1) { T t = __shfl_xor_sync(m, v, o); v = (expr); }                                \
+        return v;                                                                                                       \
+    }
+EMU_REDUX(__reduce_max_sync, unsigned, t > v ? t : v)
+EMU_REDUX(__reduce_min_sync, unsigned, t < v ? t : v)
+EMU_REDUX(__reduce_max_sync, int, t > v ? t : v)
+EMU_REDUX(__reduce_min_sync, int, t < v ? t : v)
+EMU_REDUX(__reduce_add_sync, unsigned, v + t)
+EMU_REDUX(__reduce_add_sync, int, v + t)
+EMU_REDUX(__reduce_or_sync, unsigned, v | t)
+EMU_REDUX(__reduce_and_sync, unsigned, v & t)
+#undef EMU_REDUX
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 inline void __threadfence_system() {}
