@@ -211,50 +211,66 @@ k_prepare(PrepareArgs a)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double bx = INFINITY, by = INFINITY, hmn = INFINITY, Bx = -INFINITY, By = -INFINITY, hmx = -INFINITY, hfl = INFINITY;
     if (i < a.n) {
-        bool fluid = a.label[i] == OSPH_FLUID;
-        double x, y, h = a.h[i];
-        if (!(FUSED && fluid)) { x = a.x[i]; y = a.y[i]; }
+        // Every input of the thread is requested before the first one is used.  The argument block carries no
+        // __restrict__, so a load written after a store has to wait for it: the straightforward form (load, compute,
+        // store, load the next rate, ...) walked through six dependent memory round trips per particle and re-read the
+        // rates between corrector and predictor (SASS of the first version; ncu: long_scoreboard-bound at 40 % occupancy).
+        const bool fluid = a.label[i] == OSPH_FLUID;
+        double h = a.h[i];
+        constexpr bool RATES = FUSED || (PREDICT && INTEG == OSPH_INTEGRATOR_PEC);     // ax, ay, drho, xsph are read
+        const double dt_prev = FUSED ? a.sc->dt_prev : 0.0;
+        const double dt = PREDICT ? (a.use_dev_dt ? a.sc->dt[0] : a.dt) : 0.0;
+        double x = 0.0, y = 0.0, vx = 0.0, vy = 0.0, rho = 0.0;
+        double x0 = 0.0, y0 = 0.0, vx0 = 0.0, vy0 = 0.0, rho0 = 0.0, cvx = 0.0, cvy = 0.0;
+        double xsx = 0.0, xsy = 0.0, axv = 0.0, ayv = 0.0, drhov = 0.0, m = 0.0;
+        // (the fluid rows' inputs are requested without waiting for the label: 99 % of the rows are fluid, the arrays
+        // cover every row, and the label would otherwise be one more dependent round trip)
+        if (FUSED) {
+            x0 = a.x0[i]; y0 = a.y0[i]; vx0 = a.vx0[i]; vy0 = a.vy0[i]; rho0 = a.rho0[i];
+            if (!a.integ_xsph) { cvx = a.vx[i]; cvy = a.vy[i]; }           // the corrector moves with the evaluated velocity
+            if (!fluid) { x = a.x[i]; y = a.y[i]; }
+        } else {
+            x = a.x[i]; y = a.y[i]; rho = a.rho[i];
+            if (PREDICT) { vx = a.vx[i]; vy = a.vy[i]; }
+        }
+        if (RATES) {
+            if (a.integ_xsph) { xsx = a.xsphx[i]; xsy = a.xsphy[i]; }
+            axv = a.ax[i]; ayv = a.ay[i]; drhov = a.drho[i];
+        }
+        if (a.dynamic_h == OSPH_H_DYNAMIC) m = a.m[i];
         hmn = h;
         if (fluid) {
-            double rho, vx, vy;
             if (FUSED) {
                 // corrector of the step before: PEC.py:62-88, identical operation order to k_correct
-                const double hdtp = __dmul_rn(0.5, a.sc->dt_prev);
-                const double x0 = a.x0[i], y0 = a.y0[i], vx0 = a.vx0[i], vy0 = a.vy0[i], rho0 = a.rho0[i];
-                double ux, uy;
-                if (a.integ_xsph) { ux = a.xsphx[i]; uy = a.xsphy[i]; } else { ux = a.vx[i]; uy = a.vy[i]; }
+                const double hdtp = __dmul_rn(0.5, dt_prev);
+                const double ux = a.integ_xsph ? xsx : cvx, uy = a.integ_xsph ? xsy : cvy;
                 const double mx = __dadd_rn(x0, __dmul_rn(hdtp, ux));
                 const double my = __dadd_rn(y0, __dmul_rn(hdtp, uy));
                 const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
-                const double mvx = div_den(__dadd_rn(vx0, __dmul_rn(hdtp, a.ax[i])), den, a.rden);
-                const double mvy = div_den(__dadd_rn(vy0, __dmul_rn(hdtp, a.ay[i])), den, a.rden);
+                const double mvx = div_den(__dadd_rn(vx0, __dmul_rn(hdtp, axv)), den, a.rden);
+                const double mvy = div_den(__dadd_rn(vy0, __dmul_rn(hdtp, ayv)), den, a.rden);
                 x = __dadd_rn(__dmul_rn(2.0, mx), -x0);
                 y = __dadd_rn(__dmul_rn(2.0, my), -y0);
                 vx = __dadd_rn(__dmul_rn(2.0, mvx), -vx0);
                 vy = __dadd_rn(__dmul_rn(2.0, mvy), -vy0);
-                const double mrho = __dadd_rn(rho0, __dmul_rn(hdtp, a.drho[i]));
+                const double mrho = __dadd_rn(rho0, __dmul_rn(hdtp, drhov));
                 rho = __dadd_rn(__dmul_rn(2.0, mrho), -rho0);
                 if (a.strict && rho < 0.0) rho = 0.0;
                 if (!(isfinite(x) && isfinite(y) && isfinite(vx) && isfinite(vy) && isfinite(rho)))
                     atomicOr(&a.sc->status, OSPH_S_NONFINITE);
-            } else {
-                rho = a.rho[i];
-                if (PREDICT) { vx = a.vx[i]; vy = a.vy[i]; }
             }
             if (PREDICT) {
-                const double dt = a.use_dev_dt ? a.sc->dt[0] : a.dt;
                 const double hdt = __dmul_rn(0.5, dt);
                 if (INTEG == OSPH_INTEGRATOR_PEC) {
                     a.x0[i] = x; a.y0[i] = y; a.vx0[i] = vx; a.vy0[i] = vy;
-                    double ux = vx, uy = vy;
-                    if (a.integ_xsph) { ux = a.xsphx[i]; uy = a.xsphy[i]; }
+                    const double ux = a.integ_xsph ? xsx : vx, uy = a.integ_xsph ? xsy : vy;
                     x = __dadd_rn(x, __dmul_rn(hdt, ux));
                     y = __dadd_rn(y, __dmul_rn(hdt, uy));
                     const double den = __dadd_rn(1.0, __dmul_rn(0.5, a.damping));
-                    a.vx[i] = div_den(__dadd_rn(vx, __dmul_rn(hdt, a.ax[i])), den, a.rden);
-                    a.vy[i] = div_den(__dadd_rn(vy, __dmul_rn(hdt, a.ay[i])), den, a.rden);
+                    a.vx[i] = div_den(__dadd_rn(vx, __dmul_rn(hdt, axv)), den, a.rden);
+                    a.vy[i] = div_den(__dadd_rn(vy, __dmul_rn(hdt, ayv)), den, a.rden);
                     a.rho0[i] = rho;
-                    rho = __dadd_rn(rho, __dmul_rn(hdt, a.drho[i]));
+                    rho = __dadd_rn(rho, __dmul_rn(hdt, drhov));
                     if (a.strict && rho < 0.0) rho = 0.0;
                     a.rho[i] = rho;
                 } else if (INTEG == OSPH_INTEGRATOR_VERLET) {
@@ -265,7 +281,6 @@ k_prepare(PrepareArgs a)
             }
             // smoothing-length refresh
             if (a.dynamic_h == OSPH_H_DYNAMIC) {
-                double m = a.m[i];
                 h = 0.0;
                 if (rho > 1e-12) h = __dmul_rn(a.h_sigma, sqrt(__ddiv_rn(m, rho)));
                 a.h[i] = h;
@@ -439,17 +454,21 @@ __device__ __forceinline__ double tait_ratio_pow(double ratio, double gamma)
 }
 
 template <typename Real2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)          // 5 CTAs / SM (<= 51 registers), as before the grid parameters moved into registers
 k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_hp)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n_all) return;
-    {   // K6 fused: cell table from the sorted keys (table zeroed before: empty cells have begin == end == 0)
-        unsigned int k = a.key[s];
-        if (s == 0 || a.key[s - 1] != k) a.cell_range[k].x = s;
-        if (s == a.n_all - 1 || a.key[s + 1] != k) a.cell_range[k].y = s + 1;
-    }
+    // key, neighbouring keys, slot and the grid parameters are requested together (one round trip); the gathers below are
+    // the second.  Written in program order (key, table store, idx, gathers, stores, *gp) the compiler had to keep four.
+    const unsigned int k = a.key[s];
+    const unsigned int kp = s > 0 ? a.key[s - 1] : k, kn = s < a.n_all - 1 ? a.key[s + 1] : k;
     int i = (int)a.idx[s];
+    const GridParams g = *a.gp;
+    {   // K6 fused: cell table from the sorted keys (table zeroed before: empty cells have begin == end == 0)
+        if (s == 0 || kp != k) a.cell_range[k].x = s;
+        if (s == a.n_all - 1 || kn != k) a.cell_range[k].y = s + 1;
+    }
     double x, y, vx, vy, rho, m, h;
     int lab, info;
     if (i < a.n_owned) {
@@ -469,7 +488,7 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
     Real2 v; v.x = (Real)vx; v.y = (Real)vy; s_vel[s] = v;
     Real2 rm; rm.x = (Real)rho; rm.y = (Real)m; s_rm[s] = rm;
     Real2 hp; hp.x = (Real)h; hp.y = (Real)pr2; s_hp[s] = hp;
-    CellInfo c = cell_of(x, y, *a.gp);
+    CellInfo c = cell_of(x, y, g);
     // bit2: the reference bins this particle in a cell other than the one it queries from (wrapped last column,
     // unbinned, non-finite): cell adjacency then does not follow from distance and the pair kernel tests it
     const bool irregular = c.coarse.x != c.coarse.z || c.coarse.y != c.coarse.w || !c.binned;
@@ -510,6 +529,8 @@ k_correct(CorrectArgs a)
     double hmn = INFINITY, cmx = -INFINITY, amx = -INFINITY;
     if (i < a.n && a.label[i] == OSPH_FLUID) {
         double ax = a.ax[i], ay = a.ay[i];
+        // requested here, with the other inputs: read after the stores below they cost one more dependent round trip
+        const double h_i = a.h[i], c_i = a.c_uniform ? a.co : a.c[i];
         if (CORRECT) {
             const double dt = a.use_dev_dt ? a.sc->dt[0] : a.dt;
             double drho = a.drho[i];
@@ -553,8 +574,8 @@ k_correct(CorrectArgs a)
             if (!(isfinite(x) && isfinite(y) && isfinite(vx) && isfinite(vy) && isfinite(rho)))
                 atomicOr(&a.sc->status, OSPH_S_NONFINITE);
         }
-        hmn = a.h[i];
-        cmx = a.c_uniform ? a.co : a.c[i];
+        hmn = h_i;
+        cmx = c_i;
         amx = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
         if (!(amx == amx)) amx = INFINITY;
     }
