@@ -19,11 +19,17 @@ k_sort_hist(const unsigned int *__restrict__ key, int n, int shift, int nblocks,
     for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) cnt[d] = 0;
     __syncthreads();
     int base = blockIdx.x * SORT_TILE;
+    unsigned int kk[SORT_ITEMS];                      // all loads in flight before the first vote (see k_keys)
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        int i = base + r * SORT_THREADS + threadIdx.x;
+        kk[r] = i < n ? key[i] : 0u;
+    }
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; r++) {
         int i = base + r * SORT_THREADS + threadIdx.x;
         const bool ok = i < n;
-        warp_hist_add(cnt, ok ? ((key[i] >> shift) & (RADIX - 1)) : 0u, ok);
+        warp_hist_add(cnt, ok ? ((kk[r] >> shift) & (RADIX - 1)) : 0u, ok);
     }
     __syncthreads();
     for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = cnt[d];
@@ -105,11 +111,16 @@ k_sort_scatter(const unsigned int *__restrict__ key_in, const unsigned int *__re
     const int base = blockIdx.x * SORT_TILE + w * (32 * SORT_ITEMS);
     unsigned int k[SORT_ITEMS], v[SORT_ITEMS], rank[SORT_ITEMS];
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; r++) {
+    for (int r = 0; r < SORT_ITEMS; r++) {                    // all loads in flight before the first vote (see k_keys)
         int i = base + r * 32 + lane;
         bool ok = i < n;
         k[r] = ok ? key_in[i] : 0u;
         v[r] = ok ? val_in[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        int i = base + r * 32 + lane;
+        bool ok = i < n;
         unsigned int d = ok ? ((k[r] >> shift) & (RADIX - 1)) : (unsigned int)RADIX;
         unsigned int peers = __match_any_sync(0xffffffffu, d);
         unsigned int before = __popc(peers & ((1u << lane) - 1u));

@@ -422,16 +422,23 @@ k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, 
     __syncthreads();
     const GridParams g = *gp;
     bool unbinned = false;
+    // all positions of the thread first, then the cell arithmetic: with the load inside the loop below every item waited
+    // for its own round trip behind the previous item's warp vote and shared-memory atomic (SASS of the first version)
+    double px[SORT_ITEMS], py[SORT_ITEMS];
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; r++) {
+        const int i = blockIdx.x * SORT_TILE + r * SORT_THREADS + threadIdx.x;
+        px[r] = 0.0; py[r] = 0.0;
+        if (i < n_owned) { px[r] = x[i]; py[r] = y[i]; }
+        else if (i < n_all) { const double *rec = ghost_record(ghost, gmap, i - n_owned); px[r] = rec[0]; py[r] = rec[1]; }
+    }
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; r++) {
         int i = blockIdx.x * SORT_TILE + r * SORT_THREADS + threadIdx.x;
         const bool ok = i < n_all;
         unsigned int digit = 0;
         if (ok) {
-            double px, py;
-            if (i < n_owned) { px = x[i]; py = y[i]; }
-            else { const double *rec = ghost_record(ghost, gmap, i - n_owned); px = rec[0]; py = rec[1]; }
-            CellInfo c = cell_of(px, py, g);
+            CellInfo c = cell_of(px[r], py[r], g);
             unbinned |= !c.binned;
             key[i] = c.key; idx[i] = (unsigned int)i;
             digit = c.key & (RADIX - 1);
