@@ -411,7 +411,7 @@ __device__ __forceinline__ CellInfo cell_of(double x, double y, const GridParams
 // ghosts (slab mode) are light wire records of OSPH_WIRE_HALO doubles: x y vx vy rho m h label.
 // The kernel walks the radix sort's tiles and also emits the first pass's per-tile digit histogram.
 template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 4)     // <= 64 registers: the 493 tiles of 1 M particles stay one wave (4 x 148 slots)
 k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, const double *__restrict__ ghost,
        GhostMap gmap, int n_all, const GridParams *__restrict__ gp, StepScalars *sc, unsigned int *__restrict__ key,
        unsigned int *__restrict__ idx, int nblocks, unsigned int *__restrict__ hist)
