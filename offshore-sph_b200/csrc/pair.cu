@@ -256,7 +256,7 @@ k_pair(PairArgs a)
         const Real mjf = fluid_j ? mj : Real(0);                   // continuity and momentum: fluid neighbours only
         drho += mjf * (dvx * dwx + dvy * dwy);
         // artificial viscosity only for approaching pairs: min(dot, 0) makes it branch-free
-        const Real dot = fmin(dvx * dx + dvy * dy, Real(0));
+        const Real dot = neg_part(dvx * dx + dvy * dy);
         const Real mu = hbar * dot * inv_den;
         const Real PIij = mu * (PC(beta) * mu - PC(alpha_c)) * inv_rbar;
         const Real fac = mjf * (slf + hpj.y + PIij);

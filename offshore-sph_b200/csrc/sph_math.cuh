@@ -5,31 +5,46 @@
 
 #define PI_D 3.14159265358979323846
 #ifndef OSPH_NEWTON_STEPS
-#define OSPH_NEWTON_STEPS 2      // refinement steps after the 2^-20 MUFU seed: 2^-40, then full double (tools/mufu_accuracy.cu)
-#endif
+#define OSPH_NEWTON_STEPS 0      // 0: one third-order step after the 2^-20 MUFU seed (error ~ seed^3 = 2^-60, below half an ulp);
+#endif                           // 2 / 3: that many Newton steps (2^-40, then full double: tools/mufu_accuracy.cu)
 
 template <typename Real> struct R2;
 template <> struct R2<double> { typedef double2 type; };
 template <> struct R2<float> { typedef float2 type; };
 
-// ---- fast reciprocal / rsqrt in double: MUFU seed + Newton, ~1 ulp, no special-case branches ----------
+// ---- fast reciprocal / rsqrt in double: MUFU seed + refinement, ~1 ulp, no special-case branches ----------
+// Third-order step: with y = (1/x)(1 + d), e = 1 - x y = -d exactly (fma), and 1/x = y / (1 - e) = y (1 + e + e^2 + e^3 ...):
+// y (1 + e + e^2) is off by d^3.  Three dependent DFMAs instead of the four of two Newton steps.
 __device__ __forceinline__ double rcp_fast(double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if OSPH_NEWTON_STEPS == 0
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
+#else
     double e = fma(-x, y, 1.0); y = fma(y, e, y);
     e = fma(-x, y, 1.0); y = fma(y, e, y);
 #if OSPH_NEWTON_STEPS > 2
     e = fma(-x, y, 1.0); y = fma(y, e, y);
 #endif
     return y;
+#endif
 }
 __device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
 
+// Same idea for 1/sqrt(x): e = 1 - x y^2, 1/sqrt(x) = y (1 - e)^(-1/2) = y (1 + e/2 + 3 e^2/8 + 5 e^3/16 ...); the step keeps the
+// first two terms (error 5/16 e^3 with |e| <= 2^-19).  Five FP64 instructions instead of seven.
 __device__ __forceinline__ double rsqrt_fast(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if OSPH_NEWTON_STEPS == 0
+    const double e = fma(-(x * y), y, 1.0);
+    const double t = e * fma(e, 0.375, 0.5);
+    return fma(y, t, y);
+#else
     // Newton for 1/sqrt(x): y <- y + y*(1 - x*y*y)/2
     double hx = 0.5 * x;
     double e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
@@ -38,6 +53,7 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     e = fma(-hx * y, y, 0.5); y = fma(y, e, y);
 #endif
     return y;
+#endif
 }
 __device__ __forceinline__ float rsqrt_fast(float x) { return rsqrtf(x); }
 
@@ -80,6 +96,24 @@ __device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real 
     }
 }
 
+// max(d, 0) and min(d, 0) for numbers.  fmax / fmin on doubles compile to DSETP.MAX plus six moves and selects for their
+// NaN rules, and the compiler turns every C++ spelling of `d > 0 ? d : 0` (also on the bit pattern) back into max.f64;
+// setp + selp written in PTX stay three instructions.  NaN maps to 0, as with fmax / fmin.
+__device__ __forceinline__ double pos_part(double d)
+{
+    double r;
+    asm("{ .reg .pred p; setp.gt.f64 p, %1, 0d0000000000000000; selp.f64 %0, %1, 0d0000000000000000, p; }" : "=d"(r) : "d"(d));
+    return r;
+}
+__device__ __forceinline__ double neg_part(double d)
+{
+    double r;
+    asm("{ .reg .pred p; setp.lt.f64 p, %1, 0d0000000000000000; selp.f64 %0, %1, 0d0000000000000000, p; }" : "=d"(r) : "d"(d));
+    return r;
+}
+__device__ __forceinline__ float pos_part(float d) { return fmaxf(d, 0.0f); }
+__device__ __forceinline__ float neg_part(float d) { return fminf(d, 0.0f); }
+
 // Cubic spline of the fused pair kernel: the same piecewise polynomial written with clamped terms,
 //   W/alpha = (2-q)+^3 / 4 - (1-q)+^3,   W'/alpha = -3/4 (2-q)+^2 + 3 (1-q)+^2,
 // identical to CubicSpline.py:10-70 on every branch (q <= 1, 1 < q <= 2, q > 2) up to rounding of O(1e-16) terms, without
@@ -88,7 +122,7 @@ template <typename Real>
 __device__ __forceinline__ void cubic_pair(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
 {
     const Real alpha = Real(10.0 / (7.0 * PI_D)) * inv_h * inv_h;
-    const Real t2 = fmax(Real(2) - q, Real(0)), t1 = fmax(Real(1) - q, Real(0));
+    const Real t2 = pos_part(Real(2) - q), t1 = pos_part(Real(1) - q);
     const Real s2 = t2 * t2, s1 = t1 * t1;
     const Real wv = fma(-s1, t1, Real(0.25) * s2 * t2);
     const Real gv = fma(Real(3), s1, Real(-0.75) * s2);

@@ -3,6 +3,7 @@
   kernel<T...><<<grid, block, smem, stream>>>(args)   ->  emu::launch_k(grid, block, smem, kernel<T...>, args)
   extern __shared__ [__align__(n)] T name[];          ->  T *name = (T *)emu::dyn_smem();
   asm("rcp.approx.ftz.f64 ..." / "rsqrt.approx.ftz.f64 ...")  ->  emu::rcp_approx_f64 / emu::rsqrt_approx_f64
+  asm("{ setp.gt|lt.f64 p, x, 0; selp.f64 r, x, 0, p; }")      ->  r = x > 0 ? x : 0   (pos_part / neg_part of sph_math.cuh)
 
 Everything else (kernel bodies, launch logic, the C ABI) is compiled as written.  TEST INFRASTRUCTURE ONLY.
 """
@@ -89,11 +90,15 @@ _ASM_RCP = re.compile(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;"\s*:\s*"=d"\((\w+)\)
 _ASM_RSQ = re.compile(r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;"\s*:\s*"=d"\((\w+)\)\s*:\s*"d"\((\w+)\)\);')
 
 
+_ASM_CLAMP = re.compile(r'asm\("\{ \.reg \.pred p; setp\.(gt|lt)\.f64 p, %1, 0d0+; selp\.f64 %0, %1, 0d0+, p; \}"\s*:\s*"=d"\((\w+)\)\s*:\s*"d"\((\w+)\)\);')
+
+
 def transform(src):
     src = rewrite_launches(src)
     src = _EXTERN_SHARED.sub(lambda m: "%s *%s = (%s *)emu::dyn_smem();" % (m.group(1), m.group(2), m.group(1)), src)
     src = _ASM_RCP.sub(lambda m: "%s = emu::rcp_approx_f64(%s);" % (m.group(1), m.group(2)), src)
     src = _ASM_RSQ.sub(lambda m: "%s = emu::rsqrt_approx_f64(%s);" % (m.group(1), m.group(2)), src)
+    src = _ASM_CLAMP.sub(lambda m: "%s = (%s %s 0.0) ? %s : 0.0;" % (m.group(2), m.group(3), ">" if m.group(1) == "gt" else "<", m.group(3)), src)
     if "asm(" in src or "asm volatile" in src:
         raise ValueError("inline PTX the emulator has no model for")
     return src
