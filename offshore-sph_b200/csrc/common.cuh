@@ -9,7 +9,9 @@
 #include "../../include/osph.h"
 
 #define OSPH_CAP_STAGE 512            // candidates staged in shared memory per batch of the pair kernel
+#ifndef OSPH_PAIR_THREADS
 #define OSPH_PAIR_THREADS 256         // one CTA of the pair kernel owns this many consecutive sorted particles
+#endif
 #define OSPH_MAX_CELL_BITS 28
 #define OSPH_WIRE_HALO 8               // doubles per ghost record: x y vx vy rho m h label
 #define OSPH_WIRE_FULL 21              // doubles per migrant record: 19 columns, label, global id
