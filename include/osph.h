@@ -247,6 +247,11 @@ int osph_reserve(osph_ctx *ctx, int64_t particle_capacity);
 int osph_set_row_ids(osph_ctx *ctx, const int32_t *ids, int64_t n);
 /* Enter slab mode; d_ghost has room for ghost_capacity halo records. */
 int osph_slab_configure(osph_ctx *ctx, double x_lo, double x_hi, void *d_ghost, int64_t ghost_capacity);
+/* Optional, before osph_slab_dt_local of step `step` of a sequencer call that runs `nsteps` steps: lets the library
+ * fuse the corrector of every step but the last into the next step's predictor pass (PEC), exactly as osph_step does
+ * on one GPU; results are bit-identical to unplanned steps.  The state is complete again after the last step.
+ * OSPH_SLAB_FUSED=0 in the environment disables the fusion. */
+int osph_slab_step_plan(osph_ctx *ctx, int32_t step, int32_t nsteps);
 /* d_out3 (device) <- local {h_min, -c_max, -a2_max} over the owned fluid rows (all-reduce with MIN). */
 int osph_slab_dt_local(osph_ctx *ctx, double *d_out3);
 /* Install the all-reduced triple (device pointer, may be NULL to keep the local one), form dt on the device

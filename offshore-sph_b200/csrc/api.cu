@@ -193,6 +193,7 @@ static int ingest(osph_ctx *ctx, const void *src, bool src_on_device, int64_t n,
     ctx->n = counters[0]; ctx->n_fluid = counters[1];
     if (ctx->n > 0 && (rc = osph_launch_unpack(ctx))) return rc;
     ctx->c_uniform = false; ctx->build_counter = 0; ctx->n_ghost = 0; ctx->slab = false;
+    ctx->slab_fused = 0; ctx->slab_defer = false; ctx->slab_last = true;
     invalidate_state(ctx);
     return 0;
 }

@@ -112,6 +112,9 @@ struct osph_ctx {
     bool ghost_external = false;
     unsigned int *scan_block = nullptr;   // block sums of the scan utility
     bool slab = false;
+    int slab_fused = 0;               // osph_slab_step_plan: 0 plain step, 1 first / 2 later step of a fused multi-step call
+    bool slab_defer = false;          // this step's corrector is applied by the next step's predictor pass
+    bool slab_last = true;            // osph_slab_step_plan: last step of the call (ends with the plain corrector)
     double x_lo = 0, x_hi = 0;
     int *d_slab_counters = nullptr, *d_mig_slots = nullptr, *d_tail_flag = nullptr, *d_holes = nullptr, *d_fillers = nullptr;
     int64_t slab_list_cap = 0;

@@ -7,6 +7,8 @@
 //   osph_slab_commit  removes the migrants from the owned set (hole filling), appends the received ones and
 //                     installs the all-reduced grid scalars, so every rank forms the SAME reference grid.
 // The reference has no counterpart: it is a single-threaded, single-process code.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "step.cuh"
 
@@ -162,9 +164,11 @@ k_slab_commit_small(SlabMoveArgs a, const int *__restrict__ mig_slots, int m, in
     }
 }
 
-__global__ void k_slab_dt_local(const StepScalars *sc, double *out)
+// uniform_c > 0: the step before deferred its corrector, nothing reduced c_max; it is the uniform co (k_timestep, fused == 2)
+__global__ void k_slab_dt_local(const StepScalars *sc, double *out, double uniform_c)
 {
-    out[0] = dec_f64(sc->hmin_fluid); out[1] = -dec_f64(sc->cmax_fluid); out[2] = -dec_f64(sc->a2max_fluid);
+    out[0] = dec_f64(sc->hmin_fluid); out[1] = uniform_c > 0.0 ? -uniform_c : -dec_f64(sc->cmax_fluid);
+    out[2] = -dec_f64(sc->a2max_fluid);
 }
 __global__ void k_slab_ids(const int *__restrict__ row, const signed char *__restrict__ label, int n,
                            int *__restrict__ ids, signed char *__restrict__ lab)
@@ -285,15 +289,32 @@ extern "C" int osph_slab_commit(osph_ctx *ctx, int64_t n_mig_out, const void *d_
     return osph_slab_commit_impl(ctx, n_mig_out, (const double *)d_mig_in, n_mig_in, nullptr, 0, gm, n_ghost, global_bounds);
 }
 
+// Several slab steps in one call of a sequencer: as in osph_step, the corrector of step k is applied by the predictor
+// pass of step k+1 (k_prepare<PEC, true, FUSED>), min h is reduced by that pass and max |a|^2 by the pair kernel, so the
+// separate corrector pass exists only at the end of the call.  Migrants carry x0..rho0 and the rates in their 21-double
+// records, so a particle that changed owner in between is corrected by its new owner with the same operands.
+// OSPH_SLAB_FUSED=0 in the environment keeps every step in the plain form.
+extern "C" int osph_slab_step_plan(osph_ctx *ctx, int32_t step, int32_t nsteps)
+{
+    if (!ctx || step < 0 || step >= nsteps) return OSPH_E_INVALID;
+    static const bool enabled = [] { const char *e = getenv("OSPH_SLAB_FUSED"); return !(e && e[0] == '0'); }();
+    const bool fuse = enabled && nsteps > 1 && ctx->cfg.integrator == OSPH_INTEGRATOR_PEC && !ctx->cfg.summation_density;
+    if (ctx->slab_defer && step == 0) { ctx->err = "osph_slab_step_plan: the previous call ended with a deferred corrector"; return OSPH_E_INVALID; }
+    ctx->slab_fused = fuse ? (step == 0 ? 1 : 2) : 0;
+    ctx->slab_last = step == nsteps - 1;
+    return 0;
+}
+
 extern "C" int osph_slab_dt_local(osph_ctx *ctx, double *d_out3)
 {
     CHECK_CTX();
+    if (ctx->slab_defer != (ctx->slab_fused == 2)) { ctx->err = "osph_slab_dt_local: step plan and deferred corrector disagree"; return OSPH_E_INVALID; }
     if (!ctx->reductions_valid) {
         int rc = osph_launch_correct(ctx, false, 0.0, 0.0, false);
         if (rc) return rc;
         ctx->reductions_valid = true;
     }
-    k_slab_dt_local<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, d_out3); OSPH_LAUNCH_CHECK();
+    k_slab_dt_local<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, d_out3, ctx->slab_defer ? ctx->cfg.co : 0.0); OSPH_LAUNCH_CHECK();
     return 0;
 }
 
@@ -302,24 +323,33 @@ extern "C" int osph_slab_step_begin(osph_ctx *ctx, const double *d_dt_reduced3, 
     CHECK_CTX();
     if (!ctx->slab) { ctx->err = "osph_slab_step_begin: context is not in slab mode"; return OSPH_E_INVALID; }
     int rc;
-    if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true, d_dt_reduced3))) return rc;
-    if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true))) return rc;
+    const int fused = ctx->slab_fused;
+    if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true, d_dt_reduced3, fused))) return rc;
+    if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true, fused))) return rc;      // fused == 2: corrector of the step before first
+    ctx->slab_defer = false;
     ctx->neighbours_valid = false; ctx->reductions_valid = false;
     return 0;
 }
 
 int osph_size_cell_table(osph_ctx *ctx);     // api.cu
 
+// Inside a fused call (osph_slab_step_plan) every step but the last leaves its corrector to the next predictor pass.
 extern "C" int osph_slab_step_end(osph_ctx *ctx, double damping)
 {
     CHECK_CTX();
     if (!ctx->slab) { ctx->err = "osph_slab_step_end: context is not in slab mode"; return OSPH_E_INVALID; }
     int rc;
+    const bool fuse = ctx->slab_fused != 0, defer = fuse && !ctx->slab_last;
     if ((rc = osph_size_cell_table(ctx))) return rc;
-    if ((rc = osph_launch_build(ctx, true))) return rc;
-    if ((rc = osph_launch_pair(ctx))) return rc;
+    if ((rc = osph_launch_build(ctx, !fuse))) return rc;
+    ctx->pair_reduce_a2 = fuse;
+    rc = osph_launch_pair(ctx);
+    ctx->pair_reduce_a2 = false;
+    if (rc) return rc;
     ctx->c_uniform = true;
-    if ((rc = osph_launch_correct(ctx, true, 0.0, damping, true, true))) return rc;
+    if (!defer && (rc = osph_launch_correct(ctx, true, 0.0, damping, true, true))) return rc;
+    ctx->slab_defer = defer;
+    ctx->slab_fused = 0; ctx->slab_last = true;
     ctx->prepared = false; ctx->neighbours_valid = false; ctx->reductions_valid = true;
     ctx->step_counter++;
     return 0;

@@ -162,6 +162,7 @@ extern "C" int osph_slab_run(osph_ctx *ctx, osph_slab_comm *s, int32_t nsteps, d
     const double q = s->kernel == OSPH_KERNEL_GAUSSIAN ? 3.0 : 2.0;
     int rc;
     for (int step = 0; step < nsteps; step++) {
+        if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return rc;    // corrector of step k fused into the predictor of k+1
         // ---- identical dt on every rank ----
         if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return rc;
         NCCL_CK(g_nccl.AllReduce(s->d_dt3, s->d_dt3, 3, ncclDouble, ncclMin, s->comm, ctx->stream));

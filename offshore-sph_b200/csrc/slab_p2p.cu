@@ -183,6 +183,7 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
     for (int step = 0; step < nsteps; step++) {
         s->seq++;
         const int slot = (int)(s->seq & 1ull);
+        if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return rc;    // corrector of step k fused into the predictor of k+1
         // ---- identical dt on every rank: mailbox all-gather + min ----
         if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return rc;
         k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, slot, s->d_dt3, 3, s->seq,

@@ -111,6 +111,7 @@ def lib():
         'osph_reserve': (C.c_int, [ctx, i64]),
         'osph_set_row_ids': (C.c_int, [ctx, C.POINTER(i32), i64]),
         'osph_slab_configure': (C.c_int, [ctx, dbl, dbl, C.c_void_p, i64]),
+        'osph_slab_step_plan': (C.c_int, [ctx, i32, i32]),
         'osph_slab_dt_local': (C.c_int, [ctx, C.c_void_p]),
         'osph_slab_step_begin': (C.c_int, [ctx, C.c_void_p, dbl, dbl]),
         'osph_slab_pack': (C.c_int, [ctx, dbl, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]),
@@ -364,6 +365,9 @@ class Context:
 
     def slab_configure(self, x_lo, x_hi, ghost_ptr, ghost_capacity):
         self._ck(self._L.osph_slab_configure(self._h, x_lo, x_hi, C.c_void_p(ghost_ptr), ghost_capacity))
+
+    def slab_step_plan(self, step, nsteps):
+        self._ck(self._L.osph_slab_step_plan(self._h, step, nsteps))
 
     def slab_dt_local(self, out_ptr):
         self._ck(self._L.osph_slab_dt_local(self._h, C.c_void_p(out_ptr)))

@@ -100,7 +100,8 @@ class SlabRun:
         ctx.slab_configure(self.x_lo, self.x_hi, self.ghost.data_ptr(), self.ghost_cap)
 
     def step(self, nsteps=1, fixed_dt=None, damping=0.0):
-        for _ in range(nsteps):
+        for k in range(nsteps):
+            self.ctx.slab_step_plan(k, nsteps)       # corrector of step k fused into the predictor of step k+1
             self._step(fixed_dt, damping)
 
     def _step(self, fixed_dt, damping):

@@ -51,24 +51,31 @@ def _worker(rank, world, port, lib, side, steps, kernel, q):
         single.step(steps, FIXED_DT, 0.05)
         ref = single.download(pA.copy())
         ref_dt = single.dt_log()
-    ctx = capi.Context(cfg)
-    cuts, local_pA, ids = slabs.partition(pA, world, rank)
-    run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
-                        mig_frac=0.2, ghost_frac=0.5, min_cap=256)
-    moved = 0
-    for k in range(steps):
-        run.step(1, FIXED_DT, 0.05)
-        moved += sum(run.last_counts['mig_out'])
-        if k == steps // 2:
-            slabs.rebalance(run)
-    got, seen = slabs.gather_global(run, pA, FIELDS)
-    dts = ctx.dt_log()
-    status = ctx.sync()
-    errs = {f_: field_err(got[f_], ref[f_]) for f_ in FIELDS}
-    ctx.close()
+    results = {}
+    for chunk in (1, steps // 2):                    # one step per sequencer call (plain), then 7 per call (fused corrector)
+        ctx = capi.Context(cfg)
+        cuts, local_pA, ids = slabs.partition(pA, world, rank)
+        run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
+                            mig_frac=0.2, ghost_frac=0.5, min_cap=256)
+        moved, launches0 = 0, ctx.launch_count
+        for k in range(0, steps, chunk):
+            run.step(chunk, FIXED_DT, 0.05)
+            moved += sum(run.last_counts['mig_out'])
+            if k + chunk == steps // 2:
+                slabs.rebalance(run)                 # re-cut the slabs mid-run: results must not notice
+        launches = ctx.launch_count - launches0
+        got, seen = slabs.gather_global(run, pA, FIELDS)
+        dts = ctx.dt_log()
+        status = ctx.sync()
+        errs = {f_: field_err(got[f_], ref[f_]) for f_ in FIELDS}
+        results[chunk] = (got, launches)
+        ctx.close()
+        q.put((rank, chunk, errs, bool(np.all(seen == 1)), int(status), bool(np.array_equal(dts, ref_dt)), moved, len(pA)))
+    a, b = results[1], results[steps // 2]
+    same = all(np.array_equal(a[0][f_], b[0][f_]) for f_ in FIELDS)
+    q.put((rank, 'fused-vs-plain', same, a[1], b[1]))
     dist.barrier()
     dist.destroy_process_group()
-    q.put((rank, errs, bool(np.all(seen == 1)), int(status), bool(np.array_equal(dts, ref_dt)), moved, len(pA)))
 
 
 @pytest.mark.parametrize("world,kernel", [(2, 'wendland'), (3, 'cubic')])
@@ -81,8 +88,8 @@ def test_emulated_slab_run_reproduces_single_rank_run(world, kernel):
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, lib, 60, 14, kernel, q)) for r in range(world)]
     [p.start() for p in procs]
-    res, t_end = [], time.time() + 300
-    while len(res) < world and time.time() < t_end:
+    res, t_end = [], time.time() + 400
+    while len(res) < 3 * world and time.time() < t_end:
         try:
             res.append(q.get(timeout=1.0))
         except queue.Empty:
@@ -90,11 +97,17 @@ def test_emulated_slab_run_reproduces_single_rank_run(world, kernel):
                 break
     [p.join(30) for p in procs]
     [p.kill() for p in procs if p.is_alive()]
-    assert len(res) == world and all(p.exitcode == 0 for p in procs)
-    for rank, errs, owned_once, status, dt_equal, moved, n in res:
+    assert len(res) == 3 * world and all(p.exitcode == 0 for p in procs)
+    for r in res:
+        if r[1] == 'fused-vs-plain':
+            rank, _, same, launches_plain, launches_fused = r
+            assert same, "fused multi-step slab call differs from single-step calls"
+            assert launches_fused < launches_plain          # the separate corrector passes are gone
+            continue
+        rank, chunk, errs, owned_once, status, dt_equal, moved, n = r
         assert owned_once, "a particle is owned by no rank or by two"
         assert status == 0
         assert dt_equal, "dt differs from the single-rank run"
         worst = max(errs, key=errs.get)
-        assert errs[worst] <= 1e-11, (worst, errs[worst])
-    assert sum(r[5] for r in res) > 0, "no particle migrated: the test did not exercise the exchange"
+        assert errs[worst] <= 1e-11, (chunk, worst, errs[worst])
+    assert sum(r[6] for r in res if r[1] == 1) > 0, "no particle migrated: the test did not exercise the exchange"

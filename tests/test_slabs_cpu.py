@@ -34,6 +34,8 @@ class MockContext:
 
     def reserve(self, cap): self.cap = cap
 
+    def slab_step_plan(self, step, nsteps): pass
+
     def upload(self, pA):
         self.x = pA['x'].copy(); self.y = pA['y'].copy(); self.vx = pA['vx'].copy(); self.count = np.zeros(len(pA))
 
