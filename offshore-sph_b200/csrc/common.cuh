@@ -8,7 +8,6 @@
 
 #include "../../include/osph.h"
 
-#define OSPH_CAP_STAGE 512            // candidates staged in shared memory per batch of the pair kernel
 #ifndef OSPH_PAIR_THREADS
 #define OSPH_PAIR_THREADS 256         // one CTA of the pair kernel owns this many consecutive sorted particles
 #endif

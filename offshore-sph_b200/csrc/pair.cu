@@ -520,8 +520,7 @@ int osph_launch_pair(osph_ctx *ctx)
     a.drho = ctx->f[OSPH_F_DRHO]; a.ax = ctx->f[OSPH_F_AX]; a.ay = ctx->f[OSPH_F_AY];
     a.xsphx = ctx->f[OSPH_F_XSPHX]; a.xsphy = ctx->f[OSPH_F_XSPHY];
     const osph_config &c = ctx->cfg;
-    a.alpha = c.alpha; a.beta = c.beta; a.c_half = 0.5 * c.co; a.eps = c.epsilon;
-    a.r0 = c.r0; a.D = c.D; a.p1 = c.p1; a.p2 = c.p2; a.gravity = c.gravity;
+    a.p1 = c.p1; a.p2 = c.p2; a.gravity = c.gravity;
     a.lj_42 = (c.p1 == 4.0 && c.p2 == 2.0) ? 1 : 0;
     a.alpha_c_d = c.alpha * 0.5 * c.co; a.beta_d = c.beta; a.r0_d = c.r0; a.r0sq_d = c.r0 * c.r0; a.neg_eps_d = -c.epsilon; a.D_d = c.D;
     a.alpha_c_f = (float)a.alpha_c_d; a.beta_f = (float)c.beta; a.r0_f = (float)c.r0; a.r0sq_f = a.r0_f * a.r0_f;

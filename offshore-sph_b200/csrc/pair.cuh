@@ -15,7 +15,7 @@ struct PairArgs {
     unsigned long long *a2max;        // optional: order-preserving encoding of max |a|^2 over the fluid rows (TimeStep.py:58-91)
     const double *vx, *vy;            // state columns (storage order), for xsph = v + correction
     double *drho, *ax, *ay, *xsphx, *xsphy;
-    double alpha, beta, c_half, eps, r0, D, p1, p2, gravity;
+    double p1, p2, gravity;
     int lj_42, method_xsph, summation_density;
     // loop constants precomputed on the host in both precisions: as kernel parameters they are constant-bank operands
     // of the FP instructions and do not occupy registers in the pair loop
