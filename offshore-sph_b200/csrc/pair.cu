@@ -116,6 +116,7 @@ k_pair(PairArgs a)
     int qcx = 0, qcy = 0, info_i = 0;
     bool fluid_i = false;
     const bool need_adj = gp->regime_a != 0;
+    bool adj_i = need_adj;                      // the reference-cell test is due for every pair of this particle
     int ra0 = 0x7fffffff, ra1 = 0x7fffffff, ra2 = 0x7fffffff, rb0 = 0, rb1 = 0, rb2 = 0;
     if (valid) {
         // every load of the prologue is issued before the first use: two global round trips (state + cell id, then
@@ -130,6 +131,7 @@ k_pair(PairArgs a)
         vxi = v.x; vyi = v.y; rhoi = rm.x; hi = hp.x; slf = hp.y;
         hi_half = Real(0.5) * hi; rhoi_half = Real(0.5) * rhoi;
         fluid_i = (info_i & 3) == 3;               // fluid AND owned (ghosts of a slab are sources only)
+        adj_i = need_adj || (info_i & 4);
         const int x0 = max(gc.x - 1, 0), x1 = min(gc.x + 1, gnx - 1);
         int2 cr[9];
 #pragma unroll
@@ -214,25 +216,32 @@ k_pair(PairArgs a)
         // exact test) and Lennard-Jones range
         const bool kern = r2 <= h2 * (KID == OSPH_KERNEL_GAUSSIAN ? Real(9.0 * (1.0 + 1e-6)) : Real(4));
         const bool lj = !fluid_j && r2 <= PC(r0sq);
-        bool ok = kern || lj;
         // Membership in the reference neighbour set = adjacent reference cells AND q <= 3.
         //  * cells: where the acceleration grid is finer than the reference grid (regime B) two particles within the
         //    pair radius sit in adjacent reference cells by construction, unless the reference bins one of them
         //    irregularly (info bit 2); only then, and in regime A, the stored cell ids are compared;
         //  * q <= 3 can only bind for wall pairs outside the kernel support and at the cut of the Gaussian.
+        // Everything that can reject a listed pair sits behind ONE rarely taken branch: inside the kernel support with
+        // no cell test due, the pair is a member and the common path pays one compare and one predicate for it.
         if constexpr (EXACT) {
-            if (need_adj || ((info_j | info_i) & 4)) ok = ok && abs(cbx - qcx) <= 1 && abs(cby - qcy) <= 1;
-            if (KID == OSPH_KERNEL_GAUSSIAN || !kern) {
-                ok = ok && r2 <= h2 * (9.0 * (1.0 + 1e-13));
-                if (ok && r2 > h2 * (9.0 * (1.0 - 1e-13))) {      // within 1e-13 of the threshold: decide in strict IEEE
-                    double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
-                    ok = __ddiv_rn(rr, (double)hij) <= 3.0;
+            const bool adjq = adj_i || (info_j & 4);
+            if (KID == OSPH_KERNEL_GAUSSIAN || adjq || !kern) {
+                bool ok = kern || lj;
+                if (adjq) ok = ok && abs(cbx - qcx) <= 1 && abs(cby - qcy) <= 1;
+                if (KID == OSPH_KERNEL_GAUSSIAN || !kern) {
+                    ok = ok && r2 <= h2 * (9.0 * (1.0 + 1e-13));
+                    if (ok && r2 > h2 * (9.0 * (1.0 - 1e-13))) {      // within 1e-13 of the threshold: decide in strict IEEE
+                        double rr = __dsqrt_rn(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+                        ok = __ddiv_rn(rr, (double)hij) <= 3.0;
+                    }
                 }
+                if (!ok) return;
             }
         } else {
-            if (KID == OSPH_KERNEL_GAUSSIAN || !kern) ok = ok && r2 <= h2 * Real(9);
+            if (KID == OSPH_KERNEL_GAUSSIAN || !kern) {
+                if (!((kern || lj) && r2 <= h2 * Real(9))) return;
+            }
         }
-        if (!ok) return;
 #if PAIR_NO_FMAX
         const Real rs = rsqrt_fast(r2);                            // r2 == 0: inf / NaN, discarded by the two selects below
 #else
