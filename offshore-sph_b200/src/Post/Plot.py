@@ -1,5 +1,7 @@
-"""Post-processing stub with the constructor of reference src/Post/Plot.py.  Visualisation (pyqtgraph frames
--> ffmpeg) is outside the hot path this package replaces; the class exists so example scripts import."""
+"""Post-processing stand-in with the constructor of reference src/Post/Plot.py.  Visualisation (pyqtgraph frames
+-> ffmpeg) is outside the hot path this package replaces; the class exists so that unedited example scripts import
+and run to their end (examples/Containment.py ships with plot = True): `save` reports where the data is and returns."""
+import sys
 
 
 class Plot:
@@ -8,5 +10,6 @@ class Plot:
         self.limits = (xmin, xmax, ymin, ymax)
 
     def save(self, location: str):
-        raise NotImplementedError('plotting is not part of the B200 WCSPH package; read %s with your own tools'
-                                  % self.file)
+        print('Plot.save(%s): animation rendering is not part of the B200 WCSPH package; the solver output is in %s'
+              % (location, self.file), file=sys.stderr)
+        return None

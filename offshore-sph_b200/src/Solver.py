@@ -229,7 +229,9 @@ class Solver:
         sbar = _bar(total=self.maxSettle, desc='Settling', leave=False)
         tbar = _NoBar()
 
-        while self.t < self.duration:
+        # OSPH_MAX_STEPS=<n>: stop after n steps whatever the duration (smoke runs of unedited example scripts)
+        max_steps = int(os.environ.get("OSPH_MAX_STEPS", "0")) or None
+        while self.t < self.duration and (max_steps is None or t_step < max_steps):
             if self.timeStep is None:
                 self.dt = self._minTimeStep()
             else:
@@ -401,7 +403,7 @@ class Solver:
 
 def _have_h5py():
     try:
-        import h5py  # noqa: F401
-        return True
+        import h5py
+        return hasattr(h5py, 'File')          # a namespace stub without the API counts as absent
     except ImportError:
         return False
