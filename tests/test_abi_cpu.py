@@ -69,3 +69,22 @@ def test_product_never_touches_oracle():
                         if re.search(r"^\s*(from|import)\s+oracle|liboracle|oracle/", line):
                             bad.append((f, line.strip()))
     assert not bad, bad
+
+
+def test_product_never_touches_the_emulator():
+    """tests/emu (the SIMT-emulated CPU build of the kernel sources) is test infrastructure: nothing in the product
+    package, in bench.py or in __graft_entry__.py may name it, and the default library path is the nvcc build."""
+    bad = []
+    roots = [os.path.join(ROOT, "offshore-sph_b200"), os.path.join(ROOT, "include")]
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for r in roots:
+        for d, _, fs in os.walk(r):
+            files += [os.path.join(d, f) for f in fs if f.endswith(('.py', '.cu', '.cuh', '.h', 'Makefile'))]
+    for f in files:
+        txt = open(f, errors='ignore').read()
+        if re.search(r"libosph_emu|tests/emu|OSPH_EMU\b|emu::", txt):
+            bad.append(f)
+    assert not bad, bad
+    from osph_b200 import capi
+    if not os.environ.get("OSPH_LIB"):
+        assert capi.LIB_PATH.endswith(os.path.join("lib", "libosph_b200.so"))
