@@ -23,4 +23,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pa
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --precision fp32 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_prepare|k_keys|k_sort|k_gather|k_correct' -s 20 -c 14 \
     -o $OUT/stream_fp64 -f python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-tail -40 $OUT/round_start.log
+# compile-time variants built beforehand with tools/build_round2_variants.sh (the .so files travel with gpurun)
+if ls offshore-sph_b200/lib/variants/lib_*.so > /dev/null 2>&1; then
+  names=$(ls offshore-sph_b200/lib/variants/lib_*.so | sed -E 's/.*lib_(.*)\.so/\1/')
+  { echo "== variants"; bash tools/bench_variants.sh $names; } >> $OUT/round_start.log 2>&1
+fi
+tail -60 $OUT/round_start.log
