@@ -61,7 +61,7 @@ def build(force=False, verbose=False, defines=(), tag=""):
             if r.returncode != 0:
                 raise RuntimeError("g++ failed on " + u)
             objs.append(o)
-    r = subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-Wl,--no-undefined", "-o", LIB] + objs + ["-ldl"],
+    r = subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-Wl,--no-undefined", "-o", LIB] + objs + ["-ldl", "-lrt"],
                        capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

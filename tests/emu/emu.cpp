@@ -2,11 +2,17 @@
 // makes (device memory = host memory, one in-order "stream").  TEST INFRASTRUCTURE ONLY, see emu.h.
 #include "emu.h"
 
+#include <fcntl.h>
+#include <sched.h>
 #include <stdio.h>
 #include <sys/mman.h>
+#include <unistd.h>
 
 #include <map>
+#include <string>
 #include <vector>
+
+void emu_yield_cpu() { sched_yield(); }
 
 namespace emu {
 
@@ -249,10 +255,17 @@ static cudaError_t g_last = cudaSuccess;
 // so a kernel that reads or writes past its buffer faults at the offending instruction -- a poor man's
 // compute-sanitizer memcheck.  OSPH_EMU_FILL=<byte> changes the garbage pattern fresh allocations are filled with
 // (two runs with different patterns that agree bit for bit do not depend on uninitialised device memory).
-static std::map<void *, std::pair<void *, size_t>> g_guarded;      // user pointer -> (mapping, mapped bytes)
+//
+// CUDA IPC (the peer-memory slab sequencer, slab_p2p.cu): allocations of 16 KiB and more are page-exclusive anonymous
+// mappings; cudaIpcGetMemHandle turns one into a POSIX shared-memory mapping AT THE SAME ADDRESS (contents kept) and hands
+// out its name, cudaIpcOpenMemHandle maps that object in the peer process.  Ranks are separate processes, so the mailbox
+// kernels that spin on a peer's sequence number run against real concurrency.
+struct Alloc { void *base; size_t mapped; int kind; std::string shm; };      // kind 0 heap, 1 guarded, 2 mmap, 3 shm owner, 4 shm peer
+static std::map<void *, Alloc> g_allocs;
 static bool guard_mode() { static int g = -1; if (g < 0) { const char *e = getenv("OSPH_EMU_GUARD"); g = e && *e == '1'; } return g == 1; }
 static int fill_byte() { static int f = -1; if (f < 0) { const char *e = getenv("OSPH_EMU_FILL"); f = e ? (int)strtol(e, nullptr, 0) & 255 : 0xA5; } return f; }
-
+static const size_t PAGE = 4096;
+static void unlink_all() { for (auto &kv : g_allocs) if (kv.second.kind == 3) shm_unlink(kv.second.shm.c_str()); }
 
 extern "C" {
 
@@ -264,16 +277,25 @@ const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no er
 cudaError_t cudaMalloc(void **p, size_t bytes)
 {
     if (guard_mode()) {
-        const size_t page = 4096, user = (bytes + 15) & ~(size_t)15;          // 16-byte vector loads stay aligned
-        const size_t body = (user + page - 1) / page * page, total = body + 2 * page;
+        const size_t user = (bytes + 15) & ~(size_t)15;          // 16-byte vector loads stay aligned
+        const size_t body = (user + PAGE - 1) / PAGE * PAGE, total = body + 2 * PAGE;
         unsigned char *m = (unsigned char *)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
         memset(m, fill_byte(), total);
-        mprotect(m, page, PROT_NONE);
-        mprotect(m + page + body, page, PROT_NONE);
-        unsigned char *u = m + page + body - user;
-        g_guarded[u] = std::make_pair((void *)m, total);
+        mprotect(m, PAGE, PROT_NONE);
+        mprotect(m + PAGE + body, PAGE, PROT_NONE);
+        unsigned char *u = m + PAGE + body - user;
+        g_allocs[u] = Alloc{m, total, 1, ""};
         *p = u;
+        return cudaSuccess;
+    }
+    if (bytes >= 16384) {
+        const size_t total = (bytes + PAGE - 1) / PAGE * PAGE;
+        void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+        memset(m, fill_byte(), total);
+        g_allocs[m] = Alloc{m, total, 2, ""};
+        *p = m;
         return cudaSuccess;
     }
     size_t b = (bytes + 255) & ~(size_t)255;
@@ -287,11 +309,62 @@ cudaError_t cudaMalloc(void **p, size_t bytes)
 cudaError_t cudaFree(void *p)
 {
     if (!p) return cudaSuccess;
-    auto it = g_guarded.find(p);
-    if (it != g_guarded.end()) { munmap(it->second.first, it->second.second); g_guarded.erase(it); return cudaSuccess; }
+    auto it = g_allocs.find(p);
+    if (it != g_allocs.end()) {
+        munmap(it->second.base, it->second.mapped);
+        if (it->second.kind == 3) shm_unlink(it->second.shm.c_str());
+        g_allocs.erase(it);
+        return cudaSuccess;
+    }
     free(p);
     return cudaSuccess;
 }
+
+struct IpcName { char name[48]; unsigned long long bytes; unsigned long long magic; };
+static_assert(sizeof(IpcName) == 64, "fits cudaIpcMemHandle_t");
+
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *ptr)
+{
+    auto it = g_allocs.find(ptr);
+    if (it == g_allocs.end() || (it->second.kind != 2 && it->second.kind != 3)) return cudaErrorNotSupported;
+    Alloc &a = it->second;
+    if (a.kind == 2) {
+        static int counter = 0;
+        static bool hooked = false;
+        if (!hooked) { atexit(unlink_all); hooked = true; }
+        char name[48];
+        snprintf(name, sizeof name, "/osph_emu_%d_%d", (int)getpid(), counter++);
+        int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)a.mapped) != 0) { if (fd >= 0) { close(fd); shm_unlink(name); } return cudaErrorMemoryAllocation; }
+        void *tmp = mmap(nullptr, a.mapped, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (tmp == MAP_FAILED) { close(fd); shm_unlink(name); return cudaErrorMemoryAllocation; }
+        memcpy(tmp, a.base, a.mapped);
+        munmap(tmp, a.mapped);
+        void *same = mmap(a.base, a.mapped, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0);     // same address, now shared
+        close(fd);
+        if (same != a.base) { shm_unlink(name); return cudaErrorMemoryAllocation; }
+        a.kind = 3; a.shm = name;
+    }
+    IpcName n; memset(&n, 0, sizeof n);
+    snprintf(n.name, sizeof n.name, "%s", a.shm.c_str()); n.bytes = a.mapped; n.magic = 0x6f7370686d656d75ull;
+    memcpy(h, &n, 64);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned int)
+{
+    IpcName n; memcpy(&n, &h, 64);
+    if (n.magic != 0x6f7370686d656d75ull) return cudaErrorInvalidValue;
+    int fd = shm_open(n.name, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void *m = mmap(nullptr, (size_t)n.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+    g_allocs[m] = Alloc{m, (size_t)n.bytes, 4, n.name};
+    *p = m;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *p) { return cudaFree(p); }
+
 cudaError_t cudaMallocHost(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned int) { return cudaMallocHost(p, bytes); }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
@@ -317,9 +390,6 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.
 
 cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
 
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned int) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
 cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 0; return cudaSuccess; }
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned int) { return cudaErrorNotSupported; }
 

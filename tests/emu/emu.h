@@ -111,10 +111,11 @@ EMU_REDUX(__reduce_add_sync, int, v + t)
 EMU_REDUX(__reduce_or_sync, unsigned, v | t)
 EMU_REDUX(__reduce_and_sync, unsigned, v & t)
 #undef EMU_REDUX
-inline void __threadfence() {}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() {}
-inline void __threadfence_system() {}
-inline void __nanosleep(unsigned) {}
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }     // peers are other processes (shared memory)
+void emu_yield_cpu();
+inline void __nanosleep(unsigned) { emu_yield_cpu(); }
 
 // ---- integer / conversion intrinsics --------------------------------------------------------------------------------
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -28,7 +28,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, q):
+def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
     os.environ["OSPH_LIB"] = lib                     # read by osph_b200.capi at import: this process binds the emulated build
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     root = os.path.dirname(HERE)
@@ -55,8 +55,12 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, q):
     for chunk in (1, steps // 2):                    # one step per sequencer call (plain), then 7 per call (fused corrector)
         ctx = capi.Context(cfg)
         cuts, local_pA, ids = slabs.partition(pA, world, rank)
-        run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
-                            mig_frac=0.2, ghost_frac=0.5, min_cap=256)
+        if seq == 'p2p':       # the C++ loop of slab_p2p.cu: IPC windows (POSIX shared memory here), mailbox kernels
+            run = slabs.P2PSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
+                                   mig_frac=0.2, ghost_frac=0.5, min_cap=256)
+        else:
+            run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
+                                mig_frac=0.2, ghost_frac=0.5, min_cap=256)
         moved, launches0 = 0, ctx.launch_count
         for k in range(0, steps, chunk):
             run.step(chunk, fixed_dt, 0.05)
@@ -69,6 +73,8 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, q):
         status = ctx.sync()
         errs = {f_: field_err(got[f_], ref[f_]) for f_ in FIELDS}
         results[chunk] = (got, launches)
+        if hasattr(run, 'close'):
+            run.close()
         ctx.close()
         q.put((rank, chunk, errs, bool(np.all(seen == 1)), int(status), bool(np.array_equal(dts, ref_dt)), moved, len(pA)))
     a, b = results[1], results[steps // 2]
@@ -78,8 +84,10 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kernel,fixed_dt", [(2, 'wendland', FIXED_DT), (3, 'cubic', FIXED_DT), (2, 'cubic', None)])
-def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt):
+@pytest.mark.parametrize("world,kernel,fixed_dt,seq", [(2, 'wendland', FIXED_DT, 'python'), (3, 'cubic', FIXED_DT, 'python'),
+                                                      (2, 'cubic', None, 'python'), (3, 'wendland', FIXED_DT, 'p2p'),
+                                                      (2, 'cubic', None, 'p2p')])
+def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt, seq):
     """fixed_dt None = the dynamic Courant / force time step, all-reduced every step (what bench.py --gpus N runs)."""
     import queue
     import time
@@ -87,7 +95,7 @@ def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, lib, 60, 14, kernel, fixed_dt, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, lib, 60, 14, kernel, fixed_dt, seq, q)) for r in range(world)]
     [p.start() for p in procs]
     res, t_end = [], time.time() + 400
     while len(res) < 3 * world and time.time() < t_end:
