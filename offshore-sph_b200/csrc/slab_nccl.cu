@@ -9,6 +9,7 @@
 // libnccl is resolved at run time (dlopen of the copy already loaded by torch, else by path), so the library has
 // no link-time NCCL dependency and still loads on a box without it.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -50,7 +51,11 @@ std::string g_nccl_error;
 bool load_nccl(const char *path)
 {
     if (g_nccl.ok()) return true;
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);     // the copy torch already loaded
+    // OSPH_NCCL_LIB=<path>: use exactly this NCCL build (symbols are taken from its handle, whatever else is loaded)
+    const char *forced = getenv("OSPH_NCCL_LIB");
+    void *h = forced && *forced ? dlopen(forced, RTLD_NOW | RTLD_LOCAL) : nullptr;
+    if (forced && *forced && !h) { g_nccl_error = std::string("cannot load OSPH_NCCL_LIB: ") + dlerror(); return false; }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);         // the copy torch already loaded
     if (!h && path && *path) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) { g_nccl_error = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }

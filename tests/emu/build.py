@@ -70,5 +70,18 @@ def build(force=False, verbose=False, defines=(), tag=""):
     return LIB
 
 
+def build_fake_nccl():
+    """tests/emu/libfake_nccl.so: the NCCL calls of slab_nccl.cu over shared memory between rank processes (CPU tests)."""
+    src, out = os.path.join(HERE, "fake_nccl.cpp"), os.path.join(HERE, "libfake_nccl.so")
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I", cuda_include(), src, "-o", out, "-lrt"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed on fake_nccl.cpp")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv, verbose=True))

@@ -30,6 +30,7 @@ def _free_port():
 
 def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
     os.environ["OSPH_LIB"] = lib                     # read by osph_b200.capi at import: this process binds the emulated build
+    os.environ["OSPH_NCCL_LIB"] = os.path.join(os.path.dirname(lib), "libfake_nccl.so")
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     root = os.path.dirname(HERE)
     for p in (root, os.path.join(root, "offshore-sph_b200"), HERE):
@@ -55,7 +56,10 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
     for chunk in (1, steps // 2):                    # one step per sequencer call (plain), then 7 per call (fused corrector)
         ctx = capi.Context(cfg)
         cuts, local_pA, ids = slabs.partition(pA, world, rank)
-        if seq == 'p2p':       # the C++ loop of slab_p2p.cu: IPC windows (POSIX shared memory here), mailbox kernels
+        if seq == 'nccl':      # the C++ loop of slab_nccl.cu against tests/emu/fake_nccl.cpp (OSPH_NCCL_LIB)
+            run = slabs.NcclSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
+                                    mig_frac=0.2, ghost_frac=0.5, min_cap=256)
+        elif seq == 'p2p':     # the C++ loop of slab_p2p.cu: IPC windows (POSIX shared memory here), mailbox kernels
             run = slabs.P2PSlabRun(ctx, cuts, local_pA, ids, kernel, case['r0'], case['h'], torch.device('cpu'),
                                    mig_frac=0.2, ghost_frac=0.5, min_cap=256)
         else:
@@ -86,12 +90,13 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
 
 @pytest.mark.parametrize("world,kernel,fixed_dt,seq", [(2, 'wendland', FIXED_DT, 'python'), (3, 'cubic', FIXED_DT, 'python'),
                                                       (2, 'cubic', None, 'python'), (3, 'wendland', FIXED_DT, 'p2p'),
-                                                      (2, 'cubic', None, 'p2p')])
+                                                      (2, 'cubic', None, 'p2p'), (3, 'cubic', None, 'nccl')])
 def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt, seq):
     """fixed_dt None = the dynamic Courant / force time step, all-reduced every step (what bench.py --gpus N runs)."""
     import queue
     import time
     lib = emu_build.build()
+    emu_build.build_fake_nccl()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
