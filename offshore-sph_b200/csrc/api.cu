@@ -479,7 +479,9 @@ extern "C" int osph_sync(osph_ctx *ctx, uint32_t *status)
     StepScalars sc;
     OSPH_CUDA(cudaMemcpyAsync(&sc, ctx->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
     OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (sc.status & 0x80000000u) { ctx->err = "reference grid needs more cells than the allocated table"; return OSPH_E_GRID; }
+    // bit 31: the reference grid outgrew the cell table and the steps since ran on the exact one-cell fallback
+    // (k_grid_params); reported like a coarsened grid, and the next build re-sizes the table
+    if (sc.status & 0x80000000u) { sc.status = (sc.status & 0x7fffffffu) | OSPH_S_GRID_COARSE; }
     if (status) *status = sc.status;
     unsigned int zero = 0;
     OSPH_CUDA(cudaMemcpy((char *)ctx->d_sc + offsetof(StepScalars, status), &zero, sizeof(zero), cudaMemcpyHostToDevice));

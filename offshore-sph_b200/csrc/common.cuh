@@ -30,6 +30,7 @@ struct GridParams {
     double gsize, ginv;
     int gnx, gny;
     int regime_a;          // 1: acceleration grid == reference grid (ids by the reference formula)
+    int adj_always;        // 1: one-cell fallback grid (table too small for the reference grid): test reference-cell adjacency on every pair
     int reach_set;         // cells to walk per side to cover q <= 3 (neighbour-set emitter)
     double hmax;           // max h over active particles after the refresh
     double pair_r2;        // square of the radius inside which a pair can contribute

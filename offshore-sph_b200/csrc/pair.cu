@@ -115,7 +115,7 @@ k_pair(PairArgs a)
     Real xi = 0, yi = 0, vxi = 0, vyi = 0, rhoi = 1, hi = 0, slf = 0, hi_half = 0, rhoi_half = Real(0.5);
     int qcx = 0, qcy = 0, info_i = 0;
     bool fluid_i = false;
-    const bool need_adj = gp->regime_a != 0;
+    const bool need_adj = gp->regime_a != 0 || gp->adj_always != 0;
     bool adj_i = need_adj;                      // the reference-cell test is due for every pair of this particle
     int ra0 = 0x7fffffff, ra1 = 0x7fffffff, ra2 = 0x7fffffff, rb0 = 0, rb1 = 0, rb2 = 0;
     if (valid) {

@@ -342,7 +342,7 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
     double R = fmax(pair_radius_q * hmax, lj) * (1.0 + 1e-6);
     if (!(R > 0.0)) R = cs;
     g->pair_r2 = R * R;
-    int regime_a = (R >= cs) ? 1 : 0;
+    int regime_a = (R >= cs) ? 1 : 0, adj_always = 0;
     double gs = regime_a ? cs : R;
     long long gnx, gny;
     if (regime_a) { gnx = ncx; gny = ncy; }
@@ -360,11 +360,15 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
         }
     }
     if (!(gnx >= 1 && gny >= 1 && gnx * gny + 1 <= cell_cap) || !isfinite(gs)) {
-        // regime A cannot be coarsened (it IS the reference grid), or the bounds are unusable
+        // regime A cannot be coarsened (it IS the reference grid), or the bounds are unusable: fall back to ONE cell holding
+        // everything.  Candidates are then all particles and membership is decided by the stored reference cell ids and the
+        // distance alone (adj_always), so the step stays exact -- O(n^2), but regime A only exists for a few thousand
+        // particles -- and the host re-sizes the table at its next status read (osph_sync).
         atomicOr(&sc->status, 0x80000000u);
-        gnx = 1; gny = 1; gs = fmax(fmax(xmax - xmin, ymax - ymin), 0.0) + 1.0; regime_a = 0;
+        gnx = 1; gny = 1; gs = fmax(fmax(xmax - xmin, ymax - ymin), 0.0) + 1.0; regime_a = 0; adj_always = 1;
         if (!isfinite(gs)) gs = 1.0;
     }
+    g->adj_always = adj_always;
     g->regime_a = regime_a; g->gsize = gs; g->ginv = 1.0 / gs; g->gnx = (int)gnx; g->gny = (int)gny;
     double rs = 3.0 * hmax * (1.0 + 1e-6);
     int reach = regime_a ? 1 : (int)ceil(rs / gs);

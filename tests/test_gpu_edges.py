@@ -129,24 +129,38 @@ def test_domain_outgrowing_the_cell_table_coarsens_then_resizes():
         assert seen & capi.S_GRID_COARSE
 
 
-def test_reference_grid_outgrowing_the_table_fails_loudly():
+def test_reference_grid_outgrowing_the_table_falls_back_exactly_then_resizes():
     """Where the acceleration grid IS the reference grid (pair radius >= reference cell, small N) it cannot be
-    coarsened: a domain that outgrows the table is reported as OSPH_E_GRID at the next sync, never silently."""
+    coarsened.  A domain that outgrows the table runs on a one-cell fallback grid (every particle a candidate,
+    membership by the stored reference cell ids and the distance): results stay those of the oracle, the status
+    reports it, and the next build re-sizes the table."""
     case = W.dam_break_case(40, seed=9)
     pA, c = case['pA'], case['consts']
+    w = _oracle_params(c)
     cfg = capi.make_config(c, 'cubic', 'pec', capi.FP64, case['h'])
+    P = O.Particles.from_aos(pA)
     with capi.Context(cfg) as ctx:
         ctx.upload(pA)
+        O.step(P, w, 'cubic', 'pec', True, False, 0.05, case['h'])
         ctx.step(1, None, 0.05)
         assert ctx.sync() == 0
         i = int(np.flatnonzero(pA['label'] == 0)[-1])
         x = ctx.download_fields(['x', 'y'])
         x['x'][i] = 7000.0; x['y'][i] = 1200.0
         ctx.upload_fields(x)
-        ctx.step(1, None, 0.05)
-        with pytest.raises(capi.OsphError) as e:
-            ctx.sync()
-        assert e.value.code == -6
+        P.x[i] = 7000.0; P.y[i] = 1200.0
+        for s in range(3):
+            O.step(P, w, 'cubic', 'pec', True, False, 0.05, case['h'])
+            ctx.step(1, None, 0.05)
+            cols = ctx.download_fields(list(STATE_FIELDS))
+            for f in STATE_FIELDS:
+                assert field_err(cols[f], getattr(P, f)) <= TOL, (s, f)
+            if s == 0:
+                off, idx = ctx.neighbours_csr()                      # the validation query works on the fallback grid too
+                ooff, oidx = O.Grid(P).neighbours_csr()
+                assert np.array_equal(off, ooff)
+            st = ctx.sync()
+            assert st == (capi.S_GRID_COARSE if s == 0 else 0), (s, st)
 
 
 def test_non_finite_particle_is_parked_and_reported():
