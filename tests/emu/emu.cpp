@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-void emu_yield_cpu() { sched_yield(); }
+void emu_yield_cpu();
 
 namespace emu {
 
@@ -75,6 +75,31 @@ static const std::function<void()> *body_fn = nullptr;
 static int barrier_waiting = 0, alive_threads = 0;
 static Fiber *running = nullptr;
 
+// OSPH_EMU_ORDER=reverse | shuffle[:seed] -- the order in which the scheduler resumes the ready threads of a CTA and runs the
+// CTAs of a launch.  A kernel without races (inside a CTA: every shared-memory hand-over behind a barrier or a warp
+// collective; between CTAs: no dependence on the order of the grid) gives the same bits under every order, so running the
+// parity tests under two more orders flushes out what the ascending default hides (a reader that happens to run after
+// its writer).  Default: ascending.
+static int order_mode()
+{
+    static int m = -1;
+    if (m < 0) { const char *e = getenv("OSPH_EMU_ORDER"); m = !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "shuffle", 7) ? 2 : 0)); }
+    return m;
+}
+static uint64_t order_rng()
+{
+    static uint64_t s = 0;
+    if (!s) { const char *e = getenv("OSPH_EMU_ORDER"); const char *c = e ? strchr(e, ':') : nullptr; s = 0x9e3779b97f4a7c15ull ^ (c ? strtoull(c + 1, nullptr, 0) : 1); }
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    return s;
+}
+static void fill_order(std::vector<int> &o, size_t n)
+{
+    o.resize(n);
+    for (size_t k = 0; k < n; k++) o[k] = (int)(order_mode() == 1 ? n - 1 - k : k);
+    if (order_mode() == 2) for (size_t k = n; k > 1; k--) std::swap(o[k - 1], o[order_rng() % k]);
+}
+
 static void yield_to_scheduler()
 {
     Fiber *f = running;
@@ -99,6 +124,20 @@ static void prepare_fiber(Fiber &f, int slot)
     f.sp = sp;
     f.state = READY;
 }
+
+}  // namespace emu
+
+// __nanosleep inside a spin loop (the mailbox kernels of slab_p2p.cu wait for a peer PROCESS): give the CPU away and let the
+// other fibers of the CTA run, as the other warps of a CTA do on the GPU while one of them polls.  Without the fiber switch
+// a schedule other than the ascending default can deadlock ranks against each other (rank A polls for B before the fiber
+// that publishes to C has run, B polls for C, C for A).
+void emu_yield_cpu()
+{
+    sched_yield();
+    if (emu::running) { emu::running->state = emu::READY; emu::yield_to_scheduler(); }
+}
+
+namespace emu {
 
 void block_barrier()
 {
@@ -180,9 +219,13 @@ static void run_block(dim3 grid, dim3 block, uint3 bid)
     }
     alive_threads = nthreads;
     barrier_waiting = 0;
+    static std::vector<int> order;
+    fill_order(order, (size_t)nthreads);
     while (alive_threads > 0) {
         bool progressed = false;
-        for (int t = 0; t < nthreads; t++) {
+        if (order_mode() == 2) fill_order(order, (size_t)nthreads);      // a new permutation after every switch point
+        for (int k = 0; k < nthreads; k++) {
+            const int t = order[k];
             Fiber &f = fibers[t];
             if (f.state != READY) continue;
             running = &f; cur = &f.tc;
@@ -226,12 +269,14 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
     memset(dyn.data(), 0xA5, dyn.size());
     dyn_smem_ptr = aligned;
     body_fn = &body;
-    for (unsigned z = 0; z < grid.z; z++)
-        for (unsigned y = 0; y < grid.y; y++)
-            for (unsigned x = 0; x < grid.x; x++) {
-                uint3 bid; bid.x = x; bid.y = y; bid.z = z;
-                run_block(grid, block, bid);
-            }
+    const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+    std::vector<int> border;
+    fill_order(border, nblocks);
+    for (size_t k = 0; k < nblocks; k++) {
+        const size_t b = (size_t)border[k];
+        uint3 bid; bid.x = (unsigned)(b % grid.x); bid.y = (unsigned)(b / grid.x % grid.y); bid.z = (unsigned)(b / ((size_t)grid.x * grid.y));
+        run_block(grid, block, bid);
+    }
     body_fn = nullptr; dyn_smem_ptr = nullptr;
 }
 

@@ -83,7 +83,8 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
         q.put((rank, chunk, errs, bool(np.all(seen == 1)), int(status), bool(np.array_equal(dts, ref_dt)), moved, len(pA)))
     a, b = results[1], results[steps // 2]
     same = all(np.array_equal(a[0][f_], b[0][f_]) for f_ in FIELDS)
-    q.put((rank, 'fused-vs-plain', same, a[1], b[1]))
+    diff = max(field_err(a[0][f_], b[0][f_]) for f_ in FIELDS)
+    q.put((rank, 'fused-vs-plain', same, a[1], b[1], diff))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -115,8 +116,14 @@ def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt, s
     assert len(res) == 3 * world and all(p.exitcode == 0 for p in procs)
     for r in res:
         if r[1] == 'fused-vs-plain':
-            rank, _, same, launches_plain, launches_fused = r
-            assert same, "fused multi-step slab call differs from single-step calls"
+            rank, _, same, launches_plain, launches_fused, diff = r
+            # Bit-identical under the emulator's default (ascending) schedule.  Under OSPH_EMU_ORDER=reverse / shuffle the
+            # pack kernel's atomically allocated record slots come out in another order -- as on the GPU -- and with them
+            # the summation order over ghost neighbours: equal to rounding then.
+            if os.environ.get("OSPH_EMU_ORDER", "").startswith(("reverse", "shuffle")):
+                assert diff <= 1e-12, ("fused multi-step slab call differs from single-step calls", diff)
+            else:
+                assert same, ("fused multi-step slab call differs from single-step calls", diff)
             assert launches_fused < launches_plain          # the separate corrector passes are gone
             continue
         rank, chunk, errs, owned_once, status, dt_equal, moved, n = r
