@@ -80,16 +80,22 @@ static Fiber *running = nullptr;
 // collective; between CTAs: no dependence on the order of the grid) gives the same bits under every order, so running the
 // parity tests under two more orders flushes out what the ascending default hides (a reader that happens to run after
 // its writer).  Default: ascending.
+static int g_order_mode = -1;       // -1: read OSPH_EMU_ORDER on first use
+static uint64_t g_order_state = 0;
 static int order_mode()
 {
-    static int m = -1;
-    if (m < 0) { const char *e = getenv("OSPH_EMU_ORDER"); m = !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "shuffle", 7) ? 2 : 0)); }
-    return m;
+    if (g_order_mode < 0) {
+        const char *e = getenv("OSPH_EMU_ORDER");
+        g_order_mode = !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "shuffle", 7) ? 2 : 0));
+        const char *c = e ? strchr(e, ':') : nullptr;
+        g_order_state = 0x9e3779b97f4a7c15ull ^ (c ? strtoull(c + 1, nullptr, 0) : 1);
+    }
+    return g_order_mode;
 }
 static uint64_t order_rng()
 {
-    static uint64_t s = 0;
-    if (!s) { const char *e = getenv("OSPH_EMU_ORDER"); const char *c = e ? strchr(e, ':') : nullptr; s = 0x9e3779b97f4a7c15ull ^ (c ? strtoull(c + 1, nullptr, 0) : 1); }
+    uint64_t &s = g_order_state;
+    if (!s) s = 0x9e3779b97f4a7c15ull;
     s ^= s << 13; s ^= s >> 7; s ^= s << 17;
     return s;
 }
@@ -313,6 +319,13 @@ static const size_t PAGE = 4096;
 static void unlink_all() { for (auto &kv : g_allocs) if (kv.second.kind == 3) shm_unlink(kv.second.shm.c_str()); }
 
 extern "C" {
+
+// tests switch the schedule inside one process: 0 ascending, 1 reverse, 2 shuffle (seeded)
+void emu_set_order(int mode, unsigned long long seed)
+{
+    emu::g_order_mode = mode;
+    emu::g_order_state = 0x9e3779b97f4a7c15ull ^ (seed ? seed : 1);
+}
 
 cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }

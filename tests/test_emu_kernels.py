@@ -53,4 +53,26 @@ def test_pair_kernel_batched_staging_path():
     finally:
         capi.LIB_PATH, capi._lib = saved
 
+
+@pytest.mark.parametrize("mode,seed", [(1, 0), (2, 5)])
+def test_results_do_not_depend_on_the_schedule(mode, seed):
+    """The same parity tests with the emulator resuming the threads of a CTA (and running the CTAs of a launch) in reverse
+    and in a seeded random order that changes at every barrier / warp collective: a shared-memory hand-over that is not
+    behind a barrier, or a dependence on the order of the grid, shows up as a parity failure here."""
+    import ctypes
+    from osph_b200 import capi
+    lib = ctypes.CDLL(emu_build.build())
+    lib.emu_set_order.argtypes = [ctypes.c_int, ctypes.c_ulonglong]
+    lib.emu_set_order(mode, seed)
+    try:
+        _parity.test_cells_and_neighbour_sets_bit_exact('dambreak20_cubic')
+        _parity.test_whole_steps_vs_golden('tank30_cubic_dynh')
+        _parity.test_whole_steps_vs_golden('tank16_gaussian')
+        _parity.test_fused_loop_equals_explicit_calls('dambreak20_wendland')
+        _parity.test_dam_break_vs_oracle(60, 'wendland')
+        _edges.test_cluster_denser_than_the_candidate_list()
+    finally:
+        lib.emu_set_order(0, 0)
+
+
 pytestmark = []          # the star imports brought the modules' `gpu` mark along: these run on the CPU
