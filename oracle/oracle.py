@@ -98,6 +98,14 @@ def lib():
         L.oracle_step.restype = C.c_int
         L.oracle_step.argtypes = [C.POINTER(_CParticles), C.POINTER(WCSPHParams), C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_double, C.c_double, C.c_double, u8, C.c_int64, _dp, _ip]
+        i8 = C.POINTER(C.c_int8)
+        L.oracle_eq_continuity.restype = C.c_double
+        L.oracle_eq_continuity.argtypes = [C.c_int64, i8] + [_dp] * 5
+        L.oracle_eq_momentum.argtypes = [C.c_double] * 6 + [C.c_int64, i8] + [_dp] * 13
+        L.oracle_eq_xsph.argtypes = [C.c_double, C.c_double, C.c_int64] + [_dp] * 6
+        L.oracle_eq_boundary_force.argtypes = [C.c_double] * 4 + [C.c_int64, i8] + [_dp] * 4
+        L.oracle_eq_courant.restype = C.c_double
+        L.oracle_eq_courant.argtypes = [C.c_double, C.c_int64, _dp, _dp]
         _lib = L
     return _lib
 
@@ -267,6 +275,53 @@ def kernel_gradient(kernel, x, r, h):
     out = np.zeros_like(r)
     lib().oracle_kernel_gradient(KERNELS[kernel], len(r), _d(x), _d(r), _d(h), _d(out))
     return out
+
+
+# ---- the equations as leaves on a computed-neighbour table (numpy structured array with the reference's
+# computed_dtype field names: label p rho x y vx vy r h c m w dw_x dw_y) ----
+def _col(comp, f):
+    return np.ascontiguousarray(comp[f], dtype=np.float64)
+
+
+def _lab(comp):
+    return np.ascontiguousarray(comp['label'], dtype=np.int8)
+
+
+def eq_continuity(comp):
+    lab = _lab(comp)
+    cols = [_col(comp, f) for f in ('m', 'vx', 'vy', 'dw_x', 'dw_y')]
+    return float(lib().oracle_eq_continuity(len(comp), lab.ctypes.data_as(C.POINTER(C.c_int8)), *[_d(a) for a in cols]))
+
+
+def eq_momentum(alpha, beta, p, comp):
+    """p: mapping with the self particle's p, rho, h, c (Momentum.py:6-57)."""
+    lab = _lab(comp)
+    cols = [_col(comp, f) for f in ('p', 'rho', 'x', 'y', 'vx', 'vy', 'r', 'h', 'c', 'm', 'dw_x', 'dw_y')]
+    out = np.zeros(2)
+    lib().oracle_eq_momentum(alpha, beta, float(p['p']), float(p['rho']), float(p['h']), float(p['c']), len(comp),
+                             lab.ctypes.data_as(C.POINTER(C.c_int8)), *[_d(a) for a in cols], _d(out))
+    return out
+
+
+def eq_xsph(epsilon, p, comp):
+    cols = [_col(comp, f) for f in ('rho', 'm', 'w', 'vx', 'vy')]
+    out = np.zeros(2)
+    lib().oracle_eq_xsph(epsilon, float(p['rho']), len(comp), *[_d(a) for a in cols], _d(out))
+    return out
+
+
+def eq_boundary_force(r0, D, p1, p2, comp):
+    lab = _lab(comp)
+    cols = [_col(comp, f) for f in ('r', 'x', 'y')]
+    out = np.zeros(2)
+    lib().oracle_eq_boundary_force(r0, D, p1, p2, len(comp), lab.ctypes.data_as(C.POINTER(C.c_int8)),
+                                   *[_d(a) for a in cols], _d(out))
+    return out
+
+
+def eq_courant(alpha, h, c):
+    h = np.ascontiguousarray(h, dtype=np.float64); c = np.ascontiguousarray(c, dtype=np.float64)
+    return float(lib().oracle_eq_courant(alpha, len(h), _d(h), _d(c)))
 
 
 def compute_h(sigma, m, rho):

@@ -416,6 +416,99 @@ int64_t oracle_loop(oracle_particles *P, const oracle_wcsph *w, const oracle_gri
 }
 
 /* ------------------------------------------------------------------ */
+/* The equations as stand-alone leaves on a table of J computed        */
+/* neighbours (computed_dtype, src/Common.py:59-79: differences i - j,  */
+/* comp.h = h_ij).  Same operation order as the inlined forms in        */
+/* oracle_loop; these are what the reference's own equation tests       */
+/* (test/test_numba_momentum.py, test_numba_continuity.py,              */
+/* test_eq_boundary.py, test_eq_courant.py) call, so they pin the       */
+/* per-pair formulas one by one (tests/test_oracle_golden.py).          */
+/* ------------------------------------------------------------------ */
+
+/* src/Equations/Continuity.py:5-17 */
+double oracle_eq_continuity(int64_t J, const int8_t *label, const double *m, const double *vx,
+                            const double *vy, const double *dwx, const double *dwy)
+{
+    double arho = 0.0;
+    for (int64_t j = 0; j < J; j++) {
+        if (label[j] != LABEL_FLUID) continue;
+        arho += m[j] * (vx[j] * dwx[j] + vy[j] * dwy[j]);
+    }
+    return arho;
+}
+
+/* src/Equations/Momentum.py:6-57; self = (p, rho, h, c) of particle i */
+void oracle_eq_momentum(double alpha, double beta, double self_p, double self_rho, double self_h,
+                        double self_c, int64_t J, const int8_t *label, const double *p,
+                        const double *rho, const double *x, const double *y, const double *vx,
+                        const double *vy, const double *r, const double *h, const double *c,
+                        const double *m, const double *dwx, const double *dwy, double out[2])
+{
+    double slf = self_p / (self_rho * self_rho);
+    double ax = 0.0, ay = 0.0;
+    for (int64_t j = 0; j < J; j++) {
+        if (label[j] != LABEL_FLUID) continue;
+        double othr = p[j] / (rho[j] * rho[j]);
+        double dot = vx[j] * x[j] + vy[j] * y[j];
+        double PI = 0.0;
+        if (dot < 0) {
+            double hij = 0.5 * (self_h + h[j]);
+            double cij = 0.5 * (self_c + c[j]);
+            double rhoij = 0.5 * (self_rho + rho[j]);
+            double mu = hij * dot / (r[j] * r[j] + 0.01 * hij * hij);
+            PI = mu * (beta * mu - alpha * cij) / rhoij;
+        }
+        double factor = slf + othr + PI;
+        ax += -m[j] * factor * dwx[j];
+        ay += -m[j] * factor * dwy[j];
+    }
+    out[0] = ax; out[1] = ay;
+}
+
+/* src/Equations/XSPH.py:6-31 (every label) */
+void oracle_eq_xsph(double epsilon, double self_rho, int64_t J, const double *rho, const double *m,
+                    const double *w, const double *vx, const double *vy, double out[2])
+{
+    double xs = 0.0, ys = 0.0;
+    for (int64_t j = 0; j < J; j++) {
+        double rho_ij = 0.5 * (self_rho + rho[j]);
+        double fac = -epsilon * m[j] * w[j] / rho_ij;
+        xs += fac * vx[j]; ys += fac * vy[j];
+    }
+    out[0] = xs; out[1] = ys;
+}
+
+/* src/Equations/BoundaryForce.py:7-42 */
+void oracle_eq_boundary_force(double r0, double D, double p1, double p2, int64_t J,
+                              const int8_t *label, const double *r, const double *x,
+                              const double *y, double out[2])
+{
+    double fx = 0.0, fy = 0.0;
+    for (int64_t j = 0; j < J; j++) {
+        if (label[j] == LABEL_FLUID || r[j] > r0) continue;
+        if (r[j] > 1e-12) {
+            double frac = r0 / r[j];
+            double fac = D * (pow(frac, p1) - pow(frac, p2));
+            fx += fac * x[j] / pow(r[j], 2);
+            fy += fac * y[j] / pow(r[j], 2);
+        }
+    }
+    out[0] = fx; out[1] = fy;
+}
+
+/* src/Equations/Courant.py:4-31 (unused by the Solver, which calls TimeStep; kept because
+ * test/test_eq_courant.py pins it) */
+double oracle_eq_courant(double alpha, int64_t J, const double *h, const double *c)
+{
+    double h_min = 10e10, c_max = 1e-10;
+    for (int64_t j = 0; j < J; j++) {
+        if (h[j] < h_min) h_min = h[j];
+        if (c[j] > c_max) c_max = c[j];
+    }
+    return alpha * h_min / c_max;
+}
+
+/* ------------------------------------------------------------------ */
 /* Integrators (act on the fluid rows only, src/Solver.py:380,396)      */
 /* ------------------------------------------------------------------ */
 

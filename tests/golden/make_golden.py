@@ -207,6 +207,56 @@ def verlet_case(name='verlet_leaf'):
     print('%-28s n=%d -> %.0f kB' % (name, n, os.path.getsize(path) / 1e3))
 
 
+def equations_leaf_case(name='equations_leaf'):
+    """The reference's equations called one by one (Momentum, Continuity, XSPH, BoundaryForce, Courant) on the synthetic
+    neighbour tables of its own equation tests and on a random table (tests/golden/leaf_inputs.py).  Only the results are
+    stored; the inputs are regenerated from the same module by the test."""
+    import leaf_inputs as LI
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_osph_reference_courant",
+                                                  os.path.join(refshim.REFERENCE_ROOT, "src", "Equations", "Courant.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                       # the module only needs numba
+    Courant = mod.Courant
+
+    def to_ref(pa_fields, comp):
+        pa = np.zeros(1, dtype=ref.particle_dtype)
+        for k, v in (pa_fields or {}).items():
+            pa[k] = v
+        c = np.zeros(len(comp), dtype=ref.computed_dtype)
+        for f in comp.dtype.names:
+            c[f] = comp[f]
+        return pa[0], c
+
+    out = {}
+    pa_f, comp = LI.momentum_reftest()
+    pa, c = to_ref(pa_f, comp)
+    out['momentum_reftest'] = np.asarray(ref.Momentum(0.01, 0.0, pa, c), dtype=np.float64)
+    pa, c = to_ref(None, LI.continuity_reftest())
+    out['continuity_reftest'] = np.float64(ref.Continuity(pa, c))
+    pa, c = to_ref(None, LI.boundary_reftest())
+    out['boundary_reftest'] = np.asarray(ref.BoundaryForce(1.0, 5 * 9.81 * 1.0, 4.0, 2.0, pa, c), dtype=np.float64)
+    pa_f, comp = LI.random_table()
+    pa, c = to_ref(pa_f, comp)
+    out['random_momentum'] = np.asarray(ref.Momentum(0.01, 0.0, pa, c), dtype=np.float64)
+    out['random_momentum_beta'] = np.asarray(ref.Momentum(0.3, 0.7, pa, c), dtype=np.float64)
+    out['random_continuity'] = np.float64(ref.Continuity(pa, c))
+    out['random_xsph'] = np.asarray(ref.XSPH(0.5, pa, c), dtype=np.float64)
+    out['random_boundary_42'] = np.asarray(ref.BoundaryForce(0.15, 1226.25, 4.0, 2.0, pa, c), dtype=np.float64)
+    out['random_boundary_126'] = np.asarray(ref.BoundaryForce(0.15, 1226.25, 12.0, 6.0, pa, c), dtype=np.float64)
+    out['courant'] = np.asarray([Courant(0.4, np.array([0.0]), np.array([1.0])), Courant(0.4, np.array([1.0]), np.array([1.0])),
+                                 Courant(0.4, np.array([2.0]), np.array([4.0])),
+                                 Courant(0.25, comp['h'], comp['c'])], dtype=np.float64)
+    import numba
+    out['meta'] = np.frombuffer(json.dumps(dict(name=name, numba=numba.__version__, numpy=np.__version__)).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    print('%-28s -> %.1f kB' % (name, os.path.getsize(path) / 1e3))
+    for k, v in out.items():
+        if k != 'meta':
+            print('   ', k, v)
+
+
 def main():
     # regime A: 3h > reference cell (1.0): the 3x3 coarse walk truncates the neighbourhood
     make_case('dambreak20_wendland', W.dam_break_case(20), 'wendland', True, 0.05, 3)
@@ -229,9 +279,13 @@ def main():
     # the reference Solver end to end (settle -> gate removal -> time stepping)
     solver_run_case('solver_dambreak12_wendland', 12, 'wendland', 0.03, 6)
     verlet_case()
+    equations_leaf_case()
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'leaf':         # regenerate only the leaf-equation vectors
+        equations_leaf_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'sumdens':      # regenerate only the newest case
         make_case('tank16_cubic_sumdens', W.tank_case(16, h=1.3 / 16, useXSPH=True, seed=5), 'cubic', True, 0.0, 2,
                   summation=True)

@@ -204,3 +204,126 @@ def test_tait():
     assert L.oracle_tait_p(7.0, w.B, 1000.0, 1000.0, 0) == 0.0
     assert L.oracle_tait_p(7.0, w.B, 1000.0, 1010.0, 1) == 0.0
     assert L.oracle_tait_p(7.0, w.B, 1000.0, 1010.0, 0) == pytest.approx(w.B * (1.01 ** 7 - 1), rel=1e-14)
+
+
+# ---- the equations one by one, on the tables of the reference's own equation tests --------------------------------
+def _leaf():
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import leaf_inputs as LI
+    return LI, np.load(os.path.join(here, "equations_leaf.npz"))
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_momentum_leaf_vs_reference_and_its_own_test():
+    """reference test/test_numba_momentum.py:21-90: Momentum(0.01, 0, pa, comp) on 10 000 linspace neighbours equals the
+    test's vectorised closed form (_calc_old, :92-123); golden = the reference function itself on the same table."""
+    LI, g = _leaf()
+    pa, comp = LI.momentum_reftest()
+    a = O.eq_momentum(0.01, 0.0, pa, comp)
+    assert _rel(a, g['momentum_reftest']) <= 1e-13
+    # the closed form of the reference test: pressure part only here (every v.x >= 0, no viscosity)
+    tmp = pa['p'] / pa['rho'] ** 2 + comp['p'] / comp['rho'] ** 2
+    assert a[0] == pytest.approx(np.sum(-comp['m'] * tmp * comp['dw_x']), rel=1e-12)
+    assert a[1] == pytest.approx(np.sum(-comp['m'] * tmp * comp['dw_y']), rel=1e-12)
+    # mixed labels, approaching pairs (artificial viscosity with alpha, and with beta != 0)
+    pa, comp = LI.random_table()
+    assert _rel(O.eq_momentum(0.01, 0.0, pa, comp), g['random_momentum']) <= 1e-13
+    assert _rel(O.eq_momentum(0.3, 0.7, pa, comp), g['random_momentum_beta']) <= 1e-13
+    fl = comp['label'] == 0
+    dot = comp['vx'] * comp['x'] + comp['vy'] * comp['y']
+    hij = 0.5 * (pa['h'] + comp['h']); cij = 0.5 * (pa['c'] + comp['c']); rij = 0.5 * (pa['rho'] + comp['rho'])
+    mu = hij * dot / (comp['r'] ** 2 + 0.01 * hij ** 2)
+    pi = np.where(dot < 0, mu * (0.7 * mu - 0.3 * cij) / rij, 0.0)
+    fac = pa['p'] / pa['rho'] ** 2 + comp['p'] / comp['rho'] ** 2 + pi
+    assert O.eq_momentum(0.3, 0.7, pa, comp)[0] == pytest.approx(np.sum((-comp['m'] * fac * comp['dw_x'])[fl]), rel=1e-12)
+
+
+def test_continuity_leaf_vs_reference_and_its_own_test():
+    """reference test/test_numba_continuity.py:12-66 (old_calc: sum m (v . dW)); 100 000 neighbours instead of 10 M."""
+    LI, g = _leaf()
+    comp = LI.continuity_reftest()
+    d = O.eq_continuity(comp)
+    assert abs(d / float(g['continuity_reftest']) - 1) <= 1e-12
+    assert abs(d / np.sum(comp['m'] * (comp['vx'] * comp['dw_x'] + comp['vy'] * comp['dw_y'])) - 1) <= 1e-12
+    _, comp = LI.random_table()
+    assert abs(O.eq_continuity(comp) / float(g['random_continuity']) - 1) <= 1e-13
+
+
+def test_xsph_and_boundary_force_leaves_vs_reference():
+    """reference src/Equations/XSPH.py:6-31 and BoundaryForce.py:7-42 (test/test_eq_boundary.py:9-26: the wall on the left
+    pushes to +x, nothing in y), also with the general exponents and a coincident wall particle (r <= 1e-12 skipped)."""
+    LI, g = _leaf()
+    f = O.eq_boundary_force(1.0, 5 * 9.81 * 1.0, 4.0, 2.0, LI.boundary_reftest())
+    assert f[0] > 0 and f[1] == 0.0
+    assert _rel(f, g['boundary_reftest']) <= 1e-14
+    pa, comp = LI.random_table()
+    assert _rel(O.eq_xsph(0.5, pa, comp), g['random_xsph']) <= 1e-13
+    assert _rel(O.eq_boundary_force(0.15, 1226.25, 4.0, 2.0, comp), g['random_boundary_42']) <= 1e-13
+    assert _rel(O.eq_boundary_force(0.15, 1226.25, 12.0, 6.0, comp), g['random_boundary_126']) <= 1e-13
+
+
+def test_courant_known_answers():
+    """reference test/test_eq_courant.py:8-11 (0, 0.4, 0.2) and the reference function on a random table."""
+    LI, g = _leaf()
+    assert O.eq_courant(0.4, [0.0], [1.0]) == 0.0
+    assert O.eq_courant(0.4, [1.0], [1.0]) == pytest.approx(0.4, abs=1e-15)
+    assert O.eq_courant(0.4, [2.0], [4.0]) == pytest.approx(0.2, abs=1e-15)
+    _, comp = LI.random_table()
+    got = [O.eq_courant(0.4, [0.0], [1.0]), O.eq_courant(0.4, [1.0], [1.0]), O.eq_courant(0.4, [2.0], [4.0]),
+           O.eq_courant(0.25, comp['h'], comp['c'])]
+    assert np.allclose(got, g['courant'], rtol=1e-15, atol=0)
+
+
+def test_gaussian_matches_the_reference_tests_old_implementation():
+    """reference test/test_numba_kernel.py:13-71: Gaussian.evaluate against the test's numpy `old_func`
+    (alpha / h^2 exp(-q^2) for q <= 3, else 0) on a diagonal line of 1 000 points with h = 1.3 r."""
+    x = np.linspace(0, 1000, 1000)
+    pts = np.stack([x, x], axis=1)
+    for i in (0, 1, 500, 999):
+        d = np.delete(np.hypot(*(pts[i] - pts).T), i)
+        h = d * 1.3
+        q = d / h
+        old = np.where(q <= 3, (1 / np.pi) / h ** 2 * np.exp(-q * q), 0.0)
+        assert np.allclose(O.kernel_evaluate('gaussian', d, h), old, rtol=1e-14, atol=0)
+
+
+def test_leaves_compose_to_the_loop():
+    """The stand-alone leaves, fed from the oracle's own neighbour query and kernels, reproduce oracle_loop (the composed
+    step that the golden vectors pin) particle by particle: the per-pair formulas pinned above ARE the ones in the loop."""
+    g, meta, pA = load_golden('dambreak20_wendland')
+    LI, _ = _leaf()
+    P = O.Particles.from_aos(pA)
+    w = _wcsph(meta)
+    grid = O.Grid(P, 2.0)
+    Q = P.copy()
+    O.loop(Q, w, grid, meta['kernel'])
+    fl = np.flatnonzero(P.label == 0)
+    for i in list(fl[:40]) + list(fl[-40:]):
+        hij, qij, r, idx = grid.near(int(i))
+        comp = np.zeros(len(idx), dtype=LI.COMP_DTYPE)
+        comp['label'] = P.label[idx]
+        for f_ in ('m', 'rho', 'p'):
+            comp[f_] = getattr(Q, f_)[idx]               # p after the EOS pass of the loop
+        comp['h'] = hij; comp['r'] = r; comp['q'] = qij     # comp.c stays 0 (SolverTools.py:90)
+        comp['x'] = P.x[i] - P.x[idx]; comp['y'] = P.y[i] - P.y[idx]
+        comp['vx'] = P.vx[i] - P.vx[idx]; comp['vy'] = P.vy[i] - P.vy[idx]
+        comp['w'] = O.kernel_evaluate(meta['kernel'], r, hij)
+        comp['dw_x'] = O.kernel_gradient(meta['kernel'], comp['x'], r, hij)
+        comp['dw_y'] = O.kernel_gradient(meta['kernel'], comp['y'], r, hij)
+        self_ = dict(p=Q.p[i], rho=P.rho[i], h=P.h[i], c=Q.c[i])
+        a = O.eq_momentum(w.alpha, w.beta, self_, comp)
+        b = O.eq_boundary_force(w.r0, w.D, w.p1, w.p2, comp)
+        xs = O.eq_xsph(w.epsilon, self_, comp)
+        scale = max(abs(Q.ax[i]), abs(Q.ay[i]), 1.0)
+        assert abs(a[0] + b[0] - Q.ax[i]) <= 1e-12 * scale and abs(a[1] - 9.81 + b[1] - Q.ay[i]) <= 1e-12 * scale
+        assert abs(O.eq_continuity(comp) - Q.drho[i]) <= 1e-12 * max(abs(Q.drho[i]), 1.0)
+        assert abs(P.vx[i] + xs[0] - Q.xsphx[i]) <= 1e-13 * max(abs(Q.xsphx[i]), 1.0)
+        assert abs(P.vy[i] + xs[1] - Q.xsphy[i]) <= 1e-13 * max(abs(Q.xsphy[i]), 1.0)
