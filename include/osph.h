@@ -333,6 +333,29 @@ int osph_leaf_tait_height(int device, int64_t n, const double *y, double rho0, d
                           double gamma, double *out);
 /* replaces: computeH src/Tools/SolverTools.py:106-118 */
 int osph_leaf_compute_h(int device, int64_t n, double sigma, const double *m, const double *rho, double *out);
+/*
+ * The per-neighbour equations on ONE table of J computed neighbours (the reference's computed_dtype, src/Common.py:59-105:
+ * differences are i - j, h is h_ij), for callers that use the equations outside the fused pair kernel -- the reference's
+ * own equation tests (test/test_numba_momentum.py, test_numba_continuity.py, test_eq_boundary.py) and
+ * WCSPH.compute_density_change / compute_acceleration / compute_velocity (src/Methods/WCSPH.py:151-203).
+ * cols: OSPH_COMP_NCOLS columns of J doubles each, column k at cols + k * J, in the order OSPH_COMP_*;
+ * self_*: p, rho, h, c of particle i.  One launch evaluates all four equations, deterministic summation:
+ *   out[0]    Continuity     src/Equations/Continuity.py:5-17     sum over fluid j of m (v . dW)
+ *   out[1,2]  Momentum       src/Equations/Momentum.py:6-57       (no gravity)
+ *   out[3,4]  XSPH           src/Equations/XSPH.py:6-31           (the correction, every label)
+ *   out[5,6]  BoundaryForce  src/Equations/BoundaryForce.py:7-42  (non-fluid j with 1e-12 < r <= r0)
+ */
+enum { OSPH_COMP_M = 0, OSPH_COMP_P, OSPH_COMP_RHO, OSPH_COMP_H, OSPH_COMP_C, OSPH_COMP_R, OSPH_COMP_W, OSPH_COMP_DWX,
+       OSPH_COMP_DWY, OSPH_COMP_X, OSPH_COMP_Y, OSPH_COMP_VX, OSPH_COMP_VY, OSPH_COMP_NCOLS };
+int osph_leaf_equations(int device, int64_t J, const int8_t *label, const double *cols, double self_p, double self_rho,
+                        double self_h, double self_c, double alpha, double beta, double epsilon, double r0, double D,
+                        double p1, double p2, double out[7]);
+/* The positional columns of a computed-neighbour table: differences self - neighbour of x, y, vx, vy
+ * (replaces the arithmetic of _assignProps, src/Tools/SolverTools.py:97-101; the other columns are copies).
+ * self4 = {x, y, vx, vy} of particle i; nbr / out: 4 columns of J doubles each (x, y, vx, vy), column k at + k * J. */
+int osph_leaf_differences(int device, int64_t J, const double self4[4], const double *nbr, double *out);
+/* replaces: Courant src/Equations/Courant.py:4-31 (alpha * min h / max c, with the reference's 10e10 / 1e-10 seeds) */
+int osph_leaf_courant(int device, double alpha, int64_t J, const double *h, const double *c, double *out);
 const char *osph_leaf_last_error(void);
 
 #ifdef __cplusplus

@@ -140,6 +140,9 @@ def lib():
         'osph_leaf_tait_pressure': (C.c_int, [C.c_int, i64, dp, C.POINTER(C.c_int8), dbl, dbl, dbl, dbl, dp]),
         'osph_leaf_tait_height': (C.c_int, [C.c_int, i64, dp, dbl, dbl, dbl, dbl, dp]),
         'osph_leaf_compute_h': (C.c_int, [C.c_int, i64, dbl, dp, dp, dp]),
+        'osph_leaf_equations': (C.c_int, [C.c_int, i64, C.POINTER(C.c_int8), dp] + [dbl] * 11 + [dp]),
+        'osph_leaf_courant': (C.c_int, [C.c_int, dbl, i64, dp, dp, dp]),
+        'osph_leaf_differences': (C.c_int, [C.c_int, i64, dp, dp, dp]),
         'osph_leaf_last_error': (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -549,4 +552,53 @@ def leaf_tait_height(y, rho0, H, B, gamma):
 def leaf_compute_h(sigma, m, rho):
     m = _f64(m); rho = _f64(rho); out = np.empty_like(m)
     _leaf_ck(lib().osph_leaf_compute_h(default_device(), m.size, sigma, _ptr(m), _ptr(rho), _ptr(out)))
+    return out
+
+
+#: column order of a computed-neighbour table crossing the C ABI (include/osph.h: OSPH_COMP_*)
+COMP_COLUMNS = ['m', 'p', 'rho', 'h', 'c', 'r', 'w', 'dw_x', 'dw_y', 'x', 'y', 'vx', 'vy']
+
+
+def _self_field(p, name):
+    """Field of the self particle; the reference passes a particle_dtype record, some of its tests an empty array."""
+    try:
+        return float(p[name])
+    except (KeyError, IndexError, ValueError, TypeError):
+        return 0.0
+
+
+def leaf_equations(p, comp, alpha=0.0, beta=0.0, epsilon=0.0, r0=0.0, D=0.0, p1=4.0, p2=2.0):
+    """Continuity, Momentum, XSPH and BoundaryForce of particle record `p` over the computed-neighbour table `comp`
+    (computed_dtype) in one device launch.  Returns dict(drho, a=[ax, ay], xsph=[x, y], f=[fx, fy])."""
+    comp = np.atleast_1d(comp)
+    J = len(comp)
+    cols = np.empty((len(COMP_COLUMNS), J), dtype=np.float64)
+    for k, f in enumerate(COMP_COLUMNS):
+        cols[k] = comp[f]
+    lab = np.ascontiguousarray(comp['label'], dtype=np.int8)
+    out = np.zeros(7)
+    rho_self = _self_field(p, 'rho')
+    _leaf_ck(lib().osph_leaf_equations(default_device(), J, lab.ctypes.data_as(C.POINTER(C.c_int8)), _ptr(cols),
+                                       _self_field(p, 'p'), rho_self, _self_field(p, 'h'), _self_field(p, 'c'),
+                                       float(alpha), float(beta), float(epsilon), float(r0), float(D), float(p1), float(p2),
+                                       _ptr(out)))
+    return dict(drho=float(out[0]), a=[float(out[1]), float(out[2])], xsph=[float(out[3]), float(out[4])],
+                f=[float(out[5]), float(out[6])])
+
+
+def leaf_courant(alpha, h, c):
+    h = _f64(np.atleast_1d(h)); c = _f64(np.atleast_1d(c))
+    if h.size != c.size:
+        raise ValueError("h and c must have the same length")
+    out = np.zeros(1)
+    _leaf_ck(lib().osph_leaf_courant(default_device(), float(alpha), h.size, _ptr(h), _ptr(c), _ptr(out)))
+    return float(out[0])
+
+
+def leaf_differences(self4, nbr):
+    """(x, y, vx, vy) of the self particle minus the same four columns of its neighbours; nbr: array (4, J)."""
+    nbr = _f64(nbr)
+    out = np.empty_like(nbr)
+    s4 = _f64(self4)
+    _leaf_ck(lib().osph_leaf_differences(default_device(), nbr.shape[1], _ptr(s4), _ptr(nbr), _ptr(out)))
     return out

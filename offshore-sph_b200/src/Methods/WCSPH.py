@@ -2,8 +2,8 @@
 
 Constructor and attributes mirror reference src/Methods/WCSPH.py:35-79.  The per-pair arithmetic
 (compute_density_change / compute_acceleration / compute_velocity in the reference) lives in the fused
-pair kernel; the three whole-array methods the Solver calls during setup run on the device through the
-leaf entry points of the C ABI.
+pair kernel; called stand-alone on one particle and its computed-neighbour table, those three run on the device
+through osph_leaf_equations, as do the three whole-array methods the Solver calls during setup.
 """
 import math
 
@@ -48,3 +48,19 @@ class WCSPH(Method):
 
     def compute_pressure(self, pA: np.array) -> np.array:
         return capi.leaf_tait_pressure(pA['rho'], pA['label'], self.gamma, self.B, self.rho0, self.Pb)
+
+    # ---- per-particle forms (reference WCSPH.py:151-203): one particle record + its computed-neighbour table ----
+    def compute_acceleration(self, p: np.array, comp: np.array):
+        a = capi.leaf_equations(p, comp, alpha=self.alpha, beta=self.beta)['a']
+        return [a[0], a[1] - 9.81]
+
+    def compute_velocity(self, p: np.array, comp: np.array):
+        if self.useXSPH:
+            xs = capi.leaf_equations(p, comp, epsilon=self.epsilon)['xsph']
+            return [p['vx'], p['vy'], p['vx'] + xs[0], p['vy'] + xs[1]]
+        return [p['vx'], p['vy'], 0.0, 0.0]
+
+    def compute_density_change(self, p: np.array, comp: np.array):
+        if self.useSummationDensity:
+            return 0.0
+        return capi.leaf_equations(p, comp)['drho']

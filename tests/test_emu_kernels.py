@@ -35,6 +35,7 @@ from test_gpu_solver import *  # noqa: F401,F403,E402
 from test_gpu_edges import *  # noqa: F401,F403,E402
 import test_gpu_edges as _edges  # noqa: E402
 import test_gpu_parity as _parity  # noqa: E402
+import test_gpu_solver as _solver  # noqa: E402
 
 
 def test_pair_kernel_batched_staging_path():
@@ -71,6 +72,7 @@ def test_results_do_not_depend_on_the_schedule(mode, seed):
         _parity.test_fused_loop_equals_explicit_calls('dambreak20_wendland')
         _parity.test_dam_break_vs_oracle(60, 'wendland')
         _edges.test_cluster_denser_than_the_candidate_list()
+        _solver.test_equation_functions_standalone()
     finally:
         lib.emu_set_order(0, 0)
 

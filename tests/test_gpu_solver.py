@@ -144,6 +144,125 @@ def test_method_and_tools_standalone():
     assert KineticEnergy(len(fluid), fluid) == pytest.approx(O.kinetic_energy(P), rel=1e-13)
 
 
+def test_equation_functions_standalone():
+    """The reference's equation tests pointed at this package: test/test_numba_momentum.py:21-90,
+    test_numba_continuity.py:12-46, test_eq_boundary.py:9-26, test_eq_courant.py:8-11 -- the functions of src.Equations run on
+    the device (osph_leaf_equations / osph_leaf_courant) and are held to the golden results of the reference functions
+    (tests/golden/equations_leaf.npz), the oracle leaves and the closed forms of those tests."""
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import leaf_inputs as LI
+    from src.Common import computed_dtype, particle_dtype
+    from src.Equations.BoundaryForce import BoundaryForce
+    from src.Equations.Continuity import Continuity
+    from src.Equations.Courant import Courant
+    from src.Equations.Momentum import Momentum
+    from src.Equations.XSPH import XSPH
+    from src.Methods.WCSPH import WCSPH
+    g = np.load(os.path.join(here, "equations_leaf.npz"))
+
+    def records(pa_fields, comp):
+        pa = np.zeros(1, dtype=particle_dtype)
+        for k, v in (pa_fields or {}).items():
+            pa[k] = v
+        c = np.zeros(len(comp), dtype=computed_dtype)
+        for f in comp.dtype.names:
+            c[f] = comp[f]
+        return pa[0], c
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    # test_numba_momentum.py: 10 000 neighbours; the closed form of the test is its vectorised _calc_old
+    pa, comp = records(*LI.momentum_reftest())
+    a = Momentum(0.01, 0.0, pa, comp)
+    assert rel(a, g['momentum_reftest']) <= 1e-12
+    tmp = pa['p'] / pa['rho'] ** 2 + comp['p'] / comp['rho'] ** 2
+    assert a[0] == pytest.approx(np.sum(-comp['m'] * tmp * comp['dw_x']), rel=1e-12)
+    # test_numba_continuity.py (its `p` is an empty array)
+    _, comp = records(None, LI.continuity_reftest())
+    d = Continuity(np.array([]), comp)
+    assert abs(d / float(g['continuity_reftest']) - 1) <= 1e-12
+    assert abs(d / np.sum(comp['m'] * (comp['vx'] * comp['dw_x'] + comp['vy'] * comp['dw_y'])) - 1) <= 1e-12
+    # test_eq_boundary.py: the wall on the left pushes to +x only
+    pa, comp = records(None, LI.boundary_reftest())
+    f = BoundaryForce(1.0, 5 * 9.81 * 1.0, 4.0, 2.0, pa, comp)
+    assert f[0] > 0 and f[1] == 0.0 and rel(f, g['boundary_reftest']) <= 1e-13
+    # test_eq_courant.py
+    assert Courant(0.4, np.array([0.0]), np.array([1.0])) == 0.0
+    assert Courant(0.4, np.array([1.0]), np.array([1.0])) == pytest.approx(0.4, abs=1e-15)
+    assert Courant(0.4, np.array([2.0]), np.array([4.0])) == pytest.approx(0.2, abs=1e-15)
+    # random table: mixed labels, approaching pairs, beta viscosity, general exponents, coincident wall particle
+    pa_f, comp_in = LI.random_table()
+    pa, comp = records(pa_f, comp_in)
+    assert rel(Momentum(0.01, 0.0, pa, comp), g['random_momentum']) <= 1e-12
+    assert rel(Momentum(0.3, 0.7, pa, comp), g['random_momentum_beta']) <= 1e-12
+    assert rel(Momentum(0.3, 0.7, pa, comp), O.eq_momentum(0.3, 0.7, pa_f, comp_in)) <= 1e-12
+    assert abs(Continuity(pa, comp) / float(g['random_continuity']) - 1) <= 1e-12
+    assert rel(XSPH(0.5, pa, comp), g['random_xsph']) <= 1e-12
+    assert rel(BoundaryForce(0.15, 1226.25, 4.0, 2.0, pa, comp), g['random_boundary_42']) <= 1e-12
+    assert rel(BoundaryForce(0.15, 1226.25, 12.0, 6.0, pa, comp), g['random_boundary_126']) <= 1e-12
+    assert Courant(0.25, comp['h'], comp['c']) == pytest.approx(float(g['courant'][3]), rel=1e-15)
+    # the per-particle methods of WCSPH (reference WCSPH.py:151-203)
+    m = WCSPH(1.0, 0.15, 1000.0, True, 0)
+    m.alpha, m.beta = 0.3, 0.7
+    acc = m.compute_acceleration(pa, comp)
+    assert rel([acc[0], acc[1] + 9.81], g['random_momentum_beta']) <= 1e-12
+    v = m.compute_velocity(pa, comp)
+    assert v[0] == pa['vx'] and rel([v[2] - pa['vx'], v[3] - pa['vy']], g['random_xsph']) <= 1e-12
+    assert abs(m.compute_density_change(pa, comp) / float(g['random_continuity']) - 1) <= 1e-12
+    m.useXSPH = False; m.useSummationDensity = True
+    assert m.compute_velocity(pa, comp)[2:] == [0.0, 0.0] and m.compute_density_change(pa, comp) == 0.0
+    # an empty table
+    empty = np.zeros(0, dtype=computed_dtype)
+    assert Momentum(0.01, 0.0, pa, empty) == [0.0, 0.0] and Continuity(pa, empty) == 0.0
+
+
+@pytest.mark.parametrize("name", ['tank16_gaussian', 'dambreak20_wendland'])
+def test_force_evaluation_composed_from_the_plugin_objects(name):
+    """One force evaluation written the way the reference composes it (SolverTools.py:143-173, and make_golden.py's
+    loop_gaussian for the kernel `_loop` cannot take): nn.near -> computeProps -> method.compute_density_change /
+    compute_acceleration / compute_velocity + BoundaryForce, every piece a stand-alone device leaf of this package --
+    equal to the golden vectors of the reference and to the fused pair kernel."""
+    from src.Equations.BoundaryForce import BoundaryForce
+    from src.Kernels.Gaussian import Gaussian
+    from src.Kernels.Wendland import Wendland
+    from src.Methods.WCSPH import WCSPH
+    from src.Tools.NNLinkedList import NNLinkedList
+    from src.Tools.SolverTools import computeProps, _loop
+    g, meta, pA = load_golden(name)
+    c = meta['consts']
+    K = {'gaussian': Gaussian, 'wendland': Wendland}[meta['kernel']]
+    m = WCSPH(c['height'], c['r0'], c['rho0'], meta['useXSPH'], c['Pb'])
+    pA = pA.copy()
+    pA['p'] = m.compute_pressure(pA)
+    pA['c'] = m.compute_speed_of_sound(pA)
+    nn = NNLinkedList(2.0)
+    nn.update(pA)
+    fluid = np.flatnonzero(pA['label'] == 0)
+    pick = fluid[::max(1, len(fluid) // 60)]
+    got = {f: np.zeros(len(pick)) for f in ('drho', 'ax', 'ay', 'xsphx', 'xsphy')}
+    for k, i in enumerate(pick):
+        h_i, q_i, dist, near = nn.near(int(i), pA)
+        comp = computeProps(int(i), pA, near, h_i, q_i, dist, K.evaluate, K.gradient)
+        a = m.compute_acceleration(pA[i], comp)
+        b = BoundaryForce(m.r0, m.D, m.p1, m.p2, pA[i], comp)
+        v = m.compute_velocity(pA[i], comp)
+        got['drho'][k] = m.compute_density_change(pA[i], comp)
+        got['ax'][k] = a[0] + b[0]; got['ay'][k] = a[1] + b[1]
+        got['xsphx'][k] = v[2]; got['xsphy'][k] = v[3]
+    fused = _loop(pA.copy(), K.evaluate, K.gradient, m, nn)
+    for f in got:
+        ref = g['loop_' + f]
+        scale = np.maximum(np.abs(ref[pick]), np.abs(ref).max())
+        assert np.max(np.abs(got[f] - ref[pick]) / scale) <= 1e-10, (f, 'vs golden')
+        assert np.max(np.abs(got[f] - fused[f][pick]) / scale) <= 1e-10, (f, 'vs fused kernel')
+
+
 def test_integrator_objects_standalone():
     """reference test/test_integrators_pec.py known answers through the device kernels."""
     from src.Integrators.PEC import PEC
