@@ -48,6 +48,90 @@ def test_general_lennard_jones_exponents_and_beta_viscosity(kernel):
     assert _compare_steps(case, kernel, 2, consts, w) == 0
 
 
+@pytest.mark.parametrize("kernel", ['wendland', 'cubic'])
+def test_background_pressure_and_other_gas_constants(kernel):
+    """Pb != 0 (added to the pressure of EVERY label, WCSPH.py:143-149, so the wall rows carry Pb and the fluid rows
+    Tait + Pb), gamma, alpha and epsilon away from their defaults, no damping."""
+    case = W.tank_case(24, h=1.5 / 24, useXSPH=True, seed=9)
+    over = dict(Pb=3.5e3, gamma=5.0, alpha=0.05, epsilon=0.25)
+    consts = dict(case['consts'], **over)
+    consts['B'] = consts['co'] ** 2 * consts['rho0'] / consts['gamma']           # TaitEOS_B with the changed gamma
+    w = _oracle_params(case['consts'], **dict(over, B=consts['B']))
+    assert _compare_steps(case, kernel, 2, consts, w, damping=0.0) == 0
+
+
+@pytest.mark.parametrize("scale,fluid_only", [(3.0, True), (1.0, True), (3.0, False)])
+def test_neighbour_scale_other_than_two(scale, fluid_only):
+    """NNLinkedList(scale) with scale != 2 (the reference's test_linked_list.py uses 3): reference cell = scale * min h.
+    scale = 1 makes the cell SMALLER than the 3 h_ij radius, so the 3x3 cell walk truncates the q <= 3 set and the cell
+    adjacency decides membership; with boundary rows (h = 0) the cell is the 1.0 fallback whatever the scale."""
+    case = W.tank_case(20, h=1.5 / 20, useXSPH=True, seed=6)
+    pA = case['pA'] if not fluid_only else case['pA'][case['pA']['label'] == 0]
+    P = O.Particles.from_aos(pA)
+    grid = O.Grid(P, scale)
+    cfg = capi.make_config(case['consts'], 'cubic', 'pec', capi.FP64, None, keep_h=True)
+    cfg.nn_scale = scale
+    with capi.Context(cfg) as ctx:
+        ctx.upload(pA)
+        ctx.build_neighbours()
+        g, cells = ctx.cells()
+        want = grid.params
+        assert [g['xmin'], g['xmax'], g['ymin'], g['ymax'], g['cell_size'], g['ncx'], g['ncy']] == \
+               [want[k] for k in ('xmin', 'xmax', 'ymin', 'ymax', 'cell_size', 'ncx', 'ncy')]
+        assert np.array_equal(cells, grid.cell_ids())
+        off, idx = ctx.neighbours_csr()
+        woff, widx = grid.neighbours_csr()
+        assert np.array_equal(off, woff)
+        for i in range(len(off) - 1):
+            assert np.array_equal(np.sort(idx[off[i]:off[i + 1]]), np.sort(widx[woff[i]:woff[i + 1]])), i
+        # one force evaluation on that neighbour structure
+        w = _oracle_params(case['consts'])
+        Q = P.copy()
+        O.loop(Q, w, grid, 'cubic')
+        ctx.compute()
+        cols = ctx.download_fields(['drho', 'ax', 'ay', 'xsphx', 'xsphy'])
+        for f in cols:
+            assert field_err(cols[f], getattr(Q, f)) <= TOL, (f, field_err(cols[f], getattr(Q, f)))
+        assert ctx.sync() == 0
+
+
+def test_domain_far_from_the_origin():
+    """The same dam break translated by (12 345.678, -9 876.5): the grid origin is the per-step minimum, so cell ids and
+    neighbour sets still follow the reference bit for bit, the FP64 fields agree with the oracle, and the FP32 mode (which
+    subtracts a per-CTA anchor in double before rounding to float) stays as close to FP64 as it is at the origin."""
+    case = W.dam_break_case(30, seed=8)
+    case['pA'] = case['pA'].copy()
+    case['pA']['x'] += 12345.678; case['pA']['y'] -= 9876.5
+    pA = case['pA']
+    c = dict(case['consts'])
+    # the hydrostatic reference height travels with the block (H - y enters only through the initial density, already set)
+    w = _oracle_params(c)
+    P = O.Particles.from_aos(pA)
+    grid = O.Grid(P, 2.0)
+    cfg = capi.make_config(c, 'wendland', 'pec', capi.FP64, case['h'])
+    with capi.Context(cfg) as ctx:
+        ctx.upload(pA)
+        ctx.build_neighbours()
+        g, cells = ctx.cells()
+        assert np.array_equal(cells, grid.cell_ids())
+        off, idx = ctx.neighbours_csr()
+        woff, widx = grid.neighbours_csr()
+        assert np.array_equal(off, woff)
+        assert all(np.array_equal(np.sort(idx[off[i]:off[i + 1]]), np.sort(widx[woff[i]:woff[i + 1]])) for i in range(len(off) - 1))
+    assert _compare_steps(case, 'wendland', 2, c, w) == 0
+    out = {}
+    for prec in (capi.FP64, capi.FP32):
+        with capi.Context(capi.make_config(c, 'wendland', 'pec', prec, case['h'])) as ctx:
+            ctx.upload(pA)
+            ctx.step(3, None, 0.05)
+            out[prec] = ctx.download_fields(['x', 'y', 'rho', 'ax', 'ay'])
+    r0 = case['r0']
+    assert np.max(np.abs(out[capi.FP32]['x'] - out[capi.FP64]['x'])) < 1e-4 * r0
+    assert np.max(np.abs(out[capi.FP32]['y'] - out[capi.FP64]['y'])) < 1e-4 * r0
+    assert np.max(np.abs(out[capi.FP32]['rho'] / out[capi.FP64]['rho'].clip(1.0) - out[capi.FP64]['rho'] / out[capi.FP64]['rho'].clip(1.0))) < 1e-5
+    assert field_err(out[capi.FP32]['ax'], out[capi.FP64]['ax']) < 1e-3 and field_err(out[capi.FP32]['ay'], out[capi.FP64]['ay']) < 1e-3
+
+
 def test_coincident_particles_follow_the_reference_guards():
     """Two fluid particles on one point (gradient zeroed below r = 1e-10, CubicSpline.py:47-49) and a fluid particle on
     top of a wall particle (Lennard-Jones only for r > 1e-12, BoundaryForce.py:26) must not produce NaN and must
