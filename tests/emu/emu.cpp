@@ -307,7 +307,7 @@ static cudaError_t g_last = cudaSuccess;
 // compute-sanitizer memcheck.  OSPH_EMU_FILL=<byte> changes the garbage pattern fresh allocations are filled with
 // (two runs with different patterns that agree bit for bit do not depend on uninitialised device memory).
 //
-// CUDA IPC (the peer-memory slab sequencer, slab_p2p.cu): allocations of 16 KiB and more are page-exclusive anonymous
+// CUDA IPC (the peer-memory slab sequencer, slab_p2p.cu): allocations of 4 KiB and more are page-exclusive anonymous
 // mappings; cudaIpcGetMemHandle turns one into a POSIX shared-memory mapping AT THE SAME ADDRESS (contents kept) and hands
 // out its name, cudaIpcOpenMemHandle maps that object in the peer process.  Ranks are separate processes, so the mailbox
 // kernels that spin on a peer's sequence number run against real concurrency.
@@ -347,7 +347,7 @@ cudaError_t cudaMalloc(void **p, size_t bytes)
         *p = u;
         return cudaSuccess;
     }
-    if (bytes >= 16384) {
+    if (bytes >= 4096) {
         const size_t total = (bytes + PAGE - 1) / PAGE * PAGE;
         void *m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (m == MAP_FAILED) return cudaErrorMemoryAllocation;

@@ -134,3 +134,67 @@ def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt, s
         assert errs[worst] <= 1e-11, (chunk, worst, errs[worst])
     if fixed_dt is not None:
         assert sum(r[6] for r in res if r[1] == 1) > 0, "no particle migrated: the test did not exercise the exchange"
+
+
+def _worker_overflow(rank, world, port, lib, seq, q):
+    os.environ["OSPH_LIB"] = lib
+    os.environ["OSPH_NCCL_LIB"] = os.path.join(os.path.dirname(lib), "libfake_nccl.so")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    root = os.path.dirname(HERE)
+    for p in (root, os.path.join(root, "offshore-sph_b200"), HERE):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from osph_b200 import capi, slabs, workloads as W
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = W.dam_break_case(40, seed=2)
+    pA, c = case['pA'], case['consts']
+    cfg = capi.make_config(c, 'cubic', 'pec', capi.FP64, case['h'])
+    ctx = capi.Context(cfg)
+    cuts, local_pA, ids = slabs.partition(pA, world, rank)
+    cls = {'python': None, 'nccl': slabs.NcclSlabRun, 'p2p': slabs.P2PSlabRun}[seq]
+    kw = dict(mig_frac=0.0, ghost_frac=0.0, min_cap=8)            # 8 halo records per face: far too few
+    if cls is None:
+        run = slabs.SlabRun(ctx, slabs.TorchComm(), cuts, local_pA, ids, 'cubic', case['r0'], case['h'], torch.device('cpu'), **kw)
+    else:
+        run = cls(ctx, cuts, local_pA, ids, 'cubic', case['r0'], case['h'], torch.device('cpu'), **kw)
+    msg = ""
+    try:
+        run.step(2, None, 0.05)
+    except Exception as e:      # noqa: BLE001
+        msg = "%s: %s" % (type(e).__name__, e)
+    q.put((rank, msg))
+    dist.barrier()              # every rank got here: the failure was collective, nobody is left waiting in an exchange
+    if hasattr(run, 'close'):
+        run.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("seq", ['python', 'nccl', 'p2p'])
+def test_exchange_region_overflow_is_a_loud_collective_error(seq):
+    """Halo regions sized for 8 records: every rank must come back from the step with a capacity error that names the
+    overflow (no silent truncation of the halo, no rank left spinning in a mailbox or a receive)."""
+    import queue
+    import time
+    lib = emu_build.build()
+    emu_build.build_fake_nccl()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_worker_overflow, args=(r, world, port, lib, seq, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res, t_end = [], time.time() + 200
+    while len(res) < world and time.time() < t_end:
+        try:
+            res.append(q.get(timeout=1.0))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    [p.join(30) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
+    assert len(res) == world and all(p.exitcode == 0 for p in procs), res
+    for rank, msg in res:
+        assert "overflow" in msg.lower(), (rank, msg)
