@@ -21,6 +21,8 @@
 // r/h_ij <= 3.0 re-evaluated in strict IEEE when the cheap test is within 1e-13 of the threshold).  FP32
 // instantiation = performance mode: positions are staged relative to a per-CTA anchor (subtracted in double,
 // then rounded), arithmetic in float.
+#include <type_traits>
+
 #include "common.cuh"
 #include "pair.cuh"
 
@@ -56,6 +58,13 @@
 #ifndef PAIR_CAP
 #define PAIR_CAP 1024         // candidate records resident in shared memory at once
 #endif
+#ifndef PAIR_LEAN
+#define PAIR_LEAN 1           // 1: the scan drops the self pair (it contributes exactly 0), and the r -> 0 guards of the reference and
+#endif                        // the (2 - q)+ clamp leave the common path of the heavy body: a second, guarded copy of the body serves the
+                              // pairs that came through the rarely taken branch (coincident particles, wall pairs outside the kernel
+                              // support, irregularly binned particles, the Gaussian).  Common path per listed pair, FP64 cubic, by SASS:
+                              // 131 -> 118 instructions, 80 -> 68 on the FP64 pipe, no spills.  0: one guarded body for every pair (the
+                              // build all GPU measurements of round 1 were made with; tools/build_round2_variants.sh builds it as `lean0`)
 
 // One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
 // every field at a compile-time offset.  40 B (float) / 80 B (double) keeps 8 / 16-byte vector alignment.
@@ -223,9 +232,14 @@ k_pair(PairArgs a)
         //  * q <= 3 can only bind for wall pairs outside the kernel support and at the cut of the Gaussian.
         // Everything that can reject a listed pair sits behind ONE rarely taken branch: inside the kernel support with
         // no cell test due, the pair is a member and the common path pays one compare and one predicate for it.
+        // PAIR_LEAN: a pair closer than about 1.2e-10 (high word of r2 at or below that of 1e-20: a superset of the pairs
+        // the two guards can bind for) joins the rare branch, an integer compare on the ALU pipe
+        bool via_rare = false;
+        const bool tiny = PAIR_LEAN && (sizeof(Real) == 8 ? __double2hiint((double)r2) <= 0x3BC79CA1 : r2 <= Real(1.0001e-20));
         if constexpr (EXACT) {
             const bool adjq = adj_i || (info_j & 4);
-            if (KID == OSPH_KERNEL_GAUSSIAN || adjq || !kern) {
+            if (KID == OSPH_KERNEL_GAUSSIAN || adjq || !kern || tiny) {
+                via_rare = true;
                 bool ok = kern || lj;
                 if (adjq) ok = ok && abs(cbx - qcx) <= 1 && abs(cby - qcy) <= 1;
                 if (KID == OSPH_KERNEL_GAUSSIAN || !kern) {
@@ -238,10 +252,16 @@ k_pair(PairArgs a)
                 if (!ok) return;
             }
         } else {
-            if (KID == OSPH_KERNEL_GAUSSIAN || !kern) {
+            if (KID == OSPH_KERNEL_GAUSSIAN || !kern || tiny) {
+                via_rare = true;
                 if (!((kern || lj) && r2 <= h2 * Real(9))) return;
             }
         }
+        // GUARDED: the r -> 0 guards of the reference and the clamp of the outer spline term are evaluated.  The default build
+        // always is; with PAIR_LEAN only the pairs that came through the rare branch above are (coincident particles, wall
+        // pairs outside the kernel support, the Gaussian) and the common path uses rs as it stands.
+        auto body = [&](auto guarded_tag) {
+        constexpr bool GUARDED = decltype(guarded_tag)::value;
 #if PAIR_NO_FMAX
         const Real rs = rsqrt_fast(r2);                            // r2 == 0: inf / NaN, discarded by the two selects below
 #else
@@ -252,12 +272,12 @@ k_pair(PairArgs a)
         const Real inv_rbar = rcp_fast(rbar);
         const Real hbar = fma(Real(0.5), hij, hi_half);            // h averaged twice (Momentum.py:43)
         const Real inv_den = rcp_fast(r2 + Real(0.01) * hbar * hbar);
-        const Real inv_rt = r2 > Real(1e-24) ? rs : Real(0);       // LJ guard: r > 1e-12
-        const Real inv_r = r2 > Real(1e-20) ? rs : Real(0);        // gradient guard: r >= 1e-10
+        const Real inv_rt = !GUARDED || r2 > Real(1e-24) ? rs : Real(0);       // LJ guard: r > 1e-12
+        const Real inv_r = !GUARDED || r2 > Real(1e-20) ? rs : Real(0);        // gradient guard: r >= 1e-10
         const Real r = r2 * inv_rt;
         const Real q = r * inv_h;
         Real w, g;
-        if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair<Real>(q, inv_h, inv_r, w, g);
+        if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair<Real, GUARDED>(q, inv_h, inv_r, w, g);
         else sph_kernel<Real, KID>(q, inv_h, inv_r, w, g);
         const Real dwx = g * dx, dwy = g * dy;
         const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
@@ -282,6 +302,8 @@ k_pair(PairArgs a)
             const Real fl = PC(D) * tmp * inv_rt * inv_rt;
             ax += fl * dx; ay += fl * dy;
         }
+        };      // body
+        if (PAIR_LEAN && !via_rare) body(std::false_type()); else body(std::true_type());
     };
 
     // Two-phase walk, warp-synchronous.  (1) scan: cheap distance test over the thread's own sub-interval of
@@ -306,7 +328,9 @@ k_pair(PairArgs a)
 #endif
         nl = 0;
     };
-    auto scan = [&](int j, const int j1) {          // all 32 lanes of a warp call this together
+    // skip_tag (PAIR_LEAN only): the run holds the thread's own record at index `self`; it is not listed
+    auto scan = [&](auto skip_tag, int j, const int j1, const int self) {          // all 32 lanes of a warp call this together
+        constexpr bool SKIP = PAIR_LEAN && decltype(skip_tag)::value;
         bool warp_more = __any_sync(0xffffffffu, j < j1);
 #pragma unroll 1
         while (warp_more) {
@@ -325,7 +349,7 @@ k_pair(PairArgs a)
                 }
 #pragma unroll
                 for (int u = 0; u < PAIR_SCAN; u++)
-                    if (j + u < j1 && d2[u] <= thr_f) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
+                    if (j + u < j1 && d2[u] <= thr_f && (!SKIP || j + u != self)) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
             } else {
                 Real d2[PAIR_SCAN];
 #pragma unroll
@@ -336,7 +360,7 @@ k_pair(PairArgs a)
                 }
 #pragma unroll
                 for (int u = 0; u < PAIR_SCAN; u++)
-                    if (j + u < j1 && d2[u] <= pair_r2) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
+                    if (j + u < j1 && d2[u] <= pair_r2 && (!SKIP || j + u != self)) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
             }
             j += PAIR_SCAN;
 #else
@@ -345,7 +369,7 @@ k_pair(PairArgs a)
                 if (j < j1) {
                     const Real2 pj = sh_rec[j].pos;
                     const Real dx = xi - pj.x, dy = yi - pj.y;
-                    if (dx * dx + dy * dy <= pair_r2) { sh_list[nl * NT + tid] = (unsigned short)j; nl++; }
+                    if (dx * dx + dy * dy <= pair_r2 && (!SKIP || j != self)) { sh_list[nl * NT + tid] = (unsigned short)j; nl++; }
                     j++;
                 }
             }
@@ -366,10 +390,10 @@ k_pair(PairArgs a)
         __syncthreads();
         // (an empty run is ra = INT_MAX, rb = 0: test it before doing index arithmetic on it)
         const bool h0 = fluid_i && rb0 > ra0, h1 = fluid_i && rb1 > ra1, h2 = fluid_i && rb2 > ra2;
-        scan(h0 ? ra0 - ulo0 : 0, h0 ? rb0 - ulo0 : 0);
-        scan(h1 ? ra1 - ulo1 + o1 : 0, h1 ? rb1 - ulo1 + o1 : 0);
+        scan(std::false_type(), h0 ? ra0 - ulo0 : 0, h0 ? rb0 - ulo0 : 0, -1);
+        scan(std::true_type(), h1 ? ra1 - ulo1 + o1 : 0, h1 ? rb1 - ulo1 + o1 : 0, s - ulo1 + o1);    // the middle row holds s itself
         if (fluid_i) slot = (int)a.idx[s];                       // the epilogue's loads travel under the remaining work
-        scan(h2 ? ra2 - ulo2 + o2 : 0, h2 ? rb2 - ulo2 + o2 : 0);
+        scan(std::false_type(), h2 ? ra2 - ulo2 + o2 : 0, h2 ? rb2 - ulo2 + o2 : 0, -1);
         if constexpr (!EXACT) { if (fluid_i && a.method_xsph) { vx_st = a.vx[slot]; vy_st = a.vy[slot]; have_v = true; } }
         flush();
     } else {
@@ -385,7 +409,7 @@ k_pair(PairArgs a)
                 stage(base, cnt, 0);
                 __syncthreads();
                 const bool has = fluid_i && rb > ra;
-                scan(has ? max(ra, base) - base : 0, has ? min(rb, base + cnt) - base : 0);
+                scan(std::true_type(), has ? max(ra, base) - base : 0, has ? min(rb, base + cnt) - base : 0, d == 1 ? s - base : -1);
                 flush();
             }
         }

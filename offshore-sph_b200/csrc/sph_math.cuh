@@ -118,11 +118,13 @@ __device__ __forceinline__ float neg_part(float d) { return fminf(d, 0.0f); }
 //   W/alpha = (2-q)+^3 / 4 - (1-q)+^3,   W'/alpha = -3/4 (2-q)+^2 + 3 (1-q)+^2,
 // identical to CubicSpline.py:10-70 on every branch (q <= 1, 1 < q <= 2, q > 2) up to rounding of O(1e-16) terms, without
 // evaluating both branches and selecting.
-template <typename Real>
+// CLAMP_OUTER = false (pair.cu, PAIR_LEAN): the caller knows r^2 <= 4 h^2, so 2 - q can be negative by rounding only (a few
+// 1e-16: 1e-47 in W, 1e-31 in W') and the outer term is used as it stands.
+template <typename Real, bool CLAMP_OUTER = true>
 __device__ __forceinline__ void cubic_pair(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
 {
     const Real alpha = Real(10.0 / (7.0 * PI_D)) * inv_h * inv_h;
-    const Real t2 = pos_part(Real(2) - q), t1 = pos_part(Real(1) - q);
+    const Real t2 = CLAMP_OUTER ? pos_part(Real(2) - q) : Real(2) - q, t1 = pos_part(Real(1) - q);
     const Real s2 = t2 * t2, s1 = t1 * t1;
     const Real wv = fma(-s1, t1, Real(0.25) * s2 * t2);
     const Real gv = fma(Real(3), s1, Real(-0.75) * s2);

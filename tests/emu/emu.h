@@ -123,6 +123,8 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline long long __double_as_longlong(double v) { return emu::from_bits<long long>(emu::to_bits(v)); }
 inline double __longlong_as_double(long long v) { return emu::from_bits<double>(emu::to_bits(v)); }
+inline int __double2hiint(double v) { return (int)(emu::to_bits(v) >> 32); }
+inline int __double2loint(double v) { return (int)(emu::to_bits(v) & 0xffffffffu); }
 inline int __float_as_int(float v) { return emu::from_bits<int>(emu::to_bits(v)); }
 inline float __int_as_float(int v) { return emu::from_bits<float>(emu::to_bits(v)); }
 

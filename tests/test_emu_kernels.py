@@ -55,6 +55,31 @@ def test_pair_kernel_batched_staging_path():
         capi.LIB_PATH, capi._lib = saved
 
 
+def test_pair_kernel_single_body_variant():
+    """-DPAIR_LEAN=0 (the build round 1 was measured with, kept for the A/B run of tools/build_round2_variants.sh): one
+    guarded body for every listed pair, the self pair listed.  Same parity bar as the default build."""
+    from osph_b200 import capi
+    path = emu_build.build(defines=("PAIR_LEAN=0",), tag="_lean0")
+    saved = (capi.LIB_PATH, capi._lib)
+    capi.LIB_PATH, capi._lib = path, None
+    try:
+        for name in _parity.STEP_CASES:
+            _parity.test_loop_fields_vs_golden(name)
+            _parity.test_whole_steps_vs_golden(name)
+        _parity.test_fused_loop_equals_explicit_calls('dambreak20_wendland')
+        _parity.test_multi_step_call_equals_single_step_calls(None)
+        _parity.test_dam_break_vs_oracle(60, 'wendland')
+        _parity.test_dam_break_vs_oracle(150, 'cubic')
+        _parity.test_dam_break_vs_oracle(150, 'gaussian')
+        _parity.test_fp32_mode_close_to_fp64()
+        _edges.test_coincident_particles_follow_the_reference_guards()
+        _edges.test_cluster_denser_than_the_candidate_list()
+        _edges.test_general_lennard_jones_exponents_and_beta_viscosity('cubic')
+        _edges.test_domain_far_from_the_origin()
+    finally:
+        capi.LIB_PATH, capi._lib = saved
+
+
 @pytest.mark.parametrize("mode,seed", [(1, 0), (2, 5)])
 def test_results_do_not_depend_on_the_schedule(mode, seed):
     """The same parity tests with the emulator resuming the threads of a CTA (and running the CTAs of a launch) in reverse

@@ -7,4 +7,5 @@ tools/build_variants.sh \
   newton2  "-DOSPH_NEWTON_STEPS=2" \
   scan4    "-DPAIR_SCAN=4" \
   scan8    "-DPAIR_SCAN=8" \
-  list64   "-DPAIR_LIST64=64 -DPAIR_LIST32=64"
+  list64   "-DPAIR_LIST64=64 -DPAIR_LIST32=64" \
+  lean0    "-DPAIR_LEAN=0"
