@@ -76,7 +76,7 @@ template <typename Real, bool EXACT>
 constexpr size_t pair_smem_bytes()
 {
     return sizeof(Rec<Real, EXACT>) * PAIR_CAP + sizeof(unsigned short) * (sizeof(Real) == 8 ? PAIR_LIST64 : PAIR_LIST32) * OSPH_PAIR_THREADS +
-           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6 + ((EXACT && PAIR_SCAN_F32) ? sizeof(float2) * PAIR_CAP : 0);
+           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6 + ((EXACT && PAIR_SCAN_F32) ? sizeof(float2) * (PAIR_CAP + PAIR_SCAN) : 0);
 }
 
 template <typename Real, int KID, bool EXACT>
@@ -310,11 +310,14 @@ k_pair(PairArgs a)
     // the staged records, accepted candidates appended to a per-thread list.  (2) flush: when any lane's list
     // is nearly full every lane evaluates its list.  The heavy body then runs with most lanes active instead
     // of the ~35-45% a fused test-and-evaluate loop achieves (profiles/r01).
-    int nl = 0, slot = -1;
+    // The list is addressed by its write index li = (entries so far) * NT + tid: an append is one store and one add
+    // (a separate entry count costs a multiply-add per append), the count is li / NT.
+    int li = tid, slot = -1;
     double vx_st = 0.0, vy_st = 0.0;
     bool have_v = false;
     auto flush = [&]() {
 #if PAIR_PREFETCH_IDX
+        const int nl = li / NT;
         int jn = nl > 0 ? (int)sh_list[tid] : 0;
 #pragma unroll 1
         for (int k = 0; k < nl; k++) {
@@ -323,10 +326,11 @@ k_pair(PairArgs a)
             interact(j);
         }
 #else
+        const int nl = li / NT;
 #pragma unroll 1
         for (int k = 0; k < nl; k++) interact((int)sh_list[k * NT + tid]);
 #endif
-        nl = 0;
+        li = tid;
     };
     // skip_tag (PAIR_LEAN only): the run holds the thread's own record at index `self`; it is not listed
     auto scan = [&](auto skip_tag, int j, const int j1, const int self) {          // all 32 lanes of a warp call this together
@@ -335,32 +339,34 @@ k_pair(PairArgs a)
 #pragma unroll 1
         while (warp_more) {
 #if PAIR_SCAN_ILP
-            // PAIR_SCAN candidates per round: all loads first (index clamped into the buffer, the result of a
-            // candidate past the end is discarded), then the independent distance tests, then the appends.  The
+            // PAIR_SCAN candidates per round: all loads first (a candidate past the end of the run is read and discarded:
+            // the float copies are padded by PAIR_SCAN entries, the records are followed by the candidate lists, so the
+            // address needs no clamp and the loads of a round share one base register), then the independent distance
+            // tests, then the appends.  The
             // serial form (load, test, append, next) left the warp waiting on one shared-memory load and one
             // dependent FP chain at a time: 48 % of the kernel's stall samples on 25 % of its instructions.
             if constexpr (SCANF) {
                 float d2[PAIR_SCAN];
 #pragma unroll
                 for (int u = 0; u < PAIR_SCAN; u++) {
-                    const float2 pj = sh_pf[min(j + u, CAP - 1)];
+                    const float2 pj = sh_pf[j + u];
                     const float dx = xf - pj.x, dy = yf - pj.y;
                     d2[u] = dx * dx + dy * dy;
                 }
 #pragma unroll
                 for (int u = 0; u < PAIR_SCAN; u++)
-                    if (j + u < j1 && d2[u] <= thr_f && (!SKIP || j + u != self)) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
+                    if (j + u < j1 && d2[u] <= thr_f && (!SKIP || j + u != self)) { sh_list[li] = (unsigned short)(j + u); li += NT; }
             } else {
                 Real d2[PAIR_SCAN];
 #pragma unroll
                 for (int u = 0; u < PAIR_SCAN; u++) {
-                    const Real2 pj = sh_rec[min(j + u, CAP - 1)].pos;
+                    const Real2 pj = sh_rec[j + u].pos;
                     const Real dx = xi - pj.x, dy = yi - pj.y;
                     d2[u] = dx * dx + dy * dy;
                 }
 #pragma unroll
                 for (int u = 0; u < PAIR_SCAN; u++)
-                    if (j + u < j1 && d2[u] <= pair_r2 && (!SKIP || j + u != self)) { sh_list[nl * NT + tid] = (unsigned short)(j + u); nl++; }
+                    if (j + u < j1 && d2[u] <= pair_r2 && (!SKIP || j + u != self)) { sh_list[li] = (unsigned short)(j + u); li += NT; }
             }
             j += PAIR_SCAN;
 #else
@@ -369,12 +375,12 @@ k_pair(PairArgs a)
                 if (j < j1) {
                     const Real2 pj = sh_rec[j].pos;
                     const Real dx = xi - pj.x, dy = yi - pj.y;
-                    if (dx * dx + dy * dy <= pair_r2 && (!SKIP || j != self)) { sh_list[nl * NT + tid] = (unsigned short)j; nl++; }
+                    if (dx * dx + dy * dy <= pair_r2 && (!SKIP || j != self)) { sh_list[li] = (unsigned short)j; li += NT; }
                     j++;
                 }
             }
 #endif
-            if (__any_sync(0xffffffffu, nl > PAIR_LIST - PAIR_SCAN)) flush();
+            if (__any_sync(0xffffffffu, li >= (PAIR_LIST - PAIR_SCAN + 1) * NT)) flush();      // more than PAIR_LIST - PAIR_SCAN entries
             warp_more = __any_sync(0xffffffffu, j < j1);
         }
     };
