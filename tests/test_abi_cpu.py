@@ -48,6 +48,31 @@ def test_no_cpu_fallback(libpath):
         assert e.value.code == -3 and "no CPU path" in str(e.value)
 
 
+def test_leaf_equations_have_no_cpu_path_either(libpath):
+    """The stand-alone equations (src.Equations.*) validate their arguments on the host and otherwise need the device:
+    without one they raise, they never compute on the CPU."""
+    import numpy as np
+    import torch
+    L = capi.lib()
+    out = np.full(7, 3.0)
+    dp = C.POINTER(C.c_double)
+    # J < 0, or J > 0 without columns: invalid, before any CUDA call
+    assert L.osph_leaf_equations(0, -1, None, None, 0, 1, 1, 0, 0, 0, 0, 0, 0, 4, 2, out.ctypes.data_as(dp)) == -1
+    assert L.osph_leaf_equations(0, 5, None, None, 0, 1, 1, 0, 0, 0, 0, 0, 0, 4, 2, out.ctypes.data_as(dp)) == -1
+    # an empty table is all zeros and needs no device
+    assert L.osph_leaf_equations(0, 0, None, None, 0, 1, 1, 0, 0, 0, 0, 0, 0, 4, 2, out.ctypes.data_as(dp)) == 0
+    assert not out.any()
+    if not torch.cuda.is_available():
+        from src.Common import computed_dtype
+        from src.Equations.Continuity import Continuity
+        from src.Equations.Courant import Courant
+        comp = np.zeros(4, dtype=computed_dtype)
+        with pytest.raises(capi.OsphError):
+            Continuity(np.array([]), comp)
+        with pytest.raises(capi.OsphError):
+            Courant(0.4, np.ones(3), np.ones(3))
+
+
 def test_bad_struct_size_rejected(libpath):
     cfg = capi.default_config(25.0, 0.5)
     cfg.struct_size = 8
