@@ -278,7 +278,7 @@ k_pair(PairArgs a)
         const Real q = r * inv_h;
         Real w, g;
         if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair<Real, GUARDED>(q, inv_h, inv_r, w, g);
-        else sph_kernel<Real, KID>(q, inv_h, inv_r, w, g);
+        else sph_kernel<Real, KID, GUARDED>(q, inv_h, inv_r, w, g);
         const Real dwx = g * dx, dwy = g * dy;
         const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
         const Real mj = rmj.y;

@@ -66,7 +66,9 @@ __device__ __forceinline__ float pow_gen(float a, float b) { return __powf(a, b)
 // ---- smoothing kernels: value w and gradient factor g with  grad W = g * (dx, dy) ---------------------
 // reference: CubicSpline.py:10-70, Wendland.py:9-64, Gaussian.py:16-59.  inv_r == 0 encodes r < 1e-10
 // (the reference zeroes the gradient there).
-template <typename Real, int KID>
+// CUT = false (pair.cu, PAIR_LEAN): the caller knows r^2 <= 4 h^2, so q exceeds 2 by rounding only and the polynomials are
+// used as they stand (Wendland: (1 - q/2)^5 is 1e-80 there).
+template <typename Real, int KID, bool CUT = true>
 __device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
 {
     const Real ih2 = inv_h * inv_h;
@@ -84,7 +86,7 @@ __device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real 
         Real in2 = in * in, in4 = in2 * in2, in5 = in4 * in;
         Real wv = in5 * in * (Real(35.0 / 12.0) * q * q + Real(3) * q + Real(1));
         Real gv = in5 * Real(-14.0 / 3.0) * q * (Real(1) + Real(2.5) * q);
-        if (q >= Real(2)) { wv = Real(0); gv = Real(0); }
+        if (CUT && q >= Real(2)) { wv = Real(0); gv = Real(0); }
         w = alpha * wv;
         g = alpha * gv * inv_h * inv_r;
     } else {
