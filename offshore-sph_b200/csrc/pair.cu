@@ -320,9 +320,10 @@ k_pair(PairArgs a)
         const int nl = li / NT;
         int jn = nl > 0 ? (int)sh_list[tid] : 0;
 #pragma unroll 1
-        for (int k = 0; k < nl; k++) {
+        for (int k = 0; k < nl;) {
             const int j = jn;
-            jn = (int)sh_list[min(k + 1, PAIR_LIST - 1) * NT + tid];      // next index while this pair is evaluated
+            k++;
+            if (k < nl) jn = (int)sh_list[k * NT + tid];      // next index while this pair is evaluated
             interact(j);
         }
 #else
