@@ -55,6 +55,24 @@ def test_pair_kernel_batched_staging_path():
         capi.LIB_PATH, capi._lib = saved
 
 
+def test_pair_kernel_128_thread_variant():
+    """-DOSPH_PAIR_THREADS=128 -DPAIR_CAP=512 (the `t128` build of tools/build_round2_variants.sh): four smaller CTAs per SM
+    instead of two; list stride, staging capacity and the CTA-wide run unions all change with the CTA size."""
+    from osph_b200 import capi
+    path = emu_build.build(defines=("OSPH_PAIR_THREADS=128", "PAIR_CAP=512", "PAIR_MINB64=4", "PAIR_MINB32=6"), tag="_t128")
+    saved = (capi.LIB_PATH, capi._lib)
+    capi.LIB_PATH, capi._lib = path, None
+    try:
+        for name in ('dambreak20_wendland', 'tank30_cubic_dynh', 'tank16_gaussian', 'tank24_wendland_coupled'):
+            _parity.test_whole_steps_vs_golden(name)
+        _parity.test_dam_break_vs_oracle(150, 'cubic')
+        _parity.test_fp32_mode_close_to_fp64()
+        _edges.test_cluster_denser_than_the_candidate_list()
+        _edges.test_coincident_particles_follow_the_reference_guards()
+    finally:
+        capi.LIB_PATH, capi._lib = saved
+
+
 def test_pair_kernel_single_body_variant():
     """-DPAIR_LEAN=0 (the build round 1 was measured with, kept for the A/B run of tools/build_round2_variants.sh): one
     guarded body for every listed pair, the self pair listed.  Same parity bar as the default build."""
