@@ -1,19 +1,25 @@
-"""Kernel base class; same two-method interface as reference src/Kernels/Kernel.py:5-12."""
-import abc
+"""Base of the smoothing-kernel plugins (CubicSpline, Wendland, Gaussian).
 
-import numpy as np
+The Solver only needs two things from a kernel object: which device kernel it selects (`osph_name`, one of the
+OSPH_KERNEL_* names of include/osph.h) and, for code that uses the object on its own, the two array functions of
+the reference interface (src/Kernels/Kernel.py:5-12): evaluate(r, h) -> W and gradient(x, r, h) -> dW/dx component.
+Subclasses provide both as static methods that forward to the device leaf `osph_leaf_kernel`.
+"""
 
 
-class Kernel(metaclass=abc.ABCMeta):
-    #: name understood by the C ABI (OSPH_KERNEL_*)
-    osph_name = None
+class Kernel:
+    osph_name = None                     # 'cubic' | 'wendland' | 'gaussian'
+
+    def __init_subclass__(cls, **kw):
+        super().__init_subclass__(**kw)
+        missing = [m for m in ("evaluate", "gradient") if m not in cls.__dict__]
+        if missing:
+            raise TypeError("%s must define %s" % (cls.__name__, " and ".join(missing)))
 
     @staticmethod
-    @abc.abstractmethod
-    def evaluate(r: np.array, h: np.array) -> np.array:
-        pass
+    def evaluate(r, h):
+        raise NotImplementedError("Kernel.evaluate: use CubicSpline, Wendland or Gaussian")
 
     @staticmethod
-    @abc.abstractmethod
-    def gradient(x: np.array, r: np.array, h: np.array) -> np.array:
-        pass
+    def gradient(x, r, h):
+        raise NotImplementedError("Kernel.gradient: use CubicSpline, Wendland or Gaussian")
