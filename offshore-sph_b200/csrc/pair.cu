@@ -63,7 +63,7 @@
 #endif                        // the (2 - q)+ clamp leave the common path of the heavy body: a second, guarded copy of the body serves the
                               // pairs that came through the rarely taken branch (coincident particles, wall pairs outside the kernel
                               // support, irregularly binned particles, the Gaussian).  Common path per listed pair, FP64 cubic, by SASS:
-                              // 131 -> 118 instructions, 80 -> 68 on the FP64 pipe, no spills.  0: one guarded body for every pair (the
+                              // 131 -> 116 instructions, 80 -> 68 on the FP64 pipe, no spills.  0: one guarded body for every pair (the
                               // build all GPU measurements of round 1 were made with; tools/build_round2_variants.sh builds it as `lean0`)
 
 // One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
