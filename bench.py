@@ -259,12 +259,15 @@ def run_gpu(args):
         ctx.step(1, None, DAMPING)
         ctx.download(host)
 
-    e2e_step()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    if args.no_e2e:                      # profiler / sanitizer runs only: a line without e2e is not a bench line
+        e2e_steps, e2e_value = 0, None
+    else:
         e2e_step()
-    t_e2e = time.perf_counter() - t0
-    e2e_value = n * e2e_steps / t_e2e
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        t_e2e = time.perf_counter() - t0
+        e2e_value = n * e2e_steps / t_e2e
 
     # ---- roofline of the dominant kernel (fused pair kernel) -----------------------------------
     peaks, which = measured_peaks()
@@ -344,6 +347,7 @@ def main():
                     help="multi-GPU exchange: p2p = NVLink peer-memory windows + mailbox kernels (default, falls back to "
                          "nccl), nccl = direct NCCL calls inside the library, python = osph_b200/slabs.py via torch.distributed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiler and sanitizer runs)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
     global WORKLOAD

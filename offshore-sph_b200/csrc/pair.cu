@@ -334,7 +334,7 @@ k_pair(PairArgs a)
         li = tid;
     };
     // skip_tag (PAIR_LEAN only): the run holds the thread's own record at index `self`; it is not listed
-    auto scan = [&](auto skip_tag, int j, const int j1, const int self) {          // all 32 lanes of a warp call this together
+    auto scan = [&](auto skip_tag, int j, int j1, const int self) {          // all 32 lanes of a warp call this together
         constexpr bool SKIP = PAIR_LEAN && decltype(skip_tag)::value;
         bool warp_more = __any_sync(0xffffffffu, j < j1);
 #pragma unroll 1
@@ -370,6 +370,9 @@ k_pair(PairArgs a)
                     if (j + u < j1 && d2[u] <= pair_r2 && (!SKIP || j + u != self)) { sh_list[li] = (unsigned short)(j + u); li += NT; }
             }
             j += PAIR_SCAN;
+            // a lane whose run is exhausted parks at record 0 (its tests are discarded by j + u < j1): the loads of the
+            // rounds the other lanes still need stay inside the staged records whatever the run lengths are
+            if (j >= j1) { j = 0; j1 = 0; }
 #else
 #pragma unroll
             for (int u = 0; u < PAIR_SCAN; u++) {
@@ -415,8 +418,10 @@ k_pair(PairArgs a)
                 __syncthreads();
                 stage(base, cnt, 0);
                 __syncthreads();
-                const bool has = fluid_i && rb > ra;
-                scan(std::true_type(), has ? max(ra, base) - base : 0, has ? min(rb, base + cnt) - base : 0, d == 1 ? s - base : -1);
+                // the part of the thread's run that lies in THIS batch (empty for a run in an earlier or later batch)
+                const int jb = max(ra, base), je = min(rb, base + cnt);
+                const bool has = fluid_i && rb > ra && je > jb;
+                scan(std::true_type(), has ? jb - base : 0, has ? je - base : 0, d == 1 ? s - base : -1);
                 flush();
             }
         }

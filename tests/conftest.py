@@ -20,7 +20,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# collection order of the GPU files: golden-fixture parity and the Solver drop-in first, the 1 M-particle and
+# multi-GPU files last, so that a fault at full size cannot hide the rest of the suite behind `pytest -x`
+_LATE = {"test_gpu_fullsize.py": 1, "test_gpu_multi.py": 2}
+_EARLY = {"test_gpu_parity.py": -3, "test_gpu_solver.py": -2, "test_gpu_edges.py": -1}
+
+
 def pytest_collection_modifyitems(config, items):
+    def rank(item):
+        base = os.path.basename(str(item.fspath))
+        return _LATE.get(base, _EARLY.get(base, 0))
+    items.sort(key=rank)                       # stable: the order inside a file is unchanged
     if os.environ.get("OSPH_EMU") == "1":
         # manual mode: run the GPU-marked tests against the SIMT-emulated build of the kernel sources (tests/emu);
         # `OSPH_EMU=1 pytest tests/test_gpu_parity.py -m gpu`.  The default CPU run uses tests/test_emu_kernels.py.

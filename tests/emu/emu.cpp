@@ -258,6 +258,36 @@ static void run_block(dim3 grid, dim3 block, uint3 bid)
     running = nullptr; cur = nullptr;
 }
 
+// Guarded storage: [PROT_NONE page][bytes rounded up to pages][PROT_NONE page]; the caller places its object at the END of
+// the accessible part, so the first byte past the object is already inaccessible.
+static unsigned char *guarded_pages(size_t bytes, size_t *usable)
+{
+    const size_t page = 4096, body = (bytes + page - 1) / page * page;
+    unsigned char *m = (unsigned char *)mmap(nullptr, body + 2 * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) { perror("emu: mmap"); abort(); }
+    mprotect(m, page, PROT_NONE);
+    mprotect(m + page + body, page, PROT_NONE);
+    *usable = body;
+    return m + page;
+}
+static const size_t DYN_ARENA = 256 * 1024;       // more than the 227 KB a CTA can have
+static unsigned char *dyn_arena()
+{
+    static unsigned char *a = nullptr;
+    if (!a) { size_t u; a = guarded_pages(DYN_ARENA, &u); }
+    return a;
+}
+// one `__shared__` variable of static size (preprocess.py turns the declaration into a reference to this storage)
+void *static_smem_alloc(size_t bytes, size_t align)
+{
+    size_t usable;
+    unsigned char *a = guarded_pages(bytes, &usable);
+    if (align < 1) align = 1;
+    const size_t padded = (bytes + align - 1) / align * align;      // sizeof(T) is a multiple of alignof(T) already
+    memset(a, 0xA5, usable);
+    return a + usable - padded;
+}
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
 {
     const size_t nthreads = (size_t)block.x * block.y * block.z;
@@ -270,10 +300,15 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
                                            MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (stack_pool == MAP_FAILED) { perror("emu: mmap"); abort(); }
     }
-    std::vector<unsigned char> dyn(smem + 64);
-    unsigned char *aligned = dyn.data() + ((64 - (reinterpret_cast<uintptr_t>(dyn.data()) & 63)) & 63);
-    memset(dyn.data(), 0xA5, dyn.size());
-    dyn_smem_ptr = aligned;
+    // dynamic shared memory ends right in front of an inaccessible page (and the mapping starts behind one): a CTA that
+    // reads or writes past the bytes it was launched with faults at the instruction, as it would under compute-sanitizer
+    // (round 1 shipped an overrun that a heap buffer with slack silently absorbed).  The size is rounded up to 16 bytes
+    // to keep the 16-byte alignment the kernels ask for.
+    const size_t dyn_bytes = (smem + 15) & ~size_t(15);
+    if (dyn_bytes > DYN_ARENA) { fprintf(stderr, "emu: %zu bytes of dynamic shared memory\n", smem); abort(); }
+    unsigned char *arena = dyn_arena();
+    dyn_smem_ptr = arena + DYN_ARENA - dyn_bytes;
+    memset(dyn_smem_ptr, 0xA5, dyn_bytes);
     body_fn = &body;
     const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
     std::vector<int> border;

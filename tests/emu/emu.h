@@ -8,8 +8,9 @@
 // Model: every CUDA thread of a CTA is a fiber (own stack, cooperative switch); CTAs run one after the other.
 // __syncthreads() and the *_sync warp collectives are the only switch points: a fiber that reaches one deposits its
 // operand and yields; when every live thread of the CTA / lane of the warp has arrived the scheduler computes the
-// results and resumes them.  Exited threads count as arrived.  __shared__ variables become function-local statics
-// (one CTA at a time), dynamic shared memory one buffer per launch.  tests/emu/preprocess.py rewrites the three
+// results and resumes them.  Exited threads count as arrived.  __shared__ variables become references to storage that ends
+// in front of an inaccessible page (one CTA at a time), dynamic shared memory likewise, sized per launch: an access past
+// the end of either faults at the instruction.  tests/emu/preprocess.py rewrites the three
 // constructs g++ cannot parse: kernel<<<...>>>(...) launches, `extern __shared__` declarations and the two inline-PTX
 // MUFU seeds (modelled with their documented 2^-20 accuracy: lower 32 mantissa bits zero).
 #pragma once
@@ -53,6 +54,8 @@ struct ThreadCtx {
 extern ThreadCtx *cur;
 extern unsigned char *dyn_smem_ptr;
 inline void *dyn_smem() { return dyn_smem_ptr; }
+void *static_smem_alloc(size_t bytes, size_t align);
+template <typename T> inline T *static_smem() { return (T *)static_smem_alloc(sizeof(T), alignof(T)); }
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 

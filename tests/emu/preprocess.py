@@ -1,7 +1,8 @@
 """Rewrites the three CUDA constructs g++ cannot parse so that the kernel sources compile against tests/emu/emu.h:
 
   kernel<T...><<<grid, block, smem, stream>>>(args)   ->  emu::launch_k(grid, block, smem, kernel<T...>, args)
-  extern __shared__ [__align__(n)] T name[];          ->  T *name = (T *)emu::dyn_smem();
+  extern __shared__ [__align__(n)] T name[];          ->  T *name = (T *)emu::dyn_smem();          (ends at a guard page)
+  __shared__ [__align__(n)] T name[N];                ->  T (&name)[N] = *emu::static_smem<T[N]>();    (ends at a guard page)
   asm("rcp.approx.ftz.f64 ..." / "rsqrt.approx.ftz.f64 ...")  ->  emu::rcp_approx_f64 / emu::rsqrt_approx_f64
   asm("{ setp.gt|lt.f64 p, x, 0; selp.f64 r, x, 0, p; }")      ->  r = x > 0 ? x : 0   (pos_part / neg_part of sph_math.cuh)
 
@@ -93,8 +94,28 @@ _ASM_RSQ = re.compile(r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;"\s*:\s*"=d"\((\w+)
 _ASM_CLAMP = re.compile(r'asm\("\{ \.reg \.pred p; setp\.(gt|lt)\.f64 p, %1, 0d0+; selp\.f64 %0, %1, 0d0+, p; \}"\s*:\s*"=d"\((\w+)\)\s*:\s*"d"\((\w+)\)\);')
 
 
+_STATIC_SHARED = re.compile(r"(?<![\w])(?<!extern )__shared__\s+(?:__align__\((\d+)\)\s+)?([\w:\s]+?)\s+(\w+\s*(?:\[[^;]*\])?(?:\s*,\s*\w+\s*(?:\[[^;]*\])?)*)\s*;")
+
+
+def rewrite_static_shared(src):
+    """`__shared__ T a[N][M], b;` -> references to guarded storage (emu::static_smem): an index past the end of a
+    statically sized shared array faults like one past the dynamic allocation does."""
+    def repl(m):
+        align, typ, decls = m.group(1), m.group(2).strip(), m.group(3)
+        out = []
+        for d in _split_top(decls):
+            mm = re.match(r"(\w+)\s*(.*)$", d.strip(), re.S)
+            name, dims = mm.group(1), mm.group(2).strip()
+            al = ("__attribute__((aligned(%s))) " % align) if align else ""
+            out.append("typedef %s emu_shared_t_%s %s%s; static emu_shared_t_%s &%s = *emu::static_smem<emu_shared_t_%s>();"
+                       % (typ, name, dims, (" " + al) if al else "", name, name, name))
+        return " ".join(out)
+    return _STATIC_SHARED.sub(repl, src)
+
+
 def transform(src):
     src = rewrite_launches(src)
+    src = rewrite_static_shared(src)
     src = _EXTERN_SHARED.sub(lambda m: "%s *%s = (%s *)emu::dyn_smem();" % (m.group(1), m.group(2), m.group(1)), src)
     src = _ASM_RCP.sub(lambda m: "%s = emu::rcp_approx_f64(%s);" % (m.group(1), m.group(2)), src)
     src = _ASM_RSQ.sub(lambda m: "%s = emu::rsqrt_approx_f64(%s);" % (m.group(1), m.group(2)), src)

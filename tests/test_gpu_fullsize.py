@@ -1,79 +1,27 @@
-"""GPU, BASELINE configs[1] size (dam break N = 1000, 1 009 603 particles): properties that do not need the
-full CPU oracle (≈1 min per step there), plus the oracle on a strided sample of the particles.
+"""GPU, BASELINE configs[1] size (dam break N = 1000, 1 009 603 particles).  The bodies live in tests/fullsize_cases.py and
+each runs in its own child process: a CUDA fault at full size then fails that one test instead of poisoning the CUDA
+context of the whole pytest process (round 1: one sticky error 700 here left 54 GPU tests unrun).  conftest.py also
+collects this file after the golden-fixture parity and Solver files."""
+import os
+import subprocess
+import sys
 
-The reference search visits 9 x 1600 candidates per particle at this size, so the oracle evaluates every 997th
-fluid particle (~1000 of them) against ALL particles; the GPU must agree on those to 1e-10.
-"""
-import numpy as np
 import pytest
 
-from conftest import field_err
-from oracle import oracle as O
-from osph_b200 import capi
-from osph_b200 import workloads as W
-
 pytestmark = pytest.mark.gpu
-N_SIDE = 1000
-STRIDE = 997
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def case():
-    return W.dam_break_case(N_SIDE, seed=0)
+def run_case(name, *args):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "fullsize_cases.py"), name, *args],
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, "%s%s failed (rc %d)\n%s\n%s" % (name, args, r.returncode, r.stdout[-2000:], r.stderr[-4000:])
 
 
 @pytest.mark.parametrize("kernel", ['cubic', 'wendland'])
-def test_sampled_oracle_parity_at_full_size(case, kernel):
-    pA, c = case['pA'], case['consts']
-    P = O.Particles.from_aos(pA)
-    w = O.wcsph(c['height'], c['r0'], c['rho0'], True)
-    grid = O.Grid(P)
-    O.loop(P, w, grid, kernel, STRIDE, 0)
-    sample = np.flatnonzero((np.arange(P.n) % STRIDE == 0) & (P.label == 0))
-    assert len(sample) > 900
-    cfg = capi.make_config(c, kernel, 'pec', capi.FP64, case['h'], keep_h=True)
-    with capi.Context(cfg) as ctx:
-        ctx.upload(pA)
-        ctx.compute()
-        g, cells = ctx.cells()
-        assert np.array_equal(cells, grid.cell_ids())                 # every one of the 1 M cell assignments
-        out = ctx.download(pA.copy())
-        assert ctx.sync() == 0
-    for f in ('drho', 'ax', 'ay', 'xsphx', 'xsphy'):
-        ref = getattr(P, f)[sample]
-        scale = np.maximum(np.abs(ref), np.abs(ref).max())
-        assert np.max(np.abs(out[f][sample] - ref) / scale) <= 1e-10, f
-    assert field_err(out['p'], P.p) <= 1e-12                          # EOS runs for all particles in the oracle
+def test_sampled_oracle_parity_at_full_size(kernel):
+    run_case("sampled_oracle_parity_at_full_size", kernel)
 
 
-def test_full_size_invariants(case):
-    """Determinism, row-order invariance, and agreement of the two precisions at 1 M particles."""
-    pA, c = case['pA'], case['consts']
-    cfg = capi.make_config(c, 'cubic', 'pec', capi.FP64, case['h'])
-    with capi.Context(cfg) as ctx:
-        ctx.upload(pA); ctx.step(3, None, 0.05); a = ctx.download(pA.copy()); dts = ctx.dt_log()
-        ctx.upload(pA); ctx.step(3, None, 0.05); b = ctx.download(pA.copy())
-        assert np.array_equal(ctx.dt_log(), dts)
-        assert a.tobytes() == b.tobytes()                             # bit-reproducible run to run
-        # shuffle the host rows: every particle must get the same answer up to summation order
-        perm = np.random.default_rng(1).permutation(len(pA))
-        ctx.upload(np.ascontiguousarray(pA[perm])); ctx.step(3, None, 0.05)
-        s = ctx.download(np.ascontiguousarray(pA[perm]).copy())
-        assert np.allclose(ctx.dt_log(), dts, rtol=1e-13, atol=0)
-        for f in ('x', 'y', 'vx', 'vy', 'rho', 'ax', 'ay', 'drho', 'p'):
-            assert field_err(s[f], a[f][perm]) <= 1e-11, f
-        # neighbour relation is symmetric for equal h: every (i, j) has its (j, i)
-        off, idx = ctx.neighbours_csr()
-        deg = np.diff(off)
-        fluid = s['label'] == 0
-        assert deg[~fluid].sum() == 0 and 60 < deg[fluid].mean() < 80  # ~72 = pi 4.8^2 within q <= 3
-        src = np.repeat(np.arange(len(deg)), deg)
-        ff = fluid[idx]                                               # fluid-fluid pairs only (walls have no list)
-        a_key = src[ff].astype(np.int64) * len(deg) + idx[ff]
-        b_key = idx[ff].astype(np.int64) * len(deg) + src[ff]
-        assert np.array_equal(np.sort(a_key), np.sort(b_key))
-    cfg32 = capi.make_config(c, 'cubic', 'pec', capi.FP32, case['h'])
-    with capi.Context(cfg32) as ctx:
-        ctx.upload(pA); ctx.step(3, None, 0.05); f32 = ctx.download(pA.copy())
-    assert np.max(np.hypot(f32['x'] - a['x'], f32['y'] - a['y'])) < 1e-5 * case['r0']
-    assert field_err(f32['rho'], a['rho']) < 1e-6
+def test_full_size_invariants():
+    run_case("full_size_invariants")
