@@ -56,6 +56,17 @@ def build_case(n_side, seed=0):
     return W.dam_break_case(n_side, seed=seed)
 
 
+def resolve_problem(args, world):
+    """(particles per side of the generator, "weak" | "strong").  One GPU: BASELINE configs[1], N = 1000 (1 M particles).
+    Several GPUs: the FIXED 16 M-particle dam break of configs[4] (N = 4000), i.e. strong scaling of the north star's
+    problem, unless --weak asks for 1 M particles per GPU (N = 1000 sqrt(gpus))."""
+    if world <= 1:
+        return (args.particles_per_side or 1000), "weak"
+    if args.weak:
+        return int(round((args.particles_per_side or 1000) * (world ** 0.5))), "weak"
+    return (args.particles_per_side or 4000), "strong"
+
+
 def workload_name(n_side, n, kernel, prec):
     k = {'cubic': 'cubic spline', 'wendland': 'Wendland', 'gaussian': 'Gaussian'}[kernel]
     if WORKLOAD == "containment":
@@ -81,6 +92,7 @@ def time_oracle_step(case, kernel, budget_s=12.0):
     cand = 9.0 * max(1.0, n_f / 625.0)
     est = n_f * cand * 6e-9 + n_f * 72 * 60e-9
     stride = max(1, int(np.ceil(est / budget_s)))
+    time_oracle_step.last_stride = stride
     t0 = time.perf_counter()
     dt3 = O.timestep(P, fluid)
     O.pec_predict(P, fluid, dt3[0], DAMPING, True, False)
@@ -104,9 +116,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # same workload as the GPU arm at this GPU count (weak scaling: N * sqrt(gpus) particles per side)
-    n_side = args.particles_per_side if (args.total_side or args.gpus <= 1) else \
-        int(round(args.particles_per_side * (args.gpus ** 0.5)))
+    # same workload as the GPU arm at this GPU count
+    n_side, scaling = resolve_problem(args, args.gpus)
     case = build_case(n_side)
     n = len(case['pA'])
     from oracle import oracle as O
@@ -123,9 +134,13 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
-        "scaling": "strong" if args.total_side else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n_side, n, args.kernel, "FP64"), "particles": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        # the denominator is a MODEL of a full step, not a measured one: the pair loop ran on every stride-th fluid
+        # particle and its time was multiplied by the stride (a full reference step is minutes at 1 M, hours at 16 M)
+        "extrapolated": True, "stride": time_oracle_step.last_stride,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "extrapolated": True, "stride": time_oracle_step.last_stride},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,11 +225,21 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world > 1:
         from osph_b200 import slabs
-        return slabs.bench_multi_gpu(args, rank, world, local)
+
+        def cpu_leg(case):
+            if args.no_cpu_baseline:
+                return None
+            from oracle import oracle as O
+            O.build()
+            t_cpu, sample = time_oracle_step(case, args.kernel, args.cpu_budget)
+            return {"value": len(case['pA']) / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                    "extrapolated": True, "stride": time_oracle_step.last_stride, "host_cores_available": os.cpu_count()}
+        return slabs.bench_multi_gpu(args, rank, world, local, cpu_baseline=cpu_leg)
 
     prec = capi.FP64 if args.precision == "fp64" else capi.FP32
     F = 8 if prec == capi.FP64 else 4
-    case = build_case(args.particles_per_side)
+    n_side, _ = resolve_problem(args, 1)
+    case = build_case(n_side)
     pA, c = case['pA'], case['consts']
     n = len(pA)
     cfg = capi.make_config(c, args.kernel, 'pec', prec, case['h'], device=local)
@@ -276,7 +301,7 @@ def run_gpu(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")) as f:
-            t = json.load(f).get("%s_%s_N%d" % (args.precision, args.kernel, args.particles_per_side))
+            t = json.load(f).get("%s_%s_N%d" % (args.precision, args.kernel, n_side))
             traffic = t["dram_bytes_per_launch"] if t else None
     except Exception:
         pass
@@ -308,13 +333,13 @@ def run_gpu(args):
         O.build()
         t_cpu, sample = time_oracle_step(case, args.kernel, args.cpu_budget)
         cpu = {"value": n / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-               "host_cores_available": os.cpu_count()}
+               "extrapolated": True, "stride": time_oracle_step.last_stride, "host_cores_available": os.cpu_count()}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64" if prec == capi.FP64 else "f32 pair arithmetic, f64 state", "data": "synthetic",
-        "config": {"workload": workload_name(args.particles_per_side, n, args.kernel, args.precision.upper()),
+        "config": {"workload": workload_name(n_side, n, args.kernel, args.precision.upper()),
                    "particles": n, "fluid": int((pA['label'] == 0).sum()), "damping": DAMPING, "dt": "dynamic",
                    "l2": "per-step working set (%.0f MB state + sorted copies) exceeds the 126 MB L2" % (n * 19 * 8 / 1e6),
                    "parallelism": "1 GPU"},
@@ -335,14 +360,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--kernel", default="cubic", choices=["cubic", "wendland", "gaussian"])
-    ap.add_argument("--particles-per-side", type=int, default=1000,
-                    help="N of the dam-break generator (N x N fluid particles); 1000 = BASELINE configs[1]")
+    ap.add_argument("--particles-per-side", type=int, default=None,
+                    help="N of the dam-break generator (N x N fluid particles).  Default: 1000 on one GPU (BASELINE configs[1]); "
+                         "4000 = the fixed 16 M-particle problem of configs[4] on several GPUs; with --weak it is per GPU")
     ap.add_argument("--workload", default="dam_break", choices=["dam_break", "containment", "icebreak"],
                     help="dam_break = BASELINE configs[0,1,4] (default, the metric's workload); containment = configs[2] "
                          "(use --particles-per-side 2000 --precision fp32); icebreak = configs[3] (--particles-per-side 4900)")
-    ap.add_argument("--total-side", action="store_true",
-                    help="multi-GPU: --particles-per-side is the TOTAL problem (strong scaling) instead of per-GPU "
-                         "N*sqrt(gpus) (weak scaling, default)")
+    ap.add_argument("--weak", action="store_true",
+                    help="multi-GPU: weak scaling, --particles-per-side (default 1000) is per GPU, N*sqrt(gpus) in total; "
+                         "the default on several GPUs is strong scaling of the fixed 16 M-particle problem")
+    ap.add_argument("--total-side", action="store_true", help="accepted for compatibility: strong scaling is the default now")
     ap.add_argument("--sequencer", default="p2p", choices=["p2p", "nccl", "python"],
                     help="multi-GPU exchange: p2p = NVLink peer-memory windows + mailbox kernels (default, falls back to "
                          "nccl), nccl = direct NCCL calls inside the library, python = osph_b200/slabs.py via torch.distributed")

@@ -69,6 +69,7 @@ enum osph_field {
 #define OSPH_E_CAPACITY  (-4)  /* a caller-provided buffer is too small */
 #define OSPH_E_NO_FLUID  (-5)  /* time-step reduction over zero fluid particles */
 #define OSPH_E_GRID      (-6)  /* the reference grid would need more cells than can be tabulated */
+#define OSPH_E_PEER      (-7)  /* slab mode: another rank left the step loop with an error, or did not answer in time */
 
 /* status bits reported by osph_sync() */
 #define OSPH_S_NONFINITE   1u  /* a NaN/Inf acceleration or density was produced */

@@ -32,6 +32,9 @@ int osph_slab_step_end(osph_ctx *ctx, double damping);
 
 #define P2P_MAX_WORLD 16
 #define MBOX_STRIDE 16            // doubles per (slot, sender) cell of a mailbox
+#define P2P_HDR_ABORT 8           // window header word (as u64): a rank that leaves the protocol with an error sets it in every peer
+#define P2P_ST_ABORT 1u           // status bits of k_mbox_allgather: a peer aborted / a peer did not answer within the spin limit
+#define P2P_ST_TIMEOUT 2u
 
 struct osph_slab_p2p {
     int rank = 0, world = 1;
@@ -47,15 +50,21 @@ struct osph_slab_p2p {
     size_t win_doubles = 0;
     double *d_meta = nullptr, *d_all_meta = nullptr, *d_dt3 = nullptr, *d_all_dt = nullptr, *h_all_meta = nullptr;
     unsigned long long seq = 0;
+    long long spin_limit = 0;                      // clock64 ticks a mailbox waits for one peer before it gives up
+    bool aborted = false;
     int64_t last_counts[8] = {0};
     int64_t steps = 0;
 };
 
 // One CTA, one warp per peer.  Warp r: store my payload into rank r's window, fence, publish `seq`; then wait until
 // rank r's payload for `seq` is in MY window and copy it out.  reduce_min != 0 appends the element-wise minimum.
+// The wait is bounded: it ends when the peer's sequence number arrives, when some rank has set the abort word of my
+// window (it left the protocol with an error), or after `spin_limit` clock ticks; the last two set a bit in *status,
+// which the host reads at its one synchronisation point per step -- a rank-local failure then raises on every rank
+// instead of leaving the others inside this kernel for ever.
 __global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int world, size_t off_data, size_t off_flag,
                                  int slot, const double *__restrict__ payload, int n, unsigned long long seq,
-                                 double *__restrict__ out_all, int reduce_min)
+                                 double *__restrict__ out_all, int reduce_min, long long spin_limit, unsigned int *status)
 {
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (r < world) {
@@ -67,7 +76,15 @@ __global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int 
         if (lane == 0) *dflag = seq;
         const volatile double *src = peers[me] + off_data + (size_t)(slot * world + r) * MBOX_STRIDE;
         volatile unsigned long long *sflag = reinterpret_cast<volatile unsigned long long *>(peers[me] + off_flag) + slot * world + r;
-        if (lane == 0) while (*sflag != seq) __nanosleep(64);
+        volatile unsigned long long *abort_word = reinterpret_cast<volatile unsigned long long *>(peers[me]) + P2P_HDR_ABORT;
+        if (lane == 0) {
+            const long long t0 = clock64();
+            while (*sflag != seq) {
+                if (*abort_word != 0ull) { atomicOr(status, P2P_ST_ABORT); break; }
+                if (clock64() - t0 > spin_limit) { atomicOr(status, P2P_ST_TIMEOUT); break; }
+                __nanosleep(64);
+            }
+        }
         __syncwarp();
         __threadfence_system();
         if (lane < n) out_all[r * n + lane] = src[lane];
@@ -80,6 +97,17 @@ __global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int 
             out_all[world * n + threadIdx.x] = m;
         }
     }
+}
+
+// A rank that returns an error from the step loop tells its peers first: one 8-byte store into every window header.
+static void p2p_abort_peers(osph_ctx *ctx, osph_slab_p2p *s)
+{
+    if (s->aborted) return;
+    s->aborted = true;
+    const unsigned long long one = 1ull;
+    for (int r = 0; r < s->world; r++)
+        if (s->peer[r]) cudaMemcpy(reinterpret_cast<unsigned long long *>(s->peer[r]) + P2P_HDR_ABORT, &one, sizeof(one), cudaMemcpyHostToDevice);
+    (void)ctx;
 }
 
 extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x_lo, double x_hi, double r0, double hmax,
@@ -107,10 +135,18 @@ extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x
     OSPH_CUDA(cudaMemcpy(s->win + off_header, header, sizeof(header), cudaMemcpyHostToDevice));
     OSPH_CUDA(cudaMalloc(&s->d_peer, sizeof(double *) * world));
     OSPH_CUDA(cudaMalloc(&s->d_meta, sizeof(double) * MBOX_STRIDE));
-    OSPH_CUDA(cudaMalloc(&s->d_all_meta, sizeof(double) * MBOX_STRIDE * (world + 1)));
+    OSPH_CUDA(cudaMalloc(&s->d_all_meta, sizeof(double) * MBOX_STRIDE * (world + 2)));    // + min row + the status word
+    OSPH_CUDA(cudaMemset(s->d_all_meta, 0, sizeof(double) * MBOX_STRIDE * (world + 2)));
+    {
+        // bounded mailbox waits: OSPH_P2P_SPIN_SECONDS (default 30 s; clock64 ticks at about 2 GHz)
+        const char *e = getenv("OSPH_P2P_SPIN_SECONDS");
+        double sec = e ? atof(e) : 30.0;
+        if (!(sec > 0.0)) sec = 30.0;
+        s->spin_limit = (long long)(sec * 2.0e9);
+    }
     OSPH_CUDA(cudaMalloc(&s->d_dt3, sizeof(double) * 4));
     OSPH_CUDA(cudaMalloc(&s->d_all_dt, sizeof(double) * 4 * (world + 1)));
-    OSPH_CUDA(cudaMallocHost(&s->h_all_meta, sizeof(double) * 12 * world));
+    OSPH_CUDA(cudaMallocHost(&s->h_all_meta, sizeof(double) * (12 * world + 1)));
     cudaIpcMemHandle_t h;
     OSPH_CUDA(cudaIpcGetMemHandle(&h, s->win));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -180,25 +216,46 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
     double *mig_r = right >= 0 ? s->peer[right] + s->off_mig_from_left : s->win + s->off_mig_from_right;
     double *halo_r = right >= 0 ? s->peer[right] + s->off_halo_from_left : s->win + s->off_halo_from_right;
     int rc;
+    unsigned int *d_status = reinterpret_cast<unsigned int *>(s->d_all_meta + MBOX_STRIDE * (W + 1));
+    // every error return below first sets the abort word of all peers: they leave their mailbox waits and raise too
+    auto fail = [&](int code) { p2p_abort_peers(ctx, s); return code; };
+    if (s->aborted) { ctx->err = "slab exchange: this group was aborted by an earlier error"; return OSPH_E_INVALID; }
     for (int step = 0; step < nsteps; step++) {
         s->seq++;
         const int slot = (int)(s->seq & 1ull);
-        if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return rc;    // corrector of step k fused into the predictor of k+1
+        if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return fail(rc);    // corrector of step k fused into the predictor of k+1
         // ---- identical dt on every rank: mailbox all-gather + min ----
-        if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return rc;
+        if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return fail(rc);
         k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, slot, s->d_dt3, 3, s->seq,
-                                                       s->d_all_dt, 1);
-        OSPH_LAUNCH_CHECK();
-        if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return rc;
+                                                       s->d_all_dt, 1, s->spin_limit, d_status);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
+        if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return fail(rc);
         // ---- classify + pack straight into the neighbours' windows; counts and bounds through the second mailbox ----
         const double width = std::max(q * s->hmax, std::min(s->r0, 3.0 * s->hmax)) * 1.1;
-        if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return rc;
+        if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return fail(rc);
         k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_meta, s->off_meta_flag, slot, s->d_meta, 12,
-                                                       s->seq, s->d_all_meta, 0);
-        OSPH_LAUNCH_CHECK();
-        OSPH_CUDA(cudaMemcpyAsync(s->h_all_meta, s->d_all_meta, sizeof(double) * 12 * W, cudaMemcpyDeviceToHost, ctx->stream));
-        OSPH_CUDA(cudaStreamSynchronize(ctx->stream));                  // the one host sync of the step
+                                                       s->seq, s->d_all_meta, 0, s->spin_limit, d_status);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
+        if (cudaMemcpyAsync(s->h_all_meta, s->d_all_meta, sizeof(double) * 12 * W, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(s->h_all_meta + 12 * W, d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {           // the one host sync of the step
+            ctx->err = std::string("slab exchange: ") + cudaGetErrorString(cudaGetLastError());
+            return fail(OSPH_E_CUDA);
+        }
         const double *M = s->h_all_meta;
+        {
+            unsigned int st; memcpy(&st, s->h_all_meta + 12 * W, sizeof(st));
+            if (st) {
+                char msg[200];
+                snprintf(msg, sizeof msg, "slab exchange on rank %d, step %lld: %s", me, (long long)s->steps,
+                         (st & P2P_ST_ABORT) ? "a peer rank left the step loop with an error"
+                                             : "a peer rank did not answer within OSPH_P2P_SPIN_SECONDS");
+                ctx->err = msg;
+                return fail(OSPH_E_PEER);
+            }
+        }
         double bounds[6];
         for (int k = 0; k < 6; k++) { bounds[k] = M[4 + k]; for (int r = 1; r < W; r++) bounds[k] = std::min(bounds[k], M[12 * r + 4 + k]); }
         for (int r = 0; r < W; r++)
@@ -208,7 +265,7 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
                          "halo %.0f/%.0f (cap %lld), flag %.3g, seq %llu", r, (long long)s->steps, M[12 * r], M[12 * r + 1],
                          (long long)s->mig_cap, M[12 * r + 2], M[12 * r + 3], (long long)s->halo_cap, M[12 * r + 10], s->seq);
                 ctx->err = msg;
-                return OSPH_E_CAPACITY;
+                return fail(OSPH_E_CAPACITY);
             }
         const double *mine = M + 12 * me;
         const int64_t out_l = (int64_t)mine[0], out_r = (int64_t)mine[1], halo_out_l = (int64_t)mine[2], halo_out_r = (int64_t)mine[3];
@@ -222,8 +279,8 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         const int64_t n_ghost = gm.c0 + in_halo_l + in_halo_r;
         // ---- owned set update (migrants are already here), same grid everywhere, force evaluation, corrector ----
         if ((rc = osph_slab_commit_impl(ctx, out_l + out_r, s->win + s->off_mig_from_left, in_mig_l,
-                                        s->win + s->off_mig_from_right, in_mig_r, gm, n_ghost, bounds))) return rc;
-        if ((rc = osph_slab_step_end(ctx, damping))) return rc;
+                                        s->win + s->off_mig_from_right, in_mig_r, gm, n_ghost, bounds))) return fail(rc);
+        if ((rc = osph_slab_step_end(ctx, damping))) return fail(rc);
         const int64_t c[8] = {out_l, out_r, halo_out_l, halo_out_r, in_mig_l, in_mig_r, in_halo_l, in_halo_r};
         memcpy(s->last_counts, c, sizeof(c));
         s->steps++;

@@ -375,7 +375,9 @@ def gather_global(run, pA_template, fields, group=None):
 # ------------------------------------------------------------------------------------------------
 # multi-GPU arm of bench.py
 # ------------------------------------------------------------------------------------------------
-def bench_multi_gpu(args, rank, world, local):
+def bench_multi_gpu(args, rank, world, local, cpu_baseline=None):
+    """cpu_baseline: callable(case) -> dict, supplied by bench.py (the CPU checker is test infrastructure and is not
+    known to this package); called on rank 0 only, outside the timed regions."""
     import json
     import os
     import time
@@ -384,7 +386,7 @@ def bench_multi_gpu(args, rank, world, local):
 
     prec = capi.FP64 if args.precision == "fp64" else capi.FP32
     F = 8 if prec == capi.FP64 else 4
-    n_side = args.particles_per_side if args.total_side else int(round(args.particles_per_side * math.sqrt(world)))
+    n_side, scaling = B.resolve_problem(args, world)
     B.WORKLOAD = getattr(args, 'workload', 'dam_break')
     case = B.build_case(n_side)
     pA, c = case['pA'], case['consts']
@@ -480,6 +482,17 @@ def bench_multi_gpu(args, rank, world, local):
     if rank == 0:
         peaks, which = B.measured_peaks()
         per = allowned.cpu().numpy().reshape(world, 3)
+        # DRAM bytes of one launch: the single-GPU ncu capture of the same kernel, per particle it walks, times the
+        # particles (owned + ghosts) the slowest rank's launch walks
+        traffic = None
+        try:
+            with open(os.path.join(B.ROOT, "profiles", "pair_kernel_traffic.json")) as f:
+                t = json.load(f).get("%s_%s_N1000" % (args.precision, args.kernel))
+            if t:
+                traffic = int(t["dram_bytes_per_launch"] / t.get("particles", 1009603) * float(per[:, 0].max() + per[rank, 1]))
+        except Exception:       # noqa: BLE001
+            pass
+        cpu = cpu_baseline(case) if cpu_baseline is not None else None
         n_pair = float(per[:, 0].max() + per[rank, 1])
         alg_bytes = (13 * F + 1) * float(per[:, 0].max())
         pu = float(pair_t.item())
@@ -487,7 +500,7 @@ def bench_multi_gpu(args, rank, world, local):
         line = {
             "metric": B.METRIC, "value": n_total * args.steps / t_dev, "unit": B.UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong" if args.total_side else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64" if prec == capi.FP64 else "f32 pair arithmetic, f64 state", "data": "synthetic",
             "config": {"workload": B.workload_name(n_side, n_total, args.kernel, args.precision.upper()),
                        "particles": n_total, "particles_per_gpu": [int(v) for v in per[:, 0]],
@@ -501,11 +514,12 @@ def bench_multi_gpu(args, rank, world, local):
                     "h2d_bytes_per_step": int(mv.item()), "d2h_bytes_per_step": int(mv.item()), "steps": e2e_steps,
                     "what": "per rank: osph_upload_aos(pinned slab) + one slab step + download of the owned records"},
             "roofline": {"bound": "hbm", "kernel": "k_pair (slowest rank)", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                         "traffic_source": "single-GPU ncu capture scaled by the particles this launch walks",
                          "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "avg_launch_us": pu,
                          "share_of_step": pu * 1e-6 * args.steps / t_dev,
                          "algorithmic_bytes_per_particle": 13 * F + 1, "pair_kernel_particles": n_pair},
-            "cpu_baseline": None,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     dist.barrier()

@@ -6,6 +6,7 @@
 #include <sched.h>
 #include <stdio.h>
 #include <sys/mman.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <map>
@@ -137,6 +138,13 @@ static void prepare_fiber(Fiber &f, int slot)
 // other fibers of the CTA run, as the other warps of a CTA do on the GPU while one of them polls.  Without the fiber switch
 // a schedule other than the ascending default can deadlock ranks against each other (rank A polls for B before the fiber
 // that publishes to C has run, B polls for C, C for A).
+long long emu_clock64()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ((long long)ts.tv_sec * 1000000000ll + ts.tv_nsec) * 2;
+}
+
 void emu_yield_cpu()
 {
     sched_yield();

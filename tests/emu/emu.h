@@ -119,6 +119,8 @@ inline void __threadfence_block() {}
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }     // peers are other processes (shared memory)
 void emu_yield_cpu();
 inline void __nanosleep(unsigned) { emu_yield_cpu(); }
+long long emu_clock64();                 // monotonic clock in half-nanoseconds (a 2 GHz SM clock)
+inline long long clock64() { return emu_clock64(); }
 
 // ---- integer / conversion intrinsics --------------------------------------------------------------------------------
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
