@@ -76,6 +76,7 @@ enum osph_field {
 #define OSPH_S_SMALL_DT    2u  /* dt < 1e-6 (reference src/Solver.py:220-224 records this as ts_error) */
 #define OSPH_S_UNBINNED    4u  /* a particle's reference cell id fell outside the table (reference: OOB write) */
 #define OSPH_S_GRID_COARSE 8u  /* acceleration grid was coarsened to fit the allocated cell table */
+#define OSPH_S_DENSE_CELL  16u /* a cell holds more than 32768 particles: its summation order is not canonical (results exact) */
 
 typedef struct osph_ctx osph_ctx;
 
@@ -159,6 +160,15 @@ int osph_export_end(osph_ctx *ctx, int64_t ticket, int32_t nfields, double *cons
  */
 int osph_download_rows(osph_ctx *ctx, int64_t nrows, const int64_t *rows, void *pA, int64_t stride);
 int osph_upload_rows(osph_ctx *ctx, int64_t nrows, const int64_t *rows, const void *pA, int64_t stride);
+/*
+ * Switch rows off (or back on) on the device: active[r] != 0 keeps row r of the uploaded array, 0 marks it deleted.
+ * The current state of every active row is first written back into the device-side record mirror, so a row that is
+ * switched off keeps its last state for osph_download_aos, and a row switched on again resumes from its record.
+ * n must equal the row count of the last upload.  Invalidates the neighbour structure; not available in slab mode.
+ * replaces: the removal of the TempBoundary gate after settling, `pA['deleted'][inds] = True` followed by the
+ * re-derivation of the index sets (src/Solver.py:428-442) -- n bytes cross PCIe instead of the particle array twice.
+ */
+int osph_set_active(osph_ctx *ctx, const uint8_t *active, int64_t n);
 int64_t osph_num_active(const osph_ctx *ctx);
 int64_t osph_num_fluid(const osph_ctx *ctx);
 

@@ -126,6 +126,10 @@ extern "C" int osph_create(const osph_config *cfg, osph_ctx **out)
     }
     osph_ctx *ctx = new osph_ctx();
     ctx->cfg = *cfg; ctx->device = cfg->device;
+    {   // OSPH_SORT=radix: the LSD radix sort of sort.cu instead of the counting sort by cell (same order, A/B runs)
+        const char *e = getenv("OSPH_SORT");
+        ctx->bin_sort = !(e && std::string(e) == "radix");
+    }
     auto fail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
         delete ctx; return OSPH_E_CUDA;
@@ -151,6 +155,7 @@ extern "C" int osph_destroy(osph_ctx *ctx)
     PhaseTimer::drain(ctx);
     osph_export_free(ctx);
     free_particles(ctx);
+    osph_bin_free(ctx);
     cudaFree(ctx->cell_range); cudaFree(ctx->d_grid); cudaFree(ctx->d_sc); cudaFree(ctx->d_dt_log);
     cudaFree(ctx->scan_block); cudaFree(ctx->d_slab_counters); cudaFree(ctx->d_mig_slots); cudaFree(ctx->d_tail_flag);
     cudaFree(ctx->d_holes); cudaFree(ctx->d_fillers);
@@ -173,19 +178,14 @@ static void invalidate_state(osph_ctx *ctx)
 
 // ---- transfers ---------------------------------------------------------------------------------
 
-// Upload path: raw records -> device mirror; the list of active rows is built ON the device (flags, exclusive
-// scan, compaction) so the host touches nothing but two counters.
-static int ingest(osph_ctx *ctx, const void *src, bool src_on_device, int64_t n, int64_t stride)
+// Rebuilds the active list from the device-side record mirror (flags, scan, compaction) and splits the active rows into
+// the state columns.  Shared by the uploads and osph_set_active.
+static int rebuild_active(osph_ctx *ctx)
 {
-    int rc = alloc_particles(ctx, n, n, stride);          // capacity for the case that every row is active
-    if (rc) return rc;
-    if (n != ctx->n_total) ctx->sized = false;
-    ctx->n_total = n; ctx->stride = stride;
-    OSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, src, (size_t)n * stride,
-                              src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    int rc;
     int *d_counters = (int *)ctx->d_partial;
     OSPH_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int) * 2, ctx->stream));
-    if ((rc = osph_launch_active_list(ctx, (int)n, d_counters))) return rc;
+    if ((rc = osph_launch_active_list(ctx, (int)ctx->n_total, d_counters))) return rc;
     int counters[2] = {0, 0};
     OSPH_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, ctx->stream));
     OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -198,10 +198,40 @@ static int ingest(osph_ctx *ctx, const void *src, bool src_on_device, int64_t n,
     return 0;
 }
 
+// Upload path: raw records -> device mirror; the list of active rows is built ON the device (flags, exclusive
+// scan, compaction) so the host touches nothing but two counters.
+static int ingest(osph_ctx *ctx, const void *src, bool src_on_device, int64_t n, int64_t stride)
+{
+    int rc = alloc_particles(ctx, n, n, stride);          // capacity for the case that every row is active
+    if (rc) return rc;
+    if (n != ctx->n_total) ctx->sized = false;
+    ctx->n_total = n; ctx->stride = stride;
+    OSPH_CUDA(cudaMemcpyAsync(ctx->d_aos, src, (size_t)n * stride,
+                              src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    return rebuild_active(ctx);
+}
+
+// reference src/Solver.py:428-442 (removal of the TempBoundary gate after settling): rows are switched off (or on) ON the
+// device.  The state goes back into the record mirror, the `deleted` byte of every row is set from the mask, and the active
+// list is rebuilt -- n bytes cross PCIe instead of the whole particle array twice.
+extern "C" int osph_set_active(osph_ctx *ctx, const uint8_t *active, int64_t n)
+{
+    CHECK_CTX();
+    if (!active || n != ctx->n_total || n <= 0) { ctx->err = "osph_set_active: the mask must have one byte per uploaded row"; return OSPH_E_INVALID; }
+    if (ctx->slab) { ctx->err = "osph_set_active: not available in slab mode"; return OSPH_E_INVALID; }
+    PhaseTimer t(ctx, T_TRANSFER);
+    int rc;
+    if (ctx->n > 0 && (rc = osph_launch_pack(ctx))) return rc;          // current state -> records (also of rows about to go)
+    unsigned char *d_mask = (unsigned char *)ctx->d_stage;             // one spare column: 8 bytes per particle capacity
+    OSPH_CUDA(cudaMemcpyAsync(d_mask, active, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = osph_launch_set_deleted(ctx, d_mask))) return rc;
+    return rebuild_active(ctx);
+}
+
 extern "C" int osph_upload_aos(osph_ctx *ctx, const void *pA, int64_t n, int64_t stride)
 {
     CHECK_CTX();
-    if (!pA || n < 0 || n > 0x7fffffff || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_upload_aos: bad arguments"; return OSPH_E_INVALID; }
+    if (!pA || n < 0 || n > 0x7fffffff || stride < 2 + 8 * OSPH_NUM_FIELDS || (stride & 1)) { ctx->err = "osph_upload_aos: bad arguments (the record stride must be even: fields are moved as 16-bit words)"; return OSPH_E_INVALID; }
     PhaseTimer t(ctx, T_TRANSFER);
     return ingest(ctx, pA, false, n, stride);
 }
@@ -209,7 +239,7 @@ extern "C" int osph_upload_aos(osph_ctx *ctx, const void *pA, int64_t n, int64_t
 extern "C" int osph_import_device_aos(osph_ctx *ctx, const void *d_pA, int64_t n, int64_t stride)
 {
     CHECK_CTX();
-    if (!d_pA || n < 0 || n > 0x7fffffff || stride < 2 + 8 * OSPH_NUM_FIELDS) { ctx->err = "osph_import_device_aos: bad arguments"; return OSPH_E_INVALID; }
+    if (!d_pA || n < 0 || n > 0x7fffffff || stride < 2 + 8 * OSPH_NUM_FIELDS || (stride & 1)) { ctx->err = "osph_import_device_aos: bad arguments (the record stride must be even: fields are moved as 16-bit words)"; return OSPH_E_INVALID; }
     PhaseTimer t(ctx, T_TRANSFER);
     return ingest(ctx, d_pA, true, n, stride);
 }
@@ -319,6 +349,8 @@ int osph_size_cell_table(osph_ctx *ctx)
         cudaFree(ctx->cell_range); ctx->cell_range = nullptr;
         OSPH_CUDA(cudaMalloc(&ctx->cell_range, sizeof(int2) * (size_t)want));
         ctx->cell_cap = want;
+        int rc2 = osph_bin_alloc(ctx, want);
+        if (rc2) return rc2;
     }
     int bits = 1;
     while (((int64_t)1 << bits) < ctx->cell_cap + 1) bits++;
@@ -505,8 +537,11 @@ extern "C" int osph_get_cells(osph_ctx *ctx, double grid[7], int64_t *cell_ids)
         cudaError_t e = cudaMemcpyAsync(cell_ids, d_out, sizeof(long long) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e != cudaSuccess) { cudaFree(d_out); ctx->err = cudaGetErrorString(e); return OSPH_E_CUDA; }
     }
-    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_out);
+    {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_out);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return OSPH_E_CUDA; }
+    }
     if (grid) {
         grid[0] = g.xmin; grid[1] = g.xmax; grid[2] = g.ymin; grid[3] = g.ymax; grid[4] = g.cell_size;
         grid[5] = (double)g.ncx; grid[6] = (double)g.ncy;
@@ -556,9 +591,12 @@ extern "C" int osph_near_pos(osph_ctx *ctx, double x, double y, double h, int64_
     if (!ctx->neighbours_valid && (rc = build_neighbours(ctx))) return rc;
     int64_t c = std::max<int64_t>(cap, 1);
     long long *d_idx = nullptr, *d_count = nullptr; double *d_r = nullptr;
-    OSPH_CUDA(cudaMalloc(&d_idx, sizeof(long long) * c));
-    OSPH_CUDA(cudaMalloc(&d_r, sizeof(double) * 3 * c));
-    OSPH_CUDA(cudaMalloc(&d_count, sizeof(long long)));
+    if (cudaMalloc(&d_idx, sizeof(long long) * c) != cudaSuccess || cudaMalloc(&d_r, sizeof(double) * 3 * c) != cudaSuccess ||
+        cudaMalloc(&d_count, sizeof(long long)) != cudaSuccess) {
+        ctx->err = std::string("osph_near_pos: ") + cudaGetErrorString(cudaGetLastError());
+        cudaFree(d_idx); cudaFree(d_r); cudaFree(d_count);
+        return OSPH_E_CUDA;
+    }
     rc = osph_launch_near_pos(ctx, x, y, h, cap, d_idx, d_r, d_r + c, d_r + 2 * c, d_count);
     long long cnt = 0;
     if (!rc) {

@@ -97,6 +97,12 @@ struct osph_ctx {
     // cell table of the acceleration grid: (begin, end) per cell
     int2 *cell_range = nullptr;
     int64_t cell_cap = 0;
+    // counting sort by cell (binsort.cu): cell histogram, tile states of its single-pass scan (+ the ticket counter)
+    bool bin_sort = true;             // false (OSPH_SORT=radix): LSD radix sort of sort.cu
+    unsigned int *bin_counts = nullptr;
+    unsigned int *bin_tiles = nullptr;   // totals of the scan tiles (BIN_TILE cells each), two buffers used alternately
+    int64_t bin_tile_cap = 0;
+    int bin_parity = 0;
 
     // per-particle cell info in sorted order
     int4 *s_coarse = nullptr;        // reference grid: (bin_cx, bin_cy, query_cx, query_cy); bin_cx < 0: unbinned
@@ -223,6 +229,23 @@ __device__ __forceinline__ unsigned long long enc_for_max(double v) { return v =
 
 __device__ __forceinline__ double warp_min(double v) { return dec_f64(warp_min_u64(enc_for_min(v))); }
 __device__ __forceinline__ double warp_max(double v) { return dec_f64(warp_max_u64(enc_for_max(v))); }
+// Counting sort by cell (binsort.cu): the canonical position of the particle in storage slot `mine`, which the atomics of
+// k_bin_keys placed at sorted position s of a cell occupying r = [begin, end): begin + the number of cell mates with a
+// smaller storage slot.  Cells fuller than BIN_DENSE_CELL keep their arrival order (the count would be quadratic).
+#define BIN_DENSE_CELL 32768
+#define BIN_TILE 4096                  // cells per tile of the cell-count scan
+__device__ __forceinline__ int bin_canonical_slot(int2 r, int s, unsigned int mine, const unsigned int *__restrict__ idx_arrival,
+                                                  StepScalars *sc)
+{
+    if (r.y - r.x > BIN_DENSE_CELL) {
+        if (s == r.x) atomicOr(&sc->status, OSPH_S_DENSE_CELL);
+        return s;
+    }
+    int before = 0;
+    for (int t = r.x; t < r.y; t++) before += idx_arrival[t] < mine ? 1 : 0;
+    return r.x + before;
+}
+
 __device__ __forceinline__ int warp_min_i(int v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
@@ -231,6 +254,10 @@ __device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xff
 // ---------------------------------------------------------------------------------------------
 // launchers implemented in the other translation units
 // ---------------------------------------------------------------------------------------------
+int osph_bin_alloc(osph_ctx *ctx, int64_t cell_cap);                              // binsort.cu
+void osph_bin_free(osph_ctx *ctx);
+int osph_bin_sort(osph_ctx *ctx, int64_t n_all, bool rank_now);
+inline unsigned int *osph_bin_tile_sums(osph_ctx *ctx) { return ctx->bin_tiles + (size_t)ctx->bin_parity * ctx->bin_tile_cap; }
 int osph_sort_pairs(osph_ctx *ctx, int64_t n, int bits, bool first_hist_done);   // sort.cu: key[sorted_buf], idx[sorted_buf]
 int osph_sort_alloc(osph_ctx *ctx, int64_t cap);
 void osph_sort_free(osph_ctx *ctx);

@@ -467,17 +467,31 @@ k_pair(PairArgs a)
 // density (the reference evaluates the EOS before this pass); p / rho^2 is refreshed with the new density.
 // Off in every shipped example: a plain one-thread-per-particle walk, always in double.
 // ---------------------------------------------------------------------------------------------------------
+// Slab mode: ghosts are sources of the pair kernel, and the pair kernel reads THEIR density too, so the pass also runs for
+// the ghost fluid particles (their h, m and old density come from the wire records).  osph_slab_pack doubles the halo
+// width when the option is on: a ghost within one pair radius of the face -- the only ghosts an owned particle can
+// interact with -- then has its whole kernel support inside the halo and receives the same sum its owner computes.
+struct SumDensArgs {
+    int n_owned;
+    const double *ghost;
+    GhostMap gmap;
+    const double *h64, *m64, *p_state;
+    double *rho_state;
+    double gamma, B, rho0, Pb;
+};
+
 template <int KID, typename Real2>
 __global__ void __launch_bounds__(128)
-k_summation_density(PairArgs a, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_hp, const double *__restrict__ h64,
-                    const double *__restrict__ m64, double *__restrict__ rho_state, const double *__restrict__ p_state)
+k_summation_density(PairArgs a, SumDensArgs d, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_hp)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n || (a.s_info[s] & 3) != 3) return;
+    if (s >= a.n || !(a.s_info[s] & 1)) return;
     const GridParams g = *a.gp;
     const int slot = (int)a.idx[s];
+    const bool owned = slot < d.n_owned;
+    const double *rec_i = owned ? nullptr : ghost_record(d.ghost, d.gmap, slot - d.n_owned);
     const double2 pi = a.s_pos[s];
-    const double hi = h64[slot];
+    const double hi = owned ? d.h64[slot] : rec_i[6];
     const int4 ci = a.s_coarse[s];
     const int2 gc = a.s_gcell[s];
     double rho = 0.0;
@@ -493,22 +507,33 @@ k_summation_density(PairArgs a, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_
                 const int4 cj = a.s_coarse[t];
                 if (abs(cj.x - ci.z) > 1 || abs(cj.y - ci.w) > 1) continue;
                 const int tj = (int)a.idx[t];
+                double hj, mj;
+                if (tj < d.n_owned) { hj = d.h64[tj]; mj = d.m64[tj]; }
+                else { const double *rj = ghost_record(d.ghost, d.gmap, tj - d.n_owned); hj = rj[6]; mj = rj[5]; }
                 const double2 pj = a.s_pos[t];
                 const double dx = __dadd_rn(pi.x, -pj.x), dyy = __dadd_rn(pi.y, -pj.y);
                 const double rr = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dyy, dyy)));
-                const double hij = __dmul_rn(0.5, __dadd_rn(hi, h64[tj]));
+                const double hij = __dmul_rn(0.5, __dadd_rn(hi, hj));
                 if (!(__ddiv_rn(rr, hij) <= 3.0)) continue;
                 const double inv_h = 1.0 / hij;
                 double w, gg;
                 sph_kernel<double, KID>(rr * inv_h, inv_h, 0.0, w, gg);
-                rho += m64[tj] * w;
+                rho += mj * w;
             }
         }
     }
-    rho_state[slot] = rho;
+    double p_old;
+    if (owned) { d.rho_state[slot] = rho; p_old = d.p_state[slot]; }
+    else {
+        // the owner's EOS value for the density the ghost arrived with (k_gather evaluates the same expression)
+        const double ratio = rec_i[4] / d.rho0;
+        double rp;
+        if (d.gamma == 7.0) { const double r2 = ratio * ratio, r4 = r2 * r2; rp = r4 * r2 * ratio; } else rp = pow(ratio, d.gamma);
+        p_old = (rp - 1.0) * d.B + d.Pb;
+    }
     typedef decltype(Real2().x) Real;
     Real2 rm = s_rm[s]; rm.x = (Real)rho; s_rm[s] = rm;
-    Real2 hp = s_hp[s]; hp.y = (Real)(p_state[slot] / (rho * rho)); s_hp[s] = hp;
+    Real2 hp = s_hp[s]; hp.y = (Real)(p_old / (rho * rho)); s_hp[s] = hp;
 }
 
 template <typename Real2>
@@ -516,12 +541,14 @@ static void launch_summation(osph_ctx *ctx, const PairArgs &a)
 {
     int grid = div_up(a.n, 128);
     Real2 *rm = (Real2 *)ctx->s_rm, *hp = (Real2 *)ctx->s_hp;
-    const double *h = ctx->f[OSPH_F_H], *m = ctx->f[OSPH_F_M], *p = ctx->f[OSPH_F_P];
-    double *rho = ctx->f[OSPH_F_RHO];
+    SumDensArgs d;
+    d.n_owned = (int)ctx->n; d.ghost = ctx->d_ghost; d.gmap = ctx->gmap;
+    d.h64 = ctx->f[OSPH_F_H]; d.m64 = ctx->f[OSPH_F_M]; d.p_state = ctx->f[OSPH_F_P]; d.rho_state = ctx->f[OSPH_F_RHO];
+    d.gamma = ctx->cfg.gamma; d.B = ctx->cfg.B; d.rho0 = ctx->cfg.rho0; d.Pb = ctx->cfg.Pb;
     switch (ctx->cfg.kernel) {
-    case OSPH_KERNEL_CUBIC: k_summation_density<OSPH_KERNEL_CUBIC, Real2><<<grid, 128, 0, ctx->stream>>>(a, rm, hp, h, m, rho, p); break;
-    case OSPH_KERNEL_WENDLAND: k_summation_density<OSPH_KERNEL_WENDLAND, Real2><<<grid, 128, 0, ctx->stream>>>(a, rm, hp, h, m, rho, p); break;
-    default: k_summation_density<OSPH_KERNEL_GAUSSIAN, Real2><<<grid, 128, 0, ctx->stream>>>(a, rm, hp, h, m, rho, p); break;
+    case OSPH_KERNEL_CUBIC: k_summation_density<OSPH_KERNEL_CUBIC, Real2><<<grid, 128, 0, ctx->stream>>>(a, d, rm, hp); break;
+    case OSPH_KERNEL_WENDLAND: k_summation_density<OSPH_KERNEL_WENDLAND, Real2><<<grid, 128, 0, ctx->stream>>>(a, d, rm, hp); break;
+    default: k_summation_density<OSPH_KERNEL_GAUSSIAN, Real2><<<grid, 128, 0, ctx->stream>>>(a, d, rm, hp); break;
     }
 }
 
@@ -573,7 +600,6 @@ int osph_launch_pair(osph_ctx *ctx)
     a.method_xsph = c.method_xsph; a.summation_density = c.summation_density;
     int grid = div_up(ctx->n + ctx->n_ghost, OSPH_PAIR_THREADS);
     if (c.summation_density) {
-        if (ctx->n_ghost > 0) { ctx->err = "useSummationDensity is not supported in slab mode"; return OSPH_E_INVALID; }
         if (c.precision == OSPH_FP64) launch_summation<double2>(ctx, a); else launch_summation<float2>(ctx, a);
         OSPH_LAUNCH_CHECK();
     }

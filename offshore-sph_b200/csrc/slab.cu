@@ -218,7 +218,9 @@ extern "C" int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left
     SlabPackArgs a;
     a.n = (int)ctx->n; a.label = ctx->label; a.row = ctx->d_row;
     for (int k = 0; k < OSPH_NUM_FIELDS; k++) a.f[k] = ctx->f[k];
-    a.x_lo = ctx->x_lo; a.x_hi = ctx->x_hi; a.width = halo_width;
+    a.x_lo = ctx->x_lo; a.x_hi = ctx->x_hi;
+    // summation density: the ghosts an owned particle can see need their own kernel support inside the halo (pair.cu)
+    a.width = ctx->cfg.summation_density ? 2.0 * halo_width : halo_width;
     a.mig_left = (double *)d_mig_left; a.mig_right = (double *)d_mig_right;
     a.halo_left = (double *)d_halo_left; a.halo_right = (double *)d_halo_right; a.ghost = ctx->d_ghost;
     a.mig_cap = (int)mig_cap; a.halo_cap = (int)halo_cap; a.ghost_cap = (int)ctx->ghost_cap;

@@ -40,6 +40,13 @@ __global__ void k_active_compact(const unsigned char *__restrict__ aos, long lon
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[1], __popc(m));
 }
 
+// osph_set_active: the `deleted` byte of every record from a mask of active rows
+__global__ void k_set_deleted(unsigned char *__restrict__ aos, long long stride, int n, const unsigned char *__restrict__ active)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) aos[(long long)r * stride] = active[r] ? 0 : 1;
+}
+
 __global__ void k_unpack_aos(const unsigned char *__restrict__ aos, long long stride, const int *__restrict__ row,
                              int n, Columns c, signed char *__restrict__ label)
 {
@@ -454,6 +461,66 @@ k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, 
     for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = cnt[d];
 }
 
+// K3 of the counting sort (binsort.cu): cell key + arrival rank inside the cell + cell histogram.  Neighbouring particles
+// share their cell, so the warp first groups equal keys (match_any) and the group's leader takes ONE global atomic for all
+// of them; the arrival order is made canonical later (k_bin_rank).
+#define BINK_ITEMS 4
+#define BINK_WINDOW 16            // scan tiles around the CTA's first key whose totals are collected in shared memory
+__global__ void __launch_bounds__(256)
+k_bin_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, const double *__restrict__ ghost,
+           GhostMap gmap, int n_all, const GridParams *__restrict__ gp, StepScalars *sc, unsigned int *__restrict__ key,
+           unsigned int *__restrict__ arrival, unsigned int *__restrict__ counts, unsigned int *__restrict__ tile_sums)
+{
+    // The totals of the scan tiles (BIN_TILE cells) are accumulated here so that k_bin_scan needs no look-back.  A tile is
+    // hit by thousands of particles: straight global atomics serialise on a few hundred addresses (52 us measured), so the
+    // CTA collects them in shared memory -- storage order follows cell order closely, a CTA's keys sit in one or two tiles --
+    // and flushes one atomic per tile it touched.  Keys outside the window go to global memory directly.
+    __shared__ unsigned int sh_tile[BINK_WINDOW];
+    __shared__ int sh_tile0;
+    const GridParams g = *gp;
+    const int lane = threadIdx.x & 31;
+    const int base = blockIdx.x * (256 * BINK_ITEMS) + (threadIdx.x >> 5) * (32 * BINK_ITEMS) + lane;
+    double px[BINK_ITEMS], py[BINK_ITEMS];
+#pragma unroll
+    for (int r = 0; r < BINK_ITEMS; r++) {                  // all loads of the thread first (one round trip)
+        const int i = base + r * 32;
+        px[r] = 0.0; py[r] = 0.0;
+        if (i < n_owned) { px[r] = x[i]; py[r] = y[i]; }
+        else if (i < n_all) { const double *rec = ghost_record(ghost, gmap, i - n_owned); px[r] = rec[0]; py[r] = rec[1]; }
+    }
+    if (threadIdx.x < BINK_WINDOW) sh_tile[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) sh_tile0 = (int)(cell_of(px[0], py[0], g).key / BIN_TILE) - BINK_WINDOW / 2;
+    __syncthreads();
+    const int tile0 = sh_tile0;
+    bool unbinned = false;
+#pragma unroll
+    for (int r = 0; r < BINK_ITEMS; r++) {
+        const int i = base + r * 32;
+        const bool ok = i < n_all;
+        unsigned int k = 0xffffffffu;
+        if (ok) {
+            CellInfo c = cell_of(px[r], py[r], g);
+            unbinned |= !c.binned;
+            k = c.key;
+        }
+        const unsigned int peers = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(peers) - 1;
+        unsigned int first = 0;
+        if (ok && lane == leader) {
+            const unsigned int cnt = (unsigned int)__popc(peers);
+            first = atomicAdd(&counts[k], cnt);
+            const int t = (int)(k / BIN_TILE) - tile0;
+            if (t >= 0 && t < BINK_WINDOW) atomicAdd(&sh_tile[t], cnt);
+            else atomicAdd(&tile_sums[k / BIN_TILE], cnt);
+        }
+        first = __shfl_sync(0xffffffffu, first, leader);
+        if (ok) { key[i] = k; arrival[i] = first + __popc(peers & ((1u << lane) - 1u)); }
+    }
+    if (unbinned) atomicOr(&sc->status, OSPH_S_UNBINNED);
+    __syncthreads();
+    if (threadIdx.x < BINK_WINDOW && sh_tile[threadIdx.x]) atomicAdd(&tile_sums[tile0 + (int)threadIdx.x], sh_tile[threadIdx.x]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K5: gather of the pair-kernel inputs into sorted order, fused with the Tait EOS
 // (reference WCSPH.compute_pressure, src/Methods/WCSPH.py:131-149; TaitEOS.py:6-31).
@@ -472,11 +539,16 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
     if (s >= a.n_all) return;
     // key, neighbouring keys, slot and the grid parameters are requested together (one round trip); the gathers below are
     // the second.  Written in program order (key, table store, idx, gathers, stores, *gp) the compiler had to keep four.
-    const unsigned int k = a.key[s];
-    const unsigned int kp = s > 0 ? a.key[s - 1] : k, kn = s < a.n_all - 1 ? a.key[s + 1] : k;
+    unsigned int k = 0, kp = 0, kn = 0;
+    if (a.key) {                                      // radix path only: the counting sort has written the table already
+        k = a.key[s];
+        kp = s > 0 ? a.key[s - 1] : k; kn = s < a.n_all - 1 ? a.key[s + 1] : k;
+    }
+    int2 rr = make_int2(0, 0);
+    if (a.rank_ranges) rr = a.rank_ranges[s];
     int i = (int)a.idx[s];
     const GridParams g = *a.gp;
-    {   // K6 fused: cell table from the sorted keys (table zeroed before: empty cells have begin == end == 0)
+    if (a.key) {   // K6 fused: cell table from the sorted keys (table zeroed before: empty cells have begin == end == 0)
         if (s == 0 || kp != k) a.cell_range[k].x = s;
         if (s == a.n_all - 1 || kn != k) a.cell_range[k].y = s + 1;
     }
@@ -488,6 +560,12 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
     } else {
         const double *r = ghost_record(a.ghost, a.gmap, i - a.n_owned);
         x = r[0]; y = r[1]; vx = r[2]; vy = r[3]; rho = r[4]; m = r[5]; h = r[6]; lab = (int)r[7]; info = 0;
+    }
+    if (a.rank_ranges) {
+        // counting sort: this thread holds the particle that ARRIVED at position s; its final position is decided by the
+        // storage slots of its cell mates (the state loads above are in flight while they are counted)
+        s = bin_canonical_slot(rr, s, (unsigned int)i, a.idx, a.sc);
+        a.idx_out[s] = (unsigned int)i;
     }
     bool fluid = lab == OSPH_FLUID;
     double p = a.Pb;
@@ -851,6 +929,13 @@ int osph_launch_active_list(osph_ctx *ctx, int n_total, int *d_counters)
     return 0;
 }
 
+int osph_launch_set_deleted(osph_ctx *ctx, const unsigned char *d_active)
+{
+    k_set_deleted<<<div_up(ctx->n_total, 256), 256, 0, ctx->stream>>>(ctx->d_aos, ctx->stride, (int)ctx->n_total, d_active);
+    OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
 int osph_launch_unpack(osph_ctx *ctx)
 {
     if (ctx->n == 0) return 0;
@@ -970,9 +1055,21 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt)
     int rc = osph_launch_grid_params(ctx, reset_dt);
     if (rc) return rc;
     ctx->sorted_buf = 0;
-    {
+    const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];
+    int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
+    // physical re-sort on the 3rd build after an upload, then every `every` builds: a caller that uploads, steps once
+    // and downloads (the host-buffer plugin call pattern) never pays for it, a resident run gets it early
+    const bool reorder_now = ctx->build_counter % every == (2 % every);
+    bool rank_in_gather = false;
+    if (ctx->bin_sort) {
+        // counting sort by cell: histogram + arrival ranks, then scan (= cell table), scatter, canonical order (binsort.cu)
+        k_bin_keys<<<div_up(n_all, 256 * BINK_ITEMS), 256, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid,
+                                                                            ctx->d_sc, ctx->key[0], ctx->idx[0], ctx->bin_counts, osph_bin_tile_sums(ctx));
+        OSPH_LAUNCH_CHECK();
+        if ((rc = osph_bin_sort(ctx, n_all, reorder_now))) return rc;
+        rank_in_gather = !reorder_now;
+    } else {
         const int nblocks = div_up(n_all, SORT_TILE), db = osph_sort_digit_bits(ctx->key_bits);
-        const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];
         if (db == 8)
             k_keys<8><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid, ctx->d_sc,
                                                                  ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
@@ -983,17 +1080,17 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt)
             k_keys<11><<<nblocks, SORT_THREADS, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid, ctx->d_sc,
                                                                   ctx->key[0], ctx->idx[0], nblocks, ctx->hist);
         OSPH_LAUNCH_CHECK();
+        if ((rc = osph_sort_pairs(ctx, n_all, ctx->key_bits, true))) return rc;
+        OSPH_CUDA(cudaMemsetAsync(ctx->cell_range, 0, sizeof(int2) * (size_t)ctx->cell_cap, ctx->stream));
     }
-    if ((rc = osph_sort_pairs(ctx, n_all, ctx->key_bits, true))) return rc;
-    OSPH_CUDA(cudaMemsetAsync(ctx->cell_range, 0, sizeof(int2) * (size_t)ctx->cell_cap, ctx->stream));
-    int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
-    // physical re-sort on the 3rd build after an upload, then every `every` builds: a caller that uploads, steps once
-    // and downloads (the host-buffer plugin call pattern) never pays for it, a resident run gets it early
-    if (ctx->build_counter % every == (2 % every) && (rc = reorder_state(ctx))) return rc;
+    if (reorder_now && (rc = reorder_state(ctx))) return rc;
     ctx->build_counter++;
 
     GatherArgs g;
-    g.n_owned = n; g.n_all = n_all; g.key = ctx->key[ctx->sorted_buf]; g.cell_range = ctx->cell_range; g.idx = ctx->idx[ctx->sorted_buf]; g.label = ctx->label; g.ghost = ctx->d_ghost; g.gmap = ctx->gmap;
+    g.n_owned = n; g.n_all = n_all; g.key = ctx->bin_sort ? nullptr : ctx->key[ctx->sorted_buf]; g.cell_range = ctx->cell_range;
+    g.idx = rank_in_gather ? ctx->idx[1] : ctx->idx[ctx->sorted_buf];
+    g.rank_ranges = rank_in_gather ? reinterpret_cast<const int2 *>(ctx->scratch) : nullptr; g.idx_out = ctx->idx[0]; g.sc = ctx->d_sc;
+    g.label = ctx->label; g.ghost = ctx->d_ghost; g.gmap = ctx->gmap;
     g.x = ctx->f[OSPH_F_X]; g.y = ctx->f[OSPH_F_Y]; g.vx = ctx->f[OSPH_F_VX]; g.vy = ctx->f[OSPH_F_VY];
     g.rho = ctx->f[OSPH_F_RHO]; g.m = ctx->f[OSPH_F_M]; g.h = ctx->f[OSPH_F_H]; g.p = ctx->f[OSPH_F_P];
     g.gp = ctx->d_grid;

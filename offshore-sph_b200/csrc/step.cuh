@@ -28,9 +28,14 @@ struct CorrectArgs {
 
 struct GatherArgs {
     int n_owned, n_all;
-    const unsigned int *key;      // sorted keys (cell table is written from them)
+    const unsigned int *key;      // radix sort only: sorted keys (the cell table is written from them), else nullptr
     int2 *cell_range;
-    const unsigned int *idx;
+    const unsigned int *idx;      // sorted position -> storage slot (counting sort, rank_ranges set: in arrival order)
+    // counting sort: the kernel makes the order inside each cell canonical on the way (bin_canonical_slot) -- every record
+    // is written to its final position and idx_out receives the final permutation
+    const int2 *rank_ranges;      // per sorted position: (begin, end) of its cell; nullptr: idx is final already
+    unsigned int *idx_out;
+    StepScalars *sc;
     const signed char *label;
     const double *ghost;
     GhostMap gmap;
@@ -62,6 +67,7 @@ struct NeighbourArgs {
 
 int osph_launch_setup(osph_ctx *ctx);
 int osph_launch_unpack(osph_ctx *ctx);
+int osph_launch_set_deleted(osph_ctx *ctx, const unsigned char *d_active);
 int osph_launch_active_list(osph_ctx *ctx, int n_total, int *d_counters);
 int osph_launch_pack(osph_ctx *ctx);
 int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids);

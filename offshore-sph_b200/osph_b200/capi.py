@@ -88,6 +88,7 @@ def lib():
         'osph_export_end': (C.c_int, [ctx, i64, i32, C.POINTER(dp), i64]),
         'osph_download_rows': (C.c_int, [ctx, i64, ip, C.c_void_p, i64]),
         'osph_upload_rows': (C.c_int, [ctx, i64, ip, C.c_void_p, i64]),
+        'osph_set_active': (C.c_int, [ctx, C.c_void_p, i64]),
         'osph_num_active': (i64, [ctx]),
         'osph_num_fluid': (i64, [ctx]),
         'osph_initialize': (C.c_int, [ctx]),
@@ -269,6 +270,12 @@ class Context:
         assert pA.flags['C_CONTIGUOUS'] and (len(pA), pA.dtype.itemsize) == self._shape
         self._ck(self._L.osph_upload_rows(self._h, len(rows), rows.ctypes.data_as(C.POINTER(C.c_int64)), pA.ctypes.data,
                                           pA.dtype.itemsize))
+
+    def set_active(self, active):
+        """Keep the rows with active[r] != 0, mark the others deleted -- on the device (reference src/Solver.py:428-442);
+        one byte per row of the uploaded array."""
+        m = np.ascontiguousarray(np.asarray(active) != 0, dtype=np.uint8)
+        self._ck(self._L.osph_set_active(self._h, m.ctypes.data, len(m)))
 
     def upload_fields(self, cols):
         names = list(cols)

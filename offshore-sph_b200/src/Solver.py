@@ -289,14 +289,20 @@ class Solver:
                         println('WARNING! Maximum settle steps reached, check configuration, maybe increase spacing '
                                 'between wall and particles.')
                     sbar.close()
-                    # remove the temporary boundary: mark deleted, re-upload the compacted set
-                    self._pull()
+                    # remove the temporary boundary (reference :428-442) ON the device: only the gate's own rows and a
+                    # one-byte-per-row mask cross PCIe (osph_set_active); labels and deleted flags never change on the
+                    # device, so the host mirror's copies are current even while its state columns are stale
+                    self._export_drain()
                     pa = self.particleArray
-                    inds = np.flatnonzero((pa['label'] == ParticleType.TempBoundary) & ~pa['deleted'])
+                    inds = np.flatnonzero((pa['label'] == ParticleType.TempBoundary) & ~pa['deleted']).astype(np.int64)
+                    if len(inds):
+                        ctx.download_rows(inds, pa)
+                        pa['p'][inds] = -1e15
+                        ctx.upload_rows(inds, pa)
                     pa['deleted'][inds] = True
                     self._masks()
-                    pa['p'][inds] = -1e15
-                    self._push()
+                    ctx.set_active(~pa['deleted'])
+                    self._host_dirty = True
                     self.settleTime = sum(self.dt_a)
                     self.damping = 0.0
                     self.settled = True

@@ -92,6 +92,19 @@ class OracleContext:
             getattr(self.P, f)[s] = pA[f][rows]
         self.grid = None
 
+    def set_active(self, active):
+        """Rows switched off / on: state back into the record mirror, new deleted flags, active set rebuilt."""
+        self._count('set_active')
+        active = np.asarray(active) != 0
+        assert len(active) == len(self.mirror)
+        for f in STATE:
+            self.mirror[f][self.act] = getattr(self.P, f)
+        self.mirror['deleted'] = ~active
+        self.act = active.copy()
+        self.P = O.Particles.from_aos(self.mirror[self.act])
+        self.fluid = self.P.fluid.astype(np.uint8)
+        self.grid = None
+
     @property
     def num_active(self):
         return self.P.n

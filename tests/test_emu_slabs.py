@@ -28,7 +28,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
+def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q, sumdens=False):
     os.environ["OSPH_LIB"] = lib                     # read by osph_b200.capi at import: this process binds the emulated build
     os.environ["OSPH_NCCL_LIB"] = os.path.join(os.path.dirname(lib), "libfake_nccl.so")
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -46,6 +46,8 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
     f = case['pA']['label'] == 0
     case['pA']['vx'][f] += 100.0                     # push the fluid across the slab faces
     pA, c = case['pA'], case['consts']
+    if sumdens:
+        c = dict(c, useSummationDensity=True)         # density from the kernel sum before every force evaluation
     cfg = capi.make_config(c, kernel, 'pec', capi.FP64, case['h'], reorder_every=3)
     with capi.Context(cfg) as single:
         single.upload(pA)
@@ -84,7 +86,7 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q):
     a, b = results[1], results[steps // 2]
     same = all(np.array_equal(a[0][f_], b[0][f_]) for f_ in FIELDS)
     diff = max(field_err(a[0][f_], b[0][f_]) for f_ in FIELDS)
-    q.put((rank, 'fused-vs-plain', same, a[1], b[1], diff))
+    q.put((rank, 'fused-vs-plain', same, a[1], b[1] - (1 if sumdens else 0), diff))   # (no corrector fusion with summation density)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -134,6 +136,40 @@ def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt, s
         assert errs[worst] <= 1e-11, (chunk, worst, errs[worst])
     if fixed_dt is not None:
         assert sum(r[6] for r in res if r[1] == 1) > 0, "no particle migrated: the test did not exercise the exchange"
+
+
+@pytest.mark.parametrize("world,seq", [(2, 'python'), (3, 'p2p')])
+def test_emulated_slab_run_with_summation_density(world, seq):
+    """useSummationDensity in slab mode (reference src/Tools/SolverTools.py:129-140): the density pass also runs for the
+    ghost particles, whose halo is twice as wide, so an owned particle reads the same neighbour densities as in the
+    single-rank run."""
+    import queue
+    import time
+    lib = emu_build.build()
+    emu_build.build_fake_nccl()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, lib, 40, 8, 'cubic', None, seq, q, True)) for r in range(world)]
+    [p.start() for p in procs]
+    res, t_end = [], time.time() + 400
+    while len(res) < 3 * world and time.time() < t_end:
+        try:
+            res.append(q.get(timeout=1.0))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    [p.join(30) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
+    assert len(res) == 3 * world and all(p.exitcode == 0 for p in procs)
+    for r in res:
+        if r[1] == 'fused-vs-plain':
+            assert r[5] <= 1e-12
+            continue
+        rank, chunk, errs, owned_once, status, dt_equal, moved, n = r
+        assert owned_once and status == 0 and dt_equal
+        worst = max(errs, key=errs.get)
+        assert errs[worst] <= 1e-11, (chunk, worst, errs[worst])
 
 
 def _worker_overflow(rank, world, port, lib, seq, q):

@@ -180,6 +180,33 @@ def test_reorder_cadence_does_not_change_results():
             assert field_err(o[f], outs[0][f]) <= 1e-11, f
 
 
+@pytest.mark.parametrize("precision", ['fp64', 'fp32'])
+def test_counting_sort_gives_the_order_of_the_stable_radix_sort(precision, monkeypatch):
+    """The default neighbour structure is a counting sort by cell whose in-cell order is made canonical (ascending
+    storage slot) after the atomics; OSPH_SORT=radix is the stable LSD radix sort it replaced.  Same permutation, hence
+    bit-identical results -- across a physical reorder of the state (3rd build) too."""
+    case = W.dam_break_case(60, seed=12)
+    prec = capi.FP64 if precision == 'fp64' else capi.FP32
+    outs = []
+    for mode in ('bin', 'radix', 'bin'):
+        if mode == 'radix':
+            monkeypatch.setenv("OSPH_SORT", "radix")
+        else:
+            monkeypatch.delenv("OSPH_SORT", raising=False)
+        cfg = capi.make_config(case['consts'], 'cubic', 'pec', prec, case['h'])
+        with capi.Context(cfg) as ctx:
+            ctx.upload(case['pA'])
+            ctx.step(6, None, 0.05)
+            g, cells = ctx.cells()
+            off, idx = ctx.neighbours_csr()
+            outs.append((ctx.download(case['pA'].copy()).tobytes(), cells, off, idx, ctx.dt_log()))
+            assert ctx.sync() == 0
+    for o in outs[1:]:
+        assert o[0] == outs[0][0]
+        assert np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2]) and np.array_equal(o[3], outs[0][3])
+        assert np.array_equal(o[4], outs[0][4])
+
+
 def test_fp32_mode_close_to_fp64():
     """Performance mode: float pair arithmetic on anchor-relative positions; drift bounded and reported."""
     case = W.dam_break_case(100, seed=7)
@@ -221,6 +248,38 @@ def test_deleted_rows_untouched_and_index_space():
         O.loop(P, w, og, 'wendland')
         for f in LOOP_FIELDS:
             assert field_err(out[f][~pB['deleted']], getattr(P, f)) <= TOL, f
+
+
+def test_set_active_equals_download_mark_upload():
+    """osph_set_active switches rows off (and on) on the device; the result is that of the round trip it replaces
+    (download, mark deleted, upload: reference src/Solver.py:428-442), bit for bit, and a removed row keeps its last state
+    in the record that comes back."""
+    g, meta, pA = load_golden('dambreak20_wendland')
+    gate = pA['label'] == 2
+    with _ctx(meta, keep_h=True) as a, _ctx(meta, keep_h=True) as b:
+        a.upload(pA); b.upload(pA)
+        a.step(3, None, 0.05); b.step(3, None, 0.05)
+        # old way: the whole array crosses PCIe twice
+        host = a.download(pA.copy())
+        host['deleted'][gate] = True
+        a.upload(host)
+        # new way: one byte per row
+        b.set_active(~gate)
+        assert b.num_active == a.num_active == int((~gate).sum()) and b.num_fluid == a.num_fluid
+        a.step(3, None, 0.0); b.step(3, None, 0.0)
+        ra, rb = a.download(host.copy()), b.download(pA.copy())
+        assert rb['deleted'][gate].all() and not rb['deleted'][~gate].any()
+        assert ra.tobytes() == rb.tobytes()
+        assert np.array_equal(a.dt_log()[-3:], b.dt_log()[-3:])
+        # rows come back: they resume from their records
+        b.set_active(np.ones(len(pA), dtype=bool))
+        assert b.num_active == len(pA)
+        back = b.download(pA.copy())
+        assert not back['deleted'].any()
+        for f in STATE_FIELDS:
+            assert np.array_equal(back[f][gate], host[f][gate]), f
+        with pytest.raises(capi.OsphError):
+            b.set_active(np.ones(len(pA) - 1, dtype=bool))
 
 
 def test_near_pos_matches_oracle():

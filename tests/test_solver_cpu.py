@@ -66,8 +66,9 @@ def test_solver_control_flow_matches_reference_solver(oracle_backend, monkeypatc
         assert ctx.calls.get('download_fields', 0) == s.t_step and 'export_begin' not in ctx.calls
     else:
         assert ctx.calls.get('export_begin', 0) == ctx.calls.get('export_end', 0) == s.t_step
-    # the whole array crosses the boundary only at setup, at the end of settling and at the end of the run
-    assert ctx.calls['upload'] == 2 and ctx.calls['download'] <= 4
+    # the whole array crosses the boundary only at setup and at the end of the run; the gate is removed on the device
+    # (osph_set_active: the gate's own rows and a one-byte-per-row mask)
+    assert ctx.calls['upload'] == 1 and ctx.calls['download'] <= 3 and ctx.calls['set_active'] == 1
 
 
 def test_solver_rejects_empty_and_inconsistent_particle_sets(oracle_backend):
@@ -121,8 +122,9 @@ def test_coupling_rows_only_moves_only_the_coupled_rows(oracle_backend):
         ctx = oracle_backend.instances[-1]
         assert len(seen) == s.t_step
         if rows_only:
-            assert ctx.calls['download_rows'] == ctx.calls['upload_rows'] == 3 * s.t_step
-            assert ctx.calls['upload'] == 2                       # setup + removal of the temporary boundary
+            gate = 1 if (pA['label'] == 2).any() else 0          # the removal of a temporary boundary moves its rows once more
+            assert ctx.calls['download_rows'] == ctx.calls['upload_rows'] == 3 * s.t_step + gate
+            assert ctx.calls['upload'] == 1 and ctx.calls['set_active'] == 1     # setup; gate removal on the device
         else:
             assert 'download_rows' not in ctx.calls and ctx.calls['upload'] >= 3 * s.t_step
         runs.append(s)
