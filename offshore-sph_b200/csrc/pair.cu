@@ -55,6 +55,13 @@
 #ifndef PAIR_PREFETCH_IDX
 #define PAIR_PREFETCH_IDX 1   // heavy loop: fetch the next list entry while the current pair is evaluated
 #endif
+#ifndef PAIR_SCAN2
+#define PAIR_SCAN2 0          // 1: scan on PAIRS of candidates with the packed FP32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2): the
+#endif                        // float copies of the positions are staged as (x0, x1, y0, y1) per two records, one 16-byte load and
+                              // four packed instructions test two candidates (both precisions scan on these copies then)
+#ifndef PAIR_LISTPTR
+#define PAIR_LISTPTR 0        // 1 (with PAIR_SCAN2): the candidate list is appended through a running shared-memory pointer
+#endif
 #ifndef PAIR_CAP
 #define PAIR_CAP 1024         // candidate records resident in shared memory at once
 #endif
@@ -76,7 +83,8 @@ template <typename Real, bool EXACT>
 constexpr size_t pair_smem_bytes()
 {
     return sizeof(Rec<Real, EXACT>) * PAIR_CAP + sizeof(unsigned short) * (sizeof(Real) == 8 ? PAIR_LIST64 : PAIR_LIST32) * OSPH_PAIR_THREADS +
-           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6 + ((EXACT && PAIR_SCAN_F32) ? sizeof(float2) * (PAIR_CAP + PAIR_SCAN) : 0);
+           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6 +
+           (PAIR_SCAN2 ? sizeof(float4) * ((PAIR_CAP + PAIR_SCAN + 2) / 2) : ((EXACT && PAIR_SCAN_F32) ? sizeof(float2) * (PAIR_CAP + PAIR_SCAN) : 0));
 }
 
 template <typename Real, int KID, bool EXACT>
@@ -92,9 +100,11 @@ k_pair(PairArgs a)
     RecT *sh_rec = reinterpret_cast<RecT *>(smem_raw);
     unsigned short *sh_list = reinterpret_cast<unsigned short *>(smem_raw + sizeof(RecT) * CAP);
     int(*sh_red)[6] = reinterpret_cast<int(*)[6]>(smem_raw + sizeof(RecT) * CAP + sizeof(unsigned short) * PAIR_LIST * NT);
-    constexpr bool SCANF = EXACT && PAIR_SCAN_F32;
+    constexpr bool SCAN2 = PAIR_SCAN2 != 0;
+    constexpr bool SCANF = SCAN2 || (EXACT && PAIR_SCAN_F32);
     float2 *sh_pf = reinterpret_cast<float2 *>(smem_raw + sizeof(RecT) * CAP + sizeof(unsigned short) * PAIR_LIST * NT +
                                                sizeof(int) * (NT / 32) * 6);
+    float4 *sh_pf2 = reinterpret_cast<float4 *>(sh_pf);          // SCAN2: (x0, x1, y0, y1) of records 2m and 2m + 1
 
     const Real2 *__restrict__ g_vel = reinterpret_cast<const Real2 *>(a.s_vel);
     const Real2 *__restrict__ g_rm = reinterpret_cast<const Real2 *>(a.s_rm);
@@ -113,10 +123,12 @@ k_pair(PairArgs a)
     // float scan of the double instantiation: positions relative to the CTA's first particle; every coordinate is
     // off by at most 2^-24 of the domain extent, so a radius enlarged by four such errors cannot lose a pair (a
     // candidate accepted in excess is rejected by the exact tests of the heavy body)
-    const double2 anchor_f = SCANF ? a.s_pos[s0] : make_double2(0.0, 0.0);
+    const double2 anchor_f = SCANF ? (EXACT ? a.s_pos[s0] : anchor) : make_double2(0.0, 0.0);
     float xf = 0.f, yf = 0.f, thr_f = 0.f;
     if constexpr (SCANF) {
-        const double ext = fmax(gp->xmax - gp->xmin, gp->ymax - gp->ymin);
+        // (float instantiation: the heavy body works on the same float coordinates; the margin only has to cover the
+        // different rounding order of the packed instructions, and pair_r2 itself exceeds the largest support by 2e-6)
+        const double ext = EXACT ? fmax(gp->xmax - gp->xmin, gp->ymax - gp->ymin) : 0.0;
         const double rad = sqrt(gp->pair_r2) + 4.0 * 5.97e-8 * ext;
         thr_f = __double2float_ru(rad * rad * (1.0 + 1e-6));
     }
@@ -192,7 +204,10 @@ k_pair(PairArgs a)
         RecT rec;
         double2 p = a.s_pos[g];
         rec.pos.x = (Real)(p.x - anchor.x); rec.pos.y = (Real)(p.y - anchor.y);
-        if constexpr (SCANF) sh_pf[dst] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
+        if constexpr (SCAN2) {
+            float *q = reinterpret_cast<float *>(sh_pf2 + (dst >> 1)) + (dst & 1);
+            q[0] = (float)(p.x - anchor_f.x); q[2] = (float)(p.y - anchor_f.y);
+        } else if constexpr (SCANF) sh_pf[dst] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
         rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
         rec.rm.x *= Real(0.5); rec.hp.x *= Real(0.5);       // staged as rho_j / 2 and h_j / 2: the pair means are one add
         if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
@@ -313,11 +328,26 @@ k_pair(PairArgs a)
     // The list is addressed by its write index li = (entries so far) * NT + tid: an append is one store and one add
     // (a separate entry count costs a multiply-add per append), the count is li / NT.
     int li = tid, slot = -1;
+#if PAIR_LISTPTR && PAIR_SCAN2
+    // the list is appended through a running 32-bit shared-window address: one store and one add per entry (written as
+    // sh_list[li] the compiler forms base + 2 * li for every store; through a generic pointer it adds in 64 bits)
+    const unsigned int la0 = (unsigned int)__cvta_generic_to_shared(sh_list + tid);
+    unsigned int la = la0;
+#define LIST_COUNT() ((int)((la - la0) / (2u * NT)))
+#define LIST_RESET() (la = la0)
+#define LIST_APPEND(v) do { sts_u16(la, (unsigned short)(v)); la += 2u * NT; } while (0)
+#define LIST_NEARLY_FULL() (la >= la0 + 2u * (PAIR_LIST - PAIR_SCAN + 1) * NT)
+#else
+#define LIST_COUNT() (li / NT)
+#define LIST_RESET() (li = tid)
+#define LIST_APPEND(v) do { sh_list[li] = (unsigned short)(v); li += NT; } while (0)
+#define LIST_NEARLY_FULL() (li >= (PAIR_LIST - PAIR_SCAN + 1) * NT)
+#endif
     double vx_st = 0.0, vy_st = 0.0;
     bool have_v = false;
     auto flush = [&]() {
 #if PAIR_PREFETCH_IDX
-        const int nl = li / NT;
+        const int nl = LIST_COUNT();
         int jn = nl > 0 ? (int)sh_list[tid] : 0;
 #pragma unroll 1
         for (int k = 0; k < nl;) {
@@ -327,12 +357,50 @@ k_pair(PairArgs a)
             interact(j);
         }
 #else
-        const int nl = li / NT;
+        const int nl = LIST_COUNT();
 #pragma unroll 1
         for (int k = 0; k < nl; k++) interact((int)sh_list[k * NT + tid]);
 #endif
-        li = tid;
+        LIST_RESET();
     };
+#if PAIR_SCAN2
+    // Packed scan.  Candidates are tested two at a time: record pair m = (2m, 2m + 1) is one float4 (x0, x1, y0, y1), and
+    //   d = (xi, xi) - (x0, x1);  e = (yi, yi) - (y0, y1);  r2 = d * d;  r2 = e * e + r2
+    // are four FADD2 / FMUL2 / FFMA2 instructions.  A run [j0, j1) may start and end inside a pair: membership of a record in
+    // the run is one unsigned compare (idx - j0 < j1 - j0).  Three pairs per round.
+    const unsigned long long XF2 = pack_f32x2(xf, xf), YF2 = pack_f32x2(yf, yf);
+    auto scan = [&](auto skip_tag, int j0, int j1, const int self) {          // all 32 lanes of a warp call this together
+        constexpr bool SKIP = PAIR_LEAN && decltype(skip_tag)::value;
+        constexpr int NP = PAIR_SCAN / 2;
+        int m = j0 >> 1;
+        unsigned int len = (unsigned int)(j1 - j0);
+        bool warp_more = __any_sync(0xffffffffu, j0 < j1);
+#pragma unroll 1
+        while (warp_more) {
+            unsigned long long d2[NP];
+#pragma unroll
+            for (int u = 0; u < NP; u++) {
+                const float4 pq = sh_pf2[m + u];
+                const unsigned long long dx = sub_f32x2(XF2, pack_f32x2(pq.x, pq.y)), dy = sub_f32x2(YF2, pack_f32x2(pq.z, pq.w));
+                d2[u] = fma_f32x2(dy, dy, mul_f32x2(dx, dx));
+            }
+            const int rel = 2 * m - j0;
+#pragma unroll
+            for (int u = 0; u < NP; u++) {
+                float r0v, r1v;
+                unpack_f32x2(d2[u], r0v, r1v);
+                const int i0 = 2 * (m + u), i1 = i0 + 1;
+                if ((unsigned int)(rel + 2 * u) < len && r0v <= thr_f && (!SKIP || i0 != self)) LIST_APPEND(i0);
+                if ((unsigned int)(rel + 2 * u + 1) < len && r1v <= thr_f && (!SKIP || i1 != self)) LIST_APPEND(i1);
+            }
+            m += NP;
+            // a lane whose run is exhausted parks at pair 0 with an empty run (see the scalar scan below)
+            if (2 * m >= j1) { m = 0; j0 = 0; j1 = 0; len = 0; }
+            if (__any_sync(0xffffffffu, LIST_NEARLY_FULL())) flush();
+            warp_more = __any_sync(0xffffffffu, 2 * m < j1);
+        }
+    };
+#else
     // skip_tag (PAIR_LEAN only): the run holds the thread's own record at index `self`; it is not listed
     auto scan = [&](auto skip_tag, int j, int j1, const int self) {          // all 32 lanes of a warp call this together
         constexpr bool SKIP = PAIR_LEAN && decltype(skip_tag)::value;
@@ -388,6 +456,8 @@ k_pair(PairArgs a)
             warp_more = __any_sync(0xffffffffu, j < j1);
         }
     };
+
+#endif
 
     if (len0 + len1 + len2 <= CAP) {
         // common case: the three runs of the CTA fit in shared memory together; one staging pass, the

@@ -63,6 +63,43 @@ __device__ __forceinline__ float exp_neg(float x) { return __expf(-x); }
 __device__ __forceinline__ double pow_gen(double a, double b) { return pow(a, b); }
 __device__ __forceinline__ float pow_gen(float a, float b) { return __powf(a, b); }
 
+// ---- packed single precision (sm_100: two FP32 operations per instruction, FADD2 / FMUL2 / FFMA2) ----------------
+// A pair of floats travels as one 64-bit register pair (lo = first element).
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub_f32x2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// 16-bit store through a 32-bit shared-window address (__cvta_generic_to_shared)
+__device__ __forceinline__ void sts_u16(unsigned int addr, unsigned short v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" : : "r"(addr), "h"(v) : "memory");
+}
+
 // ---- smoothing kernels: value w and gradient factor g with  grad W = g * (dx, dy) ---------------------
 // reference: CubicSpline.py:10-70, Wendland.py:9-64, Gaussian.py:16-59.  inv_r == 0 encodes r < 1e-10
 // (the reference zeroes the gradient there).

@@ -266,17 +266,19 @@ static void run_block(dim3 grid, dim3 block, uint3 bid)
     running = nullptr; cur = nullptr;
 }
 
-// Guarded storage: [PROT_NONE page][bytes rounded up to pages][PROT_NONE page]; the caller places its object at the END of
-// the accessible part, so the first byte past the object is already inaccessible.
+// Guarded storage: [PROT_NONE region][bytes rounded up to pages][PROT_NONE region]; the caller places its object at the END
+// of the accessible part, so the first byte past the object is already inaccessible.  The inaccessible regions are 16 MiB
+// wide: shared memory is indexed with up to 16 bits times a record size, so a wild index lands megabytes -- not bytes --
+// past the end (the overrun of round 1 read 43 KB past it, far beyond a single guard page).
+static const size_t GUARD_BYTES = 16u << 20;
 static unsigned char *guarded_pages(size_t bytes, size_t *usable)
 {
     const size_t page = 4096, body = (bytes + page - 1) / page * page;
-    unsigned char *m = (unsigned char *)mmap(nullptr, body + 2 * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    unsigned char *m = (unsigned char *)mmap(nullptr, body + 2 * GUARD_BYTES, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (m == MAP_FAILED) { perror("emu: mmap"); abort(); }
-    mprotect(m, page, PROT_NONE);
-    mprotect(m + page + body, page, PROT_NONE);
+    if (mprotect(m + GUARD_BYTES, body, PROT_READ | PROT_WRITE) != 0) { perror("emu: mprotect"); abort(); }
     *usable = body;
-    return m + page;
+    return m + GUARD_BYTES;
 }
 static const size_t DYN_ARENA = 256 * 1024;       // more than the 227 KB a CTA can have
 static unsigned char *dyn_arena()

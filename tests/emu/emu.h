@@ -54,6 +54,7 @@ struct ThreadCtx {
 extern ThreadCtx *cur;
 extern unsigned char *dyn_smem_ptr;
 inline void *dyn_smem() { return dyn_smem_ptr; }
+inline size_t shared_offset(const void *p) { return (size_t)((const unsigned char *)p - dyn_smem_ptr); }   // __cvta_generic_to_shared
 void *static_smem_alloc(size_t bytes, size_t align);
 template <typename T> inline T *static_smem() { return (T *)static_smem_alloc(sizeof(T), alignof(T)); }
 
@@ -70,6 +71,20 @@ enum Op { OP_SHFL_IDX, OP_SHFL_XOR, OP_SHFL_UP, OP_SHFL_DOWN, OP_BALLOT, OP_MATC
 void block_barrier();
 uint64_t warp_collective(Op op, unsigned mask, uint64_t value, int param, int width);
 
+// packed FP32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): element-wise IEEE single precision, lo element first
+inline uint64_t f32x2_pack(float lo, float hi) { uint32_t a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (uint64_t)a | ((uint64_t)b << 32); }
+inline void f32x2_unpack(uint64_t v, float &lo, float &hi) { uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32); memcpy(&lo, &a, 4); memcpy(&hi, &b, 4); }
+#define EMU_F32X2(name, expr_lo, expr_hi)                                                         \
+    inline uint64_t name(uint64_t x, uint64_t y, uint64_t z = 0)                                  \
+    {                                                                                             \
+        float x0, x1, y0, y1, z0, z1; f32x2_unpack(x, x0, x1); f32x2_unpack(y, y0, y1); f32x2_unpack(z, z0, z1); \
+        (void)z0; (void)z1;                                                                       \
+        return f32x2_pack(expr_lo, expr_hi);                                                      \
+    }
+EMU_F32X2(f32x2_sub, x0 - y0, x1 - y1)
+EMU_F32X2(f32x2_mul, x0 * y0, x1 * y1)
+EMU_F32X2(f32x2_fma, std::fmaf(x0, y0, z0), std::fmaf(x1, y1, z1))
+#undef EMU_F32X2
 double rcp_approx_f64(double x);
 double rsqrt_approx_f64(double x);
 

@@ -113,8 +113,25 @@ def rewrite_static_shared(src):
     return _STATIC_SHARED.sub(repl, src)
 
 
+# packed FP32 pairs of sm_100 (sph_math.cuh): a 64-bit value holding two floats, lo first
+_ASM_PACK = re.compile(r'asm\("mov\.b64 %0, \{%1, %2\};"\s*:\s*"=l"\((\w+)\)\s*:\s*"f"\((\w+)\),\s*"f"\((\w+)\)\);')
+_ASM_UNPACK = re.compile(r'asm\("mov\.b64 \{%0, %1\}, %2;"\s*:\s*"=f"\((\w+)\),\s*"=f"\((\w+)\)\s*:\s*"l"\((\w+)\)\);')
+_ASM_F32X2_2 = re.compile(r'asm\("(sub|mul)\.rn\.f32x2 %0, %1, %2;"\s*:\s*"=l"\((\w+)\)\s*:\s*"l"\((\w+)\),\s*"l"\((\w+)\)\);')
+_ASM_F32X2_3 = re.compile(r'asm\("fma\.rn\.f32x2 %0, %1, %2, %3;"\s*:\s*"=l"\((\w+)\)\s*:\s*"l"\((\w+)\),\s*"l"\((\w+)\),\s*"l"\((\w+)\)\);')
+
+
+_ASM_STS16 = re.compile(r'asm volatile\("st\.shared\.u16 \[%0\], %1;"\s*:\s*:\s*"r"\((\w+)\),\s*"h"\((\w+)\)\s*:\s*"memory"\);')
+
+
 def transform(src):
     src = rewrite_launches(src)
+    # shared-window addresses: offsets into the launch's dynamic shared memory
+    src = src.replace("__cvta_generic_to_shared(", "emu::shared_offset(")
+    src = _ASM_STS16.sub(lambda m: "*reinterpret_cast<unsigned short *>(emu::dyn_smem_ptr + %s) = %s;" % (m.group(1), m.group(2)), src)
+    src = _ASM_PACK.sub(lambda m: "%s = emu::f32x2_pack(%s, %s);" % m.groups(), src)
+    src = _ASM_UNPACK.sub(lambda m: "emu::f32x2_unpack(%s, %s, %s);" % (m.group(3), m.group(1), m.group(2)), src)
+    src = _ASM_F32X2_2.sub(lambda m: "%s = emu::f32x2_%s(%s, %s);" % (m.group(2), m.group(1), m.group(3), m.group(4)), src)
+    src = _ASM_F32X2_3.sub(lambda m: "%s = emu::f32x2_fma(%s, %s, %s);" % m.groups(), src)
     src = rewrite_static_shared(src)
     src = _EXTERN_SHARED.sub(lambda m: "%s *%s = (%s *)emu::dyn_smem();" % (m.group(1), m.group(2), m.group(1)), src)
     src = _ASM_RCP.sub(lambda m: "%s = emu::rcp_approx_f64(%s);" % (m.group(1), m.group(2)), src)

@@ -98,6 +98,54 @@ def test_pair_kernel_single_body_variant():
         capi.LIB_PATH, capi._lib = saved
 
 
+@pytest.mark.parametrize("precision", ['fp64', 'fp32'])
+def test_bench_workload_one_step_under_the_guarded_emulator(precision):
+    """BASELINE configs[1] itself (dam break N = 1000, 1 009 603 particles: the workload bench.py runs): one whole step of
+    the default build under the emulator, whose shared memory and device allocations end at inaccessible pages.  Round 1
+    shipped a pair kernel that overran its shared memory only at this size (the wall-row CTAs take the batched staging
+    path); this run would have died with SIGSEGV.  The oracle is compared on a strided sample by the GPU test
+    tests/test_gpu_fullsize.py; here the step must complete, stay finite and report a clean status."""
+    import numpy as np
+    from osph_b200 import capi
+    from osph_b200 import workloads as W
+    case = W.dam_break_case(1000, seed=0)
+    cfg = capi.make_config(case['consts'], 'cubic', 'pec', capi.FP64 if precision == 'fp64' else capi.FP32, case['h'])
+    with capi.Context(cfg) as ctx:
+        ctx.upload(case['pA'])
+        ctx.step(1, None, 0.05)
+        cols = ctx.download_fields(['ax', 'ay', 'drho', 'rho', 'x'])
+        assert ctx.sync() == 0
+    fluid = case['pA']['label'] == 0
+    for f, c in cols.items():
+        assert np.all(np.isfinite(c)), f
+    assert np.abs(cols['ax'][fluid]).max() > 0 and np.abs(cols['drho'][fluid]).max() > 0
+
+
+def test_pair_kernel_packed_scan_variant():
+    """-DPAIR_SCAN2=1: the scan phase tests two candidates per packed FP32 instruction (FADD2 / FMUL2 / FFMA2 of sm_100,
+    modelled element-wise here) on positions staged as (x0, x1, y0, y1); runs start and end inside a pair, both precisions
+    scan on the float copies.  Same parity bar, including the batched staging path (PAIR_CAP=96)."""
+    from osph_b200 import capi
+    for defs, tag in ((("PAIR_SCAN2=1", "PAIR_LISTPTR=1"), "_scan2"), (("PAIR_SCAN2=1", "PAIR_LISTPTR=1", "PAIR_CAP=96"), "_scan2cap96"),
+                      (("PAIR_SCAN2=1", "PAIR_LISTPTR=0", "PAIR_SCAN=8"), "_scan2w8")):
+        path = emu_build.build(defines=defs, tag=tag)
+        saved = (capi.LIB_PATH, capi._lib)
+        capi.LIB_PATH, capi._lib = path, None
+        try:
+            for name in _parity.STEP_CASES:
+                _parity.test_cells_and_neighbour_sets_bit_exact(name)
+                _parity.test_whole_steps_vs_golden(name)
+            _parity.test_dam_break_vs_oracle(60, 'wendland')
+            _parity.test_dam_break_vs_oracle(150, 'cubic')
+            _parity.test_dam_break_vs_oracle(150, 'gaussian')
+            _parity.test_fp32_mode_close_to_fp64()
+            _edges.test_coincident_particles_follow_the_reference_guards()
+            _edges.test_cluster_denser_than_the_candidate_list()
+            _edges.test_domain_far_from_the_origin()
+        finally:
+            capi.LIB_PATH, capi._lib = saved
+
+
 @pytest.mark.parametrize("mode,seed", [(1, 0), (2, 5)])
 def test_results_do_not_depend_on_the_schedule(mode, seed):
     """The same parity tests with the emulator resuming the threads of a CTA (and running the CTAs of a launch) in reverse

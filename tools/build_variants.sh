@@ -11,13 +11,14 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 while [ $# -ge 2 ]; do
   name=$1; defs=$2; shift 2
   tmp=$(mktemp -d)
-  for f in api step sort leaf scan slab slab_nccl slab_p2p export; do
+  for f in $(ls *.cu | sed 's/\.cu$//' | grep -v '^pair$'); do
     nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC $defs -c $f.cu -o $tmp/$f.o &
   done
   nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC --use_fast_math $defs -Xptxas -v -c pair.cu -o $tmp/pair.o 2> $tmp/pair.log
   wait
   grep -A2 "k_pairIdLi0ELb1\|k_pairIfLi0ELb0" $tmp/pair.log | grep "Used\|spill" | sed "s/^/[$name] /"
   nvcc -shared $ARCH -o ../lib/variants/lib_$name.so $tmp/*.o -lcudart -ldl
+  python -c "import ctypes,sys; ctypes.CDLL(sys.argv[1])" ../lib/variants/lib_$name.so      # every symbol resolves
   rm -rf $tmp
   echo "built lib/variants/lib_$name.so ($defs)"
 done
