@@ -202,6 +202,14 @@ int osph_step(osph_ctx *ctx, int32_t nsteps, double fixed_dt, double damping);
 int osph_get_dt_log(osph_ctx *ctx, double *out, int64_t cap, int64_t *count);
 /* replaces: KineticEnergy(J, pA[f_indexes])  src/Equations/KineticEnergy.py:6-12 (sum over the fluid rows) */
 int osph_kinetic_energy(osph_ctx *ctx, double *ke);
+/*
+ * Sort cadence: out[0] = neighbour-structure builds since osph_create, out[1] = those that binned and sorted the particles.
+ * The others reused the sorted order and cell table of the last sort: cells are one pair radius plus a skin wide, and the
+ * device re-sorts as soon as (pair radius + 2 x largest displacement since the sort) exceeds the cell size, so the 3 x 3
+ * cell walk stays a complete candidate set; membership is always decided on the CURRENT positions.  Environment:
+ * OSPH_SKIN = skin / pair radius ("auto" default, 0 = sort at every build).  Slab mode sorts at every build.
+ */
+int osph_sort_stats(osph_ctx *ctx, int64_t out[2]);
 /* Block until all enqueued work is done; *status receives the OSPH_S_* bits accumulated since the last call. */
 int osph_sync(osph_ctx *ctx, uint32_t *status);
 

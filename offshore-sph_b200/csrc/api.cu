@@ -43,7 +43,8 @@ static void free_particles(osph_ctx *ctx)
 {
     cudaFree(ctx->d_aos); cudaFree(ctx->d_row); cudaFree(ctx->d_act);
     for (int k = 0; k < OSPH_NUM_FIELDS; k++) { cudaFree(ctx->f[k]); ctx->f[k] = nullptr; }
-    cudaFree(ctx->label); cudaFree(ctx->scratch); cudaFree(ctx->d_stage);
+    cudaFree(ctx->label); cudaFree(ctx->scratch); cudaFree(ctx->d_stage); cudaFree(ctx->xref); cudaFree(ctx->yref);
+    ctx->xref = ctx->yref = nullptr;
     cudaFree(ctx->s_coarse); cudaFree(ctx->s_gcell); cudaFree(ctx->s_pos); cudaFree(ctx->s_vel);
     cudaFree(ctx->s_rm); cudaFree(ctx->s_hp); cudaFree(ctx->s_info);
     cudaFree(ctx->d_partial);
@@ -69,6 +70,9 @@ static int alloc_particles(osph_ctx *ctx, int64_t n_active, int64_t n_total, int
     OSPH_CUDA(cudaMalloc(&ctx->label, cap));
     OSPH_CUDA(cudaMalloc(&ctx->scratch, sizeof(double) * cap));
     OSPH_CUDA(cudaMalloc(&ctx->d_stage, sizeof(double) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->xref, sizeof(double) * cap));
+    OSPH_CUDA(cudaMalloc(&ctx->yref, sizeof(double) * cap));
+    ctx->skin_valid = false;
     OSPH_CUDA(cudaMalloc(&ctx->s_coarse, sizeof(int4) * cap));
     OSPH_CUDA(cudaMalloc(&ctx->s_gcell, sizeof(int2) * cap));
     OSPH_CUDA(cudaMalloc(&ctx->s_pos, sizeof(double2) * cap));
@@ -129,6 +133,11 @@ extern "C" int osph_create(const osph_config *cfg, osph_ctx **out)
     {   // OSPH_SORT=radix: the LSD radix sort of sort.cu instead of the counting sort by cell (same order, A/B runs)
         const char *e = getenv("OSPH_SORT");
         ctx->bin_sort = !(e && std::string(e) == "radix");
+        // OSPH_SKIN: skin of the sort cadence as a fraction of the pair radius (e.g. 0.1); "auto" / unset = sized on the
+        // device from the observed displacement per build; 0 = sort at every build (the behaviour before the cadence)
+        const char *k = getenv("OSPH_SKIN");
+        ctx->skin_frac = (k && *k && std::string(k) != "auto") ? atof(k) : -1.0;
+        if (ctx->skin_frac > 1.0) ctx->skin_frac = 1.0;
     }
     auto fail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
@@ -139,6 +148,7 @@ extern "C" int osph_create(const osph_config *cfg, osph_ctx **out)
     for (int k = 0; k < 2 * OSPH_PAIR_EVENTS; k++)
         if ((e = cudaEventCreate(&ctx->pair_ev[k])) != cudaSuccess) return fail("cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_grid, sizeof(GridParams))) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = cudaMemset(ctx->d_grid, 0, sizeof(GridParams))) != cudaSuccess) return fail("cudaMemset", e);
     if ((e = cudaMalloc(&ctx->d_sc, sizeof(StepScalars))) != cudaSuccess) return fail("cudaMalloc", e);
     ctx->dt_log_cap = 1 << 16;
     if ((e = cudaMalloc(&ctx->d_dt_log, sizeof(double) * 3 * ctx->dt_log_cap)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -194,6 +204,7 @@ static int rebuild_active(osph_ctx *ctx)
     if (ctx->n > 0 && (rc = osph_launch_unpack(ctx))) return rc;
     ctx->c_uniform = false; ctx->build_counter = 0; ctx->n_ghost = 0; ctx->slab = false;
     ctx->slab_fused = 0; ctx->slab_defer = false; ctx->slab_last = true;
+    ctx->skin_valid = false;
     invalidate_state(ctx);
     return 0;
 }
@@ -309,6 +320,7 @@ extern "C" int osph_upload_fields(osph_ctx *ctx, int32_t nfields, const int32_t 
         if (rc) return rc;
         OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    ctx->skin_valid = false;            // positions may have been replaced: the next build sorts
     invalidate_state(ctx);
     return 0;
 }
@@ -322,6 +334,7 @@ extern "C" int osph_initialize(osph_ctx *ctx)
     int rc = osph_launch_setup(ctx);
     if (rc) return rc;
     if (ctx->c_uniform) ctx->c_uniform = false;     // c now holds per-row values again (non-fluid rows keep theirs)
+    ctx->skin_valid = false;
     invalidate_state(ctx);
     return 0;
 }
@@ -334,7 +347,8 @@ int osph_size_cell_table(osph_ctx *ctx)
     if (ctx->sized) return 0;
     int64_t saved = ctx->cell_cap;
     ctx->cell_cap = (int64_t)1 << OSPH_MAX_CELL_BITS;         // "unlimited" for the sizing pass
-    int rc = osph_launch_grid_params(ctx);
+    ctx->skin_valid = false;                                  // the pass overwrites the grid parameters: the build that follows sorts
+    int rc = osph_launch_grid_params(ctx, false, 3);
     ctx->cell_cap = saved;
     if (rc) return rc;
     GridParams g;
@@ -502,6 +516,17 @@ extern "C" int osph_kinetic_energy(osph_ctx *ctx, double *ke)
     OSPH_CUDA(cudaMemcpyAsync(&sc, ctx->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
     OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
     *ke = sc.ke;
+    return 0;
+}
+
+extern "C" int osph_sort_stats(osph_ctx *ctx, int64_t out[2])
+{
+    CHECK_CTX();
+    if (!out) return OSPH_E_INVALID;
+    StepScalars sc;
+    OSPH_CUDA(cudaMemcpyAsync(&sc, ctx->d_sc, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+    OSPH_CUDA(cudaStreamSynchronize(ctx->stream));
+    out[0] = sc.builds; out[1] = sc.sorts;
     return 0;
 }
 

@@ -27,11 +27,15 @@ static_assert(BIN_TILE == BIN_THREADS * BIN_ITEMS, "scan tile = one CTA");
 // Exclusive scan of the cell counts = the cell table.  The totals of the scan tiles (BIN_TILE cells each) were accumulated
 // by k_bin_keys next to the counts, so a CTA sums the totals of the tiles before its own and scans its tile: no look-back,
 // no spinning on other CTAs (a single-pass scan with tile tickets and a look-back spent 14-16 us waiting, measured).
-// tile_sums is double-buffered by build parity: this kernel clears the buffer of the NEXT build.
+// tile_sums is double-buffered by the parity of the sort count: this kernel clears the buffer of the NEXT sort.
 __global__ void __launch_bounds__(BIN_THREADS)
 k_bin_scan(unsigned int *__restrict__ counts, const GridParams *__restrict__ gp, int2 *__restrict__ cell_range,
-           const unsigned int *__restrict__ tile_sums, unsigned int *__restrict__ tile_sums_next, int n_tiles)
+           unsigned int *__restrict__ tile_sums_base, int n_tiles)
 {
+    if (!gp->do_sort) return;                             // this build reuses the binning of the last sort (k_grid_params)
+    const unsigned int parity = gp->sort_count & 1u;
+    const unsigned int *__restrict__ tile_sums = tile_sums_base + (size_t)parity * n_tiles;
+    unsigned int *__restrict__ tile_sums_next = tile_sums_base + (size_t)(parity ^ 1u) * n_tiles;
     __shared__ unsigned int wsum[BIN_THREADS / 32];
     __shared__ unsigned int s_prefix;
     const unsigned int tile = blockIdx.x;
@@ -101,10 +105,11 @@ k_bin_scan(unsigned int *__restrict__ counts, const GridParams *__restrict__ gp,
 // ranking that follows (fused into the gather kernel, or k_bin_rank) then starts without a dependent table lookup.
 __global__ void __launch_bounds__(256)
 k_bin_scatter(const unsigned int *__restrict__ key, const unsigned int *__restrict__ arrival, int n,
-              const int2 *__restrict__ cell_range, int2 *__restrict__ range_out, unsigned int *__restrict__ idx_out)
+              const int2 *__restrict__ cell_range, int2 *__restrict__ range_out, unsigned int *__restrict__ idx_out,
+              const GridParams *__restrict__ gp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || !gp->do_sort) return;
     const int2 r = cell_range[key[i]];
     const unsigned int pos = (unsigned int)r.x + arrival[i];
     range_out[pos] = r;
@@ -115,10 +120,10 @@ k_bin_scatter(const unsigned int *__restrict__ key, const unsigned int *__restri
 // permutation before the gather); every other build ranks inside k_gather.
 __global__ void __launch_bounds__(256)
 k_bin_rank(const int2 *__restrict__ range_sorted, const unsigned int *__restrict__ idx_arrival, int n,
-           unsigned int *__restrict__ idx_out, StepScalars *sc)
+           unsigned int *__restrict__ idx_out, StepScalars *sc, const GridParams *__restrict__ gp)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= n || !gp->do_sort) return;
     const int2 r = range_sorted[s];
     const unsigned int mine = idx_arrival[s];
     idx_out[bin_canonical_slot(r, s, mine, idx_arrival, sc)] = mine;
@@ -132,7 +137,7 @@ int osph_bin_alloc(osph_ctx *ctx, int64_t cell_cap)
     OSPH_CUDA(cudaMalloc(&ctx->bin_tiles, sizeof(unsigned int) * (size_t)(2 * tiles)));      // two buffers, by build parity
     OSPH_CUDA(cudaMemsetAsync(ctx->bin_counts, 0, sizeof(unsigned int) * (size_t)(cell_cap + 1), ctx->stream));
     OSPH_CUDA(cudaMemsetAsync(ctx->bin_tiles, 0, sizeof(unsigned int) * (size_t)(2 * tiles), ctx->stream));
-    ctx->bin_tile_cap = tiles; ctx->bin_parity = 0;
+    ctx->bin_tile_cap = tiles;
     return 0;
 }
 
@@ -150,16 +155,14 @@ int osph_bin_sort(osph_ctx *ctx, int64_t n_all, bool rank_now)
 {
     if (n_all <= 0) return 0;
     const int tiles = (int)ctx->bin_tile_cap;
-    unsigned int *sums = osph_bin_tile_sums(ctx), *sums_next = ctx->bin_tiles + (size_t)(ctx->bin_parity ^ 1) * ctx->bin_tile_cap;
-    k_bin_scan<<<tiles, BIN_THREADS, 0, ctx->stream>>>(ctx->bin_counts, ctx->d_grid, ctx->cell_range, sums, sums_next, tiles);
+    k_bin_scan<<<tiles, BIN_THREADS, 0, ctx->stream>>>(ctx->bin_counts, ctx->d_grid, ctx->cell_range, ctx->bin_tiles, tiles);
     OSPH_LAUNCH_CHECK();
-    ctx->bin_parity ^= 1;
     const int grid = div_up(n_all, 256);
     int2 *ranges = reinterpret_cast<int2 *>(ctx->scratch);
-    k_bin_scatter<<<grid, 256, 0, ctx->stream>>>(ctx->key[0], ctx->idx[0], (int)n_all, ctx->cell_range, ranges, ctx->idx[1]);
+    k_bin_scatter<<<grid, 256, 0, ctx->stream>>>(ctx->key[0], ctx->idx[0], (int)n_all, ctx->cell_range, ranges, ctx->idx[1], ctx->d_grid);
     OSPH_LAUNCH_CHECK();
     if (rank_now) {
-        k_bin_rank<<<grid, 256, 0, ctx->stream>>>(ranges, ctx->idx[1], (int)n_all, ctx->idx[0], ctx->d_sc);
+        k_bin_rank<<<grid, 256, 0, ctx->stream>>>(ranges, ctx->idx[1], (int)n_all, ctx->idx[0], ctx->d_sc, ctx->d_grid);
         OSPH_LAUNCH_CHECK();
     }
     ctx->sorted_buf = 0;

@@ -34,6 +34,17 @@ struct GridParams {
     int reach_set;         // cells to walk per side to cover q <= 3 (neighbour-set emitter)
     double hmax;           // max h over active particles after the refresh
     double pair_r2;        // square of the radius inside which a pair can contribute
+    // Sort cadence (regime B, single GPU): the acceleration grid is frozen at the last sort -- origin (gox, goy), cell size
+    // gsize = pair radius + skin -- and the sorted order and the cell table are reused while
+    //     pair radius now + 2 x (largest displacement of a particle since that sort) <= gsize,
+    // i.e. while two particles within the pair radius are still guaranteed to sit in adjacent cells OF THE BINNING.
+    // k_grid_params decides per build (do_sort); the sort kernels exit at once when it is 0.
+    double gox, goy;       // origin of the acceleration grid (regime A: the reference origin)
+    double disp;           // largest displacement since the last sort (0 on a sorting build)
+    int do_sort;           // this build bins and sorts
+    unsigned int sort_count;   // sorts so far (parity selects the tile-total buffer of the counting sort)
+    int steps_since_sort;
+    int reserved_i;
 };
 
 // Ghost records live in up to three segments of the ghost buffer (slab mode): the rank's own migrants, the halo
@@ -56,6 +67,8 @@ struct StepScalars {
     double ke;
     long long dt_log_count;
     double dt_prev;                              // dt of the step before (fused corrector + predictor, step.cu)
+    unsigned long long disp2max;                 // max |x - x_ref|^2 over the particles, x_ref = position at the last sort (k_prepare)
+    long long builds, sorts;                     // neighbour-structure builds / those that sorted (osph_sort_stats)
 };
 
 struct osph_export_ring;          // export.cu
@@ -97,12 +110,15 @@ struct osph_ctx {
     // cell table of the acceleration grid: (begin, end) per cell
     int2 *cell_range = nullptr;
     int64_t cell_cap = 0;
+    // sort cadence: positions at the last sort (storage order) and whether they describe the resident particles
+    double *xref = nullptr, *yref = nullptr;
+    bool skin_valid = false;          // false: the next build must sort (upload, external edits, slab mode, table re-sized)
+    double skin_frac = -1.0;          // OSPH_SKIN: skin as a fraction of the pair radius; < 0 adaptive; 0 sorts every build
     // counting sort by cell (binsort.cu): cell histogram, tile states of its single-pass scan (+ the ticket counter)
     bool bin_sort = true;             // false (OSPH_SORT=radix): LSD radix sort of sort.cu
     unsigned int *bin_counts = nullptr;
     unsigned int *bin_tiles = nullptr;   // totals of the scan tiles (BIN_TILE cells each), two buffers used alternately
     int64_t bin_tile_cap = 0;
-    int bin_parity = 0;
 
     // per-particle cell info in sorted order
     int4 *s_coarse = nullptr;        // reference grid: (bin_cx, bin_cy, query_cx, query_cy); bin_cx < 0: unbinned
@@ -257,7 +273,7 @@ __device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xff
 int osph_bin_alloc(osph_ctx *ctx, int64_t cell_cap);                              // binsort.cu
 void osph_bin_free(osph_ctx *ctx);
 int osph_bin_sort(osph_ctx *ctx, int64_t n_all, bool rank_now);
-inline unsigned int *osph_bin_tile_sums(osph_ctx *ctx) { return ctx->bin_tiles + (size_t)ctx->bin_parity * ctx->bin_tile_cap; }
+
 int osph_sort_pairs(osph_ctx *ctx, int64_t n, int bits, bool first_hist_done);   // sort.cu: key[sorted_buf], idx[sorted_buf]
 int osph_sort_alloc(osph_ctx *ctx, int64_t cap);
 void osph_sort_free(osph_ctx *ctx);

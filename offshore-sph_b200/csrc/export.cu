@@ -270,6 +270,7 @@ extern "C" int osph_upload_rows(osph_ctx *ctx, int64_t nrows, const int64_t *row
     OSPH_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     OSPH_CUDA(cudaStreamSynchronize(ctx->stream));                 // `host` goes out of scope
     ctx->prepared = false; ctx->neighbours_valid = false; ctx->reductions_valid = false;
+    ctx->skin_valid = false;            // rows were replaced from outside: the next build sorts
     if (bad) { ctx->err = "osph_upload_rows: a row is not active (deleted); the other rows were written"; return OSPH_E_INVALID; }
     return 0;
 }

@@ -15,6 +15,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <vector>
 
@@ -50,6 +51,11 @@ struct osph_slab_p2p {
     size_t win_doubles = 0;
     double *d_meta = nullptr, *d_all_meta = nullptr, *d_dt3 = nullptr, *d_all_dt = nullptr, *h_all_meta = nullptr;
     unsigned long long seq = 0;
+    // OSPH_SLAB_PROFILE=1: CUDA events between the phases of a step (GPU timeline incl. idle gaps), summed per phase
+    bool profile = false;
+    cudaEvent_t pev[8] = {nullptr};
+    double pms[7] = {0, 0, 0, 0, 0, 0, 0}, phost_ms = 0;
+    long long psteps = 0;
     long long spin_limit = 0;                      // clock64 ticks a mailbox waits for one peer before it gives up
     bool aborted = false;
     int64_t last_counts[8] = {0};
@@ -147,6 +153,11 @@ extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x
     OSPH_CUDA(cudaMalloc(&s->d_dt3, sizeof(double) * 4));
     OSPH_CUDA(cudaMalloc(&s->d_all_dt, sizeof(double) * 4 * (world + 1)));
     OSPH_CUDA(cudaMallocHost(&s->h_all_meta, sizeof(double) * (12 * world + 1)));
+    {
+        const char *e = getenv("OSPH_SLAB_PROFILE");
+        s->profile = e && e[0] == '1';
+        if (s->profile) for (int k = 0; k < 8; k++) OSPH_CUDA(cudaEventCreate(&s->pev[k]));
+    }
     cudaIpcMemHandle_t h;
     OSPH_CUDA(cudaIpcGetMemHandle(&h, s->win));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -182,6 +193,15 @@ extern "C" int osph_slab_p2p_destroy(osph_ctx *ctx, osph_slab_p2p *s)
 {
     if (!s) return OSPH_E_INVALID;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); ctx->d_ghost = nullptr; ctx->n_ghost = 0; ctx->slab = false; }
+    if (s->profile && s->psteps > 0) {
+        static const char *names[7] = {"dt reduce + mailbox", "timestep + predictor", "pack + meta mailbox", "copy to host (wait)",
+                                       "commit", "neighbour structure + pair", "corrector / tail"};
+        fprintf(stderr, "[osph slab profile] rank %d, %lld steps, us per step:", s->rank, s->psteps);
+        double tot = 0;
+        for (int k = 0; k < 7; k++) { fprintf(stderr, " %s %.1f;", names[k], 1e3 * s->pms[k] / s->psteps); tot += s->pms[k]; }
+        fprintf(stderr, " sum %.1f; host wall between sync and last enqueue %.1f\n", 1e3 * tot / s->psteps, 1e3 * s->phost_ms / s->psteps);
+        for (int k = 0; k < 8; k++) cudaEventDestroy(s->pev[k]);
+    }
     for (int r = 0; r < s->world; r++) if (r != s->rank && s->peer[r]) cudaIpcCloseMemHandle(s->peer[r]);
     cudaFree(s->win); cudaFree(s->d_peer); cudaFree(s->d_meta); cudaFree(s->d_all_meta); cudaFree(s->d_dt3); cudaFree(s->d_all_dt);
     cudaFreeHost(s->h_all_meta);
@@ -223,6 +243,9 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
     for (int step = 0; step < nsteps; step++) {
         s->seq++;
         const int slot = (int)(s->seq & 1ull);
+        const bool prof = s->profile && step > 0 && step < nsteps - 1;       // steady-state steps of a multi-step call
+#define P2P_MARK(k) do { if (prof) cudaEventRecord(s->pev[k], ctx->stream); } while (0)
+        P2P_MARK(0);
         if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return fail(rc);    // corrector of step k fused into the predictor of k+1
         // ---- identical dt on every rank: mailbox all-gather + min ----
         if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return fail(rc);
@@ -230,7 +253,9 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
                                                        s->d_all_dt, 1, s->spin_limit, d_status);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
+        P2P_MARK(1);
         if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return fail(rc);
+        P2P_MARK(2);
         // ---- classify + pack straight into the neighbours' windows; counts and bounds through the second mailbox ----
         const double width = std::max(q * s->hmax, std::min(s->r0, 3.0 * s->hmax)) * 1.1;
         if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return fail(rc);
@@ -238,12 +263,15 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
                                                        s->seq, s->d_all_meta, 0, s->spin_limit, d_status);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
+        P2P_MARK(3);
         if (cudaMemcpyAsync(s->h_all_meta, s->d_all_meta, sizeof(double) * 12 * W, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaMemcpyAsync(s->h_all_meta + 12 * W, d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) {           // the one host sync of the step
             ctx->err = std::string("slab exchange: ") + cudaGetErrorString(cudaGetLastError());
             return fail(OSPH_E_CUDA);
         }
+        P2P_MARK(4);
+        const auto host_t0 = std::chrono::steady_clock::now();
         const double *M = s->h_all_meta;
         {
             unsigned int st; memcpy(&st, s->h_all_meta + 12 * W, sizeof(st));
@@ -280,7 +308,16 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         // ---- owned set update (migrants are already here), same grid everywhere, force evaluation, corrector ----
         if ((rc = osph_slab_commit_impl(ctx, out_l + out_r, s->win + s->off_mig_from_left, in_mig_l,
                                         s->win + s->off_mig_from_right, in_mig_r, gm, n_ghost, bounds))) return fail(rc);
+        P2P_MARK(5);
         if ((rc = osph_slab_step_end(ctx, damping))) return fail(rc);
+        P2P_MARK(6);
+        if (prof) {
+            s->phost_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+            cudaEventRecord(s->pev[7], ctx->stream);
+            cudaEventSynchronize(s->pev[7]);
+            for (int k = 0; k < 7; k++) { float ms = 0; cudaEventElapsedTime(&ms, s->pev[k], s->pev[k + 1]); s->pms[k] += ms; }
+            s->psteps++;
+        }
         const int64_t c[8] = {out_l, out_r, halo_out_l, halo_out_r, in_mig_l, in_mig_r, in_halo_l, in_halo_r};
         memcpy(s->last_counts, c, sizeof(c));
         s->steps++;

@@ -137,7 +137,7 @@ __global__ void k_setup(int n, const signed char *__restrict__ label, const doub
 __global__ void k_reset_prepare_scalars(StepScalars *sc)
 {
     sc->xmin = ENC_POS_INF; sc->ymin = ENC_POS_INF; sc->xmax = ENC_NEG_INF; sc->ymax = ENC_NEG_INF;
-    sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF;
+    sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF; sc->disp2max = ENC_NEG_INF;
 }
 __global__ void k_reset_dt_scalars(StepScalars *sc)
 {
@@ -146,6 +146,7 @@ __global__ void k_reset_dt_scalars(StepScalars *sc)
 __global__ void k_init_scalars(StepScalars *sc)
 {
     sc->status = 0; sc->dt[0] = sc->dt[1] = sc->dt[2] = 0.0; sc->ke = 0.0; sc->dt_log_count = 0;
+    sc->builds = 0; sc->sorts = 0; sc->disp2max = ENC_NEG_INF;
 }
 
 template <int NV>
@@ -217,7 +218,10 @@ k_prepare(PrepareArgs a)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double bx = INFINITY, by = INFINITY, hmn = INFINITY, Bx = -INFINITY, By = -INFINITY, hmx = -INFINITY, hfl = INFINITY;
+    double d2 = -INFINITY;            // |position after this pass - position at the last sort|^2 (sort cadence, k_grid_params)
     if (i < a.n) {
+        double xr = 0.0, yr = 0.0;
+        if (a.xref) { xr = a.xref[i]; yr = a.yref[i]; }
         // Every input of the thread is requested before the first one is used.  The argument block carries no
         // __restrict__, so a load written after a store has to wait for it: the straightforward form (load, compute,
         // store, load the next rate, ...) walked through six dependent memory round trips per particle and re-read the
@@ -297,21 +301,26 @@ k_prepare(PrepareArgs a)
             }
         }
         // a particle that has left the floating-point line must not define the grid (it is parked in the overflow cell)
-        if (isfinite(x) && isfinite(y)) { bx = x; Bx = x; by = y; By = y; }
+        if (isfinite(x) && isfinite(y)) {
+            bx = x; Bx = x; by = y; By = y;
+            const double ddx = x - xr, ddy = y - yr;
+            d2 = ddx * ddx + ddy * ddy;
+            if (!(d2 == d2)) d2 = INFINITY;        // a reference that is not a number: sort
+        }
         else atomicOr(&a.sc->status, OSPH_S_NONFINITE);
         hmx = h;
         if (fluid) hfl = h;
     }
     if (a.reduce_hmin_fluid) {
-        double v[7] = {bx, by, hmn, hfl, Bx, By, hmx};
-        unsigned long long *const p[7] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all, &a.sc->hmin_fluid,
-                                          &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all};
-        block_minmax_atomic<7>(v, p, 4);
+        double v[8] = {bx, by, hmn, hfl, Bx, By, hmx, d2};
+        unsigned long long *const p[8] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all, &a.sc->hmin_fluid,
+                                          &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all, &a.sc->disp2max};
+        block_minmax_atomic<8>(v, p, 4);
     } else {
-        double v[6] = {bx, by, hmn, Bx, By, hmx};
-        unsigned long long *const p[6] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all,
-                                          &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all};
-        block_minmax_atomic<6>(v, p, 3);
+        double v[7] = {bx, by, hmn, Bx, By, hmx, d2};
+        unsigned long long *const p[7] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all,
+                                          &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all, &a.sc->disp2max};
+        block_minmax_atomic<7>(v, p, 3);
     }
 }
 
@@ -324,7 +333,7 @@ template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, false, false>(PrepareArg
 // Grid parameters: the reference grid (NNLinkedList.py:86-127) and the acceleration grid.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, double pair_radius_q, double r0,
-                              long long cell_cap, int reset_dt)
+                              long long cell_cap, int reset_dt, int force_sort, double skin_frac)
 {
     if (reset_dt) {           // folded k_reset_dt_scalars: the corrector of this step reduces into these
         sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF;
@@ -349,12 +358,45 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
     double R = fmax(pair_radius_q * hmax, lj) * (1.0 + 1e-6);
     if (!(R > 0.0)) R = cs;
     g->pair_r2 = R * R;
+    const double rs = 3.0 * hmax * (1.0 + 1e-6);          // reach of the reference neighbour set (q <= 3)
+
+    // ---- sort cadence: can this build reuse the binning of the last sort? ----
+    // disp = largest distance of a particle from where it was binned (k_prepare).  The frozen cells are gsize wide; two
+    // particles now within R were at most R + 2 disp apart when they were binned, hence in adjacent cells as long as that
+    // does not exceed gsize.  Regime A (the acceleration grid IS the reference grid, which follows the bounds) and the
+    // one-cell fallback always sort.
+    // force_sort: 0 the device decides; 1 sort (a skin is still added, for the builds that follow); 2 sort without skin (slab
+    // mode and the radix path sort every build); 3 = the host's sizing pass for the cell table: grid only, no bookkeeping
+    const bool dry = force_sort == 3;
+    if (!dry) sc->builds++;
+    const double disp = sqrt(fmax(dec_f64(sc->disp2max), 0.0));
+    const bool reuse = !force_sort && skin_frac != 0.0 && g->sort_count > 0 && !g->regime_a && !g->adj_always && !(R >= cs) &&
+                       isfinite(disp) && R + 2.0 * disp * (1.0 + 1e-9) <= g->gsize;
+    if (reuse) {
+        g->do_sort = 0; g->disp = disp; g->steps_since_sort++;
+        int reach = (int)ceil((rs + 2.0 * disp) / g->gsize);
+        if (reach < 1) reach = 1;
+        g->reach_set = reach;
+        return;
+    }
+    // skin of the new binning.  Adaptive (skin_frac < 0): the particles needed steps_since_sort builds to use up the last
+    // skin, so the largest displacement per build was about disp / steps; size the skin for about ten builds at that pace
+    // (each percent of skin costs about two percent more candidates in the pair kernel's scan, a sort about 25 us).
+    double skin = 0.0;
+    if (!(R >= cs) && skin_frac != 0.0 && force_sort != 2 && !dry) {
+        if (skin_frac > 0.0) skin = skin_frac * R;
+        else {
+            const int steps = g->sort_count > 0 && g->steps_since_sort > 0 ? g->steps_since_sort : 0;
+            const double per_build = steps > 0 && isfinite(disp) ? disp / steps : 0.0;
+            skin = fmin(fmax(2.0 * per_build * 10.0 * 1.1, 0.03 * R), 0.25 * R);
+        }
+    }
     int regime_a = (R >= cs) ? 1 : 0, adj_always = 0;
-    double gs = regime_a ? cs : R;
+    double gs = regime_a ? cs : R + skin;
     long long gnx, gny;
     if (regime_a) { gnx = ncx; gny = ncy; }
     else {
-        // cells of the pair radius; if the table cannot hold them (the domain grew since it was sized) coarsen in one
+        // cells of the pair radius (+ skin); if the table cannot hold them (the domain grew since it was sized) coarsen in one
         // shot to the cell size that fits, then nudge
         const double ex = fmax(xmax - xmin, 0.0), ey = fmax(ymax - ymin, 0.0);
         const double fit = sqrt((ex + gs) * (ey + gs) / (0.9 * (double)(cell_cap - 2)));
@@ -377,7 +419,9 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
     }
     g->adj_always = adj_always;
     g->regime_a = regime_a; g->gsize = gs; g->ginv = 1.0 / gs; g->gnx = (int)gnx; g->gny = (int)gny;
-    double rs = 3.0 * hmax * (1.0 + 1e-6);
+    g->gox = xmin; g->goy = ymin;
+    g->do_sort = 1; g->disp = 0.0; g->steps_since_sort = 0;
+    if (!dry) { g->sort_count++; sc->sorts++; }
     int reach = regime_a ? 1 : (int)ceil(rs / gs);
     if (reach < 1) reach = 1;
     g->reach_set = reach;
@@ -411,7 +455,9 @@ __device__ __forceinline__ CellInfo cell_of(double x, double y, const GridParams
         c.gcell = make_int2((int)cx, (int)cy);                                  // query cell: raw reference ids
         c.key = c.binned ? (unsigned int)flat : (unsigned int)g.n_cells;        // bin cell: the reference's flat id
     } else {
-        int gx = (int)floor(rx * g.ginv), gy = (int)floor(ry * g.ginv);
+        // (the acceleration grid keeps the origin of the last sort; a particle outside it is clamped into the edge cells,
+        // which preserves "within one cell size => same or adjacent cells")
+        int gx = (int)floor((x - g.gox) * g.ginv), gy = (int)floor((y - g.goy) * g.ginv);
         gx = min(max(gx, 0), g.gnx - 1); gy = min(max(gy, 0), g.gny - 1);
         c.gcell = make_int2(gx, gy);
         c.key = (unsigned int)gy * (unsigned int)g.gnx + (unsigned int)gx;
@@ -469,8 +515,11 @@ k_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, 
 __global__ void __launch_bounds__(256)
 k_bin_keys(const double *__restrict__ x, const double *__restrict__ y, int n_owned, const double *__restrict__ ghost,
            GhostMap gmap, int n_all, const GridParams *__restrict__ gp, StepScalars *sc, unsigned int *__restrict__ key,
-           unsigned int *__restrict__ arrival, unsigned int *__restrict__ counts, unsigned int *__restrict__ tile_sums)
+           unsigned int *__restrict__ arrival, unsigned int *__restrict__ counts, unsigned int *__restrict__ tile_sums_base,
+           long long tile_cap, double *__restrict__ xref, double *__restrict__ yref)
 {
+    if (!gp->do_sort) return;                             // this build reuses the binning of the last sort (k_grid_params)
+    unsigned int *__restrict__ tile_sums = tile_sums_base + (size_t)(gp->sort_count & 1u) * tile_cap;
     // The totals of the scan tiles (BIN_TILE cells) are accumulated here so that k_bin_scan needs no look-back.  A tile is
     // hit by thousands of particles: straight global atomics serialise on a few hundred addresses (52 us measured), so the
     // CTA collects them in shared memory -- storage order follows cell order closely, a CTA's keys sit in one or two tiles --
@@ -487,6 +536,13 @@ k_bin_keys(const double *__restrict__ x, const double *__restrict__ y, int n_own
         px[r] = 0.0; py[r] = 0.0;
         if (i < n_owned) { px[r] = x[i]; py[r] = y[i]; }
         else if (i < n_all) { const double *rec = ghost_record(ghost, gmap, i - n_owned); px[r] = rec[0]; py[r] = rec[1]; }
+    }
+    if (xref) {                                             // where every particle is binned: the displacements count from here
+#pragma unroll
+        for (int r = 0; r < BINK_ITEMS; r++) {
+            const int i = base + r * 32;
+            if (i < n_owned) { xref[i] = px[r]; yref[i] = py[r]; }
+        }
     }
     if (threadIdx.x < BINK_WINDOW) sh_tile[threadIdx.x] = 0u;
     if (threadIdx.x == 0) sh_tile0 = (int)(cell_of(px[0], py[0], g).key / BIN_TILE) - BINK_WINDOW / 2;
@@ -544,10 +600,14 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
         k = a.key[s];
         kp = s > 0 ? a.key[s - 1] : k; kn = s < a.n_all - 1 ? a.key[s + 1] : k;
     }
+    // (both candidate slots and the cell range are requested before the grid parameters say which applies: no extra round trip)
     int2 rr = make_int2(0, 0);
-    if (a.rank_ranges) rr = a.rank_ranges[s];
-    int i = (int)a.idx[s];
+    unsigned int i_arr = 0;
+    if (a.rank_ranges) { rr = a.rank_ranges[s]; i_arr = a.idx_arrival[s]; }
+    const unsigned int i_fin = a.idx[s];
     const GridParams g = *a.gp;
+    const bool ranking = a.rank_ranges != nullptr && g.do_sort != 0;     // counting sort, on a build that sorts
+    int i = (int)(ranking ? i_arr : i_fin);
     if (a.key) {   // K6 fused: cell table from the sorted keys (table zeroed before: empty cells have begin == end == 0)
         if (s == 0 || kp != k) a.cell_range[k].x = s;
         if (s == a.n_all - 1 || kn != k) a.cell_range[k].y = s + 1;
@@ -561,10 +621,10 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
         const double *r = ghost_record(a.ghost, a.gmap, i - a.n_owned);
         x = r[0]; y = r[1]; vx = r[2]; vy = r[3]; rho = r[4]; m = r[5]; h = r[6]; lab = (int)r[7]; info = 0;
     }
-    if (a.rank_ranges) {
+    if (ranking) {
         // counting sort: this thread holds the particle that ARRIVED at position s; its final position is decided by the
         // storage slots of its cell mates (the state loads above are in flight while they are counted)
-        s = bin_canonical_slot(rr, s, (unsigned int)i, a.idx, a.sc);
+        s = bin_canonical_slot(rr, s, (unsigned int)i, a.idx_arrival, a.sc);
         a.idx_out[s] = (unsigned int)i;
     }
     bool fluid = lab == OSPH_FLUID;
@@ -583,7 +643,7 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
     const bool irregular = c.coarse.x != c.coarse.z || c.coarse.y != c.coarse.w || !c.binned;
     a.s_info[s] = info | (fluid ? 1 : 0) | (irregular ? 4 : 0);
     a.s_coarse[s] = c.coarse;
-    a.s_gcell[s] = c.gcell;
+    if (g.do_sort) a.s_gcell[s] = c.gcell;          // the cell the particle is BINNED in: unchanged while the binning is reused
 }
 template __global__ void k_gather<double2>(GatherArgs, double2 *, double2 *, double2 *);
 template __global__ void k_gather<float2>(GatherArgs, float2 *, float2 *, float2 *);
@@ -688,7 +748,7 @@ __global__ void k_timestep(StepScalars *sc, double gamma_c, double gamma_f, doub
     }
     if (reset_prepare) {      // folded k_reset_prepare_scalars: the predictor that follows reduces into these
         sc->xmin = ENC_POS_INF; sc->ymin = ENC_POS_INF; sc->xmax = ENC_NEG_INF; sc->ymax = ENC_NEG_INF;
-        sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF;
+        sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF; sc->disp2max = ENC_NEG_INF;
     }
     double out0, c = 0.0, f = 0.0;
     if (fixed_dt > 0.0) { out0 = fixed_dt; }
@@ -814,8 +874,8 @@ __global__ void k_near_pos(NeighbourArgs a, double px, double py, double ph, lon
     int gx, gy, reach;
     if (g.regime_a) { gx = qcx; gy = qcy; reach = 1; }
     else {
-        gx = (int)floor(rx * g.ginv); gy = (int)floor(ry * g.ginv);
-        double rs = 1.5 * (ph + g.hmax) * (1.0 + 1e-6);
+        gx = (int)floor((px - g.gox) * g.ginv); gy = (int)floor((py - g.goy) * g.ginv);
+        double rs = 1.5 * (ph + g.hmax) * (1.0 + 1e-6) + g.disp;      // the particles may have moved g.disp since they were binned
         reach = (int)ceil(rs / g.gsize); if (reach < 1) reach = 1;
     }
     long long cnt = 0;
@@ -856,8 +916,8 @@ k_probe_pressure(NeighbourArgs a, const double *__restrict__ m, const double *__
     int gx, gy, reach;
     if (g.regime_a) { gx = qcx; gy = qcy; reach = 1; }
     else {
-        gx = (int)floor(rx * g.ginv); gy = (int)floor(ry * g.ginv);
-        reach = (int)ceil(1.5 * (ph + g.hmax) * (1.0 + 1e-6) / g.gsize); if (reach < 1) reach = 1;
+        gx = (int)floor((x - g.gox) * g.ginv); gy = (int)floor((y - g.goy) * g.ginv);
+        reach = (int)ceil((1.5 * (ph + g.hmax) * (1.0 + 1e-6) + g.disp) / g.gsize); if (reach < 1) reach = 1;
     }
     const double inv_h = 1.0 / ph;
     double norm = 0.0, sum = 0.0;
@@ -980,6 +1040,7 @@ int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, 
     a.dynamic_h = ctx->cfg.dynamic_h;
     a.reduce_hmin_fluid = fused ? 1 : 0;
     a.rden = rden_for(damping);
+    a.xref = ctx->xref; a.yref = ctx->yref;
     if (!skip_reset) { k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
     int grid = div_up(ctx->n, 256);
     int integ = ctx->cfg.integrator;
@@ -1038,13 +1099,17 @@ static int reorder_state(osph_ctx *ctx)
     OSPH_CUDA(cudaMemcpyAsync(ctx->d_row, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     k_permute<int><<<grid, 256, 0, ctx->stream>>>(ctx->d_act, perm, n, (int *)ctx->scratch); OSPH_LAUNCH_CHECK();
     OSPH_CUDA(cudaMemcpyAsync(ctx->d_act, ctx->scratch, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    // the positions the particles were binned at (sort cadence), in the new storage order: this build sorted, so they
+    // are the current positions
+    OSPH_CUDA(cudaMemcpyAsync(ctx->xref, ctx->f[OSPH_F_X], sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    OSPH_CUDA(cudaMemcpyAsync(ctx->yref, ctx->f[OSPH_F_Y], sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
     return 0;
 }
 
-int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt)
+int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt, int force_sort)
 {
     k_grid_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->d_grid, ctx->cfg.nn_scale, pair_radius_q(ctx), ctx->cfg.r0,
-                                            (long long)ctx->cell_cap, reset_dt ? 1 : 0);
+                                            (long long)ctx->cell_cap, reset_dt ? 1 : 0, force_sort, ctx->skin_frac);
     OSPH_LAUNCH_CHECK();
     return 0;
 }
@@ -1052,19 +1117,27 @@ int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt)
 int osph_launch_build(osph_ctx *ctx, bool reset_dt)
 {
     int n = (int)ctx->n, n_all = (int)(ctx->n + ctx->n_ghost), grid = div_up(n_all, 256);
-    int rc = osph_launch_grid_params(ctx, reset_dt);
-    if (rc) return rc;
-    ctx->sorted_buf = 0;
-    const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];
     int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
     // physical re-sort on the 3rd build after an upload, then every `every` builds: a caller that uploads, steps once
     // and downloads (the host-buffer plugin call pattern) never pays for it, a resident run gets it early
     const bool reorder_now = ctx->build_counter % every == (2 % every);
+    // sort cadence (k_grid_params): the device may reuse the last binning unless the particle set was touched from outside
+    // since (skin_valid), the state is about to be reordered physically, or the build always sorts (slab mode: the ghost
+    // set changes every step; radix path)
+    const bool always = ctx->slab || ctx->n_ghost > 0 || !ctx->bin_sort || ctx->skin_frac == 0.0;
+    const int force = always ? 2 : ((!ctx->skin_valid || reorder_now) ? 1 : 0);
+    int rc = osph_launch_grid_params(ctx, reset_dt, force);
+    if (rc) return rc;
+    ctx->skin_valid = !always;
+    ctx->sorted_buf = 0;
+    const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];
     bool rank_in_gather = false;
     if (ctx->bin_sort) {
         // counting sort by cell: histogram + arrival ranks, then scan (= cell table), scatter, canonical order (binsort.cu)
         k_bin_keys<<<div_up(n_all, 256 * BINK_ITEMS), 256, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid,
-                                                                            ctx->d_sc, ctx->key[0], ctx->idx[0], ctx->bin_counts, osph_bin_tile_sums(ctx));
+                                                                            ctx->d_sc, ctx->key[0], ctx->idx[0], ctx->bin_counts, ctx->bin_tiles,
+                                                                            (long long)ctx->bin_tile_cap, always ? nullptr : ctx->xref,
+                                                                            always ? nullptr : ctx->yref);
         OSPH_LAUNCH_CHECK();
         if ((rc = osph_bin_sort(ctx, n_all, reorder_now))) return rc;
         rank_in_gather = !reorder_now;
@@ -1088,7 +1161,7 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt)
 
     GatherArgs g;
     g.n_owned = n; g.n_all = n_all; g.key = ctx->bin_sort ? nullptr : ctx->key[ctx->sorted_buf]; g.cell_range = ctx->cell_range;
-    g.idx = rank_in_gather ? ctx->idx[1] : ctx->idx[ctx->sorted_buf];
+    g.idx = ctx->idx[ctx->sorted_buf]; g.idx_arrival = ctx->idx[1];
     g.rank_ranges = rank_in_gather ? reinterpret_cast<const int2 *>(ctx->scratch) : nullptr; g.idx_out = ctx->idx[0]; g.sc = ctx->d_sc;
     g.label = ctx->label; g.ghost = ctx->d_ghost; g.gmap = ctx->gmap;
     g.x = ctx->f[OSPH_F_X]; g.y = ctx->f[OSPH_F_Y]; g.vx = ctx->f[OSPH_F_VX]; g.vy = ctx->f[OSPH_F_VY];

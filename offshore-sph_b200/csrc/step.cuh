@@ -11,6 +11,7 @@ struct PrepareArgs {
     StepScalars *sc;
     double dt, damping, fixed_h, h_sigma;
     int use_dev_dt, integ_xsph, strict, dynamic_h;
+    const double *xref, *yref;        // positions at the last sort (nullptr: no displacement reduction)
     int reduce_hmin_fluid;            // fused loop: min h over the fluid rows (TimeStep of the next step) is taken here
     double rden;                      // RN(1 / (1 + damping / 2)) for div_den, 0: divide
 };
@@ -30,10 +31,12 @@ struct GatherArgs {
     int n_owned, n_all;
     const unsigned int *key;      // radix sort only: sorted keys (the cell table is written from them), else nullptr
     int2 *cell_range;
-    const unsigned int *idx;      // sorted position -> storage slot (counting sort, rank_ranges set: in arrival order)
+    const unsigned int *idx;      // sorted position -> storage slot, final (radix sort; counting sort on a build that does
+                                  // not sort, or whose order k_bin_rank made canonical)
+    const unsigned int *idx_arrival;   // counting sort, sorting build: the same in arrival order inside each cell
     // counting sort: the kernel makes the order inside each cell canonical on the way (bin_canonical_slot) -- every record
     // is written to its final position and idx_out receives the final permutation
-    const int2 *rank_ranges;      // per sorted position: (begin, end) of its cell; nullptr: idx is final already
+    const int2 *rank_ranges;      // per sorted position: (begin, end) of its cell; nullptr: idx is final on every build
     unsigned int *idx_out;
     StepScalars *sc;
     const signed char *label;
@@ -77,7 +80,7 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt = false);   // grid params, k
 int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
 int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare = false,
                          const double *d_reduced3 = nullptr, int fused = 0);   // fused 1: reset the dt scalars after use; 2: c_max = co too
-int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt = false);
+int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt = false, int force_sort = 1);   // force_sort: see k_grid_params
 int osph_launch_ke(osph_ctx *ctx);
 int osph_launch_neighbours(osph_ctx *ctx, int mode, long long *d_counts, const long long *d_offsets, long long *d_out);
 int osph_launch_near_pos(osph_ctx *ctx, double x, double y, double h, long long cap, long long *d_idx, double *d_r,

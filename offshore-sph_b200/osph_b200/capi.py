@@ -89,6 +89,7 @@ def lib():
         'osph_download_rows': (C.c_int, [ctx, i64, ip, C.c_void_p, i64]),
         'osph_upload_rows': (C.c_int, [ctx, i64, ip, C.c_void_p, i64]),
         'osph_set_active': (C.c_int, [ctx, C.c_void_p, i64]),
+        'osph_sort_stats': (C.c_int, [ctx, C.POINTER(C.c_int64)]),
         'osph_num_active': (i64, [ctx]),
         'osph_num_fluid': (i64, [ctx]),
         'osph_initialize': (C.c_int, [ctx]),
@@ -327,6 +328,12 @@ class Context:
         ke = C.c_double(0)
         self._ck(self._L.osph_kinetic_energy(self._h, C.byref(ke)))
         return ke.value
+
+    def sort_stats(self):
+        """(builds, sorts): neighbour-structure builds so far and how many of them sorted (the rest reused the last binning)."""
+        out = (C.c_int64 * 2)()
+        self._ck(self._L.osph_sort_stats(self._h, out))
+        return int(out[0]), int(out[1])
 
     def sync(self):
         st = C.c_uint32(0)

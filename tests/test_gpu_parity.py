@@ -207,6 +207,49 @@ def test_counting_sort_gives_the_order_of_the_stable_radix_sort(precision, monke
         assert np.array_equal(o[4], outs[0][4])
 
 
+@pytest.mark.parametrize("kernel,push,side,steps", [('cubic', 0.0, 100, 30), ('wendland', 20.0, 100, 30), ('gaussian', 0.0, 150, 12)])
+def test_sort_cadence_reuses_the_binning_and_changes_nothing(kernel, push, side, steps, monkeypatch):
+    """Between two sorts the device reuses the sorted order and the cell table (cells = pair radius + skin, re-sort as soon
+    as pair radius + 2 x largest displacement exceeds the cell: k_grid_params).  Membership is decided on the current
+    positions, so nothing may change: same neighbour sets as the oracle on the moved particles, fields equal to the run
+    that sorts at every build (OSPH_SKIN=0) up to summation order, same dt.  push: fluid thrown at 20 m/s with a fixed time
+    step -- a 10 % skin is used up every few steps and the run must re-sort on its own."""
+    case = W.dam_break_case(side, seed=21)            # pair radius 0.8 m < reference cell 1 m: the fine-cell regime
+    pA = case['pA'].copy()
+    pA['vx'][pA['label'] == 0] += push
+    runs = {}
+    for skin in ('0', 'auto', '0.1'):
+        monkeypatch.setenv("OSPH_SKIN", skin)
+        cfg = capi.make_config(case['consts'], kernel, 'pec', capi.FP64, case['h'])
+        with capi.Context(cfg) as ctx:
+            ctx.upload(pA)
+            ctx.step(steps, 4e-4 if push else None, 0.0)
+            builds, sorts = ctx.sort_stats()
+            off, idx = ctx.neighbours_csr()                   # queried on a binning that may be several steps old
+            out = ctx.download(pA.copy())
+            g, cells = ctx.cells()
+            runs[skin] = dict(out=out, off=off, idx=idx, cells=cells, dts=ctx.dt_log(), builds=builds, sorts=sorts)
+            assert ctx.sync() == 0
+            if skin == '0.1':
+                # neighbour sets of the final positions against the reference search of the oracle
+                P = O.Particles.from_aos(out[~out['deleted']])
+                ooff, oidx = O.Grid(P).neighbours_csr()
+                assert np.array_equal(off, ooff)
+                assert all(np.array_equal(a, b) for a, b in zip(_sorted_lists(off, idx), _sorted_lists(ooff, oidx)))
+                assert np.array_equal(cells, O.Grid(P).cell_ids())
+    ref = runs['0']
+    assert ref['sorts'] == ref['builds'] >= steps
+    for skin in ('auto', '0.1'):
+        r = runs[skin]
+        assert r['builds'] == ref['builds'] and 2 <= r['sorts'] < r['builds'], (skin, r['builds'], r['sorts'])
+        assert np.array_equal(r['off'], ref['off']) and np.array_equal(r['idx'], ref['idx']) and np.array_equal(r['cells'], ref['cells'])
+        assert np.allclose(r['dts'], ref['dts'], rtol=1e-12, atol=0)
+        for f in STATE_FIELDS:
+            assert field_err(r['out'][f], ref['out'][f]) <= 1e-11, (skin, f)
+    if push:
+        assert runs['0.1']['sorts'] > 3, "the thrown fluid must outrun a 10 % skin several times in 30 steps"
+
+
 def test_fp32_mode_close_to_fp64():
     """Performance mode: float pair arithmetic on anchor-relative positions; drift bounded and reported."""
     case = W.dam_break_case(100, seed=7)
