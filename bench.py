@@ -263,6 +263,7 @@ def run_gpu(args):
     ctx.step(args.warmup, None, DAMPING)
     ctx.sync(); ctx.pair_kernel_time()
     l0 = ctx.launch_count
+    builds0, sorts0 = ctx.sort_stats()
     clocks.mark_start()
     # one osph_step call for all K steps: the library fuses the corrector of step k with the predictor of step k+1
     t_dev = timed_region(lambda: ctx.step(args.steps, None, DAMPING), 1)
@@ -271,6 +272,7 @@ def run_gpu(args):
     launches = ctx.launch_count - l0
     pair_us, pair_n = ctx.pair_kernel_time()
     status = ctx.sync()
+    builds1, sorts1 = ctx.sort_stats()
     value = n * args.steps / t_dev
 
     # ---- end to end through the plugin boundary, host buffers ---------------------------------
@@ -310,7 +312,8 @@ def run_gpu(args):
                 "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "avg_launch_us": pair_us, "launches_timed": pair_n, "share_of_step": pair_us * 1e-6 * args.steps / t_dev,
                 "algorithmic_bytes_per_particle": 13 * F + 1,
-                "note": "k_pair is FP-pipe / latency bound, not HBM bound (DESIGN.md section 4); see fp_pipe"}
+                "note": "k_pair is bound by the FP pipe / dependent-instruction latency, not by HBM (DESIGN.md section 4): "
+                        "fp_pipe is the fraction to read first, frac (HBM, as the contract defines it) second"}
     # FP-pipe view of the same kernel: SURVEY 8(d) flop model (70 flop per contributing pair, 10 per rejected
     # candidate) against the FMA peak measured with tools/fp64_pipe.cu on this pool
     try:
@@ -321,6 +324,8 @@ def run_gpu(args):
         flops = (70.0 * pairs + 10.0 * (cand - pairs)) * int((pA['label'] == 0).sum())
         peak = fp["fp64_tflops"] if prec == capi.FP64 else fp["fp32_tflops"]
         ach = flops / (pair_us * 1e-6) / 1e12 if pair_us > 0 else 0.0
+        roofline["fp64_tflops_peak"] = fp["fp64_tflops"]; roofline["fp32_tflops_peak"] = fp["fp32_tflops"]
+        roofline["primary"] = "fp_pipe"
         roofline["fp_pipe"] = {"achieved_tflops_model": ach, "peak_tflops_measured": peak, "frac": ach / peak,
                                "pair_interactions_per_s": pairs * int((pA['label'] == 0).sum()) / (pair_us * 1e-6) if pair_us > 0 else 0.0,
                                "model": "70 flop x %.1f contributing pairs + 10 flop x %.1f rejected candidates per fluid particle" % (pairs, cand - pairs)}
@@ -342,6 +347,8 @@ def run_gpu(args):
         "config": {"workload": workload_name(n_side, n, args.kernel, args.precision.upper()),
                    "particles": n, "fluid": int((pA['label'] == 0).sum()), "damping": DAMPING, "dt": "dynamic",
                    "l2": "per-step working set (%.0f MB state + sorted copies) exceeds the 126 MB L2" % (n * 19 * 8 / 1e6),
+                   "neighbour_structure": "counting sort by cell; %d of the %d timed builds sorted, the others reused the binning "
+                                          "(cells = pair radius + skin, OSPH_SKIN)" % (sorts1 - sorts0, builds1 - builds0),
                    "parallelism": "1 GPU"},
         "clocks": clk, "gpu_launches": launches, "status_bits": status,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 154, "d2h_bytes_per_step": n * 154,

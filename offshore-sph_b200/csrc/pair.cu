@@ -76,14 +76,14 @@
 // One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
 // every field at a compile-time offset.  40 B (float) / 80 B (double) keeps 8 / 16-byte vector alignment.
 template <typename Real, bool EXACT> struct Rec;
-template <> struct __align__(8) Rec<float, false> { float2 pos, vel, rm, hp; int info; int pad; };
+template <> struct __align__(8) Rec<float, false> { float2 pos, vel, rm, hp; int info; int cell16; };    // cell16: reference bin cell, 16 + 16 bits
 template <> struct __align__(16) Rec<double, true> { double2 pos, vel, rm, hp; int info; int cbx, cby; int pad; };
 
 template <typename Real, bool EXACT>
 constexpr size_t pair_smem_bytes()
 {
     return sizeof(Rec<Real, EXACT>) * PAIR_CAP + sizeof(unsigned short) * (sizeof(Real) == 8 ? PAIR_LIST64 : PAIR_LIST32) * OSPH_PAIR_THREADS +
-           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6 +
+           sizeof(int) * (OSPH_PAIR_THREADS / 32) * 6 + (EXACT ? 0 : sizeof(int2) * OSPH_PAIR_THREADS) +
            (PAIR_SCAN2 ? sizeof(float4) * ((PAIR_CAP + PAIR_SCAN + 2) / 2) : ((EXACT && PAIR_SCAN_F32) ? sizeof(float2) * (PAIR_CAP + PAIR_SCAN) : 0));
 }
 
@@ -105,6 +105,10 @@ k_pair(PairArgs a)
     float2 *sh_pf = reinterpret_cast<float2 *>(smem_raw + sizeof(RecT) * CAP + sizeof(unsigned short) * PAIR_LIST * NT +
                                                sizeof(int) * (NT / 32) * 6);
     float4 *sh_pf2 = reinterpret_cast<float4 *>(sh_pf);          // SCAN2: (x0, x1, y0, y1) of records 2m and 2m + 1
+    // float instantiation: the thread's reference query cell, read back only on the rarely taken set-membership branch (a
+    // register pair, or a global load there, spills the 80-register build)
+    int2 *sh_qcell = reinterpret_cast<int2 *>(reinterpret_cast<unsigned char *>(sh_pf) +
+                                             (PAIR_SCAN2 ? sizeof(float4) * ((PAIR_CAP + PAIR_SCAN + 2) / 2) : 0));
 
     const Real2 *__restrict__ g_vel = reinterpret_cast<const Real2 *>(a.s_vel);
     const Real2 *__restrict__ g_rm = reinterpret_cast<const Real2 *>(a.s_rm);
@@ -146,7 +150,10 @@ k_pair(PairArgs a)
         const Real2 v = g_vel[s], rm = g_rm[s], hp = g_hp[s];
         info_i = a.s_info[s];
         const int2 gc = a.s_gcell[s];
+        // (the reference cells are only compared where adjacency does not follow from distance: regime A, the one-cell
+        // fallback, irregularly binned particles; the float instantiation loads them only then)
         if constexpr (EXACT) { int4 c = a.s_coarse[s]; qcx = c.z; qcy = c.w; }
+        else if (need_adj || (info_i & 4)) { int4 c = a.s_coarse[s]; sh_qcell[tid] = make_int2(c.z, c.w); }    // own slot: no barrier needed
         xi = (Real)(p.x - anchor.x); yi = (Real)(p.y - anchor.y);
         if constexpr (SCANF) { xf = (float)(p.x - anchor_f.x); yf = (float)(p.y - anchor_f.y); }
         vxi = v.x; vyi = v.y; rhoi = rm.x; hi = hp.x; slf = hp.y;
@@ -210,8 +217,14 @@ k_pair(PairArgs a)
         } else if constexpr (SCANF) sh_pf[dst] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
         rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
         rec.rm.x *= Real(0.5); rec.hp.x *= Real(0.5);       // staged as rho_j / 2 and h_j / 2: the pair means are one add
-        if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
-        rec.pad = 0;
+        if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; rec.pad = 0; }
+        else {
+            // float records carry the reference bin cell modulo 2^16 per axis, and only where it can be asked for.  Two
+            // particles within the pair radius are a handful of cells apart, so "adjacent" survives the truncation:
+            // the difference modulo 2^16, read as a signed 16-bit number, is in [-1, 1] exactly when the cells are adjacent
+            rec.cell16 = 0;
+            if (need_adj || (rec.info & 4)) { int4 c = a.s_coarse[g]; rec.cell16 = (c.x & 0xffff) | (c.y << 16); }
+        }
         sh_rec[dst] = rec;
     };
     auto stage = [&](int g0, int cnt, int dst) {
@@ -230,7 +243,7 @@ k_pair(PairArgs a)
         const Real2 rmj = rj->rm;
         const int info_j = rj->info;
         int cbx = 0, cby = 0;
-        if constexpr (EXACT) { cbx = rj->cbx; cby = rj->cby; }
+        if constexpr (EXACT) { cbx = rj->cbx; cby = rj->cby; }        // (float: read on the rare path)
         const Real dx = xi - pj.x, dy = yi - pj.y;
         const Real r2 = dx * dx + dy * dy;
         const Real hij = hi_half + hpj.x;                          // == 0.5 * (h_i + h_j) bit for bit
@@ -267,9 +280,19 @@ k_pair(PairArgs a)
                 if (!ok) return;
             }
         } else {
-            if (KID == OSPH_KERNEL_GAUSSIAN || !kern || tiny) {
+            // float instantiation: the same set rule (adjacent reference cells where distance does not imply it, q <= 3)
+            // in float arithmetic -- without the cell test FP32 and FP64 mode would differ in WHICH pairs exist in regime A
+            const bool adjq = adj_i || (info_j & 4);
+            if (KID == OSPH_KERNEL_GAUSSIAN || adjq || !kern || tiny) {
                 via_rare = true;
-                if (!((kern || lj) && r2 <= h2 * Real(9))) return;
+                bool ok = (kern || lj) && r2 <= h2 * Real(9);
+                if (adjq && ok) {
+                    const int2 qc = sh_qcell[tid];
+                    const int c16 = rj->cell16;
+                    const int ddx = (short)((c16 & 0xffff) - qc.x), ddy = (short)((c16 >> 16) - qc.y);
+                    ok = abs(ddx) <= 1 && abs(ddy) <= 1 && !(info_j & 8);        // bit 3: the reference does not bin j at all
+                }
+                if (!ok) return;
             }
         }
         // GUARDED: the r -> 0 guards of the reference and the clamp of the outer spline term are evaluated.  The default build

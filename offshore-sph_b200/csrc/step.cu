@@ -212,11 +212,20 @@ static double rden_for(double damping)
 // FUSED (PEC only, osph_step's multi-step loop): the corrector of the PREVIOUS step (same arithmetic as k_correct, with
 // sc->dt_prev) is applied in registers first, so the corrected state is never written and re-read between two steps:
 // one pass over the state per step boundary instead of two.
+#ifndef PREP_ITEMS
+#define PREP_ITEMS 8
+#endif
 template <int INTEG, bool PREDICT, bool FUSED>
 __global__ void __launch_bounds__(256)
 k_prepare(PrepareArgs a)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // A CTA walks PREP_ITEMS consecutive groups of 256 particles and reduces once: the eight-value block reduction and the
+    // CTA launch are paid per 256 * PREP_ITEMS particles (the reduction was most of the kernel's instructions).
+    double Tbx = INFINITY, Tby = INFINITY, Thmn = INFINITY, TBx = -INFINITY, TBy = -INFINITY, Thmx = -INFINITY, Thfl = INFINITY;
+    double Td2 = -INFINITY;
+#pragma unroll 1
+    for (int it = 0; it < PREP_ITEMS; it++) {
+    const int i = blockIdx.x * (256 * PREP_ITEMS) + it * 256 + threadIdx.x;
     double bx = INFINITY, by = INFINITY, hmn = INFINITY, Bx = -INFINITY, By = -INFINITY, hmx = -INFINITY, hfl = INFINITY;
     double d2 = -INFINITY;            // |position after this pass - position at the last sort|^2 (sort cadence, k_grid_params)
     if (i < a.n) {
@@ -311,6 +320,10 @@ k_prepare(PrepareArgs a)
         hmx = h;
         if (fluid) hfl = h;
     }
+    Tbx = fmin(Tbx, bx); Tby = fmin(Tby, by); Thmn = fmin(Thmn, hmn); Thfl = fmin(Thfl, hfl);
+    TBx = fmax(TBx, Bx); TBy = fmax(TBy, By); Thmx = fmax(Thmx, hmx); Td2 = fmax(Td2, d2);
+    }
+    const double bx = Tbx, by = Tby, hmn = Thmn, hfl = Thfl, Bx = TBx, By = TBy, hmx = Thmx, d2 = Td2;
     if (a.reduce_hmin_fluid) {
         double v[8] = {bx, by, hmn, hfl, Bx, By, hmx, d2};
         unsigned long long *const p[8] = {&a.sc->xmin, &a.sc->ymin, &a.sc->hmin_all, &a.sc->hmin_fluid,
@@ -641,7 +654,7 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
     // bit2: the reference bins this particle in a cell other than the one it queries from (wrapped last column,
     // unbinned, non-finite): cell adjacency then does not follow from distance and the pair kernel tests it
     const bool irregular = c.coarse.x != c.coarse.z || c.coarse.y != c.coarse.w || !c.binned;
-    a.s_info[s] = info | (fluid ? 1 : 0) | (irregular ? 4 : 0);
+    a.s_info[s] = info | (fluid ? 1 : 0) | (irregular ? 4 : 0) | (c.binned ? 0 : 8);      // bit3: not binned by the reference (never found)
     a.s_coarse[s] = c.coarse;
     if (g.do_sort) a.s_gcell[s] = c.gcell;          // the cell the particle is BINNED in: unchanged while the binning is reused
 }
@@ -1042,7 +1055,7 @@ int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, 
     a.rden = rden_for(damping);
     a.xref = ctx->xref; a.yref = ctx->yref;
     if (!skip_reset) { k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
-    int grid = div_up(ctx->n, 256);
+    int grid = div_up(ctx->n, 256 * PREP_ITEMS);
     int integ = ctx->cfg.integrator;
     if (fused == 2) {
         if (!(predict && integ == OSPH_INTEGRATOR_PEC)) { ctx->err = "fused corrector + predictor exists for PEC only"; return OSPH_E_INVALID; }

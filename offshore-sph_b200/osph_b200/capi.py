@@ -25,7 +25,7 @@ FIELDS = ['m', 'rho', 'p', 'c', 'drho', 'h', 'x', 'y', 'vx', 'vy', 'ax', 'ay',
           'xsphx', 'xsphy', 'x0', 'y0', 'vx0', 'vy0', 'rho0']
 FIELD_ID = {f: i for i, f in enumerate(FIELDS)}
 
-S_NONFINITE, S_SMALL_DT, S_UNBINNED, S_GRID_COARSE = 1, 2, 4, 8
+S_NONFINITE, S_SMALL_DT, S_UNBINNED, S_GRID_COARSE, S_DENSE_CELL = 1, 2, 4, 8, 16
 
 
 class OsphError(RuntimeError):

@@ -277,6 +277,12 @@ class Solver:
                 self.t += self.dt
             t_step += 1
 
+            # Status of the device every 32 steps (the loop synchronises once per step anyway, for dt): a domain that outgrew
+            # its cell table is re-sized at the next build instead of running on coarsened cells for the rest of the run,
+            # and a non-finite state is reported when it appears, not after the last step.
+            if t_step % 32 == 0:
+                self._poll_status()
+
             if not self.settled and t_step > 1:
                 ke = 1e12; cs = False
                 if self.customSettle is None:
@@ -319,9 +325,7 @@ class Solver:
         tbar.close()
         self._export_drain()
         self._pull()
-        status = ctx.sync()
-        if status & capi.S_NONFINITE:
-            println('WARNING! non-finite particle state produced on the device.')
+        self._poll_status()
         self.timing_data['total'] = perf_counter() - start_all
         self.t_step = t_step
         println('Solved!')
@@ -358,6 +362,15 @@ class Solver:
         # row-space columns: already the full per-row arrays (deleted rows keep their uploaded values)
         for key, col in self._ctx.export_end(self._export_pending.pop(0)).items():
             self.export[key].append(col)
+
+    def _poll_status(self):
+        """osph_sync: reads and clears the device's status bits; a coarsened grid makes the next build re-size its table."""
+        status = self._ctx.sync()
+        self.device_status = getattr(self, 'device_status', 0) | status
+        if status & capi.S_NONFINITE and not getattr(self, '_warned_nonfinite', False):
+            self._warned_nonfinite = True
+            println('WARNING! non-finite particle state produced on the device.')
+        return status
 
     def _export_drain(self):
         while self._export_pending:

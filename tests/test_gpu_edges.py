@@ -295,3 +295,28 @@ def test_empty_and_fluid_free_inputs():
             assert np.array_equal(out[f], walls[f]), f
         off, idx = ctx.neighbours_csr()
         assert int(off[-1]) == 0                                      # wall particles are never queried
+
+
+def test_fp32_mode_uses_the_reference_cell_rule_too():
+    """Membership of a pair is decided by the reference cells (3 x 3) AND the distance.  Candidates normally come from
+    adjacent cells by construction; on the one-cell fallback grid (reference grid outgrew the table) and for irregularly
+    binned particles they do not, and the cell test has to bind.  The float instantiation applies it like the double one
+    (it used to decide by distance alone there): the two modes agree to float rounding, far below one pair's share."""
+    case = W.dam_break_case(40, seed=9)            # pair radius 2 m > reference cell 1 m: support reaches two cells away
+    pA, c = case['pA'], case['consts']
+    outs = {}
+    for prec in (capi.FP64, capi.FP32):
+        cfg = capi.make_config(c, 'cubic', 'pec', prec, case['h'])
+        with capi.Context(cfg) as ctx:
+            ctx.upload(pA)
+            ctx.step(1, None, 0.05)
+            assert ctx.sync() == 0
+            i = int(np.flatnonzero(pA['label'] == 0)[-1])
+            x = ctx.download_fields(['x', 'y'])
+            x['x'][i] = 7000.0; x['y'][i] = 1200.0                 # the reference grid no longer fits the cell table
+            ctx.upload_fields(x)
+            ctx.compute()
+            outs[prec] = ctx.download_fields(['drho', 'ax', 'ay', 'xsphx', 'xsphy'])
+            assert ctx.sync() == capi.S_GRID_COARSE                # ran on the one-cell fallback
+    for f in outs[capi.FP64]:
+        assert field_err(outs[capi.FP32][f], outs[capi.FP64][f]) <= 5e-4, f
