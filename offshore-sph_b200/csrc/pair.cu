@@ -76,7 +76,7 @@
 // One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
 // every field at a compile-time offset.  40 B (float) / 80 B (double) keeps 8 / 16-byte vector alignment.
 template <typename Real, bool EXACT> struct Rec;
-template <> struct __align__(8) Rec<float, false> { float2 pos, vel, rm, hp; int info; int cell16; };    // cell16: reference bin cell, 16 + 16 bits
+template <> struct __align__(8) Rec<float, false> { float2 pos, vel, rm, hp; int info; int pad; };    // info carries the bin cell mod 2^14
 template <> struct __align__(16) Rec<double, true> { double2 pos, vel, rm, hp; int info; int cbx, cby; int pad; };
 
 template <typename Real, bool EXACT>
@@ -207,6 +207,7 @@ k_pair(PairArgs a)
     Real drho = 0, ax = 0, ay = 0, xs = 0, ys = 0;          // the wall force is accumulated into (ax, ay) as well
 
     // stage sorted particles [g0, g0 + cnt) into records [dst, dst + cnt)
+    int stage_adj = 0;                   // this thread staged a record of an irregularly binned particle
     auto stage_one = [&](const int g, const int dst) {
         RecT rec;
         double2 p = a.s_pos[g];
@@ -216,15 +217,10 @@ k_pair(PairArgs a)
             q[0] = (float)(p.x - anchor_f.x); q[2] = (float)(p.y - anchor_f.y);
         } else if constexpr (SCANF) sh_pf[dst] = make_float2((float)(p.x - anchor_f.x), (float)(p.y - anchor_f.y));
         rec.vel = g_vel[g]; rec.rm = g_rm[g]; rec.hp = g_hp[g]; rec.info = a.s_info[g];
+        if constexpr (!EXACT) stage_adj |= rec.info & 4;
         rec.rm.x *= Real(0.5); rec.hp.x *= Real(0.5);       // staged as rho_j / 2 and h_j / 2: the pair means are one add
-        if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; rec.pad = 0; }
-        else {
-            // float records carry the reference bin cell modulo 2^16 per axis, and only where it can be asked for.  Two
-            // particles within the pair radius are a handful of cells apart, so "adjacent" survives the truncation:
-            // the difference modulo 2^16, read as a signed 16-bit number, is in [-1, 1] exactly when the cells are adjacent
-            rec.cell16 = 0;
-            if (need_adj || (rec.info & 4)) { int4 c = a.s_coarse[g]; rec.cell16 = (c.x & 0xffff) | (c.y << 16); }
-        }
+        if constexpr (EXACT) { int4 c = a.s_coarse[g]; rec.cbx = c.x; rec.cby = c.y; }
+        rec.pad = 0;
         sh_rec[dst] = rec;
     };
     auto stage = [&](int g0, int cnt, int dst) {
@@ -235,7 +231,11 @@ k_pair(PairArgs a)
     // line (all shared-memory loads first, one early exit, the four reciprocal / rsqrt Newton chains independent of
     // each other, fluid-only terms masked instead of branched) so the scheduler can overlap the FP64 latencies;
     // only the rare paths (exact-predicate band, Lennard-Jones wall force) branch.
-    auto interact = [&](const int j) {
+    // adj_tag: compile-time switch of the reference-cell test.  It is only due in CTAs that hold a particle the reference bins
+    // irregularly, in regime A and on the one-cell fallback (cta_adj below); everywhere else the per-pair flag logic is
+    // compiled out of the loop.
+    auto interact = [&](auto adj_tag, const int j) {
+        constexpr bool ADJ = decltype(adj_tag)::value;
         const RecT *__restrict__ rj = sh_rec + j;
         const Real2 pj = rj->pos;
         const Real2 hpj = rj->hp;
@@ -265,7 +265,7 @@ k_pair(PairArgs a)
         bool via_rare = false;
         const bool tiny = PAIR_LEAN && (sizeof(Real) == 8 ? __double2hiint((double)r2) <= 0x3BC79CA1 : r2 <= Real(1.0001e-20));
         if constexpr (EXACT) {
-            const bool adjq = adj_i || (info_j & 4);
+            const bool adjq = ADJ && (adj_i || (info_j & 4));
             if (KID == OSPH_KERNEL_GAUSSIAN || adjq || !kern || tiny) {
                 via_rare = true;
                 bool ok = kern || lj;
@@ -282,14 +282,14 @@ k_pair(PairArgs a)
         } else {
             // float instantiation: the same set rule (adjacent reference cells where distance does not imply it, q <= 3)
             // in float arithmetic -- without the cell test FP32 and FP64 mode would differ in WHICH pairs exist in regime A
-            const bool adjq = adj_i || (info_j & 4);
+            const bool adjq = ADJ && (adj_i || (info_j & 4));
             if (KID == OSPH_KERNEL_GAUSSIAN || adjq || !kern || tiny) {
                 via_rare = true;
                 bool ok = (kern || lj) && r2 <= h2 * Real(9);
                 if (adjq && ok) {
                     const int2 qc = sh_qcell[tid];
-                    const int c16 = rj->cell16;
-                    const int ddx = (short)((c16 & 0xffff) - qc.x), ddy = (short)((c16 >> 16) - qc.y);
+                    // bin cell of j modulo 2^14 from its info word (k_gather); differences as signed 14-bit numbers
+                    const int ddx = (((info_j >> 4) - qc.x) << 18) >> 18, ddy = (((int)((unsigned int)info_j >> 18) - qc.y) << 18) >> 18;
                     ok = abs(ddx) <= 1 && abs(ddy) <= 1 && !(info_j & 8);        // bit 3: the reference does not bin j at all
                 }
                 if (!ok) return;
@@ -368,7 +368,7 @@ k_pair(PairArgs a)
 #endif
     double vx_st = 0.0, vy_st = 0.0;
     bool have_v = false;
-    auto flush = [&]() {
+    auto flush = [&](auto adj_tag) {
 #if PAIR_PREFETCH_IDX
         const int nl = LIST_COUNT();
         int jn = nl > 0 ? (int)sh_list[tid] : 0;
@@ -377,12 +377,12 @@ k_pair(PairArgs a)
             const int j = jn;
             k++;
             if (k < nl) jn = (int)sh_list[k * NT + tid];      // next index while this pair is evaluated
-            interact(j);
+            interact(adj_tag, j);
         }
 #else
         const int nl = LIST_COUNT();
 #pragma unroll 1
-        for (int k = 0; k < nl; k++) interact((int)sh_list[k * NT + tid]);
+        for (int k = 0; k < nl; k++) interact(adj_tag, (int)sh_list[k * NT + tid]);
 #endif
         LIST_RESET();
     };
@@ -392,7 +392,7 @@ k_pair(PairArgs a)
     // are four FADD2 / FMUL2 / FFMA2 instructions.  A run [j0, j1) may start and end inside a pair: membership of a record in
     // the run is one unsigned compare (idx - j0 < j1 - j0).  Three pairs per round.
     const unsigned long long XF2 = pack_f32x2(xf, xf), YF2 = pack_f32x2(yf, yf);
-    auto scan = [&](auto skip_tag, int j0, int j1, const int self) {          // all 32 lanes of a warp call this together
+    auto scan = [&](auto adj_tag, auto skip_tag, int j0, int j1, const int self) {          // all 32 lanes of a warp call this together
         constexpr bool SKIP = PAIR_LEAN && decltype(skip_tag)::value;
         constexpr int NP = PAIR_SCAN / 2;
         int m = j0 >> 1;
@@ -419,13 +419,13 @@ k_pair(PairArgs a)
             m += NP;
             // a lane whose run is exhausted parks at pair 0 with an empty run (see the scalar scan below)
             if (2 * m >= j1) { m = 0; j0 = 0; j1 = 0; len = 0; }
-            if (__any_sync(0xffffffffu, LIST_NEARLY_FULL())) flush();
+            if (__any_sync(0xffffffffu, LIST_NEARLY_FULL())) flush(adj_tag);
             warp_more = __any_sync(0xffffffffu, 2 * m < j1);
         }
     };
 #else
     // skip_tag (PAIR_LEAN only): the run holds the thread's own record at index `self`; it is not listed
-    auto scan = [&](auto skip_tag, int j, int j1, const int self) {          // all 32 lanes of a warp call this together
+    auto scan = [&](auto adj_tag, auto skip_tag, int j, int j1, const int self) {          // all 32 lanes of a warp call this together
         constexpr bool SKIP = PAIR_LEAN && decltype(skip_tag)::value;
         bool warp_more = __any_sync(0xffffffffu, j < j1);
 #pragma unroll 1
@@ -475,7 +475,7 @@ k_pair(PairArgs a)
                 }
             }
 #endif
-            if (__any_sync(0xffffffffu, li >= (PAIR_LIST - PAIR_SCAN + 1) * NT)) flush();      // more than PAIR_LIST - PAIR_SCAN entries
+            if (__any_sync(0xffffffffu, li >= (PAIR_LIST - PAIR_SCAN + 1) * NT)) flush(adj_tag);      // more than PAIR_LIST - PAIR_SCAN entries
             warp_more = __any_sync(0xffffffffu, j < j1);
         }
     };
@@ -490,15 +490,26 @@ k_pair(PairArgs a)
 #pragma unroll 4
         for (int t = tid; t < total; t += NT)
             stage_one(t < o1 ? ulo0 + t : (t < o2 ? ulo1 + (t - o1) : ulo2 + (t - o2)), t);
-        __syncthreads();
+        // the barrier that publishes the records also tells whether any pair of this CTA needs the reference-cell test
+        // (float instantiation only: it is bound by instruction issue; the double one keeps a single copy of its loops, a
+        // second one makes it spill)
+        bool cta_adj = true;
+        if constexpr (EXACT) __syncthreads();
+        else cta_adj = __syncthreads_or((need_adj || stage_adj || (info_i & 4)) ? 1 : 0) != 0;
         // (an empty run is ra = INT_MAX, rb = 0: test it before doing index arithmetic on it)
         const bool h0 = fluid_i && rb0 > ra0, h1 = fluid_i && rb1 > ra1, h2 = fluid_i && rb2 > ra2;
-        scan(std::false_type(), h0 ? ra0 - ulo0 : 0, h0 ? rb0 - ulo0 : 0, -1);
-        scan(std::true_type(), h1 ? ra1 - ulo1 + o1 : 0, h1 ? rb1 - ulo1 + o1 : 0, s - ulo1 + o1);    // the middle row holds s itself
-        if (fluid_i) slot = (int)a.idx[s];                       // the epilogue's loads travel under the remaining work
-        scan(std::false_type(), h2 ? ra2 - ulo2 + o2 : 0, h2 ? rb2 - ulo2 + o2 : 0, -1);
-        if constexpr (!EXACT) { if (fluid_i && a.method_xsph) { vx_st = a.vx[slot]; vy_st = a.vy[slot]; have_v = true; } }
-        flush();
+#define PAIR_ROWS(adj_tag)                                                                                                             \
+        do {                                                                                                                           \
+            scan(adj_tag, std::false_type(), h0 ? ra0 - ulo0 : 0, h0 ? rb0 - ulo0 : 0, -1);                                            \
+            scan(adj_tag, std::true_type(), h1 ? ra1 - ulo1 + o1 : 0, h1 ? rb1 - ulo1 + o1 : 0, s - ulo1 + o1);   /* holds s itself */   \
+            if (fluid_i) slot = (int)a.idx[s];                       /* the epilogue's loads travel under the remaining work */         \
+            scan(adj_tag, std::false_type(), h2 ? ra2 - ulo2 + o2 : 0, h2 ? rb2 - ulo2 + o2 : 0, -1);                                  \
+            if constexpr (!EXACT) { if (fluid_i && a.method_xsph) { vx_st = a.vx[slot]; vy_st = a.vy[slot]; have_v = true; } }         \
+            flush(adj_tag);                                                                                                            \
+        } while (0)
+        if constexpr (EXACT) PAIR_ROWS(std::true_type());
+        else { if (cta_adj) PAIR_ROWS(std::true_type()); else PAIR_ROWS(std::false_type()); }
+#undef PAIR_ROWS
     } else {
         // rare: a run longer than the buffer (very dense cells or sparse rows spanning the domain): batches
 #pragma unroll 1
@@ -514,8 +525,8 @@ k_pair(PairArgs a)
                 // the part of the thread's run that lies in THIS batch (empty for a run in an earlier or later batch)
                 const int jb = max(ra, base), je = min(rb, base + cnt);
                 const bool has = fluid_i && rb > ra && je > jb;
-                scan(std::true_type(), has ? jb - base : 0, has ? je - base : 0, d == 1 ? s - base : -1);
-                flush();
+                scan(std::true_type(), std::true_type(), has ? jb - base : 0, has ? je - base : 0, d == 1 ? s - base : -1);
+                flush(std::true_type());
             }
         }
     }

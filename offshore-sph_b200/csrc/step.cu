@@ -654,7 +654,11 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
     // bit2: the reference bins this particle in a cell other than the one it queries from (wrapped last column,
     // unbinned, non-finite): cell adjacency then does not follow from distance and the pair kernel tests it
     const bool irregular = c.coarse.x != c.coarse.z || c.coarse.y != c.coarse.w || !c.binned;
-    a.s_info[s] = info | (fluid ? 1 : 0) | (irregular ? 4 : 0) | (c.binned ? 0 : 8);      // bit3: not binned by the reference (never found)
+    // bit3: not binned by the reference (never found).  Bits 4..17 / 18..31: the reference bin cell modulo 2^14 per axis, for
+    // the float pair kernel's adjacency test (two particles within the pair radius are a handful of cells apart, so the
+    // difference modulo 2^14, read as a signed 14-bit number, is in [-1, 1] exactly when the cells are adjacent)
+    a.s_info[s] = info | (fluid ? 1 : 0) | (irregular ? 4 : 0) | (c.binned ? 0 : 8) |
+                  ((c.coarse.x & 0x3fff) << 4) | (int)((unsigned int)(c.coarse.y & 0x3fff) << 18);
     a.s_coarse[s] = c.coarse;
     if (g.do_sort) a.s_gcell[s] = c.gcell;          // the cell the particle is BINNED in: unchanged while the binning is reused
 }

@@ -18,6 +18,7 @@ void emu_yield_cpu();
 namespace emu {
 
 ThreadCtx *cur = nullptr;
+int block_or_flag = 0;
 unsigned char *dyn_smem_ptr = nullptr;
 
 // ---- context switch ---------------------------------------------------------------------------------------------------

@@ -104,6 +104,19 @@ template <typename T> inline cudaError_t cudaFuncSetAttribute(T *, cudaFuncAttri
 
 // ---- synchronisation and warp collectives ---------------------------------------------------------------------------
 inline void __syncthreads() { emu::block_barrier(); }
+// barrier + OR over the CTA: set between two barriers, read, and cleared by thread 0 behind a third one (the next call starts
+// with a barrier, so the clearing cannot overtake a later contribution)
+namespace emu { extern int block_or_flag; }
+inline int __syncthreads_or(int pred)
+{
+    emu::block_barrier();
+    if (pred) emu::block_or_flag = 1;
+    emu::block_barrier();
+    const int r = emu::block_or_flag;
+    emu::block_barrier();
+    if (emu::cur->linear == 0) emu::block_or_flag = 0;
+    return r;
+}
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_collective(emu::OP_SYNC, mask, 0, 0, 32); }
 template <typename T> inline T __shfl_sync(unsigned m, T v, int src, int w = 32) { return emu::from_bits<T>(emu::warp_collective(emu::OP_SHFL_IDX, m, emu::to_bits(v), src, w)); }
 template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x, int w = 32) { return emu::from_bits<T>(emu::warp_collective(emu::OP_SHFL_XOR, m, emu::to_bits(v), x, w)); }
