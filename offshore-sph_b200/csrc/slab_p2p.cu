@@ -15,6 +15,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <vector>
@@ -70,7 +71,8 @@ struct osph_slab_p2p {
 // instead of leaving the others inside this kernel for ever.
 __global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int world, size_t off_data, size_t off_flag,
                                  int slot, const double *__restrict__ payload, int n, unsigned long long seq,
-                                 double *__restrict__ out_all, int reduce_min, long long spin_limit, unsigned int *status)
+                                 double *__restrict__ out_all, int reduce_min, long long spin_limit, unsigned int *status,
+                                 double *host_all, volatile unsigned long long *host_flag)
 {
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (r < world) {
@@ -102,6 +104,16 @@ __global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int 
             for (int q = 1; q < world; q++) m = fmin(m, out_all[q * n + threadIdx.x]);
             out_all[world * n + threadIdx.x] = m;
         }
+    }
+    if (host_all) {
+        // The host needs this gather (message sizes of the step): it goes straight into pinned host memory, followed by the
+        // sequence number the host spins on -- no cudaMemcpy + stream synchronisation on the critical path of the step.
+        __syncthreads();
+        for (int k = threadIdx.x; k < world * n; k += blockDim.x) host_all[k] = out_all[k];
+        if (threadIdx.x == 0) reinterpret_cast<unsigned int *>(host_all + world * n)[0] = *status;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) *host_flag = seq;
     }
 }
 
@@ -152,7 +164,8 @@ extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x
     }
     OSPH_CUDA(cudaMalloc(&s->d_dt3, sizeof(double) * 4));
     OSPH_CUDA(cudaMalloc(&s->d_all_dt, sizeof(double) * 4 * (world + 1)));
-    OSPH_CUDA(cudaMallocHost(&s->h_all_meta, sizeof(double) * (12 * world + 1)));
+    OSPH_CUDA(cudaMallocHost(&s->h_all_meta, sizeof(double) * (12 * world + 2)));      // + status word + sequence flag (device-written)
+    memset(s->h_all_meta, 0, sizeof(double) * (12 * world + 2));
     {
         const char *e = getenv("OSPH_SLAB_PROFILE");
         s->profile = e && e[0] == '1';
@@ -250,7 +263,7 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         // ---- identical dt on every rank: mailbox all-gather + min ----
         if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return fail(rc);
         k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, slot, s->d_dt3, 3, s->seq,
-                                                       s->d_all_dt, 1, s->spin_limit, d_status);
+                                                       s->d_all_dt, 1, s->spin_limit, d_status, nullptr, nullptr);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
         P2P_MARK(1);
@@ -260,15 +273,28 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         const double width = std::max(q * s->hmax, std::min(s->r0, 3.0 * s->hmax)) * 1.1;
         if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return fail(rc);
         k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_meta, s->off_meta_flag, slot, s->d_meta, 12,
-                                                       s->seq, s->d_all_meta, 0, s->spin_limit, d_status);
+                                                       s->seq, s->d_all_meta, 0, s->spin_limit, d_status, s->h_all_meta,
+                                                       reinterpret_cast<volatile unsigned long long *>(s->h_all_meta + 12 * W + 1));
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
         P2P_MARK(3);
-        if (cudaMemcpyAsync(s->h_all_meta, s->d_all_meta, sizeof(double) * 12 * W, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaMemcpyAsync(s->h_all_meta + 12 * W, d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {           // the one host sync of the step
-            ctx->err = std::string("slab exchange: ") + cudaGetErrorString(cudaGetLastError());
-            return fail(OSPH_E_CUDA);
+        {
+            // wait for the kernel's sequence number in pinned memory (the one host wait of the step); a CUDA error or a dead
+            // stream ends the wait through cudaStreamQuery
+            volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(s->h_all_meta + 12 * W + 1);
+            const auto t0 = std::chrono::steady_clock::now();
+            long long spins = 0;
+            while (*flag != s->seq) {
+                if ((++spins & 0xfff) == 0) {
+                    const cudaError_t q = cudaStreamQuery(ctx->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) { ctx->err = std::string("slab exchange: ") + cudaGetErrorString(q); return fail(OSPH_E_CUDA); }
+                    if (q == cudaSuccess && *flag != s->seq) { ctx->err = "slab exchange: the mailbox kernel ended without publishing its result"; return fail(OSPH_E_CUDA); }
+                    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0 * (double)s->spin_limit / 2.0e9 + 5.0) {
+                        ctx->err = "slab exchange: timed out waiting for the meta mailbox"; return fail(OSPH_E_PEER);
+                    }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
         }
         P2P_MARK(4);
         const auto host_t0 = std::chrono::steady_clock::now();

@@ -469,6 +469,7 @@ cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned int)
 }
 cudaError_t cudaIpcCloseMemHandle(void *p) { return cudaFree(p); }
 
+cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }      // launches run to completion before they return
 cudaError_t cudaMallocHost(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned int) { return cudaMallocHost(p, bytes); }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
