@@ -47,7 +47,7 @@ if has ncu; then
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pair -s 4 -c 1 -o $OUT/pair_fp32 -f \
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --precision fp32 > /dev/null 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_prepare|k_keys|k_sort|k_gather|k_correct|k_cell' -s 30 -c 16 \
+  timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_prepare|k_bin|k_gather|k_correct|k_grid|k_timestep' -s 14 -c 16 \
       -o $OUT/stream_fp64 -f python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 fi
 tail -120 $LOG
