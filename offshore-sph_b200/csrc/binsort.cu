@@ -103,17 +103,30 @@ k_bin_scan(unsigned int *__restrict__ counts, const GridParams *__restrict__ gp,
 
 // slot = begin[cell] + arrival rank.  Besides the storage slot, every sorted position receives its cell's (begin, end): the
 // ranking that follows (fused into the gather kernel, or k_bin_rank) then starts without a dependent table lookup.
+#define BIN_SCATTER_ITEMS 4
 __global__ void __launch_bounds__(256)
 k_bin_scatter(const unsigned int *__restrict__ key, const unsigned int *__restrict__ arrival, int n,
               const int2 *__restrict__ cell_range, int2 *__restrict__ range_out, unsigned int *__restrict__ idx_out,
               const GridParams *__restrict__ gp)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !gp->do_sort) return;
-    const int2 r = cell_range[key[i]];
-    const unsigned int pos = (unsigned int)r.x + arrival[i];
-    range_out[pos] = r;
-    idx_out[pos] = (unsigned int)i;
+    if (!gp->do_sort) return;                             // (a quarter of the CTAs of a one-item kernel: the early exit is cheaper)
+    unsigned int k[BIN_SCATTER_ITEMS], a[BIN_SCATTER_ITEMS];
+    const int base = blockIdx.x * (256 * BIN_SCATTER_ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < BIN_SCATTER_ITEMS; r++) {
+        const int i = base + r * 256;
+        k[r] = i < n ? key[i] : 0u; a[r] = i < n ? arrival[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < BIN_SCATTER_ITEMS; r++) {
+        const int i = base + r * 256;
+        if (i < n) {
+            const int2 rg = cell_range[k[r]];
+            const unsigned int pos = (unsigned int)rg.x + a[r];
+            range_out[pos] = rg;
+            idx_out[pos] = (unsigned int)i;
+        }
+    }
 }
 
 // Canonical order as a kernel of its own: only on the builds that physically reorder the state (it needs the final
@@ -159,7 +172,8 @@ int osph_bin_sort(osph_ctx *ctx, int64_t n_all, bool rank_now)
     OSPH_LAUNCH_CHECK();
     const int grid = div_up(n_all, 256);
     int2 *ranges = reinterpret_cast<int2 *>(ctx->scratch);
-    k_bin_scatter<<<grid, 256, 0, ctx->stream>>>(ctx->key[0], ctx->idx[0], (int)n_all, ctx->cell_range, ranges, ctx->idx[1], ctx->d_grid);
+    k_bin_scatter<<<div_up(n_all, 256 * BIN_SCATTER_ITEMS), 256, 0, ctx->stream>>>(ctx->key[0], ctx->idx[0], (int)n_all, ctx->cell_range, ranges,
+                                                                                  ctx->idx[1], ctx->d_grid);
     OSPH_LAUNCH_CHECK();
     if (rank_now) {
         k_bin_rank<<<grid, 256, 0, ctx->stream>>>(ranges, ctx->idx[1], (int)n_all, ctx->idx[0], ctx->d_sc, ctx->d_grid);
