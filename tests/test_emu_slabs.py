@@ -234,3 +234,64 @@ def test_exchange_region_overflow_is_a_loud_collective_error(seq):
     assert len(res) == world and all(p.exitcode == 0 for p in procs), res
     for rank, msg in res:
         assert "overflow" in msg.lower(), (rank, msg)
+
+
+def _worker_silent_peer(rank, world, port, lib, q):
+    os.environ["OSPH_LIB"] = lib
+    os.environ["OSPH_P2P_SPIN_SECONDS"] = "3"
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    root = os.path.dirname(HERE)
+    for p in (root, os.path.join(root, "offshore-sph_b200"), HERE):
+        sys.path.insert(0, p)
+    import time
+    import torch
+    import torch.distributed as dist
+    from osph_b200 import capi, slabs, workloads as W
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = W.dam_break_case(40, seed=2)
+    pA, c = case['pA'], case['consts']
+    cfg = capi.make_config(c, 'cubic', 'pec', capi.FP64, case['h'])
+    ctx = capi.Context(cfg)
+    cuts, local_pA, ids = slabs.partition(pA, world, rank)
+    run = slabs.P2PSlabRun(ctx, cuts, local_pA, ids, 'cubic', case['r0'], case['h'], torch.device('cpu'),
+                           mig_frac=0.2, ghost_frac=0.5, min_cap=256)
+    msg, t0 = "", time.time()
+    if rank == 0:
+        msg = "stayed out"                      # e.g. a Python exception on this rank before its step: it never joins the exchange
+    else:
+        try:
+            run.step(2, None, 0.05)
+        except Exception as e:      # noqa: BLE001
+            msg = "%s: %s" % (type(e).__name__, e)
+    q.put((rank, msg, time.time() - t0))
+    dist.barrier()
+    run.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_a_silent_peer_is_a_timeout_not_a_hang():
+    """Peer-memory sequencer: a rank that never joins the step (it failed elsewhere) must not leave the others inside a
+    mailbox kernel for ever.  The waits are bounded (OSPH_P2P_SPIN_SECONDS): the waiting rank comes back with OSPH_E_PEER."""
+    import queue
+    import time
+    lib = emu_build.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_silent_peer, args=(r, 2, port, lib, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res, t_end = [], time.time() + 120
+    while len(res) < 2 and time.time() < t_end:
+        try:
+            res.append(q.get(timeout=1.0))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    [p.join(30) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
+    assert len(res) == 2 and all(p.exitcode == 0 for p in procs), res
+    waited = [r for r in res if r[0] == 1][0]
+    assert "did not answer" in waited[1] or "peer" in waited[1].lower(), waited
+    assert waited[2] < 60, waited
