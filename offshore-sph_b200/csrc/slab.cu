@@ -37,32 +37,44 @@ __device__ __forceinline__ void write_full(double *dst, const SlabPackArgs &a, i
     dst[OSPH_NUM_FIELDS + 1] = (double)a.row[i];
 }
 
+// One slot per lane of a group, one atomic per warp: the lanes that take part (`take`) are counted with a ballot, the first
+// of them reserves that many slots, every lane gets base + its rank.  Halo particles come in runs of a few dozen
+// consecutive particles (the cells next to a face, row by row), so a warp usually reserves several slots at once
+// instead of hitting one counter per particle.  All 32 lanes must call.
+__device__ __forceinline__ int warp_reserve(int *counter, bool take)
+{
+    const unsigned int m = __ballot_sync(0xffffffffu, take);
+    if (m == 0) return 0;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(256)
 k_slab_pack(SlabPackArgs a)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    double x = a.f[OSPH_F_X][i];
-    int side = x < a.x_lo ? 0 : (x >= a.x_hi ? 1 : -1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < a.n;
+    const double x = valid ? a.f[OSPH_F_X][i] : 0.0;
+    const int side = !valid ? -1 : (x < a.x_lo ? 0 : (x >= a.x_hi ? 1 : -1));
+    // migrants: full record to the new owner, light copy kept here as a ghost, slot remembered for the hole filling
+    const int kl = warp_reserve(&a.counters[0], side == 0), kr = warp_reserve(&a.counters[1], side == 1);
+    const int g = warp_reserve(&a.counters[4], side >= 0), m = warp_reserve(&a.counters[6], side >= 0);
     if (side >= 0) {
-        int k = atomicAdd(&a.counters[side], 1);
-        int g = atomicAdd(&a.counters[4], 1);
-        int m = atomicAdd(&a.counters[6], 1);
+        const int k = side ? kr : kl;
         if (k < a.mig_cap && g < a.ghost_cap) {
             write_full((side ? a.mig_right : a.mig_left) + (size_t)k * OSPH_WIRE_FULL, a, i);
             write_light(a.ghost + (size_t)g * OSPH_WIRE_HALO, a, i);
             a.mig_slots[m] = i;
         } else a.counters[5] = 1;
-        return;
     }
-    if (x < a.x_lo + a.width) {
-        int k = atomicAdd(&a.counters[2], 1);
-        if (k < a.halo_cap) write_light(a.halo_left + (size_t)k * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1;
-    }
-    if (x >= a.x_hi - a.width) {
-        int k = atomicAdd(&a.counters[3], 1);
-        if (k < a.halo_cap) write_light(a.halo_right + (size_t)k * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1;
-    }
+    // halo: light records for the neighbour on that side (a particle of a narrow slab can be in both halos)
+    const bool hl = valid && side < 0 && x < a.x_lo + a.width, hr = valid && side < 0 && x >= a.x_hi - a.width;
+    const int khl = warp_reserve(&a.counters[2], hl), khr = warp_reserve(&a.counters[3], hr);
+    if (hl) { if (khl < a.halo_cap) write_light(a.halo_left + (size_t)khl * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1; }
+    if (hr) { if (khr < a.halo_cap) write_light(a.halo_right + (size_t)khr * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1; }
 }
 
 __global__ void k_slab_meta(const int *counters, const StepScalars *sc, double *meta)
