@@ -135,6 +135,13 @@ extern "C" int osph_create(const osph_config *cfg, osph_ctx **out)
         ctx->bin_sort = !(e && std::string(e) == "radix");
         // OSPH_SKIN: skin of the sort cadence as a fraction of the pair radius (e.g. 0.1); "auto" / unset = sized on the
         // device from the observed displacement per build; 0 = sort at every build (the behaviour before the cadence)
+        // OSPH_FUSE_SCALARS (A/B runs, default 0): bit 0 = k_grid_params in the last CTA of the predictor pass, bit 1 =
+        // k_timestep in the last CTA of the pair kernel.  Measured on the B200 (profiles/r02/README.md): neither pays -- the
+        // single-thread tail is as long as the one-thread kernel it replaces (0.4027 vs 0.4014 ms per step), and in the pair
+        // kernel the fence + barrier + ticket of every CTA costs 10 us (305 vs 295 us).
+        const char *f = getenv("OSPH_FUSE_SCALARS");
+        const int bits = f ? atoi(f) : 0;
+        ctx->grid_fusion = (bits & 1) != 0; ctx->timestep_fusion = (bits & 2) != 0;
         const char *k = getenv("OSPH_SKIN");
         ctx->skin_frac = (k && *k && std::string(k) != "auto") ? atof(k) : -1.0;
         if (ctx->skin_frac > 1.0) ctx->skin_frac = 1.0;
@@ -467,19 +474,29 @@ extern "C" int osph_step(osph_ctx *ctx, int32_t nsteps, double fixed_dt, double 
     // call ends with the plain corrector, so the state and the reductions are complete when the call returns.
     const bool fuse = nsteps > 1 && ctx->cfg.integrator == OSPH_INTEGRATOR_PEC && !ctx->slab && ctx->n_fluid > 0 &&
                       !ctx->cfg.summation_density;
+    const bool ts_in_pair = fuse && ctx->timestep_fusion;
     for (int s = 0; s < nsteps; s++) {
         const bool fused_step = fuse && s > 0;
         if (!fused_step && (rc = ensure_reductions(ctx))) return rc;
         // the scalar resets ride along in k_timestep / k_grid_params
-        if ((rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true, nullptr, fuse ? (fused_step ? 2 : 1) : 0)))
+        // (from the second step of a fused call on, dt was computed by the last CTA of the previous step's pair kernel)
+        const bool dt_done = fused_step && ts_in_pair;
+        if (!dt_done && (rc = osph_launch_timestep(ctx, fixed_dt > 0 ? fixed_dt : -1.0, true, true, nullptr, fuse ? (fused_step ? 2 : 1) : 0)))
             return rc;
-        if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true, fuse ? (fused_step ? 2 : 1) : 0))) return rc;
+        // the predictor pass also forms the grid and the sort decision (last CTA) once the cell table has been sized
+        BuildPlan plan = osph_plan_build(ctx);
+        const bool grid_in_prepare = ctx->sized && ctx->grid_fusion;
+        if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true, fuse ? (fused_step ? 2 : 1) : 0,
+                                      grid_in_prepare ? &plan : nullptr, !fuse))) return rc;
         ctx->prepared = true;
         if ((rc = osph_size_cell_table(ctx))) return rc;
-        if ((rc = osph_launch_build(ctx, !fuse))) return rc;
+        plan.grid_done = grid_in_prepare;
+        if ((rc = osph_launch_build(ctx, !fuse, &plan))) return rc;
         ctx->pair_reduce_a2 = fuse;
+        ctx->pair_next_timestep = ts_in_pair && s < nsteps - 1;       // the next step of this call is a fused one: its dt here
+        ctx->pair_ts_fixed_dt = fixed_dt > 0 ? fixed_dt : -1.0;
         rc = osph_launch_pair(ctx);
-        ctx->pair_reduce_a2 = false;
+        ctx->pair_reduce_a2 = false; ctx->pair_next_timestep = false;
         if (rc) return rc;
         ctx->c_uniform = true;
         if (!fuse || s == nsteps - 1) {

@@ -69,6 +69,7 @@ struct StepScalars {
     double dt_prev;                              // dt of the step before (fused corrector + predictor, step.cu)
     unsigned long long disp2max;                 // max |x - x_ref|^2 over the particles, x_ref = position at the last sort (k_prepare)
     long long builds, sorts;                     // neighbour-structure builds / those that sorted (osph_sort_stats)
+    unsigned int prepare_ticket, pair_ticket;    // CTAs done: the last one of k_prepare / k_pair runs the fused scalar kernel
 };
 
 struct osph_export_ring;          // export.cu
@@ -112,6 +113,8 @@ struct osph_ctx {
     int64_t cell_cap = 0;
     // sort cadence: positions at the last sort (storage order) and whether they describe the resident particles
     double *xref = nullptr, *yref = nullptr;
+    bool timestep_fusion = false;
+    bool grid_fusion = false;          // osph_step: k_grid_params runs in the last CTA of the predictor pass, k_timestep in the pair kernel's
     bool skin_valid = false;          // false: the next build must sort (upload, external edits, slab mode, table re-sized)
     double skin_frac = -1.0;          // OSPH_SKIN: skin as a fraction of the pair radius; < 0 adaptive; 0 sorts every build
     // counting sort by cell (binsort.cu): cell histogram, tile states of its single-pass scan (+ the ticket counter)
@@ -164,6 +167,8 @@ struct osph_ctx {
     cudaEvent_t pair_ev[2 * OSPH_PAIR_EVENTS] = {nullptr};   // (start, stop) per pair-kernel launch
     int pair_ev_used = 0;
     bool time_pair = true;
+    bool pair_next_timestep = false; // osph_step's fused loop: the pair kernel's last CTA computes the next step's dt (k_timestep fused)
+    double pair_ts_fixed_dt = -1.0;
     bool pair_reduce_a2 = false;     // osph_step's fused loop: the pair kernel reduces max |a|^2 for the next dt
 
     // pinned staging for transfers
@@ -260,6 +265,41 @@ __device__ __forceinline__ int bin_canonical_slot(int2 r, int s, unsigned int mi
     int before = 0;
     for (int t = r.x; t < r.y; t++) before += idx_arrival[t] < mine ? 1 : 0;
     return r.x + before;
+}
+
+// TimeStep.compute / courant / force (src/Equations/TimeStep.py:11-56), strict IEEE: one thread.  Kernel of its own
+// (k_timestep, step.cu) or the tail of the pair kernel's last CTA (osph_step's loop).
+// fused: 1 = the dt scalars are reset here, right after use (the predictor and the pair kernel of this step reduce the next
+// ones); 2 = additionally c_max is the uniform co (no corrector pass reduced it).
+// All reads of *sc are volatile: in a last-CTA tail the words were just written by the atomics of other CTAs.
+__device__ __attribute__((noinline)) static void timestep_body(StepScalars *sc, double gamma_c, double gamma_f, double fixed_dt, double *dt_log,
+                                                  long long dt_log_cap, int reset_prepare, const double *reduced3, int fused, double co)
+{
+    auto rd = [](const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); };
+    if (reduced3) {           // slab mode: all-reduced {h_min, -c_max, -a2_max} replaces the local reduction
+        sc->hmin_fluid = enc_f64(reduced3[0]); sc->cmax_fluid = enc_f64(-reduced3[1]); sc->a2max_fluid = enc_f64(-reduced3[2]);
+    }
+    if (reset_prepare) {      // folded k_reset_prepare_scalars: the predictor that follows reduces into these
+        sc->xmin = ENC_POS_INF; sc->ymin = ENC_POS_INF; sc->xmax = ENC_NEG_INF; sc->ymax = ENC_NEG_INF;
+        sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF; sc->disp2max = ENC_NEG_INF;
+    }
+    double out0, c = 0.0, f = 0.0;
+    if (fixed_dt > 0.0) { out0 = fixed_dt; }
+    else {
+        double hmin = dec_f64(rd(&sc->hmin_fluid)), cmax = fused == 2 ? co : dec_f64(rd(&sc->cmax_fluid)), a2 = dec_f64(rd(&sc->a2max_fluid));
+        c = __ddiv_rn(__dmul_rn(gamma_c, hmin), cmax);
+        f = (a2 < 1e-12) ? 1e10 : __dmul_rn(gamma_f, __dsqrt_rn(__ddiv_rn(hmin, a2)));
+        out0 = c < f ? c : f;
+        if (out0 < 1e-6) atomicOr(&sc->status, OSPH_S_SMALL_DT);
+    }
+    if (fused) { sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF; }
+    sc->dt_prev = *reinterpret_cast<const volatile double *>(&sc->dt[0]);
+    sc->dt[0] = out0; sc->dt[1] = c; sc->dt[2] = f;
+    if (dt_log) {
+        long long k = *reinterpret_cast<const volatile long long *>(&sc->dt_log_count);
+        if (k < dt_log_cap) { dt_log[3 * k] = out0; dt_log[3 * k + 1] = c; dt_log[3 * k + 2] = f; }
+        sc->dt_log_count = k + 1;
+    }
 }
 
 __device__ __forceinline__ int warp_min_i(int v) { return __reduce_min_sync(0xffffffffu, v); }

@@ -561,6 +561,21 @@ k_pair(PairArgs a)
             a.xsphx[slot] = 0.0; a.xsphy[slot] = 0.0;
         }
     }
+    if (a.ts_sc) {
+        // Fused time step of the next step: every CTA has reduced its max |a|^2 (the warps' atomics above) and min h came
+        // from this step's predictor pass, so the CTA that finishes last computes dt -- no k_timestep launch between two
+        // steps.  (The outputs stored above are not read by it.)
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int ticket = atomicAdd(&a.ts_sc->pair_ticket, 1u);
+            if (ticket == gridDim.x - 1) {
+                a.ts_sc->pair_ticket = 0u;
+                __threadfence();
+                timestep_body(a.ts_sc, a.ts_gamma_c, a.ts_gamma_f, a.ts_fixed_dt, a.ts_dt_log, a.ts_dt_log_cap, 1, nullptr, a.ts_fused, a.ts_co);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -702,6 +717,11 @@ int osph_launch_pair(osph_ctx *ctx)
     a.alpha_c_f = (float)a.alpha_c_d; a.beta_f = (float)c.beta; a.r0_f = (float)c.r0; a.r0sq_f = a.r0_f * a.r0_f;
     a.neg_eps_f = (float)a.neg_eps_d; a.D_f = (float)c.D;
     a.method_xsph = c.method_xsph; a.summation_density = c.summation_density;
+    a.ts_sc = nullptr; a.ts_gamma_c = a.ts_gamma_f = a.ts_fixed_dt = a.ts_co = 0.0; a.ts_dt_log = nullptr; a.ts_dt_log_cap = 0; a.ts_fused = 0;
+    if (ctx->pair_next_timestep) {
+        a.ts_sc = ctx->d_sc; a.ts_gamma_c = c.cfl_courant; a.ts_gamma_f = c.cfl_force; a.ts_fixed_dt = ctx->pair_ts_fixed_dt;
+        a.ts_co = c.co; a.ts_dt_log = ctx->d_dt_log; a.ts_dt_log_cap = (long long)ctx->dt_log_cap; a.ts_fused = 2;
+    }
     int grid = div_up(ctx->n + ctx->n_ghost, OSPH_PAIR_THREADS);
     if (c.summation_density) {
         if (c.precision == OSPH_FP64) launch_summation<double2>(ctx, a); else launch_summation<float2>(ctx, a);

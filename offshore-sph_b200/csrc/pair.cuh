@@ -21,4 +21,10 @@ struct PairArgs {
     // of the FP instructions and do not occupy registers in the pair loop
     double alpha_c_d, beta_d, r0_d, r0sq_d, neg_eps_d, D_d;
     float alpha_c_f, beta_f, r0_f, r0sq_f, neg_eps_f, D_f;
+    // fused k_timestep of the NEXT step (osph_step's loop): run by the CTA that finishes last; ts_sc == nullptr: not fused
+    StepScalars *ts_sc;
+    double ts_gamma_c, ts_gamma_f, ts_fixed_dt, ts_co;
+    double *ts_dt_log;
+    long long ts_dt_log_cap;
+    int ts_fused;
 };

@@ -146,7 +146,7 @@ __global__ void k_reset_dt_scalars(StepScalars *sc)
 __global__ void k_init_scalars(StepScalars *sc)
 {
     sc->status = 0; sc->dt[0] = sc->dt[1] = sc->dt[2] = 0.0; sc->ke = 0.0; sc->dt_log_count = 0;
-    sc->builds = 0; sc->sorts = 0; sc->disp2max = ENC_NEG_INF;
+    sc->builds = 0; sc->sorts = 0; sc->disp2max = ENC_NEG_INF; sc->prepare_ticket = 0u; sc->pair_ticket = 0u;
 }
 
 template <int NV>
@@ -215,6 +215,8 @@ static double rden_for(double damping)
 #ifndef PREP_ITEMS
 #define PREP_ITEMS 8
 #endif
+__device__ void grid_params_body(StepScalars *sc, GridParams *g, double nn_scale, double pair_radius_q, double r0,
+                                 long long cell_cap, int reset_dt, int force_sort, double skin_frac);
 template <int INTEG, bool PREDICT, bool FUSED>
 __global__ void __launch_bounds__(256)
 k_prepare(PrepareArgs a)
@@ -335,6 +337,21 @@ k_prepare(PrepareArgs a)
                                           &a.sc->xmax, &a.sc->ymax, &a.sc->hmax_all, &a.sc->disp2max};
         block_minmax_atomic<7>(v, p, 3);
     }
+    if (a.grid) {
+        // Fused grid parameters (osph_step's loop): the CTA that finishes last has every reduction of the pass behind it and
+        // forms the grid and the sort decision right here -- no k_grid_params launch between this pass and the sort kernels.
+        // Thread 0 issued this CTA's atomics itself (lane 0 of warp 0), so its fence orders them before the ticket.
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int ticket = atomicAdd(&a.sc->prepare_ticket, 1u);
+            if (ticket == gridDim.x - 1) {
+                a.sc->prepare_ticket = 0u;
+                __threadfence();
+                grid_params_body(a.sc, a.grid, a.g_nn_scale, a.g_pair_radius_q, a.g_r0, a.g_cell_cap, a.g_reset_dt, a.g_force_sort,
+                                 a.g_skin_frac);
+            }
+        }
+    }
 }
 
 template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, true, false>(PrepareArgs);
@@ -345,14 +362,17 @@ template __global__ void k_prepare<OSPH_INTEGRATOR_PEC, false, false>(PrepareArg
 // ---------------------------------------------------------------------------------------------
 // Grid parameters: the reference grid (NNLinkedList.py:86-127) and the acceleration grid.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, double pair_radius_q, double r0,
-                              long long cell_cap, int reset_dt, int force_sort, double skin_frac)
+__device__ void grid_params_body(StepScalars *sc, GridParams *g, double nn_scale, double pair_radius_q, double r0,
+                                 long long cell_cap, int reset_dt, int force_sort, double skin_frac)
 {
     if (reset_dt) {           // folded k_reset_dt_scalars: the corrector of this step reduces into these
         sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF;
         }
-    double xmin = dec_f64(sc->xmin), xmax = dec_f64(sc->xmax), ymin = dec_f64(sc->ymin), ymax = dec_f64(sc->ymax);
-    double hmin = dec_f64(sc->hmin_all), hmax = dec_f64(sc->hmax_all);
+    // (volatile: inside k_prepare's last CTA these words were just written by the atomics of other CTAs, and the SM may
+    // hold an older copy of the line in L1 from its own plain loads of sc->dt)
+    auto rd = [](const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); };
+    double xmin = dec_f64(rd(&sc->xmin)), xmax = dec_f64(rd(&sc->xmax)), ymin = dec_f64(rd(&sc->ymin)), ymax = dec_f64(rd(&sc->ymax));
+    double hmin = dec_f64(rd(&sc->hmin_all)), hmax = dec_f64(rd(&sc->hmax_all));
     g->xmin = xmin; g->xmax = xmax; g->ymin = ymin; g->ymax = ymax; g->hmax = hmax;
     double cs = __dmul_rn(hmin, nn_scale);           // :104-105
     if (cs < 1e-6) cs = 1.0;                          // :107-108
@@ -382,7 +402,7 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
     // mode and the radix path sort every build); 3 = the host's sizing pass for the cell table: grid only, no bookkeeping
     const bool dry = force_sort == 3;
     if (!dry) sc->builds++;
-    const double disp = sqrt(fmax(dec_f64(sc->disp2max), 0.0));
+    const double disp = sqrt(fmax(dec_f64(rd(&sc->disp2max)), 0.0));
     const bool reuse = !force_sort && skin_frac != 0.0 && g->sort_count > 0 && !g->regime_a && !g->adj_always && !(R >= cs) &&
                        isfinite(disp) && R + 2.0 * disp * (1.0 + 1e-9) <= g->gsize;
     if (reuse) {
@@ -438,6 +458,12 @@ __global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, d
     int reach = regime_a ? 1 : (int)ceil(rs / gs);
     if (reach < 1) reach = 1;
     g->reach_set = reach;
+}
+
+__global__ void k_grid_params(StepScalars *sc, GridParams *g, double nn_scale, double pair_radius_q, double r0,
+                              long long cell_cap, int reset_dt, int force_sort, double skin_frac)
+{
+    grid_params_body(sc, g, nn_scale, pair_radius_q, r0, cell_cap, reset_dt, force_sort, skin_frac);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -760,30 +786,7 @@ template __global__ void k_correct<OSPH_INTEGRATOR_PEC, false>(CorrectArgs);
 __global__ void k_timestep(StepScalars *sc, double gamma_c, double gamma_f, double fixed_dt,
                            double *dt_log, long long dt_log_cap, int reset_prepare, const double *reduced3, int fused, double co)
 {
-    if (reduced3) {           // slab mode: all-reduced {h_min, -c_max, -a2_max} replaces the local reduction
-        sc->hmin_fluid = enc_f64(reduced3[0]); sc->cmax_fluid = enc_f64(-reduced3[1]); sc->a2max_fluid = enc_f64(-reduced3[2]);
-    }
-    if (reset_prepare) {      // folded k_reset_prepare_scalars: the predictor that follows reduces into these
-        sc->xmin = ENC_POS_INF; sc->ymin = ENC_POS_INF; sc->xmax = ENC_NEG_INF; sc->ymax = ENC_NEG_INF;
-        sc->hmin_all = ENC_POS_INF; sc->hmax_all = ENC_NEG_INF; sc->disp2max = ENC_NEG_INF;
-    }
-    double out0, c = 0.0, f = 0.0;
-    if (fixed_dt > 0.0) { out0 = fixed_dt; }
-    else {
-        double hmin = dec_f64(sc->hmin_fluid), cmax = fused == 2 ? co : dec_f64(sc->cmax_fluid), a2 = dec_f64(sc->a2max_fluid);
-        c = __ddiv_rn(__dmul_rn(gamma_c, hmin), cmax);
-        f = (a2 < 1e-12) ? 1e10 : __dmul_rn(gamma_f, __dsqrt_rn(__ddiv_rn(hmin, a2)));
-        out0 = c < f ? c : f;
-        if (out0 < 1e-6) atomicOr(&sc->status, OSPH_S_SMALL_DT);
-    }
-    if (fused) { sc->hmin_fluid = ENC_POS_INF; sc->cmax_fluid = ENC_NEG_INF; sc->a2max_fluid = ENC_NEG_INF; }
-    sc->dt_prev = sc->dt[0];
-    sc->dt[0] = out0; sc->dt[1] = c; sc->dt[2] = f;
-    if (dt_log) {
-        long long k = sc->dt_log_count;
-        if (k < dt_log_cap) { dt_log[3 * k] = out0; dt_log[3 * k + 1] = c; dt_log[3 * k + 2] = f; }
-        sc->dt_log_count = k + 1;
-    }
+    timestep_body(sc, gamma_c, gamma_f, fixed_dt, dt_log, dt_log_cap, reset_prepare, reduced3, fused, co);
 }
 
 // KineticEnergy (src/Equations/KineticEnergy.py:6-12) over the fluid rows; deterministic two-stage sum.
@@ -1042,7 +1045,10 @@ int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids)
     return 0;
 }
 
-int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset, int fused)
+static double pair_radius_q(const osph_ctx *ctx);
+
+int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset, int fused,
+                        const BuildPlan *grid_plan, bool grid_reset_dt)
 {
     PrepareArgs a;
     a.n = (int)ctx->n; a.label = ctx->label;
@@ -1058,6 +1064,14 @@ int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, 
     a.reduce_hmin_fluid = fused ? 1 : 0;
     a.rden = rden_for(damping);
     a.xref = ctx->xref; a.yref = ctx->yref;
+    a.grid = nullptr;
+    if (grid_plan) {
+        a.grid = ctx->d_grid; a.g_nn_scale = ctx->cfg.nn_scale; a.g_pair_radius_q = pair_radius_q(ctx); a.g_r0 = ctx->cfg.r0;
+        a.g_skin_frac = ctx->skin_frac; a.g_cell_cap = (long long)ctx->cell_cap; a.g_reset_dt = grid_reset_dt ? 1 : 0;
+        a.g_force_sort = grid_plan->force;
+    } else {
+        a.g_nn_scale = a.g_pair_radius_q = a.g_r0 = a.g_skin_frac = 0.0; a.g_cell_cap = 0; a.g_reset_dt = a.g_force_sort = 0;
+    }
     if (!skip_reset) { k_reset_prepare_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_sc); OSPH_LAUNCH_CHECK(); }
     int grid = div_up(ctx->n, 256 * PREP_ITEMS);
     int integ = ctx->cfg.integrator;
@@ -1131,20 +1145,29 @@ int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt, int force_sort)
     return 0;
 }
 
-int osph_launch_build(osph_ctx *ctx, bool reset_dt)
+BuildPlan osph_plan_build(osph_ctx *ctx)
 {
-    int n = (int)ctx->n, n_all = (int)(ctx->n + ctx->n_ghost), grid = div_up(n_all, 256);
+    BuildPlan p;
     int every = ctx->cfg.reorder_every > 0 ? ctx->cfg.reorder_every : 32;
     // physical re-sort on the 3rd build after an upload, then every `every` builds: a caller that uploads, steps once
     // and downloads (the host-buffer plugin call pattern) never pays for it, a resident run gets it early
-    const bool reorder_now = ctx->build_counter % every == (2 % every);
+    p.reorder_now = ctx->build_counter % every == (2 % every);
     // sort cadence (k_grid_params): the device may reuse the last binning unless the particle set was touched from outside
     // since (skin_valid), the state is about to be reordered physically, or the build always sorts (slab mode: the ghost
     // set changes every step; radix path)
-    const bool always = ctx->slab || ctx->n_ghost > 0 || !ctx->bin_sort || ctx->skin_frac == 0.0;
-    const int force = always ? 2 : ((!ctx->skin_valid || reorder_now) ? 1 : 0);
-    int rc = osph_launch_grid_params(ctx, reset_dt, force);
-    if (rc) return rc;
+    p.always = ctx->slab || ctx->n_ghost > 0 || !ctx->bin_sort || ctx->skin_frac == 0.0;
+    p.force = p.always ? 2 : ((!ctx->skin_valid || p.reorder_now) ? 1 : 0);
+    p.grid_done = false;
+    return p;
+}
+
+int osph_launch_build(osph_ctx *ctx, bool reset_dt, const BuildPlan *given)
+{
+    int n = (int)ctx->n, n_all = (int)(ctx->n + ctx->n_ghost), grid = div_up(n_all, 256);
+    const BuildPlan plan = given ? *given : osph_plan_build(ctx);
+    const bool reorder_now = plan.reorder_now, always = plan.always;
+    int rc = 0;
+    if (!plan.grid_done && (rc = osph_launch_grid_params(ctx, reset_dt, plan.force))) return rc;
     ctx->skin_valid = !always;
     ctx->sorted_buf = 0;
     const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];

@@ -12,6 +12,11 @@ struct PrepareArgs {
     double dt, damping, fixed_h, h_sigma;
     int use_dev_dt, integ_xsph, strict, dynamic_h;
     const double *xref, *yref;        // positions at the last sort (nullptr: no displacement reduction)
+    // fused k_grid_params (last CTA): nullptr = separate launch
+    GridParams *grid;
+    double g_nn_scale, g_pair_radius_q, g_r0, g_skin_frac;
+    long long g_cell_cap;
+    int g_reset_dt, g_force_sort;
     int reduce_hmin_fluid;            // fused loop: min h over the fluid rows (TimeStep of the next step) is taken here
     double rden;                      // RN(1 / (1 + damping / 2)) for div_den, 0: divide
 };
@@ -74,9 +79,15 @@ int osph_launch_set_deleted(osph_ctx *ctx, const unsigned char *d_active);
 int osph_launch_active_list(osph_ctx *ctx, int n_total, int *d_counters);
 int osph_launch_pack(osph_ctx *ctx);
 int osph_launch_pack_owned(osph_ctx *ctx, int *d_ids);
+// What the next neighbour-structure build will do, decided on the host before the predictor pass is launched (the pass can
+// then run k_grid_params in its last CTA): force_sort as k_grid_params takes it, physical reorder of the state or not.
+struct BuildPlan { int force; bool reorder_now; bool always; bool grid_done; };
+BuildPlan osph_plan_build(osph_ctx *ctx);
 int osph_launch_prepare(osph_ctx *ctx, bool predict, double dt, double damping, bool use_dev_dt, bool skip_reset = false,
-                        int fused = 0);   // fused 1: reduce fluid h_min too; 2: also apply the previous step's corrector first
-int osph_launch_build(osph_ctx *ctx, bool reset_dt = false);   // grid params, keys, sort, (reorder), gather + cell table
+                        int fused = 0, const BuildPlan *grid_plan = nullptr, bool grid_reset_dt = false);
+                        // fused 1: reduce fluid h_min too; 2: also apply the previous step's corrector first
+                        // grid_plan: run k_grid_params inside this pass (its last CTA) with that plan
+int osph_launch_build(osph_ctx *ctx, bool reset_dt = false, const BuildPlan *plan = nullptr);   // grid params (unless plan->grid_done), keys, sort, (reorder), gather
 int osph_launch_correct(osph_ctx *ctx, bool correct, double dt, double damping, bool use_dev_dt, bool skip_reset = false);
 int osph_launch_timestep(osph_ctx *ctx, double fixed_dt, bool log, bool reset_prepare = false,
                          const double *d_reduced3 = nullptr, int fused = 0);   // fused 1: reset the dt scalars after use; 2: c_max = co too

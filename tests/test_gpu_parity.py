@@ -250,6 +250,24 @@ def test_sort_cadence_reuses_the_binning_and_changes_nothing(kernel, push, side,
         assert runs['0.1']['sorts'] > 3, "the thrown fluid must outrun a 10 % skin several times in 30 steps"
 
 
+@pytest.mark.parametrize("bits", ['1', '3'])
+def test_scalar_kernels_fused_into_their_producers_change_nothing(bits, monkeypatch):
+    """OSPH_FUSE_SCALARS (off by default, measured not to pay): k_grid_params run by the last CTA of the predictor pass,
+    k_timestep by the last CTA of the pair kernel.  Same operations on the same scalars: bit-identical state and dt."""
+    case = W.dam_break_case(100, seed=4)
+    outs = []
+    for b in ('0', bits):
+        monkeypatch.setenv("OSPH_FUSE_SCALARS", b)
+        cfg = capi.make_config(case['consts'], 'cubic', 'pec', capi.FP64, case['h'])
+        with capi.Context(cfg) as ctx:
+            ctx.upload(case['pA'])
+            ctx.step(9, None, 0.05)
+            ctx.step(1, None, 0.05)
+            outs.append((ctx.download(case['pA'].copy()).tobytes(), ctx.dt_log(), ctx.sort_stats()))
+            assert ctx.sync() == 0
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
 def test_fp32_mode_close_to_fp64():
     """Performance mode: float pair arithmetic on anchor-relative positions; drift bounded and reported."""
     case = W.dam_break_case(100, seed=7)
