@@ -76,6 +76,7 @@ enum osph_field {
 #define OSPH_S_SMALL_DT    2u  /* dt < 1e-6 (reference src/Solver.py:220-224 records this as ts_error) */
 #define OSPH_S_UNBINNED    4u  /* a particle's reference cell id fell outside the table (reference: OOB write) */
 #define OSPH_S_GRID_COARSE 8u  /* acceleration grid was coarsened to fit the allocated cell table */
+#define OSPH_S_SKIN_EXHAUSTED 32u /* slab cadence: a build reused the binning although the particles had moved too far (pairs may be missing) */
 #define OSPH_S_DENSE_CELL  16u /* a cell holds more than 32768 particles: its summation order is not canonical (results exact) */
 
 typedef struct osph_ctx osph_ctx;
@@ -337,6 +338,10 @@ int osph_slab_p2p_attach(osph_ctx *ctx, osph_slab_p2p *p2p);
 int osph_slab_p2p_set_bounds(osph_ctx *ctx, osph_slab_p2p *p2p, double x_lo, double x_hi);
 int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *p2p, int32_t nsteps, double fixed_dt, double damping);
 int osph_slab_p2p_last_counts(const osph_slab_p2p *p2p, int64_t out[8]);
+/* Slab cadence: out[0] = steps that sorted (migration, fresh halo lists), out[1] = steps that reused the binning: the same
+ * halo particles re-sent into the same record slots, no migration, no host wait.  The ranks decide together from the
+ * all-gathered displacement of the step before.  OSPH_SLAB_CADENCE=0: every step sorts. */
+int osph_slab_p2p_stats(const osph_slab_p2p *p2p, int64_t out[2]);
 
 /* ---- stand-alone leaf functions on host arrays (context-free; `device` is a CUDA ordinal) ---------- */
 

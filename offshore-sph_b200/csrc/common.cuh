@@ -141,6 +141,8 @@ struct osph_ctx {
     bool slab_defer = false;          // this step's corrector is applied by the next step's predictor pass
     bool slab_last = true;            // osph_slab_step_plan: last step of the call (ends with the plain corrector)
     double x_lo = 0, x_hi = 0;
+    int slab_cadence_force = 0;       // slab cadence (slab_p2p.cu): 0 off; else what the next build does: 1 sort, 4 reuse
+    double slab_skin = 0.0;           // ... with this skin (fraction of the pair radius), the same on every rank
     int *d_slab_counters = nullptr, *d_mig_slots = nullptr, *d_tail_flag = nullptr, *d_holes = nullptr, *d_fillers = nullptr;
     int64_t slab_list_cap = 0;
     int64_t reserve = 0;              // particle capacity requested by osph_reserve

@@ -22,6 +22,8 @@ struct SlabPackArgs {
     int mig_cap, halo_cap, ghost_cap;
     int *counters;      // [0] mig_left [1] mig_right [2] halo_left [3] halo_right [4] ghosts [5] overflow flag
     int *mig_slots;     // slots of the migrants (unordered)
+    int mode;           // bit 0: classify and pack migrants, bit 1: halos (slab cadence: two passes on a sorting step)
+    int *halo_idx_l, *halo_idx_r;   // optional: storage slot of the particle behind every halo record (frozen halo lists)
 };
 
 __device__ __forceinline__ void write_light(double *dst, const SlabPackArgs &a, int i)
@@ -58,7 +60,9 @@ k_slab_pack(SlabPackArgs a)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < a.n;
     const double x = valid ? a.f[OSPH_F_X][i] : 0.0;
-    const int side = !valid ? -1 : (x < a.x_lo ? 0 : (x >= a.x_hi ? 1 : -1));
+    int side = !valid ? -1 : (x < a.x_lo ? 0 : (x >= a.x_hi ? 1 : -1));
+    const bool outside = side >= 0;
+    if (!(a.mode & 1)) side = -1;                  // halo-only pass: nobody migrates (the migrants of this step have left already)
     // migrants: full record to the new owner, light copy kept here as a ghost, slot remembered for the hole filling
     const int kl = warp_reserve(&a.counters[0], side == 0), kr = warp_reserve(&a.counters[1], side == 1);
     const int g = warp_reserve(&a.counters[4], side >= 0), m = warp_reserve(&a.counters[6], side >= 0);
@@ -71,10 +75,17 @@ k_slab_pack(SlabPackArgs a)
         } else a.counters[5] = 1;
     }
     // halo: light records for the neighbour on that side (a particle of a narrow slab can be in both halos)
-    const bool hl = valid && side < 0 && x < a.x_lo + a.width, hr = valid && side < 0 && x >= a.x_hi - a.width;
+    const bool halo = valid && (a.mode & 2) && !(outside && (a.mode & 1));
+    const bool hl = halo && x < a.x_lo + a.width, hr = halo && x >= a.x_hi - a.width;
     const int khl = warp_reserve(&a.counters[2], hl), khr = warp_reserve(&a.counters[3], hr);
-    if (hl) { if (khl < a.halo_cap) write_light(a.halo_left + (size_t)khl * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1; }
-    if (hr) { if (khr < a.halo_cap) write_light(a.halo_right + (size_t)khr * OSPH_WIRE_HALO, a, i); else a.counters[5] = 1; }
+    if (hl) {
+        if (khl < a.halo_cap) { write_light(a.halo_left + (size_t)khl * OSPH_WIRE_HALO, a, i); if (a.halo_idx_l) a.halo_idx_l[khl] = i; }
+        else a.counters[5] = 1;
+    }
+    if (hr) {
+        if (khr < a.halo_cap) { write_light(a.halo_right + (size_t)khr * OSPH_WIRE_HALO, a, i); if (a.halo_idx_r) a.halo_idx_r[khr] = i; }
+        else a.counters[5] = 1;
+    }
 }
 
 __global__ void k_slab_meta(const int *counters, const StepScalars *sc, double *meta)
@@ -83,7 +94,7 @@ __global__ void k_slab_meta(const int *counters, const StepScalars *sc, double *
     meta[4] = dec_f64(sc->xmin); meta[5] = -dec_f64(sc->xmax); meta[6] = dec_f64(sc->ymin); meta[7] = -dec_f64(sc->ymax);
     meta[8] = dec_f64(sc->hmin_all); meta[9] = -dec_f64(sc->hmax_all);
     meta[10] = counters[5];
-    meta[11] = 0.0;
+    meta[11] = -dec_f64(sc->disp2max);        // (negated: the ranks' values are combined with min) largest displacement^2 since the last sort
 }
 
 __global__ void k_slab_set_bounds(StepScalars *sc, double xmin, double nxmax, double ymin, double nymax, double hmin,
@@ -91,6 +102,31 @@ __global__ void k_slab_set_bounds(StepScalars *sc, double xmin, double nxmax, do
 {
     sc->xmin = enc_f64(xmin); sc->xmax = enc_f64(-nxmax); sc->ymin = enc_f64(ymin); sc->ymax = enc_f64(-nymax);
     sc->hmin_all = enc_f64(hmin); sc->hmax_all = enc_f64(-nhmax);
+}
+
+// Slab cadence, a step that reuses the binning: the SAME particles as at the last sort, in the same record slots, with their
+// current values (the receiver's sorted order refers to these slots).  No atomics, no classification.
+__global__ void __launch_bounds__(256)
+k_slab_repack(SlabPackArgs a, const int *__restrict__ idx_l, int n_l, const int *__restrict__ idx_r, int n_r)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_l) write_light(a.halo_left + (size_t)k * OSPH_WIRE_HALO, a, idx_l[k]);
+    else if (k < n_l + n_r) write_light(a.halo_right + (size_t)(k - n_l) * OSPH_WIRE_HALO, a, idx_r[k - n_l]);
+}
+
+// ... and the receiver's side of such a step: global bounds, h extrema and displacement from the all-gathered meta rows,
+// on the device (on a sorting step the host does this on its way through the counts).
+__global__ void k_slab_install(const double *__restrict__ all_meta, int world, StepScalars *sc)
+{
+    double b[6], d = all_meta[11];
+    for (int k = 0; k < 6; k++) b[k] = all_meta[4 + k];
+    for (int r = 1; r < world; r++) {
+        for (int k = 0; k < 6; k++) b[k] = fmin(b[k], all_meta[12 * r + 4 + k]);
+        d = fmin(d, all_meta[12 * r + 11]);
+    }
+    sc->xmin = enc_f64(b[0]); sc->xmax = enc_f64(-b[1]); sc->ymin = enc_f64(b[2]); sc->ymax = enc_f64(-b[3]);
+    sc->hmin_all = enc_f64(b[4]); sc->hmax_all = enc_f64(-b[5]);
+    sc->disp2max = enc_f64(-d);
 }
 
 // hole filling: the m migrants leave; the last m slots are vacated, their non-migrant occupants fill the holes
@@ -206,6 +242,7 @@ extern "C" int osph_slab_configure(osph_ctx *ctx, double x_lo, double x_hi, void
     CHECK_CTX();
     if (!(x_lo < x_hi) || !d_ghost || ghost_capacity <= 0) { ctx->err = "osph_slab_configure: bad arguments"; return OSPH_E_INVALID; }
     ctx->slab = true; ctx->x_lo = x_lo; ctx->x_hi = x_hi;
+    ctx->slab_cadence_force = 0;             // a sequencer with a cadence sets it anew at every step
     ctx->d_ghost = (double *)d_ghost; ctx->ghost_cap = ghost_capacity; ctx->n_ghost = 0;
     if (!ctx->d_slab_counters) {
         OSPH_CUDA(cudaMalloc(&ctx->d_slab_counters, sizeof(int) * 16));
@@ -213,10 +250,9 @@ extern "C" int osph_slab_configure(osph_ctx *ctx, double x_lo, double x_hi, void
     return 0;
 }
 
-extern "C" int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
-                              void *d_halo_left, void *d_halo_right, int64_t halo_cap, double *d_meta)
+static int slab_pack_impl(osph_ctx *ctx, double halo_width, int mode, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
+                          void *d_halo_left, void *d_halo_right, int64_t halo_cap, int *d_idx_l, int *d_idx_r, double *d_meta)
 {
-    CHECK_CTX();
     if (!ctx->slab || ctx->n <= 0) { ctx->err = "osph_slab_pack: context is not in slab mode"; return OSPH_E_INVALID; }
     if (mig_cap > ctx->slab_list_cap) {
         cudaFree(ctx->d_mig_slots); cudaFree(ctx->d_tail_flag); cudaFree(ctx->d_holes); cudaFree(ctx->d_fillers);
@@ -237,8 +273,49 @@ extern "C" int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left
     a.halo_left = (double *)d_halo_left; a.halo_right = (double *)d_halo_right; a.ghost = ctx->d_ghost;
     a.mig_cap = (int)mig_cap; a.halo_cap = (int)halo_cap; a.ghost_cap = (int)ctx->ghost_cap;
     a.counters = ctx->d_slab_counters; a.mig_slots = ctx->d_mig_slots;
+    a.mode = mode; a.halo_idx_l = d_idx_l; a.halo_idx_r = d_idx_r;
     k_slab_pack<<<div_up(ctx->n, 256), 256, 0, ctx->stream>>>(a); OSPH_LAUNCH_CHECK();
     k_slab_meta<<<1, 1, 0, ctx->stream>>>(ctx->d_slab_counters, ctx->d_sc, d_meta); OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
+                              void *d_halo_left, void *d_halo_right, int64_t halo_cap, double *d_meta)
+{
+    CHECK_CTX();
+    return slab_pack_impl(ctx, halo_width, 3, d_mig_left, d_mig_right, mig_cap, d_halo_left, d_halo_right, halo_cap, nullptr, nullptr, d_meta);
+}
+
+// Slab cadence (slab_p2p.cu).  mode 1: migrants only; mode 2: halos only, the storage slot behind every record is kept in
+// d_idx_l / d_idx_r (capacity halo_cap each).
+int osph_slab_pack_mode(osph_ctx *ctx, double halo_width, int mode, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
+                        void *d_halo_left, void *d_halo_right, int64_t halo_cap, int *d_idx_l, int *d_idx_r, double *d_meta)
+{
+    return slab_pack_impl(ctx, halo_width, mode, d_mig_left, d_mig_right, mig_cap, d_halo_left, d_halo_right, halo_cap, d_idx_l, d_idx_r, d_meta);
+}
+
+// Slab cadence, reuse step: refresh the records of the frozen halo lists in the neighbours' regions, then the meta row.
+int osph_slab_repack(osph_ctx *ctx, const int *d_idx_l, int64_t n_l, void *d_halo_left, const int *d_idx_r, int64_t n_r,
+                     void *d_halo_right, double *d_meta)
+{
+    SlabPackArgs a;
+    a.n = (int)ctx->n; a.label = ctx->label; a.row = ctx->d_row;
+    for (int k = 0; k < OSPH_NUM_FIELDS; k++) a.f[k] = ctx->f[k];
+    a.halo_left = (double *)d_halo_left; a.halo_right = (double *)d_halo_right;
+    a.mig_left = a.mig_right = a.ghost = nullptr; a.counters = nullptr; a.mig_slots = nullptr; a.halo_idx_l = a.halo_idx_r = nullptr;
+    a.mig_cap = a.halo_cap = a.ghost_cap = 0; a.mode = 0; a.x_lo = a.x_hi = a.width = 0.0;
+    if (n_l + n_r > 0) {
+        k_slab_repack<<<div_up(n_l + n_r, 256), 256, 0, ctx->stream>>>(a, d_idx_l, (int)n_l, d_idx_r, (int)n_r); OSPH_LAUNCH_CHECK();
+    }
+    OSPH_CUDA(cudaMemsetAsync(ctx->d_slab_counters, 0, sizeof(int) * 16, ctx->stream));
+    k_slab_meta<<<1, 1, 0, ctx->stream>>>(ctx->d_slab_counters, ctx->d_sc, d_meta); OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+int osph_slab_install(osph_ctx *ctx, const double *d_all_meta, int world)
+{
+    k_slab_install<<<1, 1, 0, ctx->stream>>>(d_all_meta, world, ctx->d_sc); OSPH_LAUNCH_CHECK();
+    ctx->prepared = true;
     return 0;
 }
 

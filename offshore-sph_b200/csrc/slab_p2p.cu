@@ -31,6 +31,12 @@ int osph_slab_pack(osph_ctx *ctx, double halo_width, void *d_mig_left, void *d_m
                    void *d_halo_left, void *d_halo_right, int64_t halo_cap, double *d_meta);
 int osph_slab_step_end(osph_ctx *ctx, double damping);
 }
+// slab.cu, slab cadence
+int osph_slab_pack_mode(osph_ctx *ctx, double halo_width, int mode, void *d_mig_left, void *d_mig_right, int64_t mig_cap,
+                        void *d_halo_left, void *d_halo_right, int64_t halo_cap, int *d_idx_l, int *d_idx_r, double *d_meta);
+int osph_slab_repack(osph_ctx *ctx, const int *d_idx_l, int64_t n_l, void *d_halo_left, const int *d_idx_r, int64_t n_r,
+                     void *d_halo_right, double *d_meta);
+int osph_slab_install(osph_ctx *ctx, const double *d_all_meta, int world);
 
 #define P2P_MAX_WORLD 16
 #define MBOX_STRIDE 16            // doubles per (slot, sender) cell of a mailbox
@@ -40,7 +46,7 @@ int osph_slab_step_end(osph_ctx *ctx, double damping);
 
 struct osph_slab_p2p {
     int rank = 0, world = 1;
-    double x_lo = 0, x_hi = 0, r0 = 0, hmax = 0;
+    double x_lo = 0, x_hi = 0, r0 = 0, hmax = 0, hmin = 0;       // hmin: smallest h over ALL active particles (reference cell size)
     int kernel = 0;
     int64_t mig_cap = 0, halo_cap = 0;
     double *win = nullptr;                         // this rank's window
@@ -59,6 +65,17 @@ struct osph_slab_p2p {
     long long psteps = 0;
     long long spin_limit = 0;                      // clock64 ticks a mailbox waits for one peer before it gives up
     bool aborted = false;
+    // ---- slab cadence: the ranks sort TOGETHER every few steps; in between the halo is the same particles in the same
+    // record slots (frozen lists), migration waits for the next sort, and the host waits for nothing ----
+    bool cadence = false;              // OSPH_SLAB_CADENCE
+    bool lists_valid = false;          // frozen halo lists describe the resident particles
+    int *d_idx_l = nullptr, *d_idx_r = nullptr;      // storage slots behind my halo records towards the left / right neighbour
+    int64_t halo_n_l = 0, halo_n_r = 0;
+    double skin = 0.1, gs = 0.0;       // skin (fraction of the pair radius) and cell size of the current binning
+    double D_known = 0.0, dstep = -1.0;              // largest displacement since the sort (all ranks, lagged one step) and per step
+    int steps_since_sort = 0;
+    unsigned long long pending_seq = 0;              // meta mailbox of a reuse step whose host copy has not been read yet
+    int64_t sorts = 0, reuses = 0;
     int64_t last_counts[8] = {0};
     int64_t steps = 0;
 };
@@ -167,6 +184,15 @@ extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x
     OSPH_CUDA(cudaMallocHost(&s->h_all_meta, sizeof(double) * (12 * world + 2)));      // + status word + sequence flag (device-written)
     memset(s->h_all_meta, 0, sizeof(double) * (12 * world + 2));
     {
+        // OSPH_SLAB_CADENCE=0 restores the exchange that sorts, migrates and re-packs the halo at every step
+        const char *e = getenv("OSPH_SLAB_CADENCE");
+        s->cadence = !(e && e[0] == '0') && !ctx->cfg.summation_density;
+        if (s->cadence) {
+            OSPH_CUDA(cudaMalloc(&s->d_idx_l, sizeof(int) * (size_t)halo_cap));
+            OSPH_CUDA(cudaMalloc(&s->d_idx_r, sizeof(int) * (size_t)halo_cap));
+        }
+    }
+    {
         const char *e = getenv("OSPH_SLAB_PROFILE");
         s->profile = e && e[0] == '1';
         if (s->profile) for (int k = 0; k < 8; k++) OSPH_CUDA(cudaEventCreate(&s->pev[k]));
@@ -216,6 +242,8 @@ extern "C" int osph_slab_p2p_destroy(osph_ctx *ctx, osph_slab_p2p *s)
         for (int k = 0; k < 8; k++) cudaEventDestroy(s->pev[k]);
     }
     for (int r = 0; r < s->world; r++) if (r != s->rank && s->peer[r]) cudaIpcCloseMemHandle(s->peer[r]);
+    cudaFree(s->d_idx_l); cudaFree(s->d_idx_r);
+    if (ctx) ctx->slab_cadence_force = 0;
     cudaFree(s->win); cudaFree(s->d_peer); cudaFree(s->d_meta); cudaFree(s->d_all_meta); cudaFree(s->d_dt3); cudaFree(s->d_all_dt);
     cudaFreeHost(s->h_all_meta);
     delete s;
@@ -225,6 +253,7 @@ extern "C" int osph_slab_p2p_destroy(osph_ctx *ctx, osph_slab_p2p *s)
 extern "C" int osph_slab_p2p_attach(osph_ctx *ctx, osph_slab_p2p *s)
 {
     if (!ctx || !s) return OSPH_E_INVALID;
+    s->lists_valid = false;                      // the particle set was replaced: the next step sorts
     return osph_slab_configure(ctx, s->x_lo, s->x_hi, s->win + s->off_ghost, 2 * s->mig_cap);
 }
 
@@ -232,6 +261,7 @@ extern "C" int osph_slab_p2p_set_bounds(osph_ctx *ctx, osph_slab_p2p *s, double 
 {
     if (!ctx || !s || !(x_lo < x_hi)) return OSPH_E_INVALID;
     s->x_lo = x_lo; s->x_hi = x_hi;
+    s->lists_valid = false;                      // new cuts: the next step migrates and sorts
     return osph_slab_configure(ctx, x_lo, x_hi, s->win + s->off_ghost, 2 * s->mig_cap);
 }
 
@@ -253,65 +283,44 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
     // every error return below first sets the abort word of all peers: they leave their mailbox waits and raise too
     auto fail = [&](int code) { p2p_abort_peers(ctx, s); return code; };
     if (s->aborted) { ctx->err = "slab exchange: this group was aborted by an earlier error"; return OSPH_E_INVALID; }
-    for (int step = 0; step < nsteps; step++) {
-        s->seq++;
-        const int slot = (int)(s->seq & 1ull);
-        const bool prof = s->profile && step > 0 && step < nsteps - 1;       // steady-state steps of a multi-step call
-#define P2P_MARK(k) do { if (prof) cudaEventRecord(s->pev[k], ctx->stream); } while (0)
-        P2P_MARK(0);
-        if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return fail(rc);    // corrector of step k fused into the predictor of k+1
-        // ---- identical dt on every rank: mailbox all-gather + min ----
-        if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return fail(rc);
-        k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, slot, s->d_dt3, 3, s->seq,
-                                                       s->d_all_dt, 1, s->spin_limit, d_status, nullptr, nullptr);
-        ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
-        P2P_MARK(1);
-        if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return fail(rc);
-        P2P_MARK(2);
-        // ---- classify + pack straight into the neighbours' windows; counts and bounds through the second mailbox ----
-        const double width = std::max(q * s->hmax, std::min(s->r0, 3.0 * s->hmax)) * 1.1;
-        if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return fail(rc);
-        k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_meta, s->off_meta_flag, slot, s->d_meta, 12,
-                                                       s->seq, s->d_all_meta, 0, s->spin_limit, d_status, s->h_all_meta,
-                                                       reinterpret_cast<volatile unsigned long long *>(s->h_all_meta + 12 * W + 1));
-        ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
-        P2P_MARK(3);
-        {
-            // wait for the kernel's sequence number in pinned memory (the one host wait of the step); a CUDA error or a dead
-            // stream ends the wait through cudaStreamQuery
-            volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(s->h_all_meta + 12 * W + 1);
-            const auto t0 = std::chrono::steady_clock::now();
-            long long spins = 0;
-            while (*flag != s->seq) {
-                if ((++spins & 0xfff) == 0) {
-                    const cudaError_t q = cudaStreamQuery(ctx->stream);
-                    if (q != cudaSuccess && q != cudaErrorNotReady) { ctx->err = std::string("slab exchange: ") + cudaGetErrorString(q); return fail(OSPH_E_CUDA); }
-                    if (q == cudaSuccess && *flag != s->seq) { ctx->err = "slab exchange: the mailbox kernel ended without publishing its result"; return fail(OSPH_E_CUDA); }
-                    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0 * (double)s->spin_limit / 2.0e9 + 5.0) {
-                        ctx->err = "slab exchange: timed out waiting for the meta mailbox"; return fail(OSPH_E_PEER);
-                    }
+    volatile unsigned long long *const host_flag = reinterpret_cast<volatile unsigned long long *>(s->h_all_meta + 12 * W + 1);
+    // wait until the meta mailbox with sequence number `want` has arrived in pinned host memory (a CUDA error or a dead
+    // stream ends the wait through cudaStreamQuery), then check the status word it carries
+    auto wait_meta = [&](unsigned long long want) -> int {
+        const auto t0 = std::chrono::steady_clock::now();
+        long long spins = 0;
+        while (*host_flag != want) {
+            if ((++spins & 0xfff) == 0) {
+                const cudaError_t qe = cudaStreamQuery(ctx->stream);
+                if (qe != cudaSuccess && qe != cudaErrorNotReady) { ctx->err = std::string("slab exchange: ") + cudaGetErrorString(qe); return OSPH_E_CUDA; }
+                if (qe == cudaSuccess && *host_flag != want) { ctx->err = "slab exchange: the mailbox kernel ended without publishing its result"; return OSPH_E_CUDA; }
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0 * (double)s->spin_limit / 2.0e9 + 5.0) {
+                    ctx->err = "slab exchange: timed out waiting for the meta mailbox"; return OSPH_E_PEER;
                 }
             }
-            std::atomic_thread_fence(std::memory_order_acquire);
         }
-        P2P_MARK(4);
-        const auto host_t0 = std::chrono::steady_clock::now();
-        const double *M = s->h_all_meta;
-        {
-            unsigned int st; memcpy(&st, s->h_all_meta + 12 * W, sizeof(st));
-            if (st) {
-                char msg[200];
-                snprintf(msg, sizeof msg, "slab exchange on rank %d, step %lld: %s", me, (long long)s->steps,
-                         (st & P2P_ST_ABORT) ? "a peer rank left the step loop with an error"
-                                             : "a peer rank did not answer within OSPH_P2P_SPIN_SECONDS");
-                ctx->err = msg;
-                return fail(OSPH_E_PEER);
-            }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        unsigned int st; memcpy(&st, s->h_all_meta + 12 * W, sizeof(st));
+        if (st) {
+            char msg[200];
+            snprintf(msg, sizeof msg, "slab exchange on rank %d, step %lld: %s", me, (long long)s->steps,
+                     (st & P2P_ST_ABORT) ? "a peer rank left the step loop with an error"
+                                         : "a peer rank did not answer within OSPH_P2P_SPIN_SECONDS");
+            ctx->err = msg;
+            return OSPH_E_PEER;
         }
-        double bounds[6];
-        for (int k = 0; k < 6; k++) { bounds[k] = M[4 + k]; for (int r = 1; r < W; r++) bounds[k] = std::min(bounds[k], M[12 * r + 4 + k]); }
+        return 0;
+    };
+    // all-gather of this rank's meta row (s->d_meta) through the second mailbox; the result also lands in pinned host memory
+    auto meta_mailbox = [&]() -> int {
+        s->seq++;
+        k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_meta, s->off_meta_flag, (int)(s->seq & 1ull), s->d_meta, 12,
+                                                       s->seq, s->d_all_meta, 0, s->spin_limit, d_status, s->h_all_meta, host_flag);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return OSPH_E_CUDA; }
+        return 0;
+    };
+    auto check_overflow = [&](const double *M) -> int {
         for (int r = 0; r < W; r++)
             if (M[12 * r + 10] != 0.0) {
                 char msg[320];
@@ -319,21 +328,133 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
                          "halo %.0f/%.0f (cap %lld), flag %.3g, seq %llu", r, (long long)s->steps, M[12 * r], M[12 * r + 1],
                          (long long)s->mig_cap, M[12 * r + 2], M[12 * r + 3], (long long)s->halo_cap, M[12 * r + 10], s->seq);
                 ctx->err = msg;
-                return fail(OSPH_E_CAPACITY);
+                return OSPH_E_CAPACITY;
             }
-        const double *mine = M + 12 * me;
-        const int64_t out_l = (int64_t)mine[0], out_r = (int64_t)mine[1], halo_out_l = (int64_t)mine[2], halo_out_r = (int64_t)mine[3];
-        const int64_t in_mig_l = left >= 0 ? (int64_t)M[12 * left + 1] : 0, in_halo_l = left >= 0 ? (int64_t)M[12 * left + 3] : 0;
-        const int64_t in_mig_r = right >= 0 ? (int64_t)M[12 * right + 0] : 0, in_halo_r = right >= 0 ? (int64_t)M[12 * right + 2] : 0;
-        s->hmax = -bounds[5];
-        GhostMap gm;
-        gm.c0 = (int)(out_l + out_r); gm.c1 = (int)in_halo_l;
-        gm.b1 = (long long)((s->off_halo_from_left - s->off_ghost) / OSPH_WIRE_HALO);
-        gm.b2 = (long long)((s->off_halo_from_right - s->off_ghost) / OSPH_WIRE_HALO);
-        const int64_t n_ghost = gm.c0 + in_halo_l + in_halo_r;
-        // ---- owned set update (migrants are already here), same grid everywhere, force evaluation, corrector ----
-        if ((rc = osph_slab_commit_impl(ctx, out_l + out_r, s->win + s->off_mig_from_left, in_mig_l,
-                                        s->win + s->off_mig_from_right, in_mig_r, gm, n_ghost, bounds))) return fail(rc);
+        return 0;
+    };
+    auto pair_radius = [&](double hmax) { return std::max(q * hmax, std::min(s->r0, 3.0 * hmax)); };
+    const double *M = s->h_all_meta;
+    GhostMap gm;
+    gm.b1 = (long long)((s->off_halo_from_left - s->off_ghost) / OSPH_WIRE_HALO);
+    gm.b2 = (long long)((s->off_halo_from_right - s->off_ghost) / OSPH_WIRE_HALO);
+
+    for (int step = 0; step < nsteps; step++) {
+        const bool prof = s->profile && step > 0 && step < nsteps - 1;       // steady-state steps of a multi-step call
+#define P2P_MARK(k) do { if (prof) cudaEventRecord(s->pev[k], ctx->stream); } while (0)
+        P2P_MARK(0);
+        // ---- slab cadence: does this step sort (migrate, re-pack the halo) or reuse?  Decided from numbers every rank has
+        // (the all-gathered meta rows of the step before), so all ranks decide alike. ----
+        bool sort_step = true;
+        if (s->cadence) {
+            if (s->pending_seq) {                        // the previous step reused: its meta row has not been looked at yet
+                if ((rc = wait_meta(s->pending_seq))) return fail(rc);
+                s->pending_seq = 0;
+                double d2 = M[11], nh = M[9];
+                for (int r = 1; r < W; r++) { d2 = std::min(d2, M[12 * r + 11]); nh = std::min(nh, M[12 * r + 9]); }
+                const double D = std::sqrt(std::max(-d2, 0.0));
+                s->dstep = std::max(D - s->D_known, D / std::max(1, s->steps_since_sort));
+                s->D_known = D; s->hmax = -nh;
+                double hm = M[8];
+                for (int r = 1; r < W; r++) hm = std::min(hm, M[12 * r + 8]);
+                s->hmin = hm;
+            }
+            // the displacement is known up to the step before this one; this step adds at most about dstep (x 2: margin)
+            const double R_now = pair_radius(s->hmax) * 1.02 * (1.0 + 1e-6);
+            // (where the pair radius reaches the reference cell -- small N -- the acceleration grid IS the reference grid and
+            // follows the bounds: k_grid_params sorts at every build there, and so does this loop)
+            double cs = s->hmin * ctx->cfg.nn_scale;
+            if (cs < 1e-6) cs = 1.0;
+            sort_step = !s->lists_valid || !(s->dstep >= 0.0) || !std::isfinite(s->D_known) || R_now >= cs ||
+                        R_now + 2.0 * (s->D_known + 2.0 * s->dstep) > s->gs;
+        }
+        if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return fail(rc);    // corrector of step k fused into the predictor of k+1
+        // ---- identical dt on every rank: mailbox all-gather + min ----
+        if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return fail(rc);
+        s->seq++;
+        k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, (int)(s->seq & 1ull), s->d_dt3, 3, s->seq,
+                                                       s->d_all_dt, 1, s->spin_limit, d_status, nullptr, nullptr);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
+        P2P_MARK(1);
+        if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return fail(rc);
+        P2P_MARK(2);
+        const auto host_t0 = std::chrono::steady_clock::now();
+        if (!s->cadence) {
+            // ---- every step: classify + pack straight into the neighbours' windows; counts and bounds through the mailbox ----
+            const double width = pair_radius(s->hmax) * 1.1;
+            if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return fail(rc);
+            if ((rc = meta_mailbox())) return fail(rc);
+            P2P_MARK(3);
+            if ((rc = wait_meta(s->seq))) return fail(rc);                // the one host wait of the step
+            P2P_MARK(4);
+            double bounds[6];
+            for (int k = 0; k < 6; k++) { bounds[k] = M[4 + k]; for (int r = 1; r < W; r++) bounds[k] = std::min(bounds[k], M[12 * r + 4 + k]); }
+            if ((rc = check_overflow(M))) return fail(rc);
+            const double *mine = M + 12 * me;
+            const int64_t out_l = (int64_t)mine[0], out_r = (int64_t)mine[1], halo_out_l = (int64_t)mine[2], halo_out_r = (int64_t)mine[3];
+            const int64_t in_mig_l = left >= 0 ? (int64_t)M[12 * left + 1] : 0, in_halo_l = left >= 0 ? (int64_t)M[12 * left + 3] : 0;
+            const int64_t in_mig_r = right >= 0 ? (int64_t)M[12 * right + 0] : 0, in_halo_r = right >= 0 ? (int64_t)M[12 * right + 2] : 0;
+            s->hmax = -bounds[5];
+            gm.c0 = (int)(out_l + out_r); gm.c1 = (int)in_halo_l;
+            const int64_t n_ghost = gm.c0 + in_halo_l + in_halo_r;
+            // ---- owned set update (migrants are already here), same grid everywhere ----
+            if ((rc = osph_slab_commit_impl(ctx, out_l + out_r, s->win + s->off_mig_from_left, in_mig_l,
+                                            s->win + s->off_mig_from_right, in_mig_r, gm, n_ghost, bounds))) return fail(rc);
+            const int64_t c[8] = {out_l, out_r, halo_out_l, halo_out_r, in_mig_l, in_mig_r, in_halo_l, in_halo_r};
+            memcpy(s->last_counts, c, sizeof(c));
+        } else if (sort_step) {
+            // ---- sorting step, pass A: the migrants change owner first, so that the halo lists of pass B are built on the
+            // final owned set (and nobody keeps stale copies of particles it gave away) ----
+            if ((rc = osph_slab_pack_mode(ctx, 0.0, 1, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, nullptr, nullptr, s->d_meta))) return fail(rc);
+            if ((rc = meta_mailbox())) return fail(rc);
+            if ((rc = wait_meta(s->seq))) return fail(rc);
+            if ((rc = check_overflow(M))) return fail(rc);
+            const int64_t out_l = (int64_t)M[12 * me + 0], out_r = (int64_t)M[12 * me + 1];
+            const int64_t in_mig_l = left >= 0 ? (int64_t)M[12 * left + 1] : 0, in_mig_r = right >= 0 ? (int64_t)M[12 * right + 0] : 0;
+            gm.c0 = 0; gm.c1 = 0;
+            if ((rc = osph_slab_commit_impl(ctx, out_l + out_r, s->win + s->off_mig_from_left, in_mig_l,
+                                            s->win + s->off_mig_from_right, in_mig_r, gm, 0, nullptr))) return fail(rc);
+            // ---- pass B: halos, with a skin; the storage slot behind every record is remembered ----
+            // skin: about ten steps' worth of the displacement per step observed since the last sort, 3 %..25 % of the radius
+            const double R = pair_radius(s->hmax);
+            s->skin = s->dstep >= 0.0 ? std::min(std::max(2.0 * s->dstep * 10.0 * 1.1 / R, 0.03), 0.25) : 0.1;
+            const double width = R * (1.0 + s->skin) * 1.1;
+            if ((rc = osph_slab_pack_mode(ctx, width, 2, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_idx_l, s->d_idx_r, s->d_meta))) return fail(rc);
+            if ((rc = meta_mailbox())) return fail(rc);
+            P2P_MARK(3);
+            if ((rc = wait_meta(s->seq))) return fail(rc);
+            P2P_MARK(4);
+            if ((rc = check_overflow(M))) return fail(rc);
+            double bounds[6], d2 = M[11];
+            for (int k = 0; k < 6; k++) { bounds[k] = M[4 + k]; for (int r = 1; r < W; r++) bounds[k] = std::min(bounds[k], M[12 * r + 4 + k]); }
+            for (int r = 1; r < W; r++) d2 = std::min(d2, M[12 * r + 11]);
+            const int64_t halo_out_l = (int64_t)M[12 * me + 2], halo_out_r = (int64_t)M[12 * me + 3];
+            const int64_t in_halo_l = left >= 0 ? (int64_t)M[12 * left + 3] : 0, in_halo_r = right >= 0 ? (int64_t)M[12 * right + 2] : 0;
+            // displacement per step, from the stretch that ends here (valid when the lists were: the reference positions were)
+            const double D = std::sqrt(std::max(-d2, 0.0));
+            if (s->lists_valid && std::isfinite(D) && s->steps_since_sort > 0)
+                s->dstep = std::max(D - s->D_known, D / s->steps_since_sort);
+            s->hmax = -bounds[5]; s->hmin = bounds[4];
+            s->gs = pair_radius(s->hmax) * (1.0 + 1e-6) * (1.0 + s->skin);          // what k_grid_params forms from the same numbers
+            s->halo_n_l = halo_out_l; s->halo_n_r = halo_out_r;
+            s->D_known = 0.0; s->steps_since_sort = 0; s->lists_valid = true; s->sorts++;
+            gm.c0 = 0; gm.c1 = (int)in_halo_l;
+            if ((rc = osph_slab_commit_impl(ctx, 0, nullptr, 0, nullptr, 0, gm, in_halo_l + in_halo_r, bounds))) return fail(rc);
+            ctx->slab_cadence_force = 1; ctx->slab_skin = s->skin;
+            const int64_t c[8] = {out_l, out_r, halo_out_l, halo_out_r, in_mig_l, in_mig_r, in_halo_l, in_halo_r};
+            memcpy(s->last_counts, c, sizeof(c));
+        } else {
+            // ---- reuse: same particles, same record slots, current values; nothing for the host to wait for.  The meta
+            // mailbox still runs: it is the "records have landed" signal and carries bounds and displacement ----
+            if ((rc = osph_slab_repack(ctx, s->d_idx_l, s->halo_n_l, halo_l, s->d_idx_r, s->halo_n_r, halo_r, s->d_meta))) return fail(rc);
+            if ((rc = meta_mailbox())) return fail(rc);
+            s->pending_seq = s->seq;
+            P2P_MARK(3); P2P_MARK(4);
+            if ((rc = osph_slab_install(ctx, s->d_all_meta, W))) return fail(rc);
+            ctx->slab_cadence_force = 4; ctx->slab_skin = s->skin;
+            s->reuses++;
+        }
+        s->steps_since_sort++;
         P2P_MARK(5);
         if ((rc = osph_slab_step_end(ctx, damping))) return fail(rc);
         P2P_MARK(6);
@@ -344,9 +465,18 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
             for (int k = 0; k < 7; k++) { float ms = 0; cudaEventElapsedTime(&ms, s->pev[k], s->pev[k + 1]); s->pms[k] += ms; }
             s->psteps++;
         }
-        const int64_t c[8] = {out_l, out_r, halo_out_l, halo_out_r, in_mig_l, in_mig_r, in_halo_l, in_halo_r};
-        memcpy(s->last_counts, c, sizeof(c));
         s->steps++;
+    }
+    if (s->cadence && s->pending_seq) {
+        // the call ends on a reuse step: pick up its meta row now (status, displacement), so that errors of the last step are
+        // not carried into a later call and the host's view is complete when the caller looks at the results
+        if ((rc = wait_meta(s->pending_seq))) return fail(rc);
+        s->pending_seq = 0;
+        double d2 = M[11], nh = M[9];
+        for (int r = 1; r < W; r++) { d2 = std::min(d2, M[12 * r + 11]); nh = std::min(nh, M[12 * r + 9]); }
+        const double D = std::sqrt(std::max(-d2, 0.0));
+        s->dstep = std::max(D - s->D_known, D / std::max(1, s->steps_since_sort));
+        s->D_known = D; s->hmax = -nh;
     }
     return 0;
 }
@@ -355,5 +485,13 @@ extern "C" int osph_slab_p2p_last_counts(const osph_slab_p2p *s, int64_t out[8])
 {
     if (!s) return OSPH_E_INVALID;
     memcpy(out, s->last_counts, sizeof(s->last_counts));
+    return 0;
+}
+
+// steps of this group that sorted (migration + fresh halo lists) / that reused the binning and the frozen halo lists
+extern "C" int osph_slab_p2p_stats(const osph_slab_p2p *s, int64_t out[2])
+{
+    if (!s || !out) return OSPH_E_INVALID;
+    out[0] = s->cadence ? s->sorts : s->steps; out[1] = s->cadence ? s->reuses : 0;
     return 0;
 }

@@ -399,12 +399,21 @@ __device__ void grid_params_body(StepScalars *sc, GridParams *g, double nn_scale
     // does not exceed gsize.  Regime A (the acceleration grid IS the reference grid, which follows the bounds) and the
     // one-cell fallback always sort.
     // force_sort: 0 the device decides; 1 sort (a skin is still added, for the builds that follow); 2 sort without skin (slab
-    // mode and the radix path sort every build); 3 = the host's sizing pass for the cell table: grid only, no bookkeeping
+    // mode without cadence and the radix path sort every build); 3 = the host's sizing pass for the cell table: grid only, no
+    // bookkeeping; 4 = reuse, decided by the host (slab cadence)
     const bool dry = force_sort == 3;
     if (!dry) sc->builds++;
     const double disp = sqrt(fmax(dec_f64(rd(&sc->disp2max)), 0.0));
-    const bool reuse = !force_sort && skin_frac != 0.0 && g->sort_count > 0 && !g->regime_a && !g->adj_always && !(R >= cs) &&
+    const bool valid = g->sort_count > 0 && !g->regime_a && !g->adj_always && !(R >= cs) &&
                        isfinite(disp) && R + 2.0 * disp * (1.0 + 1e-9) <= g->gsize;
+    bool reuse = !force_sort && skin_frac != 0.0 && valid;
+    if (force_sort == 4) {
+        // slab cadence (slab_p2p.cu): the ranks decided TOGETHER, on the host, that this build reuses the binning -- the ghost
+        // records arrived in the slots of the last sort, so sorting on one's own is not an option.  The host plans with a
+        // margin; should the condition fail all the same, pairs may be missing: say so loudly.
+        reuse = true;
+        if (!valid) atomicOr(&sc->status, OSPH_S_SKIN_EXHAUSTED);
+    }
     if (reuse) {
         g->do_sort = 0; g->disp = disp; g->steps_since_sort++;
         int reach = (int)ceil((rs + 2.0 * disp) / g->gsize);
@@ -1140,7 +1149,8 @@ static int reorder_state(osph_ctx *ctx)
 int osph_launch_grid_params(osph_ctx *ctx, bool reset_dt, int force_sort)
 {
     k_grid_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, ctx->d_grid, ctx->cfg.nn_scale, pair_radius_q(ctx), ctx->cfg.r0,
-                                            (long long)ctx->cell_cap, reset_dt ? 1 : 0, force_sort, ctx->skin_frac);
+                                            (long long)ctx->cell_cap, reset_dt ? 1 : 0, force_sort,
+                                            (ctx->slab && ctx->slab_cadence_force) ? ctx->slab_skin : ctx->skin_frac);
     OSPH_LAUNCH_CHECK();
     return 0;
 }
@@ -1157,6 +1167,11 @@ BuildPlan osph_plan_build(osph_ctx *ctx)
     // set changes every step; radix path)
     p.always = ctx->slab || ctx->n_ghost > 0 || !ctx->bin_sort || ctx->skin_frac == 0.0;
     p.force = p.always ? 2 : ((!ctx->skin_valid || p.reorder_now) ? 1 : 0);
+    if (ctx->slab && ctx->slab_cadence_force && ctx->bin_sort) {
+        // slab cadence: the sequencer tells every build whether it sorts (1) or reuses (4); no physical reorder (the frozen
+        // halo lists hold storage slots)
+        p.always = false; p.reorder_now = false; p.force = ctx->slab_cadence_force;
+    }
     p.grid_done = false;
     return p;
 }
@@ -1172,7 +1187,9 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt, const BuildPlan *given)
     ctx->sorted_buf = 0;
     const double *px = ctx->f[OSPH_F_X], *py = ctx->f[OSPH_F_Y];
     bool rank_in_gather = false;
-    if (ctx->bin_sort) {
+    if (ctx->bin_sort && plan.force == 4) {
+        // host-planned reuse (slab cadence): nothing to launch, the gather kernel takes the stored permutation
+    } else if (ctx->bin_sort) {
         // counting sort by cell: histogram + arrival ranks, then scan (= cell table), scatter, canonical order (binsort.cu)
         k_bin_keys<<<div_up(n_all, 256 * BINK_ITEMS), 256, 0, ctx->stream>>>(px, py, n, ctx->d_ghost, ctx->gmap, n_all, ctx->d_grid,
                                                                             ctx->d_sc, ctx->key[0], ctx->idx[0], ctx->bin_counts, ctx->bin_tiles,

@@ -138,6 +138,7 @@ def lib():
         'osph_slab_p2p_set_bounds': (C.c_int, [ctx, C.c_void_p, dbl, dbl]),
         'osph_slab_p2p_run': (C.c_int, [ctx, C.c_void_p, i32, dbl, dbl]),
         'osph_slab_p2p_last_counts': (C.c_int, [C.c_void_p, ip]),
+        'osph_slab_p2p_stats': (C.c_int, [C.c_void_p, ip]),
         'osph_leaf_kernel': (C.c_int, [C.c_int, C.c_int, C.c_int, i64, dp, dp, dp, dp]),
         'osph_leaf_tait_pressure': (C.c_int, [C.c_int, i64, dp, C.POINTER(C.c_int8), dbl, dbl, dbl, dbl, dp]),
         'osph_leaf_tait_height': (C.c_int, [C.c_int, i64, dp, dbl, dbl, dbl, dbl, dp]),
@@ -474,6 +475,12 @@ class Context:
         out = (C.c_int64 * 8)()
         self._L.osph_slab_p2p_last_counts(p2p, out)
         return list(out)
+
+    def slab_p2p_stats(self, p2p):
+        """(sorting steps, reusing steps) of the peer-memory sequencer's slab cadence."""
+        out = (C.c_int64 * 2)()
+        self._ck(self._L.osph_slab_p2p_stats(p2p, out))
+        return int(out[0]), int(out[1])
 
     def timers(self):
         out = (C.c_double * 6)()

@@ -269,6 +269,11 @@ class P2PSlabRun(NcclSlabRun):
         return dict(mig_out=(c[0], c[1]), halo_out=(c[2], c[3]), mig_in=(c[4], c[5]), halo_in=(c[6], c[7]),
                     ghosts=c[0] + c[1] + c[6] + c[7], owned=self.ctx.num_active)
 
+    @property
+    def cadence_stats(self):
+        """(steps that sorted, steps that reused the binning and the frozen halo lists)."""
+        return self.ctx.slab_p2p_stats(self.comm)
+
     def reattach(self):
         self.ctx.slab_p2p_attach(self.comm)
 

@@ -73,10 +73,11 @@ def main():
         tot_moved = torch.tensor([moved], device='cuda'); dist.all_reduce(tot_moved)
         good = bool(np.all(seen == 1)) and worst <= tol and status == 0 and \
             np.allclose(dts, ref_dt, rtol=1e-12 if prec == capi.FP64 else 1e-4, atol=0)
+        cadence = " sorted/reused=%d/%d" % run.cadence_stats if hasattr(run, 'cadence_stats') else ""
         if rank == 0:
-            print("%-9s %s %-6s ranks=%d n=%d steps=%d migrants=%d worst_err=%.2e (%s) dt_equal=%s -> %s" % (
+            print("%-9s %s %-6s ranks=%d n=%d steps=%d migrants=%d worst_err=%.2e (%s) dt_equal=%s%s -> %s" % (
                 kernel, 'fp64' if prec == capi.FP64 else 'fp32', seq, world, len(pA), a.steps, int(tot_moved.item()), worst,
-                max(errs, key=errs.get), np.allclose(dts, ref_dt, rtol=1e-12, atol=0), 'OK' if good else 'FAIL'), flush=True)
+                max(errs, key=errs.get), np.allclose(dts, ref_dt, rtol=1e-12, atol=0), cadence, 'OK' if good else 'FAIL'), flush=True)
         ok = ok and good and (a.steps < 10 or int(tot_moved.item()) > 0)
         torch.cuda.synchronize()
         torch.cuda.set_stream(torch.cuda.default_stream())      # never leave torch on a stream about to be destroyed
