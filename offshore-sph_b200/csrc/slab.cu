@@ -295,6 +295,7 @@ int osph_slab_pack_mode(osph_ctx *ctx, double halo_width, int mode, void *d_mig_
 }
 
 // Slab cadence, reuse step: refresh the records of the frozen halo lists in the neighbours' regions, then the meta row.
+// d_meta == nullptr: the caller's mailbox kernel forms the meta row itself
 int osph_slab_repack(osph_ctx *ctx, const int *d_idx_l, int64_t n_l, void *d_halo_left, const int *d_idx_r, int64_t n_r,
                      void *d_halo_right, double *d_meta)
 {
@@ -307,8 +308,10 @@ int osph_slab_repack(osph_ctx *ctx, const int *d_idx_l, int64_t n_l, void *d_hal
     if (n_l + n_r > 0) {
         k_slab_repack<<<div_up(n_l + n_r, 256), 256, 0, ctx->stream>>>(a, d_idx_l, (int)n_l, d_idx_r, (int)n_r); OSPH_LAUNCH_CHECK();
     }
-    OSPH_CUDA(cudaMemsetAsync(ctx->d_slab_counters, 0, sizeof(int) * 16, ctx->stream));
-    k_slab_meta<<<1, 1, 0, ctx->stream>>>(ctx->d_slab_counters, ctx->d_sc, d_meta); OSPH_LAUNCH_CHECK();
+    if (d_meta) {
+        OSPH_CUDA(cudaMemsetAsync(ctx->d_slab_counters, 0, sizeof(int) * 16, ctx->stream));
+        k_slab_meta<<<1, 1, 0, ctx->stream>>>(ctx->d_slab_counters, ctx->d_sc, d_meta); OSPH_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -406,6 +409,30 @@ extern "C" int osph_slab_dt_local(osph_ctx *ctx, double *d_out3)
         ctx->reductions_valid = true;
     }
     k_slab_dt_local<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, d_out3, ctx->slab_defer ? ctx->cfg.co : 0.0); OSPH_LAUNCH_CHECK();
+    return 0;
+}
+
+// The same two calls for a sequencer whose dt mailbox computes the local triple and runs the time-step kernel itself
+// (slab_p2p.cu: k_mbox_allgather, MboxExtra): the host-side checks of osph_slab_dt_local without its kernel ...
+int osph_slab_dt_prepare(osph_ctx *ctx, double *uniform_c)
+{
+    if (ctx->slab_defer != (ctx->slab_fused == 2)) { ctx->err = "osph_slab_dt_local: step plan and deferred corrector disagree"; return OSPH_E_INVALID; }
+    if (!ctx->reductions_valid) {
+        int rc = osph_launch_correct(ctx, false, 0.0, 0.0, false);
+        if (rc) return rc;
+        ctx->reductions_valid = true;
+    }
+    *uniform_c = ctx->slab_defer ? ctx->cfg.co : 0.0;
+    return 0;
+}
+// ... and osph_slab_step_begin without its k_timestep launch
+int osph_slab_step_begin_after_dt(osph_ctx *ctx, double damping)
+{
+    if (!ctx->slab) { ctx->err = "osph_slab_step_begin: context is not in slab mode"; return OSPH_E_INVALID; }
+    int rc;
+    if ((rc = osph_launch_prepare(ctx, true, 0.0, damping, true, true, ctx->slab_fused))) return rc;
+    ctx->slab_defer = false;
+    ctx->neighbours_valid = false; ctx->reductions_valid = false;
     return 0;
 }
 

@@ -37,6 +37,8 @@ int osph_slab_pack_mode(osph_ctx *ctx, double halo_width, int mode, void *d_mig_
 int osph_slab_repack(osph_ctx *ctx, const int *d_idx_l, int64_t n_l, void *d_halo_left, const int *d_idx_r, int64_t n_r,
                      void *d_halo_right, double *d_meta);
 int osph_slab_install(osph_ctx *ctx, const double *d_all_meta, int world);
+int osph_slab_dt_prepare(osph_ctx *ctx, double *uniform_c);
+int osph_slab_step_begin_after_dt(osph_ctx *ctx, double damping);
 
 #define P2P_MAX_WORLD 16
 #define MBOX_STRIDE 16            // doubles per (slot, sender) cell of a mailbox
@@ -67,6 +69,7 @@ struct osph_slab_p2p {
     bool aborted = false;
     // ---- slab cadence: the ranks sort TOGETHER every few steps; in between the halo is the same particles in the same
     // record slots (frozen lists), migration waits for the next sort, and the host waits for nothing ----
+    bool merge = true;                 // OSPH_SLAB_MERGE: scalar kernels of the step folded into the mailbox kernels
     bool cadence = false;              // OSPH_SLAB_CADENCE
     bool lists_valid = false;          // frozen halo lists describe the resident particles
     int *d_idx_l = nullptr, *d_idx_r = nullptr;      // storage slots behind my halo records towards the left / right neighbour
@@ -86,16 +89,47 @@ struct osph_slab_p2p {
 // window (it left the protocol with an error), or after `spin_limit` clock ticks; the last two set a bit in *status,
 // which the host reads at its one synchronisation point per step -- a rank-local failure then raises on every rank
 // instead of leaving the others inside this kernel for ever.
+// What a mailbox kernel does besides the all-gather (the slab step is a chain of latency-bound launches: every scalar kernel
+// folded into a mailbox is a launch less on that chain).
+struct MboxExtra {
+    // payload computed here instead of by a kernel before: 1 = the dt triple {h_min, -c_max, -a2_max} of this rank
+    // (k_slab_dt_local), 2 = the meta row with zero counts (k_slab_meta of a reuse step)
+    int payload_from_sc;
+    double uniform_c;
+    StepScalars *sc;
+    // tail, run by thread 0 after the gather: 1 = k_timestep with the all-reduced triple, 2 = k_slab_install (global bounds,
+    // h extrema and displacement of a reuse step)
+    int tail;
+    double gamma_c, gamma_f, fixed_dt, co;
+    double *dt_log;
+    long long dt_log_cap;
+    int ts_fused;
+};
+
 __global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int world, size_t off_data, size_t off_flag,
                                  int slot, const double *__restrict__ payload, int n, unsigned long long seq,
                                  double *__restrict__ out_all, int reduce_min, long long spin_limit, unsigned int *status,
-                                 double *host_all, volatile unsigned long long *host_flag)
+                                 double *host_all, volatile unsigned long long *host_flag, MboxExtra x)
 {
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (r < world) {
         double *dst = peers[r] + off_data + (size_t)(slot * world + me) * MBOX_STRIDE;
         volatile unsigned long long *dflag = reinterpret_cast<volatile unsigned long long *>(peers[r] + off_flag) + slot * world + me;
-        if (lane < n) dst[lane] = payload[lane];
+        if (lane < n) {
+            double v;
+            if (x.payload_from_sc == 1) {
+                const StepScalars *sc = x.sc;
+                v = lane == 0 ? dec_f64(sc->hmin_fluid) : (lane == 1 ? (x.uniform_c > 0.0 ? -x.uniform_c : -dec_f64(sc->cmax_fluid)) : -dec_f64(sc->a2max_fluid));
+            } else if (x.payload_from_sc == 2) {
+                const StepScalars *sc = x.sc;
+                v = 0.0;
+                if (lane == 4) v = dec_f64(sc->xmin); else if (lane == 5) v = -dec_f64(sc->xmax);
+                else if (lane == 6) v = dec_f64(sc->ymin); else if (lane == 7) v = -dec_f64(sc->ymax);
+                else if (lane == 8) v = dec_f64(sc->hmin_all); else if (lane == 9) v = -dec_f64(sc->hmax_all);
+                else if (lane == 11) v = -dec_f64(sc->disp2max);
+            } else v = payload[lane];
+            dst[lane] = v;
+        }
         __threadfence_system();
         __syncwarp();
         if (lane == 0) *dflag = seq;
@@ -120,6 +154,27 @@ __global__ void k_mbox_allgather(double *const *__restrict__ peers, int me, int 
             double m = out_all[threadIdx.x];
             for (int q = 1; q < world; q++) m = fmin(m, out_all[q * n + threadIdx.x]);
             out_all[world * n + threadIdx.x] = m;
+        }
+    }
+    if (x.tail) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (x.tail == 1) {
+                // k_timestep of the step, with the all-reduced triple (as osph_slab_step_begin would launch it)
+                timestep_body(x.sc, x.gamma_c, x.gamma_f, x.fixed_dt, x.dt_log, x.dt_log_cap, 1, out_all + world * n, x.ts_fused, x.co);
+            } else {
+                // k_slab_install: global bounds, h extrema, displacement
+                StepScalars *sc = x.sc;
+                double b[6], d = out_all[11];
+                for (int k = 0; k < 6; k++) b[k] = out_all[4 + k];
+                for (int q = 1; q < world; q++) {
+                    for (int k = 0; k < 6; k++) b[k] = fmin(b[k], out_all[n * q + 4 + k]);
+                    d = fmin(d, out_all[n * q + 11]);
+                }
+                sc->xmin = enc_f64(b[0]); sc->xmax = enc_f64(-b[1]); sc->ymin = enc_f64(b[2]); sc->ymax = enc_f64(-b[3]);
+                sc->hmin_all = enc_f64(b[4]); sc->hmax_all = enc_f64(-b[5]);
+                sc->disp2max = enc_f64(-d);
+            }
         }
     }
     if (host_all) {
@@ -187,6 +242,8 @@ extern "C" int osph_slab_p2p_create(osph_ctx *ctx, int rank, int world, double x
         // OSPH_SLAB_CADENCE=0 restores the exchange that sorts, migrates and re-packs the halo at every step
         const char *e = getenv("OSPH_SLAB_CADENCE");
         s->cadence = !(e && e[0] == '0') && !ctx->cfg.summation_density;
+        const char *m = getenv("OSPH_SLAB_MERGE");
+        s->merge = !(m && m[0] == '0');
         if (s->cadence) {
             OSPH_CUDA(cudaMalloc(&s->d_idx_l, sizeof(int) * (size_t)halo_cap));
             OSPH_CUDA(cudaMalloc(&s->d_idx_r, sizeof(int) * (size_t)halo_cap));
@@ -312,10 +369,15 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         return 0;
     };
     // all-gather of this rank's meta row (s->d_meta) through the second mailbox; the result also lands in pinned host memory
-    auto meta_mailbox = [&]() -> int {
+    MboxExtra plain; memset(&plain, 0, sizeof(plain));
+    // reuse: 1 = a step that reuses the binning: the kernel forms the meta row itself (no counts) and installs the global
+    // bounds and displacement afterwards (with OSPH_SLAB_MERGE)
+    auto meta_mailbox = [&](bool reuse_merged) -> int {
         s->seq++;
+        MboxExtra x = plain;
+        if (reuse_merged) { x.payload_from_sc = 2; x.sc = ctx->d_sc; x.tail = 2; }
         k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_meta, s->off_meta_flag, (int)(s->seq & 1ull), s->d_meta, 12,
-                                                       s->seq, s->d_all_meta, 0, s->spin_limit, d_status, s->h_all_meta, host_flag);
+                                                       s->seq, s->d_all_meta, 0, s->spin_limit, d_status, s->h_all_meta, host_flag, x);
         ctx->launches++;
         if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return OSPH_E_CUDA; }
         return 0;
@@ -368,22 +430,38 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
                         R_now + 2.0 * (s->D_known + 2.0 * s->dstep) > s->gs;
         }
         if ((rc = osph_slab_step_plan(ctx, step, nsteps))) return fail(rc);    // corrector of step k fused into the predictor of k+1
-        // ---- identical dt on every rank: mailbox all-gather + min ----
-        if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return fail(rc);
-        s->seq++;
-        k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, (int)(s->seq & 1ull), s->d_dt3, 3, s->seq,
-                                                       s->d_all_dt, 1, s->spin_limit, d_status, nullptr, nullptr);
-        ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
-        P2P_MARK(1);
-        if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return fail(rc);
+        // ---- identical dt on every rank: mailbox all-gather + min (+ the local triple before and k_timestep after it, in
+        // the same kernel) ----
+        if (s->merge) {
+            MboxExtra x = plain;
+            if ((rc = osph_slab_dt_prepare(ctx, &x.uniform_c))) return fail(rc);
+            x.payload_from_sc = 1; x.sc = ctx->d_sc; x.tail = 1;
+            x.gamma_c = ctx->cfg.cfl_courant; x.gamma_f = ctx->cfg.cfl_force; x.fixed_dt = fixed_dt > 0 ? fixed_dt : -1.0; x.co = ctx->cfg.co;
+            x.dt_log = ctx->d_dt_log; x.dt_log_cap = (long long)ctx->dt_log_cap; x.ts_fused = ctx->slab_fused;
+            s->seq++;
+            k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, (int)(s->seq & 1ull), s->d_dt3, 3, s->seq,
+                                                           s->d_all_dt, 1, s->spin_limit, d_status, nullptr, nullptr, x);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
+            P2P_MARK(1);
+            if ((rc = osph_slab_step_begin_after_dt(ctx, damping))) return fail(rc);
+        } else {
+            if ((rc = osph_slab_dt_local(ctx, s->d_dt3))) return fail(rc);
+            s->seq++;
+            k_mbox_allgather<<<1, 32 * W, 0, ctx->stream>>>(s->d_peer, me, W, s->off_dt, s->off_dt_flag, (int)(s->seq & 1ull), s->d_dt3, 3, s->seq,
+                                                           s->d_all_dt, 1, s->spin_limit, d_status, nullptr, nullptr, plain);
+            ctx->launches++;
+            if (cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch: mailbox all-gather"; return fail(OSPH_E_CUDA); }
+            P2P_MARK(1);
+            if ((rc = osph_slab_step_begin(ctx, s->d_all_dt + W * 3, fixed_dt, damping))) return fail(rc);
+        }
         P2P_MARK(2);
         const auto host_t0 = std::chrono::steady_clock::now();
         if (!s->cadence) {
             // ---- every step: classify + pack straight into the neighbours' windows; counts and bounds through the mailbox ----
             const double width = pair_radius(s->hmax) * 1.1;
             if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return fail(rc);
-            if ((rc = meta_mailbox())) return fail(rc);
+            if ((rc = meta_mailbox(false))) return fail(rc);
             P2P_MARK(3);
             if ((rc = wait_meta(s->seq))) return fail(rc);                // the one host wait of the step
             P2P_MARK(4);
@@ -406,7 +484,7 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
             // ---- sorting step, pass A: the migrants change owner first, so that the halo lists of pass B are built on the
             // final owned set (and nobody keeps stale copies of particles it gave away) ----
             if ((rc = osph_slab_pack_mode(ctx, 0.0, 1, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, nullptr, nullptr, s->d_meta))) return fail(rc);
-            if ((rc = meta_mailbox())) return fail(rc);
+            if ((rc = meta_mailbox(false))) return fail(rc);
             if ((rc = wait_meta(s->seq))) return fail(rc);
             if ((rc = check_overflow(M))) return fail(rc);
             const int64_t out_l = (int64_t)M[12 * me + 0], out_r = (int64_t)M[12 * me + 1];
@@ -420,7 +498,7 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
             s->skin = s->dstep >= 0.0 ? std::min(std::max(2.0 * s->dstep * 10.0 * 1.1 / R, 0.03), 0.25) : 0.1;
             const double width = R * (1.0 + s->skin) * 1.1;
             if ((rc = osph_slab_pack_mode(ctx, width, 2, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_idx_l, s->d_idx_r, s->d_meta))) return fail(rc);
-            if ((rc = meta_mailbox())) return fail(rc);
+            if ((rc = meta_mailbox(false))) return fail(rc);
             P2P_MARK(3);
             if ((rc = wait_meta(s->seq))) return fail(rc);
             P2P_MARK(4);
@@ -446,11 +524,12 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         } else {
             // ---- reuse: same particles, same record slots, current values; nothing for the host to wait for.  The meta
             // mailbox still runs: it is the "records have landed" signal and carries bounds and displacement ----
-            if ((rc = osph_slab_repack(ctx, s->d_idx_l, s->halo_n_l, halo_l, s->d_idx_r, s->halo_n_r, halo_r, s->d_meta))) return fail(rc);
-            if ((rc = meta_mailbox())) return fail(rc);
+            if ((rc = osph_slab_repack(ctx, s->d_idx_l, s->halo_n_l, halo_l, s->d_idx_r, s->halo_n_r, halo_r, s->merge ? nullptr : s->d_meta))) return fail(rc);
+            if ((rc = meta_mailbox(s->merge))) return fail(rc);
             s->pending_seq = s->seq;
             P2P_MARK(3); P2P_MARK(4);
-            if ((rc = osph_slab_install(ctx, s->d_all_meta, W))) return fail(rc);
+            if (s->merge) ctx->prepared = true;
+            else if ((rc = osph_slab_install(ctx, s->d_all_meta, W))) return fail(rc);
             ctx->slab_cadence_force = 4; ctx->slab_skin = s->skin;
             s->reuses++;
         }
