@@ -349,3 +349,65 @@ def test_emulated_slab_cadence_reuses_the_halo_lists(world, fixed_dt):
         assert errs[worst] <= 1e-11, (chunk, worst, errs[worst])
     print("cadence:", [r[2:] for r in res if r[1] == 'cadence'])
     assert reused > 0, "no step reused the binning: the test did not exercise the cadence"
+
+
+def _worker_tank(rank, world, port, lib, q):
+    os.environ["OSPH_LIB"] = lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    root = os.path.dirname(HERE)
+    for p in (root, os.path.join(root, "offshore-sph_b200"), HERE):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from conftest import field_err
+    from osph_b200 import capi, slabs, workloads as W
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = W.tank_case(50, h=None, useXSPH=False, seed=3)            # Containment set-up: h = 1.3 sqrt(m / rho), refreshed every step
+    pA, c = case['pA'], case['consts']
+    pA['vx'][pA['label'] == 0] += 0.5
+    cfg = capi.make_config(c, 'cubic', 'pec', capi.FP64, None)
+    steps = 20
+    with capi.Context(cfg) as single:
+        single.upload(pA); single.step(steps, None, 0.0)
+        ref, ref_dt = single.download(pA.copy()), single.dt_log()
+    ctx = capi.Context(cfg)
+    cuts, local_pA, ids = slabs.partition(pA, world, rank)
+    run = slabs.P2PSlabRun(ctx, cuts, local_pA, ids, 'cubic', case['r0'], float(pA['h'].max()), torch.device('cpu'),
+                           mig_frac=0.2, ghost_frac=0.6, min_cap=256)
+    run.step(steps, None, 0.0)
+    fields = ['x', 'y', 'vx', 'vy', 'rho', 'p', 'ax', 'ay', 'drho', 'h']
+    got, seen = slabs.gather_global(run, pA, fields)
+    errs = {k: field_err(got[k], ref[k]) for k in fields}
+    q.put((rank, run.cadence_stats, ctx.sync(), bool(np.all(seen == 1)), max(errs.values()), max(errs, key=errs.get),
+           bool(np.allclose(ctx.dt_log(), ref_dt, rtol=1e-10, atol=0))))
+    dist.barrier()
+    run.close(); ctx.close()
+    dist.destroy_process_group()
+
+
+def test_emulated_slab_cadence_with_dynamic_h():
+    """The Containment set-up (smoothing length refreshed from the density every step, so the pair radius moves) through the
+    slab cadence: the host plans the reuse with a margin on the radius, the device verifies it (status must stay 0)."""
+    import queue
+    import time
+    lib = emu_build.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_tank, args=(r, 2, port, lib, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res, t_end = [], time.time() + 400
+    while len(res) < 2 and time.time() < t_end:
+        try:
+            res.append(q.get(timeout=1.0))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    [p.join(30) for p in procs]
+    [p.kill() for p in procs if p.is_alive()]
+    assert len(res) == 2 and all(p.exitcode == 0 for p in procs), res
+    for rank, (sorts, reuses), status, owned_once, err, worst, dt_ok in res:
+        assert sorts + reuses == 20 and reuses >= 10, (sorts, reuses)
+        assert status == 0 and owned_once and dt_ok
+        assert err <= 1e-11, (worst, err)
