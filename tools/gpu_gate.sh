@@ -4,6 +4,7 @@
 #   tests     pytest -m gpu (no -x: every failure is listed), smoke()
 #   sanitize  compute-sanitizer memcheck on the bench workload (1 M particles, both precisions, 2 steps) and on one golden
 #             case; racecheck on the golden case ("race detection")
+#   sanitize_multi  (needs 2 GPUs) memcheck over tests/multi_gpu_check.py: the three slab sequencers incl. the slab cadence
 #   bench     bench.py in both precisions (default K / W) and the reference arm
 #   launches  ncu launch list of one short bench run (shares of the step, not absolutes)
 #   ncu       ncu --set full of k_pair (both precisions) and of the streaming kernels
@@ -28,6 +29,12 @@ if has sanitize; then
     done
     echo "== memcheck golden cases"; timeout 600 compute-sanitizer --tool memcheck --error-exitcode 99 python tools/sanitize_small.py 2>&1 | tail -8
     echo "== racecheck golden case"; timeout 600 compute-sanitizer --tool racecheck --error-exitcode 99 python tools/sanitize_small.py 2>&1 | tail -8
+  } >> $LOG 2>&1
+fi
+if has sanitize_multi; then
+  { echo "== memcheck multi-GPU check"
+    timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 99 python -m torch.distributed.run --nnodes=1 \
+        --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tests/multi_gpu_check.py --steps 12 2>&1 | grep -E "OK|FAIL|ERROR SUMMARY|Invalid" | tail -12
   } >> $LOG 2>&1
 fi
 if has bench; then
