@@ -12,6 +12,7 @@
 #define OSPH_PAIR_THREADS 256         // one CTA of the pair kernel owns this many consecutive sorted particles
 #endif
 #define OSPH_MAX_CELL_BITS 28
+#define OSPH_SKIN_MAX 0.04             // largest adaptive skin of the sort cadence, as a fraction of the pair radius (k_grid_params)
 #define OSPH_WIRE_HALO 8               // doubles per ghost record: x y vx vy rho m h label
 #define OSPH_WIRE_FULL 21              // doubles per migrant record: 19 columns, label, global id
 #define OSPH_PAIR_EVENTS 512           // pair-kernel launches timed between two osph_pair_kernel_time calls

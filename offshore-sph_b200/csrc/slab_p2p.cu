@@ -457,7 +457,12 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
         }
         P2P_MARK(2);
         const auto host_t0 = std::chrono::steady_clock::now();
-        if (!s->cadence) {
+        // A flow too fast for the largest skin (not even one reusing step between two sorts) takes the one-pass exchange
+        // below: one host wait instead of the two of a sorting step.  The builds keep writing the reference positions, so the
+        // displacement per step stays known and the cadence resumes when the flow calms down.
+        const bool fast_flow = s->cadence && sort_step && s->dstep >= 0.0 &&
+                               s->dstep > OSPH_SKIN_MAX * pair_radius(s->hmax) / 4.0;
+        if (!s->cadence || fast_flow) {
             // ---- every step: classify + pack straight into the neighbours' windows; counts and bounds through the mailbox ----
             const double width = pair_radius(s->hmax) * 1.1;
             if ((rc = osph_slab_pack(ctx, width, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_meta))) return fail(rc);
@@ -480,6 +485,15 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
                                             s->win + s->off_mig_from_right, in_mig_r, gm, n_ghost, bounds))) return fail(rc);
             const int64_t c[8] = {out_l, out_r, halo_out_l, halo_out_r, in_mig_l, in_mig_r, in_halo_l, in_halo_r};
             memcpy(s->last_counts, c, sizeof(c));
+            if (fast_flow) {
+                double d2 = M[11];
+                for (int r = 1; r < W; r++) d2 = std::min(d2, M[12 * r + 11]);
+                const double D = std::sqrt(std::max(-d2, 0.0));
+                if (std::isfinite(D) && s->steps_since_sort > 0) s->dstep = std::max(D - s->D_known, D / s->steps_since_sort);
+                s->hmin = bounds[4];
+                s->D_known = 0.0; s->steps_since_sort = 0; s->lists_valid = false; s->sorts++;
+                ctx->slab_cadence_force = 1; ctx->slab_skin = 0.0;        // sort, no skin, reference positions refreshed
+            }
         } else if (sort_step) {
             // ---- sorting step, pass A: the migrants change owner first, so that the halo lists of pass B are built on the
             // final owned set (and nobody keeps stale copies of particles it gave away) ----
@@ -495,7 +509,8 @@ extern "C" int osph_slab_p2p_run(osph_ctx *ctx, osph_slab_p2p *s, int32_t nsteps
             // ---- pass B: halos, with a skin; the storage slot behind every record is remembered ----
             // skin: about ten steps' worth of the displacement per step observed since the last sort, 3 %..25 % of the radius
             const double R = pair_radius(s->hmax);
-            s->skin = s->dstep >= 0.0 ? std::min(std::max(2.0 * s->dstep * 10.0 * 1.1 / R, 0.03), 0.25) : 0.1;
+            // (capped where the pair kernel's staged candidate rows still fit its shared-memory records: k_grid_params)
+            s->skin = s->dstep >= 0.0 ? std::min(std::max(2.0 * s->dstep * 10.0 * 1.1 / R, 0.03), (double)OSPH_SKIN_MAX) : 0.03;
             const double width = R * (1.0 + s->skin) * 1.1;
             if ((rc = osph_slab_pack_mode(ctx, width, 2, mig_l, mig_r, s->mig_cap, halo_l, halo_r, s->halo_cap, s->d_idx_l, s->d_idx_r, s->d_meta))) return fail(rc);
             if ((rc = meta_mailbox(false))) return fail(rc);

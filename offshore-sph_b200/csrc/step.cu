@@ -430,7 +430,12 @@ __device__ void grid_params_body(StepScalars *sc, GridParams *g, double nn_scale
         else {
             const int steps = g->sort_count > 0 && g->steps_since_sort > 0 ? g->steps_since_sort : 0;
             const double per_build = steps > 0 && isfinite(disp) ? disp / steps : 0.0;
-            skin = fmin(fmax(2.0 * per_build * 10.0 * 1.1, 0.03 * R), 0.25 * R);
+            // Capped at 4 % of R: the pair kernel stages the three candidate rows of a CTA in shared memory (PAIR_CAP
+            // records), typically 835 of 1024 at skin 0; from about 5 % on a growing share of the CTAs falls back to batched
+            // staging (measured: 294 us at 3 %, 308 us at 5 %).  A flow too fast to get two builds out of that skin sorts at
+            // every build instead (skin 0: no candidates paid for nothing).
+            skin = fmin(fmax(2.0 * per_build * 10.0 * 1.1, 0.03 * R), OSPH_SKIN_MAX * R);
+            if (per_build > 0.0 && skin < 2.0 * per_build * 2.0) skin = 0.0;
         }
     }
     int regime_a = (R >= cs) ? 1 : 0, adj_always = 0;
@@ -636,7 +641,10 @@ __device__ __forceinline__ double tait_ratio_pow(double ratio, double gamma)
 }
 
 template <typename Real2>
-__global__ void __launch_bounds__(256, 5)          // 5 CTAs / SM (<= 51 registers), as before the grid parameters moved into registers
+#ifndef GATHER_MINB
+#define GATHER_MINB 5
+#endif
+__global__ void __launch_bounds__(256, GATHER_MINB)          // 5 CTAs / SM (<= 51 registers), as before the grid parameters moved into registers
 k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real2 *__restrict__ s_hp)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
