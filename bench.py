@@ -14,7 +14,8 @@ Solver.setup() does, jittered deterministically so pair forces do not vanish.
   e2e            the same through the plugin boundary with HOST buffers: every step uploads the packed
                  particle_dtype array from pinned memory, runs one step, downloads it again
   roofline       the fused pair kernel against the measured HBM peak (algorithmic bytes 13F+1 per particle)
-  cpu_baseline   the CPU oracle (a C port of the reference's single-threaded numba path) on a bounded sample
+  cpu_baseline   the CPU oracle (a C port of the reference's numba path, pair loop on all host threads): a full step where it
+                 fits the budget (1 M particles), else a strided sample scaled back -- the line says which
 """
 import argparse
 import json
@@ -79,40 +80,66 @@ def workload_name(n_side, n, kernel, prec):
 # ------------------------------------------------------------------------------------------------
 # CPU oracle timing (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def time_oracle_step(case, kernel, budget_s=12.0):
-    """One step of the oracle port; the pair loop runs on every `stride`-th fluid particle and is
-    scaled back (all other phases run on all particles).  Returns (seconds per full step, sample text)."""
+def host_threads():
+    """Host threads the CPU legs may use: the cores this process is allowed on."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def time_oracle_step(case, kernel, budget_s=12.0, threads=None):
+    """One step of the oracle port with its pair loop on `threads` host threads (default: all the process may use; the
+    reference itself is single-threaded numba, the other phases run on one thread and are 0.1 % of the step).  When a
+    full step does not fit the budget the pair loop runs on every `stride`-th fluid particle and is scaled back.
+    Returns (seconds per full step, sample text)."""
     from oracle import oracle as O
+    threads = threads or host_threads()
     pA, c = case['pA'], case['consts']
     P = O.Particles.from_aos(pA)
     w = O.wcsph(c['height'], c['r0'], c['rho0'], True)
     fluid = P.fluid
     n_f = int(fluid.sum())
-    # cost model of the reference search: 9 cells of 1 m^2 -> candidates per particle
+    # cost model of the reference search: 9 cells of 1 m^2 -> candidates per particle (one thread: 3 ns per candidate,
+    # 36 ns per accepted pair, measured with this port; threads scale it by about 0.7 per thread)
     cand = 9.0 * max(1.0, n_f / 625.0)
-    est = n_f * cand * 6e-9 + n_f * 72 * 60e-9
+    est = (n_f * cand * 3e-9 + n_f * 72 * 36e-9) / max(1.0, 0.7 * threads)
     stride = max(1, int(np.ceil(est / budget_s)))
     time_oracle_step.last_stride = stride
+    time_oracle_step.last_threads = threads
     t0 = time.perf_counter()
     dt3 = O.timestep(P, fluid)
     O.pec_predict(P, fluid, dt3[0], DAMPING, True, False)
     grid = O.Grid(P, 2.0)
     P.h[fluid.astype(bool)] = case['h']
     t1 = time.perf_counter()
-    pairs = O.loop(P, w, grid, kernel, stride, 0)
+    pairs = O.loop(P, w, grid, kernel, stride, 0, threads=threads)
     t2 = time.perf_counter()
     O.pec_correct(P, fluid, dt3[0], DAMPING, True, False)
     t3 = time.perf_counter()
     t_full = (t1 - t0) + (t3 - t2) + (t2 - t1) * stride
-    sample = ("1 step; pair loop on every %d-th fluid particle (%d of %d, %d pairs, %.1f s) scaled by %d; "
-              "other phases on all %d particles (%.2f s)" % (stride, (n_f + stride - 1) // stride, n_f, pairs,
-                                                            t2 - t1, stride, P.n, (t1 - t0) + (t3 - t2)))
+    if stride == 1:
+        sample = ("1 full step on all %d particles: pair loop on %d host threads (%d pairs, %.1f s), other phases on one "
+                  "thread (%.2f s)" % (P.n, threads, pairs, t2 - t1, (t1 - t0) + (t3 - t2)))
+    else:
+        sample = ("1 step; pair loop on %d host threads over every %d-th fluid particle (%d of %d, %d pairs, %.1f s) scaled "
+                  "by %d; other phases on all %d particles (%.2f s)" % (threads, stride, (n_f + stride - 1) // stride, n_f,
+                                                                       pairs, t2 - t1, stride, P.n, (t1 - t0) + (t3 - t2)))
     return t_full, sample
 
 
+def cpu_baseline_entry(value, sample):
+    """The cpu_baseline object of a bench line, from the last time_oracle_step call."""
+    stride = time_oracle_step.last_stride
+    return {"value": value, "unit": UNIT, "cores": time_oracle_step.last_threads, "kind": "port", "sample": sample,
+            "extrapolated": stride > 1, "stride": stride, "host_cores_available": os.cpu_count(),
+            "note": "C port of the reference's numba loop (the reference is single-threaded and about 5x slower per "
+                    "thread, BASELINE.md); the pair loop is spread over the host threads"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port, 1 thread like the reference's
-    non-parallel numba loop) on the box's host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port; pair loop on all host threads the process may
+    use -- the reference's own numba loop is single-threaded) on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -124,7 +151,7 @@ def run_reference(args):
     O.build()
     times = []
     sample = ""
-    budget = max(0.5, min(12.0, 150.0 / max(1, args.steps + args.warmup)))      # the whole run stays near 2.5 minutes of CPU work
+    budget = max(0.5, min(40.0, 180.0 / max(1, args.steps + args.warmup)))      # the whole run stays near 3 minutes of CPU work
     for s in range(args.warmup + args.steps):
         t, sample = time_oracle_step(case, args.kernel, budget)
         if s >= args.warmup:
@@ -136,11 +163,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n_side, n, args.kernel, "FP64"), "particles": n},
-        # the denominator is a MODEL of a full step, not a measured one: the pair loop ran on every stride-th fluid
-        # particle and its time was multiplied by the stride (a full reference step is minutes at 1 M, hours at 16 M)
-        "extrapolated": True, "stride": time_oracle_step.last_stride,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                         "extrapolated": True, "stride": time_oracle_step.last_stride},
+        # stride > 1: the denominator is a MODEL of a full step, not a measured one -- the pair loop ran on every stride-th
+        # fluid particle and its time was multiplied by the stride (a full step is hours at 16 M); stride 1: measured
+        "extrapolated": time_oracle_step.last_stride > 1, "stride": time_oracle_step.last_stride,
+        "cpu_baseline": cpu_baseline_entry(value, sample),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -232,8 +258,7 @@ def run_gpu(args):
             from oracle import oracle as O
             O.build()
             t_cpu, sample = time_oracle_step(case, args.kernel, args.cpu_budget)
-            return {"value": len(case['pA']) / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                    "extrapolated": True, "stride": time_oracle_step.last_stride, "host_cores_available": os.cpu_count()}
+            return cpu_baseline_entry(len(case['pA']) / t_cpu, sample)
         return slabs.bench_multi_gpu(args, rank, world, local, cpu_baseline=cpu_leg)
 
     prec = capi.FP64 if args.precision == "fp64" else capi.FP32
@@ -337,8 +362,7 @@ def run_gpu(args):
         from oracle import oracle as O
         O.build()
         t_cpu, sample = time_oracle_step(case, args.kernel, args.cpu_budget)
-        cpu = {"value": n / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-               "extrapolated": True, "stride": time_oracle_step.last_stride, "host_cores_available": os.cpu_count()}
+        cpu = cpu_baseline_entry(n / t_cpu, sample)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,

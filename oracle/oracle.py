@@ -85,6 +85,9 @@ def lib():
         L.oracle_loop.restype = C.c_int64
         L.oracle_loop.argtypes = [C.POINTER(_CParticles), C.POINTER(WCSPHParams), C.POINTER(_CGrid),
                                   C.c_int, C.c_int64, C.c_int64]
+        L.oracle_loop_mt.restype = C.c_int64
+        L.oracle_loop_mt.argtypes = [C.POINTER(_CParticles), C.POINTER(WCSPHParams), C.POINTER(_CGrid),
+                                     C.c_int, C.c_int64, C.c_int64, C.c_int]
         u8 = C.POINTER(C.c_uint8)
         L.oracle_pec_predict.argtypes = [C.POINTER(_CParticles), u8, C.c_double, C.c_double, C.c_int, C.c_int]
         L.oracle_pec_correct.argtypes = [C.POINTER(_CParticles), u8, C.c_double, C.c_double, C.c_int, C.c_int]
@@ -225,8 +228,11 @@ class Grid:
         return off, idx[:total]
 
 
-def loop(P, w, grid, kernel='cubic', stride=1, phase=0):
-    """Reference `_loop` (src/Tools/SolverTools.py:120-174), in place on P. Returns #pairs."""
+def loop(P, w, grid, kernel='cubic', stride=1, phase=0, threads=1):
+    """Reference `_loop` (src/Tools/SolverTools.py:120-174), in place on P. Returns #pairs.
+    threads > 1: the pair loop on that many host threads (same arithmetic per particle, bit-identical results)."""
+    if threads > 1:
+        return lib().oracle_loop_mt(P.cref(), C.byref(w), C.byref(grid.g), KERNELS[kernel], stride, phase, int(threads))
     return lib().oracle_loop(P.cref(), C.byref(w), C.byref(grid.g), KERNELS[kernel], stride, phase)
 
 

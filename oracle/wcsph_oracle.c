@@ -1,7 +1,8 @@
 /*
  * wcsph_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * A single-threaded, plain-C restatement of the WCSPH time step of
+ * A plain-C restatement (single-threaded like the reference; oracle_loop_mt runs the
+ * same pair loop on several host threads for the bench's CPU legs) of the WCSPH time step of
  * KoningJasper/Offshore-SPH (the reference is pure Python + numba).  It is the
  * checker the CUDA path is compared against; nothing under offshore-sph_b200/
  * may link, import or call it.  Only tests/, __graft_entry__.smoke() and the
@@ -24,6 +25,7 @@
  * Citations are file:line into the reference tree.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -299,51 +301,18 @@ int64_t oracle_neighbours_csr(const oracle_grid *g, int64_t n, const int8_t *lab
 /* _loop: EOS + pair interactions                                       */
 /* ------------------------------------------------------------------ */
 
-/*
- * src/Tools/SolverTools.py:120-174 with the equations it calls:
- * Continuity.py:5-17, Momentum.py:6-57 (+gravity WCSPH.py:151-169),
- * BoundaryForce.py:7-42, XSPH.py:6-31 (+WCSPH.py:171-189).
- * `stride`/`phase` restrict the main loop to fluid particles with
- * (i % stride) == phase (bounded CPU-baseline samples); use 1, 0 for all.
- * Returns the number of accepted pairs evaluated.
- */
-int64_t oracle_loop(oracle_particles *P, const oracle_wcsph *w, const oracle_grid *g,
-                    int kid, int64_t stride, int64_t phase)
+/* main loop of `_loop` (:143-173) over the particles [i0, i1); every particle writes only its own rates
+ * (drho, ax, ay, xsphx, xsphy) and reads fields no iteration writes, so ranges are independent of each other. */
+static int64_t loop_range(oracle_particles *P, const oracle_wcsph *w, const oracle_grid *g,
+                          int kid, int64_t stride, int64_t phase, int64_t i0, int64_t i1)
 {
-    int64_t n = P->n, pairs = 0;
+    int64_t pairs = 0;
     int64_t cap = 256;
     int64_t *nb = (int64_t *)malloc(sizeof(int64_t) * cap);
     double *rr = (double *)malloc(sizeof(double) * cap);
     double *qq = (double *)malloc(sizeof(double) * cap);
     double *hh = (double *)malloc(sizeof(double) * cap);
-
-    /* :121-127 pressure and speed of sound for every active particle */
-    for (int64_t i = 0; i < n; i++) {
-        P->p[i] = oracle_tait_p(w->gamma, w->B, w->rho0, P->rho[i], P->label[i]) + w->Pb;
-        P->c[i] = w->co;
-    }
-
-    /* :129-140 optional summation density, applied in place in index order */
-    if (w->useSummationDensity) {
-        for (int64_t i = 0; i < n; i++) {
-            if (P->label[i] != LABEL_FLUID) continue;
-            int64_t J = oracle_near_pos(g, P->x[i], P->y[i], P->h[i], P->x, P->y, P->h,
-                                        cap, nb, rr, qq, hh);
-            if (J > cap) {
-                cap = J * 2;
-                nb = realloc(nb, sizeof(int64_t) * cap); rr = realloc(rr, sizeof(double) * cap);
-                qq = realloc(qq, sizeof(double) * cap); hh = realloc(hh, sizeof(double) * cap);
-                J = oracle_near_pos(g, P->x[i], P->y[i], P->h[i], P->x, P->y, P->h,
-                                    cap, nb, rr, qq, hh);
-            }
-            double rho = 0.0; /* SummationDensity.py:6-13 */
-            for (int64_t k = 0; k < J; k++)
-                if (P->label[nb[k]] == LABEL_FLUID) rho += P->m[nb[k]] * kernel_w(kid, rr[k], hh[k]);
-            P->rho[i] = rho;
-        }
-    }
-
-    for (int64_t i = 0; i < n; i++) {
+    for (int64_t i = i0; i < i1; i++) {
         if (P->label[i] != LABEL_FLUID) continue;
         if (stride > 1 && (i % stride) != phase) continue;
         int64_t J = oracle_near_pos(g, P->x[i], P->y[i], P->h[i], P->x, P->y, P->h,
@@ -412,6 +381,110 @@ int64_t oracle_loop(oracle_particles *P, const oracle_wcsph *w, const oracle_gri
         else { P->xsphx[i] = 0.0; P->xsphy[i] = 0.0; }
     }
     free(nb); free(rr); free(qq); free(hh);
+    return pairs;
+}
+
+/* :121-140: EOS for every active particle, then the optional summation density (in place, index order) */
+static void loop_head(oracle_particles *P, const oracle_wcsph *w, const oracle_grid *g, int kid)
+{
+    int64_t n = P->n;
+    int64_t cap = 256;
+    int64_t *nb = (int64_t *)malloc(sizeof(int64_t) * cap);
+    double *rr = (double *)malloc(sizeof(double) * cap);
+    double *qq = (double *)malloc(sizeof(double) * cap);
+    double *hh = (double *)malloc(sizeof(double) * cap);
+    /* :121-127 pressure and speed of sound for every active particle */
+    for (int64_t i = 0; i < n; i++) {
+        P->p[i] = oracle_tait_p(w->gamma, w->B, w->rho0, P->rho[i], P->label[i]) + w->Pb;
+        P->c[i] = w->co;
+    }
+
+    /* :129-140 optional summation density, applied in place in index order */
+    if (w->useSummationDensity) {
+        for (int64_t i = 0; i < n; i++) {
+            if (P->label[i] != LABEL_FLUID) continue;
+            int64_t J = oracle_near_pos(g, P->x[i], P->y[i], P->h[i], P->x, P->y, P->h,
+                                        cap, nb, rr, qq, hh);
+            if (J > cap) {
+                cap = J * 2;
+                nb = realloc(nb, sizeof(int64_t) * cap); rr = realloc(rr, sizeof(double) * cap);
+                qq = realloc(qq, sizeof(double) * cap); hh = realloc(hh, sizeof(double) * cap);
+                J = oracle_near_pos(g, P->x[i], P->y[i], P->h[i], P->x, P->y, P->h,
+                                    cap, nb, rr, qq, hh);
+            }
+            double rho = 0.0; /* SummationDensity.py:6-13 */
+            for (int64_t k = 0; k < J; k++)
+                if (P->label[nb[k]] == LABEL_FLUID) rho += P->m[nb[k]] * kernel_w(kid, rr[k], hh[k]);
+            P->rho[i] = rho;
+        }
+    }
+
+    free(nb); free(rr); free(qq); free(hh);
+}
+
+/*
+ * src/Tools/SolverTools.py:120-174 with the equations it calls:
+ * Continuity.py:5-17, Momentum.py:6-57 (+gravity WCSPH.py:151-169),
+ * BoundaryForce.py:7-42, XSPH.py:6-31 (+WCSPH.py:171-189).
+ * `stride`/`phase` restrict the main loop to fluid particles with
+ * (i % stride) == phase (bounded CPU-baseline samples); use 1, 0 for all.
+ * Returns the number of accepted pairs evaluated.
+ */
+int64_t oracle_loop(oracle_particles *P, const oracle_wcsph *w, const oracle_grid *g,
+                    int kid, int64_t stride, int64_t phase)
+{
+    loop_head(P, w, g, kid);
+    return loop_range(P, w, g, kid, stride, phase, 0, P->n);
+}
+
+/*
+ * The same loop on `nthreads` host threads (bench.py's cpu_baseline / --impl reference legs: "all the host threads it
+ * can use").  The reference itself is single-threaded (numba without parallel=True); per-particle arithmetic and its
+ * order are those of oracle_loop, so the results are bit-identical to it (tests/test_oracle_golden.py).  Blocks of
+ * OR_MT_BLOCK particles are dealt round-robin to the threads.  The EOS pass and the summation-density pass (in place,
+ * order-dependent) stay serial.
+ */
+#define OR_MT_BLOCK 2048
+typedef struct {
+    oracle_particles *P; const oracle_wcsph *w; const oracle_grid *g;
+    int kid, tid, nthreads; int64_t stride, phase, pairs;
+} loop_job;
+
+static void *loop_worker(void *arg)
+{
+    loop_job *j = (loop_job *)arg;
+    int64_t n = j->P->n, pairs = 0;
+    for (int64_t b = (int64_t)j->tid * OR_MT_BLOCK; b < n; b += (int64_t)j->nthreads * OR_MT_BLOCK) {
+        int64_t e = b + OR_MT_BLOCK < n ? b + OR_MT_BLOCK : n;
+        pairs += loop_range(j->P, j->w, j->g, j->kid, j->stride, j->phase, b, e);
+    }
+    j->pairs = pairs;
+    return NULL;
+}
+
+int64_t oracle_loop_mt(oracle_particles *P, const oracle_wcsph *w, const oracle_grid *g,
+                       int kid, int64_t stride, int64_t phase, int nthreads)
+{
+    if (nthreads < 2) return oracle_loop(P, w, g, kid, stride, phase);
+    if (nthreads > 256) nthreads = 256;
+    loop_head(P, w, g, kid);
+    pthread_t th[256];
+    loop_job job[256];
+    int started = 0;
+    for (int t = 0; t < nthreads; t++) {
+        job[t].P = P; job[t].w = w; job[t].g = g; job[t].kid = kid; job[t].tid = t; job[t].nthreads = nthreads;
+        job[t].stride = stride; job[t].phase = phase; job[t].pairs = 0;
+    }
+    for (int t = 1; t < nthreads; t++) {
+        if (pthread_create(&th[t], NULL, loop_worker, &job[t]) != 0) break;
+        started = t;
+    }
+    /* threads that could not be started: their blocks are walked here, after the caller's own */
+    loop_worker(&job[0]);
+    for (int t = started + 1; t < nthreads; t++) loop_worker(&job[t]);
+    int64_t pairs = 0;
+    for (int t = 1; t <= started; t++) pthread_join(th[t], NULL);
+    for (int t = 0; t < nthreads; t++) pairs += job[t].pairs;
     return pairs;
 }
 

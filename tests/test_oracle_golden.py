@@ -46,6 +46,22 @@ def test_loop_fields(name):
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
+def test_threaded_loop_is_the_same_loop(name):
+    """oracle_loop_mt (bench.py's CPU legs: the pair loop on all host threads) against oracle_loop: every particle's
+    arithmetic and its order are the same, so the results must be bit-identical -- also with a strided sample and with
+    more threads than blocks of particles."""
+    g, meta, pA = load_golden(name)
+    for stride, threads in ((1, 3), (1, 64), (4, 5)):
+        P1, Pn = O.Particles.from_aos(pA), O.Particles.from_aos(pA)
+        g1, gn = O.Grid(P1, meta['scale']), O.Grid(Pn, meta['scale'])
+        pairs1 = O.loop(P1, _wcsph(meta), g1, meta['kernel'], stride, 1 % stride)
+        pairsn = O.loop(Pn, _wcsph(meta), gn, meta['kernel'], stride, 1 % stride, threads=threads)
+        assert pairs1 == pairsn
+        for f in ('rho', 'p', 'c', 'drho', 'ax', 'ay', 'xsphx', 'xsphy'):
+            assert np.array_equal(getattr(P1, f), getattr(Pn, f), equal_nan=True), (f, stride, threads)
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
 def test_whole_steps(name):
     g, meta, pA = load_golden(name)
     P = O.Particles.from_aos(pA)
