@@ -77,6 +77,7 @@ enum osph_field {
 #define OSPH_S_UNBINNED    4u  /* a particle's reference cell id fell outside the table (reference: OOB write) */
 #define OSPH_S_GRID_COARSE 8u  /* acceleration grid was coarsened to fit the allocated cell table */
 #define OSPH_S_SKIN_EXHAUSTED 32u /* slab cadence: a build reused the binning although the particles had moved too far (pairs may be missing) */
+#define OSPH_S_H_NOT_UNIFORM 64u /* OSPH_H_FIXED: a fluid particle reached the pair kernel's inputs with h != fixed_h (internal error) */
 #define OSPH_S_DENSE_CELL  16u /* a cell holds more than 32768 particles: its summation order is not canonical (results exact) */
 
 typedef struct osph_ctx osph_ctx;
@@ -249,6 +250,13 @@ int64_t osph_launch_count(const osph_ctx *ctx);
 uint64_t osph_stream(const osph_ctx *ctx);
 /* Average device time of the fused pair kernel over the launches since the last call, microseconds. */
 int osph_pair_kernel_time(osph_ctx *ctx, double *avg_us, int64_t *launches);
+/*
+ * out[0] = launches of the fused pair kernel since osph_create, out[1] = those that ran its uniform-smoothing-length
+ * instantiation: with OSPH_H_FIXED (Solver(h=value), the reference's DamBreak set-up) every fluid particle carries the same
+ * h, so h_ij, 1/h_ij, the support test and the kernel normalisation of a fluid-fluid pair are loop constants.  Results are
+ * the bits of the general instantiation (tests/test_gpu_parity.py); OSPH_UH=0 in the environment selects the general one.
+ */
+int osph_pair_kernel_info(osph_ctx *ctx, int64_t out[2]);
 
 /* ---- 1-D slab decomposition: one context per GPU, exchange buffers owned by the caller -------------------
  *

@@ -175,7 +175,7 @@ extern "C" int osph_destroy(osph_ctx *ctx)
     osph_bin_free(ctx);
     cudaFree(ctx->cell_range); cudaFree(ctx->d_grid); cudaFree(ctx->d_sc); cudaFree(ctx->d_dt_log);
     cudaFree(ctx->scan_block); cudaFree(ctx->d_slab_counters); cudaFree(ctx->d_mig_slots); cudaFree(ctx->d_tail_flag);
-    cudaFree(ctx->d_holes); cudaFree(ctx->d_fillers);
+    cudaFree(ctx->d_holes); cudaFree(ctx->d_fillers); cudaFree(ctx->d_uh);
     for (int k = 0; k < 2 * OSPH_PAIR_EVENTS; k++) if (ctx->pair_ev[k]) cudaEventDestroy(ctx->pair_ev[k]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -691,6 +691,14 @@ extern "C" int osph_get_timers(osph_ctx *ctx, double out_ms[6])
 
 extern "C" int64_t osph_launch_count(const osph_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t osph_stream(const osph_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+extern "C" int osph_pair_kernel_info(osph_ctx *ctx, int64_t out[2])
+{
+    CHECK_CTX();
+    if (!out) return OSPH_E_INVALID;
+    out[0] = ctx->pair_launches; out[1] = ctx->pair_uh_launches;
+    return 0;
+}
 
 extern "C" int osph_pair_kernel_time(osph_ctx *ctx, double *avg_us, int64_t *launches)
 {

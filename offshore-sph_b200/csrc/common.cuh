@@ -11,6 +11,9 @@
 #ifndef OSPH_PAIR_THREADS
 #define OSPH_PAIR_THREADS 256         // one CTA of the pair kernel owns this many consecutive sorted particles
 #endif
+#ifndef PAIR_UH
+#define PAIR_UH 0                      // 1: Solver(h=value) runs the pair kernel's uniform-smoothing-length instantiation (pair.cu)
+#endif
 #define OSPH_MAX_CELL_BITS 28
 #define OSPH_SKIN_MAX 0.04             // largest adaptive skin of the sort cadence, as a fraction of the pair radius (k_grid_params)
 #define OSPH_WIRE_HALO 8               // doubles per ghost record: x y vx vy rho m h label
@@ -177,6 +180,15 @@ struct osph_ctx {
     // pinned staging for transfers
     unsigned char *h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
+
+    // PAIR_UH: loop constants of the uniform-smoothing-length pair kernel, valid for (uh_for_h, uh_for_kernel, uh_for_prec)
+    bool uh_ready = false;
+    double uh_for_h = 0.0;
+    int uh_for_kernel = -1, uh_for_prec = -1;
+    double uh_d[5] = {0, 0, 0, 0, 0};
+    float uh_f[5] = {0, 0, 0, 0, 0};
+    double *d_uh = nullptr;
+    int64_t pair_launches = 0, pair_uh_launches = 0;    // osph_pair_kernel_info
 
     osph_export_ring *xring = nullptr;   // asynchronous column export (export.cu), created on first use
     unsigned char *d_rows_buf = nullptr; // workspace of the row transfers (export.cu)

@@ -21,6 +21,8 @@
 // r/h_ij <= 3.0 re-evaluated in strict IEEE when the cheap test is within 1e-13 of the threshold).  FP32
 // instantiation = performance mode: positions are staged relative to a per-CTA anchor (subtracted in double,
 // then rounded), arithmetic in float.
+#include <cmath>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -73,6 +75,16 @@
                               // 131 -> 116 instructions, 80 -> 68 on the FP64 pipe, no spills.  0: one guarded body for every pair (the
                               // build all GPU measurements of round 1 were made with; tools/build_round2_variants.sh builds it as `lean0`)
 
+#ifndef PAIR_ISIGN
+#define PAIR_ISIGN 0          // 1: the two clamps of the common path (inner spline term, approaching pairs) are decided by the sign bit on
+#endif                        // the ALU pipe instead of a DSETP on the FP64 pipe, and the r > 1e-12 guard of the wall force -- implied by
+                              // the `tiny` test for every pair on the common path -- leaves it: three FP64-pipe instructions per pair less
+// PAIR_UH (common.cuh; 1: built in): Solver(h=value) gives every fluid particle the same smoothing length (k_prepare writes
+// it before every build), so for a fluid neighbour h_ij, 1/h_ij, the support test, h~ of the viscosity and the kernel
+// normalisation are loop constants.  k_pair<.., UH = true> takes them from the constant bank (PairArgs::uh_*; k_uh_constants
+// forms them with the operations of the general body, so the results are the same bits) and sends every non-fluid neighbour
+// through the general bodies: 68 -> 54 FP64-pipe instructions and one MUFU less per common pair (FP64 cubic).
+
 // One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
 // every field at a compile-time offset.  40 B (float) / 80 B (double) keeps 8 / 16-byte vector alignment.
 template <typename Real, bool EXACT> struct Rec;
@@ -87,7 +99,7 @@ constexpr size_t pair_smem_bytes()
            (PAIR_SCAN2 ? sizeof(float4) * ((PAIR_CAP + PAIR_SCAN + 2) / 2) : ((EXACT && PAIR_SCAN_F32) ? sizeof(float2) * (PAIR_CAP + PAIR_SCAN) : 0));
 }
 
-template <typename Real, int KID, bool EXACT>
+template <typename Real, int KID, bool EXACT, bool UH>
 __global__ void __launch_bounds__(OSPH_PAIR_THREADS, sizeof(Real) == 8 ? PAIR_MINB64 : PAIR_MINB32)
 k_pair(PairArgs a)
 {
@@ -203,6 +215,7 @@ k_pair(PairArgs a)
 
     // alpha_c = alpha * 0.5 * c_i (comp.c is never filled); all of these come straight from the constant bank
 #define PC(name) (sizeof(Real) == 8 ? (Real)a.name##_d : (Real)a.name##_f)
+#define UHC(name) (sizeof(Real) == 8 ? (Real)a.uh_##name##_d : (Real)a.uh_##name##_f)
     const bool use_xsph = a.method_xsph != 0;
     Real drho = 0, ax = 0, ay = 0, xs = 0, ys = 0;          // the wall force is accumulated into (ax, ay) as well
 
@@ -246,9 +259,70 @@ k_pair(PairArgs a)
         if constexpr (EXACT) { cbx = rj->cbx; cby = rj->cby; }        // (float: read on the rare path)
         const Real dx = xi - pj.x, dy = yi - pj.y;
         const Real r2 = dx * dx + dy * dy;
+        const bool fluid_j = (info_j & 1) != 0;
+        // PAIR_LEAN: a pair closer than about 1.2e-10 (high word of r2 at or below that of 1e-20: a superset of the pairs
+        // the two guards can bind for) joins the rare branch, an integer compare on the ALU pipe
+#define PAIR_TINY() (PAIR_LEAN && (sizeof(Real) == 8 ? __double2hiint((double)r2) <= 0x3BC79CA1 : r2 <= Real(1.0001e-20)))
+        auto body = [&](auto guarded_tag, auto uh_tag, const Real hij, const bool lj) {
+        constexpr bool GUARDED = decltype(guarded_tag)::value;
+        constexpr bool UHB = decltype(uh_tag)::value;              // fluid neighbour of the uniform-h kernel: loop constants
+        constexpr bool ISG = PAIR_ISIGN && !GUARDED;
+#if PAIR_NO_FMAX
+        const Real rs = rsqrt_fast(r2);                            // r2 == 0: inf / NaN, discarded by the two selects below
+#else
+        const Real rs = rsqrt_fast(fmax(r2, Real(1e-30)));
+#endif
+        const Real inv_h = UHB ? UHC(inv_h) : rcp_fast(hij);
+        const Real rbar = rhoi_half + rmj.x;                       // == 0.5 * (rho_i + rho_j)
+        const Real inv_rbar = rcp_fast(rbar);
+        const Real hbar = UHB ? UHC(h) : fma(Real(0.5), hij, hi_half);            // h averaged twice (Momentum.py:43)
+        const Real inv_den = rcp_fast(UHB ? r2 + UHC(c01) * hbar : r2 + Real(0.01) * hbar * hbar);
+        const Real inv_rt = !GUARDED || r2 > Real(1e-24) ? rs : Real(0);       // LJ guard: r > 1e-12
+        const Real inv_r = !GUARDED || r2 > Real(1e-20) ? rs : Real(0);        // gradient guard: r >= 1e-10
+        const Real r = r2 * inv_rt;
+        const Real q = r * inv_h;
+        Real w, g;
+        if constexpr (UHB) {
+            if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair_a<Real, GUARDED, ISG>(q, UHC(alpha), inv_h, inv_r, w, g);
+            else sph_kernel_a<Real, KID, GUARDED>(q, UHC(alpha), inv_h, inv_r, w, g);
+        } else {
+            if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair<Real, GUARDED, ISG>(q, inv_h, inv_r, w, g);
+            else sph_kernel<Real, KID, GUARDED>(q, inv_h, inv_r, w, g);
+        }
+        const Real dwx = g * dx, dwy = g * dy;
+        const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
+        const Real mj = rmj.y;
+        const Real mjf = (UHB || fluid_j) ? mj : Real(0);          // continuity and momentum: fluid neighbours only
+        drho += mjf * (dvx * dwx + dvy * dwy);
+        // artificial viscosity only for approaching pairs: min(dot, 0) makes it branch-free
+        const Real dot = ISG ? neg_part_s(dvx * dx + dvy * dy) : neg_part(dvx * dx + dvy * dy);
+        const Real mu = hbar * dot * inv_den;
+        const Real PIij = mu * (PC(beta) * mu - PC(alpha_c)) * inv_rbar;
+        const Real fac = mjf * (slf + hpj.y + PIij);
+        ax -= fac * dwx; ay -= fac * dwy;
+        if (use_xsph) {
+            const Real fx = mj * w * inv_rbar;                     // -epsilon is applied once, to the sums
+            xs += fx * dvx; ys += fx * dvy;
+        }
+        if constexpr (!UHB) {
+        if (lj && (ISG || r2 > Real(1e-24))) {                     // wall / coupled particle inside r0 (ISG: not `tiny`, so r > 1e-10)
+            const Real frac = PC(r0) * inv_rt;
+            Real tmp;
+            if (a.lj_42) { const Real f2 = frac * frac; tmp = f2 * f2 - f2; }
+            else tmp = pow_gen(frac, (Real)a.p1) - pow_gen(frac, (Real)a.p2);
+            const Real fl = PC(D) * tmp * inv_rt * inv_rt;
+            ax += fl * dx; ay += fl * dy;
+        }
+        }
+        };      // body
+        if constexpr (UH && PAIR_LEAN && KID != OSPH_KERNEL_GAUSSIAN) {
+            // uniform smoothing length: a fluid neighbour inside the (constant) support, no cell test due, not `tiny` -- the
+            // common pair -- needs none of the per-pair h terms
+            const bool adjq_u = ADJ && (adj_i || (info_j & 4));
+            if (fluid_j && r2 <= UHC(h2c) && !PAIR_TINY() && !adjq_u) { body(std::false_type(), std::true_type(), Real(0), false); return; }
+        }
         const Real hij = hi_half + hpj.x;                          // == 0.5 * (h_i + h_j) bit for bit
         const Real h2 = hij * hij;
-        const bool fluid_j = (info_j & 1) != 0;
         // kernel support (q <= 2, or the q <= 3 cut of the Gaussian, which IS the set boundary: keep a band for the
         // exact test) and Lennard-Jones range
         const bool kern = r2 <= h2 * (KID == OSPH_KERNEL_GAUSSIAN ? Real(9.0 * (1.0 + 1e-6)) : Real(4));
@@ -260,10 +334,8 @@ k_pair(PairArgs a)
         //  * q <= 3 can only bind for wall pairs outside the kernel support and at the cut of the Gaussian.
         // Everything that can reject a listed pair sits behind ONE rarely taken branch: inside the kernel support with
         // no cell test due, the pair is a member and the common path pays one compare and one predicate for it.
-        // PAIR_LEAN: a pair closer than about 1.2e-10 (high word of r2 at or below that of 1e-20: a superset of the pairs
-        // the two guards can bind for) joins the rare branch, an integer compare on the ALU pipe
         bool via_rare = false;
-        const bool tiny = PAIR_LEAN && (sizeof(Real) == 8 ? __double2hiint((double)r2) <= 0x3BC79CA1 : r2 <= Real(1.0001e-20));
+        const bool tiny = PAIR_TINY();
         if constexpr (EXACT) {
             const bool adjq = ADJ && (adj_i || (info_j & 4));
             if (KID == OSPH_KERNEL_GAUSSIAN || adjq || !kern || tiny) {
@@ -295,53 +367,10 @@ k_pair(PairArgs a)
                 if (!ok) return;
             }
         }
-        // GUARDED: the r -> 0 guards of the reference and the clamp of the outer spline term are evaluated.  The default build
-        // always is; with PAIR_LEAN only the pairs that came through the rare branch above are (coincident particles, wall
-        // pairs outside the kernel support, the Gaussian) and the common path uses rs as it stands.
-        auto body = [&](auto guarded_tag) {
-        constexpr bool GUARDED = decltype(guarded_tag)::value;
-#if PAIR_NO_FMAX
-        const Real rs = rsqrt_fast(r2);                            // r2 == 0: inf / NaN, discarded by the two selects below
-#else
-        const Real rs = rsqrt_fast(fmax(r2, Real(1e-30)));
-#endif
-        const Real inv_h = rcp_fast(hij);
-        const Real rbar = rhoi_half + rmj.x;                       // == 0.5 * (rho_i + rho_j)
-        const Real inv_rbar = rcp_fast(rbar);
-        const Real hbar = fma(Real(0.5), hij, hi_half);            // h averaged twice (Momentum.py:43)
-        const Real inv_den = rcp_fast(r2 + Real(0.01) * hbar * hbar);
-        const Real inv_rt = !GUARDED || r2 > Real(1e-24) ? rs : Real(0);       // LJ guard: r > 1e-12
-        const Real inv_r = !GUARDED || r2 > Real(1e-20) ? rs : Real(0);        // gradient guard: r >= 1e-10
-        const Real r = r2 * inv_rt;
-        const Real q = r * inv_h;
-        Real w, g;
-        if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair<Real, GUARDED>(q, inv_h, inv_r, w, g);
-        else sph_kernel<Real, KID, GUARDED>(q, inv_h, inv_r, w, g);
-        const Real dwx = g * dx, dwy = g * dy;
-        const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
-        const Real mj = rmj.y;
-        const Real mjf = fluid_j ? mj : Real(0);                   // continuity and momentum: fluid neighbours only
-        drho += mjf * (dvx * dwx + dvy * dwy);
-        // artificial viscosity only for approaching pairs: min(dot, 0) makes it branch-free
-        const Real dot = neg_part(dvx * dx + dvy * dy);
-        const Real mu = hbar * dot * inv_den;
-        const Real PIij = mu * (PC(beta) * mu - PC(alpha_c)) * inv_rbar;
-        const Real fac = mjf * (slf + hpj.y + PIij);
-        ax -= fac * dwx; ay -= fac * dwy;
-        if (use_xsph) {
-            const Real fx = mj * w * inv_rbar;                     // -epsilon is applied once, to the sums
-            xs += fx * dvx; ys += fx * dvy;
-        }
-        if (lj && r2 > Real(1e-24)) {                              // wall / coupled particle inside r0
-            const Real frac = PC(r0) * inv_rt;
-            Real tmp;
-            if (a.lj_42) { const Real f2 = frac * frac; tmp = f2 * f2 - f2; }
-            else tmp = pow_gen(frac, (Real)a.p1) - pow_gen(frac, (Real)a.p2);
-            const Real fl = PC(D) * tmp * inv_rt * inv_rt;
-            ax += fl * dx; ay += fl * dy;
-        }
-        };      // body
-        if (PAIR_LEAN && !via_rare) body(std::false_type()); else body(std::true_type());
+        // GUARDED body: the r -> 0 guards of the reference and the clamp of the outer spline term are evaluated.  The default
+        // build always is; with PAIR_LEAN only the pairs that came through the rare branch above are (coincident particles,
+        // wall pairs outside the kernel support, the Gaussian) and the common path uses rs as it stands.
+        if (PAIR_LEAN && !via_rare) body(std::false_type(), std::false_type(), hij, lj); else body(std::true_type(), std::false_type(), hij, lj);
     };
 
     // Two-phase walk, warp-synchronous.  (1) scan: cheap distance test over the thread's own sub-interval of
@@ -671,32 +700,90 @@ static void launch_summation(osph_ctx *ctx, const PairArgs &a)
     }
 }
 
-template <typename Real, int KID, bool EXACT>
+template <typename Real, int KID, bool EXACT, bool UH>
 static cudaError_t launch_one(const PairArgs &a, int grid, cudaStream_t stream, int device)
 {
     static unsigned long long configured = 0;           // one bit per device ordinal (the attribute is per device)
     constexpr size_t smem = pair_smem_bytes<Real, EXACT>();
     if (!(configured >> (device & 63) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(k_pair<Real, KID, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_pair<Real, KID, EXACT, UH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured |= 1ull << (device & 63);
     }
-    k_pair<Real, KID, EXACT><<<grid, OSPH_PAIR_THREADS, smem, stream>>>(a);
+    k_pair<Real, KID, EXACT, UH><<<grid, OSPH_PAIR_THREADS, smem, stream>>>(a);
     return cudaSuccess;
 }
 
 template <typename Real, bool EXACT>
-static int launch_kid(osph_ctx *ctx, const PairArgs &a, int grid)
+static int launch_kid(osph_ctx *ctx, const PairArgs &a, int grid, bool uh)
 {
     cudaError_t e;
     switch (ctx->cfg.kernel) {
-    case OSPH_KERNEL_CUBIC: e = launch_one<Real, OSPH_KERNEL_CUBIC, EXACT>(a, grid, ctx->stream, ctx->device); break;
-    case OSPH_KERNEL_WENDLAND: e = launch_one<Real, OSPH_KERNEL_WENDLAND, EXACT>(a, grid, ctx->stream, ctx->device); break;
-    default: e = launch_one<Real, OSPH_KERNEL_GAUSSIAN, EXACT>(a, grid, ctx->stream, ctx->device); break;
+#if PAIR_UH
+    case OSPH_KERNEL_CUBIC:
+        e = uh ? launch_one<Real, OSPH_KERNEL_CUBIC, EXACT, true>(a, grid, ctx->stream, ctx->device)
+               : launch_one<Real, OSPH_KERNEL_CUBIC, EXACT, false>(a, grid, ctx->stream, ctx->device);
+        break;
+    case OSPH_KERNEL_WENDLAND:
+        e = uh ? launch_one<Real, OSPH_KERNEL_WENDLAND, EXACT, true>(a, grid, ctx->stream, ctx->device)
+               : launch_one<Real, OSPH_KERNEL_WENDLAND, EXACT, false>(a, grid, ctx->stream, ctx->device);
+        break;
+#else
+    case OSPH_KERNEL_CUBIC: e = launch_one<Real, OSPH_KERNEL_CUBIC, EXACT, false>(a, grid, ctx->stream, ctx->device); break;
+    case OSPH_KERNEL_WENDLAND: e = launch_one<Real, OSPH_KERNEL_WENDLAND, EXACT, false>(a, grid, ctx->stream, ctx->device); break;
+#endif
+    default: e = launch_one<Real, OSPH_KERNEL_GAUSSIAN, EXACT, false>(a, grid, ctx->stream, ctx->device); break;
     }
     if (e != cudaSuccess) { ctx->err = std::string("pair kernel configuration: ") + cudaGetErrorString(e); return OSPH_E_CUDA; }
     return 0;
 }
+
+#if PAIR_UH
+// Loop constants of the uniform-h instantiation, formed ON THE DEVICE with the operations the general body applies to every
+// pair (the staged halves h_i / 2 + h_j / 2, rcp_fast, the kernel's own normalisation), so that a pair evaluated with them
+// gives the bits the general body gives.  out: h_ij, 1 / h_ij, support threshold, 0.01 h~, alpha.
+template <typename Real, int KID>
+__global__ void k_uh_constants(double h, Real *out)
+{
+    const Real hh = Real(0.5) * (Real)h;                // k_pair: hi_half; staging: rec.hp.x *= 0.5
+    const Real hij = hh + hh;
+    const Real inv_h = rcp_fast(hij);
+    const Real hbar = fma(Real(0.5), hij, hh);
+    out[0] = hbar;                                      // == hij == h (exact halves): h~ of the viscosity
+    out[1] = inv_h;
+    out[2] = (hij * hij) * Real(4);
+    out[3] = Real(0.01) * hbar;
+    out[4] = kernel_alpha_pair<Real, KID>(inv_h);
+}
+
+// 0: use the general kernel; 1: a.uh_* are filled
+static int pair_uh_constants(osph_ctx *ctx, PairArgs &a)
+{
+    const char *env = getenv("OSPH_UH");                 // read per launch: tests switch it inside one process
+    const bool off = env && env[0] == '0';
+    const osph_config &c = ctx->cfg;
+    if (off || c.dynamic_h != OSPH_H_FIXED || !(c.fixed_h > 0.0) || !std::isfinite(c.fixed_h) || c.kernel == OSPH_KERNEL_GAUSSIAN) return 0;
+    if (!(ctx->uh_ready && ctx->uh_for_h == c.fixed_h && ctx->uh_for_kernel == c.kernel && ctx->uh_for_prec == c.precision)) {
+        if (!ctx->d_uh && cudaMalloc(&ctx->d_uh, 8 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return 0; }
+        const bool cubic = c.kernel == OSPH_KERNEL_CUBIC;
+        if (c.precision == OSPH_FP64) {
+            if (cubic) k_uh_constants<double, OSPH_KERNEL_CUBIC><<<1, 1, 0, ctx->stream>>>(c.fixed_h, ctx->d_uh);
+            else k_uh_constants<double, OSPH_KERNEL_WENDLAND><<<1, 1, 0, ctx->stream>>>(c.fixed_h, ctx->d_uh);
+            if (cudaMemcpyAsync(ctx->uh_d, ctx->d_uh, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+        } else {
+            if (cubic) k_uh_constants<float, OSPH_KERNEL_CUBIC><<<1, 1, 0, ctx->stream>>>(c.fixed_h, (float *)ctx->d_uh);
+            else k_uh_constants<float, OSPH_KERNEL_WENDLAND><<<1, 1, 0, ctx->stream>>>(c.fixed_h, (float *)ctx->d_uh);
+            if (cudaMemcpyAsync(ctx->uh_f, ctx->d_uh, 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return 0;
+        }
+        ctx->launches++;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;       // once per context and smoothing length
+        ctx->uh_ready = true; ctx->uh_for_h = c.fixed_h; ctx->uh_for_kernel = c.kernel; ctx->uh_for_prec = c.precision;
+    }
+    a.uh_h_d = ctx->uh_d[0]; a.uh_inv_h_d = ctx->uh_d[1]; a.uh_h2c_d = ctx->uh_d[2]; a.uh_c01_d = ctx->uh_d[3]; a.uh_alpha_d = ctx->uh_d[4];
+    a.uh_h_f = ctx->uh_f[0]; a.uh_inv_h_f = ctx->uh_f[1]; a.uh_h2c_f = ctx->uh_f[2]; a.uh_c01_f = ctx->uh_f[3]; a.uh_alpha_f = ctx->uh_f[4];
+    return 1;
+}
+#endif
 
 int osph_launch_pair(osph_ctx *ctx)
 {
@@ -727,11 +814,19 @@ int osph_launch_pair(osph_ctx *ctx)
         if (c.precision == OSPH_FP64) launch_summation<double2>(ctx, a); else launch_summation<float2>(ctx, a);
         OSPH_LAUNCH_CHECK();
     }
+    bool uh = false;
+    a.uh_h_d = a.uh_inv_h_d = a.uh_h2c_d = a.uh_c01_d = a.uh_alpha_d = 0.0;
+    a.uh_h_f = a.uh_inv_h_f = a.uh_h2c_f = a.uh_c01_f = a.uh_alpha_f = 0.f;
+#if PAIR_UH
+    uh = pair_uh_constants(ctx, a) != 0;
+#endif
     const bool timed = ctx->time_pair && ctx->pair_ev_used < OSPH_PAIR_EVENTS;
     if (timed) cudaEventRecord(ctx->pair_ev[2 * ctx->pair_ev_used], ctx->stream);
-    int rc = c.precision == OSPH_FP64 ? launch_kid<double, true>(ctx, a, grid) : launch_kid<float, false>(ctx, a, grid);
+    int rc = c.precision == OSPH_FP64 ? launch_kid<double, true>(ctx, a, grid, uh) : launch_kid<float, false>(ctx, a, grid, uh);
     if (rc) return rc;
     OSPH_LAUNCH_CHECK();
     if (timed) { cudaEventRecord(ctx->pair_ev[2 * ctx->pair_ev_used + 1], ctx->stream); ctx->pair_ev_used++; }
+    ctx->pair_launches++;
+    if (uh) ctx->pair_uh_launches++;
     return 0;
 }

@@ -27,4 +27,8 @@ struct PairArgs {
     double *ts_dt_log;
     long long ts_dt_log_cap;
     int ts_fused;
+    // PAIR_UH (uniform smoothing length, Solver(h=value)): loop constants formed on the device once per context by
+    // k_uh_constants with the very operations the general body applies per pair, then passed here (constant bank)
+    double uh_h_d, uh_inv_h_d, uh_h2c_d, uh_c01_d, uh_alpha_d;
+    float uh_h_f, uh_inv_h_f, uh_h2c_f, uh_c01_f, uh_alpha_f;
 };

@@ -105,12 +105,33 @@ __device__ __forceinline__ void sts_u16(unsigned int addr, unsigned short v)
 // (the reference zeroes the gradient there).
 // CUT = false (pair.cu, PAIR_LEAN): the caller knows r^2 <= 4 h^2, so q exceeds 2 by rounding only and the polynomials are
 // used as they stand (Wendland: (1 - q/2)^5 is 1e-80 there).
+// Normalisation of kernel KID, formed exactly as the pair kernel's evaluation forms it (the cubic spline of the fused kernel
+// goes through cubic_pair, whose product is associated differently: see kernel_alpha_pair).
+template <typename Real, int KID>
+__device__ __forceinline__ Real kernel_alpha(Real inv_h)
+{
+    const Real ih2 = inv_h * inv_h;
+    return Real(KID == OSPH_KERNEL_CUBIC ? 10.0 / (7.0 * PI_D) : (KID == OSPH_KERNEL_WENDLAND ? 9.0 / (4.0 * PI_D) : 1.0 / PI_D)) * ih2;
+}
+template <typename Real, int KID>
+__device__ __forceinline__ Real kernel_alpha_pair(Real inv_h)
+{
+    if (KID == OSPH_KERNEL_CUBIC) return Real(10.0 / (7.0 * PI_D)) * inv_h * inv_h;
+    return kernel_alpha<Real, KID>(inv_h);
+}
+template <typename Real, int KID, bool CUT = true>
+__device__ __forceinline__ void sph_kernel_a(Real q, Real alpha, Real inv_h, Real inv_r, Real &w, Real &g);
+
 template <typename Real, int KID, bool CUT = true>
 __device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
 {
-    const Real ih2 = inv_h * inv_h;
+    sph_kernel_a<Real, KID, CUT>(q, kernel_alpha<Real, KID>(inv_h), inv_h, inv_r, w, g);
+}
+
+template <typename Real, int KID, bool CUT>
+__device__ __forceinline__ void sph_kernel_a(Real q, Real alpha, Real inv_h, Real inv_r, Real &w, Real &g)
+{
     if (KID == OSPH_KERNEL_CUBIC) {
-        const Real alpha = Real(10.0 / (7.0 * PI_D)) * ih2;
         Real wv, gv;
         if (q > Real(1)) { Real t = Real(2) - q; Real t2 = t * t; wv = Real(0.25) * t2 * t; gv = Real(-0.75) * t2; }
         else { wv = Real(1) - Real(1.5) * q * q * (Real(1) - Real(0.5) * q); gv = Real(-3) * q * (Real(1) - Real(0.75) * q); }
@@ -118,7 +139,6 @@ __device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real 
         w = alpha * wv;
         g = alpha * gv * inv_h * inv_r;
     } else if (KID == OSPH_KERNEL_WENDLAND) {
-        const Real alpha = Real(9.0 / (4.0 * PI_D)) * ih2;
         Real in = Real(1) - Real(0.5) * q;
         Real in2 = in * in, in4 = in2 * in2, in5 = in4 * in;
         Real wv = in5 * in * (Real(35.0 / 12.0) * q * q + Real(3) * q + Real(1));
@@ -127,7 +147,6 @@ __device__ __forceinline__ void sph_kernel(Real q, Real inv_h, Real inv_r, Real 
         w = alpha * wv;
         g = alpha * gv * inv_h * inv_r;
     } else {
-        const Real alpha = Real(1.0 / PI_D) * ih2;
         Real e = exp_neg(q * q);
         Real wv = alpha * e;                          // q <= 3 is decided by the caller (set membership)
         w = wv;
@@ -152,6 +171,24 @@ __device__ __forceinline__ double neg_part(double d)
 }
 __device__ __forceinline__ float pos_part(float d) { return fmaxf(d, 0.0f); }
 __device__ __forceinline__ float neg_part(float d) { return fminf(d, 0.0f); }
+// The same two selections decided by the SIGN BIT, an integer compare on the ALU pipe instead of a DSETP on the FP64 pipe
+// (PAIR_ISIGN, pair.cu: the heavy loop of the double instantiation keeps that pipe 74 % busy).  For finite d the result is
+// the same number (d = -0 yields -0 from neg_part_s where neg_part yields +0: the sums that follow cannot tell); a NaN with
+// a clear sign bit passes pos_part_s -- the callers only use it where d is finite.
+__device__ __forceinline__ double pos_part_s(double d)
+{
+    double r;
+    asm("{ .reg .pred p; .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; setp.ge.s32 p, hi, 0; selp.f64 %0, %1, 0d0000000000000000, p; }" : "=d"(r) : "d"(d));
+    return r;
+}
+__device__ __forceinline__ double neg_part_s(double d)
+{
+    double r;
+    asm("{ .reg .pred p; .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; setp.lt.s32 p, hi, 0; selp.f64 %0, %1, 0d0000000000000000, p; }" : "=d"(r) : "d"(d));
+    return r;
+}
+__device__ __forceinline__ float pos_part_s(float d) { return fmaxf(d, 0.0f); }
+__device__ __forceinline__ float neg_part_s(float d) { return fminf(d, 0.0f); }
 
 // Cubic spline of the fused pair kernel: the same piecewise polynomial written with clamped terms,
 //   W/alpha = (2-q)+^3 / 4 - (1-q)+^3,   W'/alpha = -3/4 (2-q)+^2 + 3 (1-q)+^2,
@@ -159,15 +196,21 @@ __device__ __forceinline__ float neg_part(float d) { return fminf(d, 0.0f); }
 // evaluating both branches and selecting.
 // CLAMP_OUTER = false (pair.cu, PAIR_LEAN): the caller knows r^2 <= 4 h^2, so 2 - q can be negative by rounding only (a few
 // 1e-16: 1e-47 in W, 1e-31 in W') and the outer term is used as it stands.
-template <typename Real, bool CLAMP_OUTER = true>
-__device__ __forceinline__ void cubic_pair(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
+// ISIGN: the inner clamp by the sign bit (pos_part_s).  The *_a form takes the normalisation alpha = kernel_alpha(inv_h) from
+// the caller (uniform smoothing length: a loop constant, pair.cu PAIR_UH).
+template <typename Real, bool CLAMP_OUTER = true, bool ISIGN = false>
+__device__ __forceinline__ void cubic_pair_a(Real q, Real alpha, Real inv_h, Real inv_r, Real &w, Real &g)
 {
-    const Real alpha = Real(10.0 / (7.0 * PI_D)) * inv_h * inv_h;
-    const Real t2 = CLAMP_OUTER ? pos_part(Real(2) - q) : Real(2) - q, t1 = pos_part(Real(1) - q);
+    const Real t2 = CLAMP_OUTER ? pos_part(Real(2) - q) : Real(2) - q, t1 = ISIGN ? pos_part_s(Real(1) - q) : pos_part(Real(1) - q);
     const Real s2 = t2 * t2, s1 = t1 * t1;
     const Real wv = fma(-s1, t1, Real(0.25) * s2 * t2);
     const Real gv = fma(Real(3), s1, Real(-0.75) * s2);
     w = alpha * wv;
     g = alpha * gv * inv_h * inv_r;
+}
+template <typename Real, bool CLAMP_OUTER = true, bool ISIGN = false>
+__device__ __forceinline__ void cubic_pair(Real q, Real inv_h, Real inv_r, Real &w, Real &g)
+{
+    cubic_pair_a<Real, CLAMP_OUTER, ISIGN>(q, Real(10.0 / (7.0 * PI_D)) * inv_h * inv_h, inv_h, inv_r, w, g);
 }
 

@@ -684,6 +684,11 @@ k_gather(GatherArgs a, Real2 *__restrict__ s_vel, Real2 *__restrict__ s_rm, Real
         a.idx_out[s] = (unsigned int)i;
     }
     bool fluid = lab == OSPH_FLUID;
+#if PAIR_UH
+    // the uniform-h pair kernel takes h of every fluid particle from a constant: hold the state to it (k_prepare wrote
+    // fixed_h into every owned fluid row, ghosts carry what their owner wrote), loudly
+    if (a.uh_h != 0.0 && fluid && h != a.uh_h) atomicOr(&a.sc->status, OSPH_S_H_NOT_UNIFORM);
+#endif
     double p = a.Pb;
     if (fluid) p = (tait_ratio_pow(rho / a.rho0, a.gamma) - 1.0) * a.B + a.Pb;
     if (i < a.n_owned) a.p[i] = p;
@@ -1234,6 +1239,7 @@ int osph_launch_build(osph_ctx *ctx, bool reset_dt, const BuildPlan *given)
     g.gp = ctx->d_grid;
     g.s_pos = ctx->s_pos; g.s_info = ctx->s_info; g.s_coarse = ctx->s_coarse; g.s_gcell = ctx->s_gcell;
     g.gamma = ctx->cfg.gamma; g.B = ctx->cfg.B; g.rho0 = ctx->cfg.rho0; g.Pb = ctx->cfg.Pb;
+    g.uh_h = (ctx->cfg.dynamic_h == OSPH_H_FIXED && ctx->cfg.fixed_h > 0.0) ? ctx->cfg.fixed_h : 0.0;
     if (ctx->cfg.precision == OSPH_FP64)
         k_gather<double2><<<grid, 256, 0, ctx->stream>>>(g, (double2 *)ctx->s_vel, (double2 *)ctx->s_rm, (double2 *)ctx->s_hp);
     else

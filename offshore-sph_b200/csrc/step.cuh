@@ -55,6 +55,7 @@ struct GatherArgs {
     int4 *s_coarse;
     int2 *s_gcell;
     double gamma, B, rho0, Pb;
+    double uh_h;                  // PAIR_UH, OSPH_H_FIXED: the smoothing length every fluid particle must carry (0: not checked)
 };
 
 struct NeighbourArgs {

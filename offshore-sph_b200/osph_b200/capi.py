@@ -26,6 +26,7 @@ FIELDS = ['m', 'rho', 'p', 'c', 'drho', 'h', 'x', 'y', 'vx', 'vy', 'ax', 'ay',
 FIELD_ID = {f: i for i, f in enumerate(FIELDS)}
 
 S_NONFINITE, S_SMALL_DT, S_UNBINNED, S_GRID_COARSE, S_DENSE_CELL = 1, 2, 4, 8, 16
+S_SKIN_EXHAUSTED, S_H_NOT_UNIFORM = 32, 64
 
 
 class OsphError(RuntimeError):
@@ -110,6 +111,7 @@ def lib():
         'osph_launch_count': (i64, [ctx]),
         'osph_stream': (C.c_uint64, [ctx]),
         'osph_pair_kernel_time': (C.c_int, [ctx, dp, ip]),
+        'osph_pair_kernel_info': (C.c_int, [ctx, C.POINTER(C.c_int64)]),
         'osph_reserve': (C.c_int, [ctx, i64]),
         'osph_set_row_ids': (C.c_int, [ctx, C.POINTER(i32), i64]),
         'osph_slab_configure': (C.c_int, [ctx, dbl, dbl, C.c_void_p, i64]),
@@ -495,6 +497,12 @@ class Context:
     @property
     def stream(self):
         return int(self._L.osph_stream(self._h))
+
+    def pair_kernel_info(self):
+        """(launches of the fused pair kernel so far, those that ran its uniform-smoothing-length instantiation)."""
+        out = (C.c_int64 * 2)()
+        self._ck(self._L.osph_pair_kernel_info(self._h, out))
+        return int(out[0]), int(out[1])
 
     def pair_kernel_time(self):
         us = C.c_double(0); n = C.c_int64(0)

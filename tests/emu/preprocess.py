@@ -5,6 +5,7 @@
   __shared__ [__align__(n)] T name[N];                ->  T (&name)[N] = *emu::static_smem<T[N]>();    (ends at a guard page)
   asm("rcp.approx.ftz.f64 ..." / "rsqrt.approx.ftz.f64 ...")  ->  emu::rcp_approx_f64 / emu::rsqrt_approx_f64
   asm("{ setp.gt|lt.f64 p, x, 0; selp.f64 r, x, 0, p; }")      ->  r = x > 0 ? x : 0   (pos_part / neg_part of sph_math.cuh)
+  asm("{ mov.b64 {lo,hi}, x; setp.ge|lt.s32 p, hi, 0; selp.f64 r, x, 0, p; }")  ->  the same by the sign bit (pos_part_s / neg_part_s)
 
 Everything else (kernel bodies, launch logic, the C ABI) is compiled as written.  TEST INFRASTRUCTURE ONLY.
 """
@@ -94,6 +95,10 @@ _ASM_RSQ = re.compile(r'asm\("rsqrt\.approx\.ftz\.f64 %0, %1;"\s*:\s*"=d"\((\w+)
 _ASM_CLAMP = re.compile(r'asm\("\{ \.reg \.pred p; setp\.(gt|lt)\.f64 p, %1, 0d0+; selp\.f64 %0, %1, 0d0+, p; \}"\s*:\s*"=d"\((\w+)\)\s*:\s*"d"\((\w+)\)\);')
 
 
+# the same selections by the sign bit (pos_part_s / neg_part_s): modelled on the bit pattern, as the instruction sees it
+_ASM_CLAMP_S = re.compile(r'asm\("\{ \.reg \.pred p; \.reg \.b32 lo, hi; mov\.b64 \{lo, hi\}, %1; setp\.(ge|lt)\.s32 p, hi, 0; selp\.f64 %0, %1, 0d0+, p; \}"\s*:\s*"=d"\((\w+)\)\s*:\s*"d"\((\w+)\)\);')
+
+
 _STATIC_SHARED = re.compile(r"(?<![\w])(?<!extern )__shared__\s+(?:__align__\((\d+)\)\s+)?([\w:\s]+?)\s+(\w+\s*(?:\[[^;]*\])?(?:\s*,\s*\w+\s*(?:\[[^;]*\])?)*)\s*;")
 
 
@@ -137,6 +142,8 @@ def transform(src):
     src = _ASM_RCP.sub(lambda m: "%s = emu::rcp_approx_f64(%s);" % (m.group(1), m.group(2)), src)
     src = _ASM_RSQ.sub(lambda m: "%s = emu::rsqrt_approx_f64(%s);" % (m.group(1), m.group(2)), src)
     src = _ASM_CLAMP.sub(lambda m: "%s = (%s %s 0.0) ? %s : 0.0;" % (m.group(2), m.group(3), ">" if m.group(1) == "gt" else "<", m.group(3)), src)
+    src = _ASM_CLAMP_S.sub(lambda m: "%s = (((long long)__double_as_longlong(%s) %s 0) ? %s : 0.0);" %
+                           (m.group(2), m.group(3), ">=" if m.group(1) == "ge" else "<", m.group(3)), src)
     if "asm(" in src or "asm volatile" in src:
         raise ValueError("inline PTX the emulator has no model for")
     return src

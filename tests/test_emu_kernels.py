@@ -98,6 +98,37 @@ def test_pair_kernel_single_body_variant():
         capi.LIB_PATH, capi._lib = saved
 
 
+def test_pair_kernel_uniform_h_variant():
+    """-DPAIR_UH=1 -DPAIR_ISIGN=1: with Solver(h=value) the pair kernel's uniform-smoothing-length instantiation runs (loop
+    constants instead of the per-pair h terms for fluid neighbours, sign-bit clamps).  Same parity bar as the default build
+    on every golden case and oracle comparison, and the bits of the general instantiation (OSPH_UH=0) on the same input."""
+    from osph_b200 import capi
+    path = emu_build.build(defines=("PAIR_UH=1", "PAIR_ISIGN=1"), tag="_uhs")
+    saved = (capi.LIB_PATH, capi._lib)
+    capi.LIB_PATH, capi._lib = path, None
+    mp = pytest.MonkeyPatch()
+    try:
+        for name in _parity.STEP_CASES:
+            _parity.test_loop_fields_vs_golden(name)
+            _parity.test_whole_steps_vs_golden(name)
+        _parity.test_fused_loop_equals_explicit_calls('dambreak20_wendland')
+        _parity.test_multi_step_call_equals_single_step_calls(None)
+        _parity.test_dam_break_vs_oracle(60, 'wendland')
+        _parity.test_dam_break_vs_oracle(150, 'cubic')
+        _parity.test_dam_break_vs_oracle(150, 'gaussian')
+        _parity.test_fp32_mode_close_to_fp64()
+        for kernel, precision in (('cubic', 'fp64'), ('wendland', 'fp64'), ('cubic', 'fp32'), ('wendland', 'fp32')):
+            _parity.test_uniform_h_instantiation_gives_the_bits_of_the_general_one(kernel, precision, mp)
+        _edges.test_coincident_particles_follow_the_reference_guards()
+        _edges.test_cluster_denser_than_the_candidate_list()
+        _edges.test_general_lennard_jones_exponents_and_beta_viscosity('cubic')
+        _edges.test_domain_far_from_the_origin()
+        _edges.test_fp32_mode_uses_the_reference_cell_rule_too()
+    finally:
+        mp.undo()
+        capi.LIB_PATH, capi._lib = saved
+
+
 @pytest.mark.parametrize("precision", ['fp64', 'fp32'])
 def test_bench_workload_one_step_under_the_guarded_emulator(precision):
     """BASELINE configs[1] itself (dam break N = 1000, 1 009 603 particles: the workload bench.py runs): one whole step of

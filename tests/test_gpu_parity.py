@@ -268,6 +268,41 @@ def test_scalar_kernels_fused_into_their_producers_change_nothing(bits, monkeypa
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
 
 
+@pytest.mark.parametrize("kernel,precision", [('cubic', 'fp64'), ('wendland', 'fp64'), ('cubic', 'fp32'), ('wendland', 'fp32')])
+def test_uniform_h_instantiation_gives_the_bits_of_the_general_one(kernel, precision, monkeypatch):
+    """Solver(h=value): k_pair<.., UH> takes h_ij, 1/h_ij, the support test, h~ and the kernel normalisation of a fluid-fluid
+    pair from constants that k_uh_constants formed with the operations of the general body; wall and gate neighbours (h = 0)
+    go through the general bodies.  Same operations on the same operands: the state after several steps must be the SAME
+    BITS as with OSPH_UH=0 (general instantiation), dt included, and the h-uniformity check of k_gather must stay silent.
+    A set-up with a hand-edited fluid h under OSPH_H_KEEP must not use the instantiation."""
+    case = W.dam_break_case(100, seed=9)
+    prec = capi.FP64 if precision == 'fp64' else capi.FP32
+    outs = []
+    for env in ('0', '1'):
+        monkeypatch.setenv("OSPH_UH", env)
+        cfg = capi.make_config(case['consts'], kernel, 'pec', prec, case['h'])
+        with capi.Context(cfg) as ctx:
+            ctx.upload(case['pA'])
+            ctx.step(6, None, 0.05)
+            ctx.compute()                                   # explicit-call path as well
+            outs.append((ctx.download(case['pA'].copy()), ctx.dt_log(), ctx.pair_kernel_info()))
+            assert ctx.sync() == 0
+    (a, dta, ia), (b, dtb, ib) = outs
+    assert ia == (7, 0)
+    if ib[1] == 0:
+        pytest.skip("library built without PAIR_UH: the general instantiation ran both times")
+    assert ib == (7, 7)
+    for f in STATE_FIELDS:
+        assert np.array_equal(a[f], b[f]), f              # -0 == +0: the sign-bit clamps may differ there
+    assert np.array_equal(dta, dtb)
+    # smoothing length kept as uploaded: never the uniform-h instantiation, whatever the values are
+    cfg = capi.make_config(case['consts'], kernel, 'pec', prec, case['h'], keep_h=True)
+    with capi.Context(cfg) as ctx:
+        ctx.upload(case['pA'])
+        ctx.step(2, None, 0.05)
+        assert ctx.pair_kernel_info() == (2, 0)
+
+
 def test_fp32_mode_close_to_fp64():
     """Performance mode: float pair arithmetic on anchor-relative positions; drift bounded and reported."""
     case = W.dam_break_case(100, seed=7)

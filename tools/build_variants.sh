@@ -16,7 +16,7 @@ while [ $# -ge 2 ]; do
   done
   nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC --use_fast_math $defs -Xptxas -v -c pair.cu -o $tmp/pair.o 2> $tmp/pair.log
   wait
-  grep -A2 "k_pairIdLi0ELb1\|k_pairIfLi0ELb0" $tmp/pair.log | grep "Used\|spill" | sed "s/^/[$name] /"
+  grep -A2 "k_pairIdLi0ELb1\|k_pairIfLi0ELb0" $tmp/pair.log | grep "Function\|Used\|spill" | sed "s/ptxas info    : //" | paste - - - | sed "s/^/[$name] /"
   nvcc -shared $ARCH -o ../lib/variants/lib_$name.so $tmp/*.o -lcudart -ldl
   python -c "import ctypes,sys; ctypes.CDLL(sys.argv[1])" ../lib/variants/lib_$name.so      # every symbol resolves
   rm -rf $tmp
