@@ -253,10 +253,13 @@ int osph_pair_kernel_time(osph_ctx *ctx, double *avg_us, int64_t *launches);
 /*
  * out[0] = launches of the fused pair kernel since osph_create, out[1] = those that ran its uniform-smoothing-length
  * instantiation: with OSPH_H_FIXED (Solver(h=value), the reference's DamBreak set-up) every fluid particle carries the same
- * h, so h_ij, 1/h_ij, the support test and the kernel normalisation of a fluid-fluid pair are loop constants.  Results are
- * the bits of the general instantiation (tests/test_gpu_parity.py); OSPH_UH=0 in the environment selects the general one.
+ * h, so h_ij, 1/h_ij, the support test and the kernel normalisation of a fluid-fluid pair are loop constants.  Every pair is
+ * evaluated with the operations of the general instantiation (tests/test_gpu_parity.py holds the two to the same bits, or,
+ * where the software-pipelined flush loop defers the rare pairs of a flush, to summation order); OSPH_UH=0 in the environment
+ * selects the general one.  out[2] = how the library was built: bit 0 uniform-h instantiation present (PAIR_UH), bit 1
+ * sign-bit clamps (PAIR_ISIGN), bit 2 software-pipelined flush loop (PAIR_UH_PIPE).
  */
-int osph_pair_kernel_info(osph_ctx *ctx, int64_t out[2]);
+int osph_pair_kernel_info(osph_ctx *ctx, int64_t out[3]);
 
 /* ---- 1-D slab decomposition: one context per GPU, exchange buffers owned by the caller -------------------
  *

@@ -692,11 +692,13 @@ extern "C" int osph_get_timers(osph_ctx *ctx, double out_ms[6])
 extern "C" int64_t osph_launch_count(const osph_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t osph_stream(const osph_ctx *ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 
-extern "C" int osph_pair_kernel_info(osph_ctx *ctx, int64_t out[2])
+int osph_pair_build_flags();       // pair.cu
+
+extern "C" int osph_pair_kernel_info(osph_ctx *ctx, int64_t out[3])
 {
     CHECK_CTX();
     if (!out) return OSPH_E_INVALID;
-    out[0] = ctx->pair_launches; out[1] = ctx->pair_uh_launches;
+    out[0] = ctx->pair_launches; out[1] = ctx->pair_uh_launches; out[2] = osph_pair_build_flags();
     return 0;
 }
 

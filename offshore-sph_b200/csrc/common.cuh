@@ -12,7 +12,7 @@
 #define OSPH_PAIR_THREADS 256         // one CTA of the pair kernel owns this many consecutive sorted particles
 #endif
 #ifndef PAIR_UH
-#define PAIR_UH 0                      // 1: Solver(h=value) runs the pair kernel's uniform-smoothing-length instantiation (pair.cu)
+#define PAIR_UH 1                      // 1: Solver(h=value) runs the pair kernel's uniform-smoothing-length instantiation (pair.cu)
 #endif
 #define OSPH_MAX_CELL_BITS 28
 #define OSPH_SKIN_MAX 0.04             // largest adaptive skin of the sort cadence, as a fraction of the pair radius (k_grid_params)

@@ -76,7 +76,7 @@
                               // build all GPU measurements of round 1 were made with; tools/build_round2_variants.sh builds it as `lean0`)
 
 #ifndef PAIR_ISIGN
-#define PAIR_ISIGN 0          // 1: the two clamps of the common path (inner spline term, approaching pairs) are decided by the sign bit on
+#define PAIR_ISIGN 1          // 1: the two clamps of the common path (inner spline term, approaching pairs) are decided by the sign bit on
 #endif                        // the ALU pipe instead of a DSETP on the FP64 pipe, and the r > 1e-12 guard of the wall force -- implied by
                               // the `tiny` test for every pair on the common path -- leaves it: three FP64-pipe instructions per pair less
 // PAIR_UH (common.cuh; 1: built in): Solver(h=value) gives every fluid particle the same smoothing length (k_prepare writes
@@ -84,6 +84,30 @@
 // normalisation are loop constants.  k_pair<.., UH = true> takes them from the constant bank (PairArgs::uh_*; k_uh_constants
 // forms them with the operations of the general body, so the results are the same bits) and sends every non-fluid neighbour
 // through the general bodies: 68 -> 54 FP64-pipe instructions and one MUFU less per common pair (FP64 cubic).
+
+// Software-pipelined flush loop (PAIR_UH_PIPE: the uniform-h instantiation, PAIR_GEN_PIPE: the general one; bit 0 double, bit 1
+// float).  Stage A of entry k + 1 -- record position, separation, r^2, the "common pair" test, rsqrt seed and first residual --
+// is issued with stage B of entry k (everything else), so the front of one pair's dependency chain (shared-memory load, three
+// FP64 operations, MUFU, two more: about a third of it) runs under the previous pair's tail.  At four warps per scheduler the
+// kernel was bound by that chain, not by instruction count: the uniform-h body removed 18 % of the instructions and 3 % of
+// the time, this loop 13 % more.  Pairs that need the bodies of `interact` (wall and gate neighbours, the rare branch) are
+// written back into the list and evaluated after the common ones of the same flush: same pairs, same arithmetic per pair,
+// the summation order of the rare ones changed.  Measured on the B200, pair kernel, 1 M particles, FP64 / FP32 (profiles/r02):
+//   uniform-h instantiation   not pipelined 286.7 / 164.9 us, unrolled by 1: 250.5 / 170.8, by 2: 248.0 / 161.2, by 3: 268.9 / 165.2
+//   general instantiation     not pipelined 292.5 / 171.4 us, unrolled by 1: 264.6 / 177.9, by 2: 273.3 / 169.8
+// hence: uniform-h both precisions unrolled by two (two entries' chains share one basic block), general double only, by one.
+#ifndef PAIR_UH_PIPE
+#define PAIR_UH_PIPE 3
+#endif
+#ifndef PAIR_GEN_PIPE
+#define PAIR_GEN_PIPE 1
+#endif
+#ifndef PAIR_PIPE_UNROLL
+#define PAIR_PIPE_UNROLL 2
+#endif
+#ifndef PAIR_GEN_PIPE_UNROLL
+#define PAIR_GEN_PIPE_UNROLL 1
+#endif
 
 // One staged candidate.  Array-of-structures in shared memory: a single address computation per candidate,
 // every field at a compile-time offset.  40 B (float) / 80 B (double) keeps 8 / 16-byte vector alignment.
@@ -398,6 +422,92 @@ k_pair(PairArgs a)
     double vx_st = 0.0, vy_st = 0.0;
     bool have_v = false;
     auto flush = [&](auto adj_tag) {
+#if (PAIR_UH_PIPE || PAIR_GEN_PIPE) && PAIR_LEAN
+        constexpr int PIPE_BIT = sizeof(Real) == 8 ? 1 : 2;
+        if constexpr (KID != OSPH_KERNEL_GAUSSIAN && (((UH ? PAIR_UH_PIPE : PAIR_GEN_PIPE) & PIPE_BIT) != 0)) {
+            constexpr bool ADJ = decltype(adj_tag)::value;
+            const int nl = LIST_COUNT();
+            // One basic block per entry, so that the instruction scheduler interleaves stage A of entry k + 1 with stage B of
+            // entry k (a warp issues in order: a stage A behind a branch of its own would simply run first).  Hence no
+            // branches: stage A always runs (past the end it re-reads the last entry), stage B always runs, on operands made
+            // harmless for an entry that is not a common pair -- r^2 := 1, h_ij := 1, m_j := 0, so every contribution is an
+            // exact zero -- and such an entry goes back into the list, behind the read position, for the bodies of `interact`.
+            // A common pair: fluid neighbour inside the kernel support, not `tiny`, no reference-cell test due.
+            int wr = tid;
+            int jn = 0;
+            Real dxn = 0, dyn = 0, r2n = 1, yn = 0, en = 0, hijn = 1;
+            bool qn = false;
+            auto stage_a = [&](const int j) {
+                const RecT *__restrict__ rj = sh_rec + j;
+                const Real2 pj = rj->pos;
+                const int info_j = rj->info;
+                dxn = xi - pj.x; dyn = yi - pj.y;
+                const Real r2 = dxn * dxn + dyn * dyn;
+                Real thr = UHC(h2c), hij = 1;
+                if constexpr (!UH) { hij = hi_half + rj->hp.x; thr = (hij * hij) * Real(4); }
+                const bool adjq_u = ADJ && (adj_i || (info_j & 4));
+                qn = (info_j & 1) != 0 && r2 <= thr && !PAIR_TINY() && !adjq_u;
+                // (the seed is taken from r^2 as it stands and made harmless afterwards: the selects stay off the MUFU chain)
+                Real y, e;
+                rsqrt_begin(r2, y, e);
+                r2n = qn ? r2 : Real(1); yn = qn ? y : Real(1); en = qn ? e : Real(0);
+                if constexpr (!UH) hijn = qn ? hij : Real(1);
+            };
+            if (nl > 0) { jn = (int)sh_list[tid]; stage_a(jn); }
+            const int last = (nl - 1) * NT + tid;
+            int rd = tid;
+            constexpr int PIPE_UNROLL = UH ? PAIR_PIPE_UNROLL : PAIR_GEN_PIPE_UNROLL;
+#pragma unroll PIPE_UNROLL
+            for (int k = 0; k < nl; k++) {
+                const int j = jn;
+                const Real dx = dxn, dy = dyn, r2 = r2n, y0 = yn, e0 = en, hij = hijn;
+                const bool quick = qn;
+                rd = min(rd + NT, last);
+                jn = (int)sh_list[rd];
+                stage_a(jn);
+                // stage B: the common body -- the expressions of `body` (not GUARDED; UHB in the uniform-h instantiation), with rs
+                // from its two halves: the same bits for the same pair
+                const RecT *__restrict__ rj = sh_rec + j;
+                const Real2 hpj = rj->hp;
+                const Real2 vj = rj->vel;
+                const Real2 rmj = rj->rm;
+                const Real rs = rsqrt_end(y0, e0);
+                const Real inv_h = UH ? UHC(inv_h) : rcp_fast(hij);
+                const Real rbar = rhoi_half + rmj.x;
+                const Real inv_rbar = rcp_fast(rbar);
+                const Real hbar = UH ? UHC(h) : fma(Real(0.5), hij, hi_half);
+                const Real inv_den = rcp_fast(UH ? r2 + UHC(c01) * hbar : r2 + Real(0.01) * hbar * hbar);
+                const Real r = r2 * rs;
+                const Real q = r * inv_h;
+                Real w, g;
+                if constexpr (UH) {
+                    if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair_a<Real, false, PAIR_ISIGN != 0>(q, UHC(alpha), inv_h, rs, w, g);
+                    else sph_kernel_a<Real, KID, false>(q, UHC(alpha), inv_h, rs, w, g);
+                } else {
+                    if constexpr (KID == OSPH_KERNEL_CUBIC) cubic_pair<Real, false, PAIR_ISIGN != 0>(q, inv_h, rs, w, g);
+                    else sph_kernel<Real, KID, false>(q, inv_h, rs, w, g);
+                }
+                const Real dwx = g * dx, dwy = g * dy;
+                const Real dvx = vxi - vj.x, dvy = vyi - vj.y;
+                const Real mj = quick ? rmj.y : Real(0);
+                drho += mj * (dvx * dwx + dvy * dwy);
+                const Real dot = PAIR_ISIGN ? neg_part_s(dvx * dx + dvy * dy) : neg_part(dvx * dx + dvy * dy);
+                const Real mu = hbar * dot * inv_den;
+                const Real PIij = mu * (PC(beta) * mu - PC(alpha_c)) * inv_rbar;
+                const Real fac = mj * (slf + hpj.y + PIij);
+                ax -= fac * dwx; ay -= fac * dwy;
+                if (use_xsph) {
+                    const Real fx = mj * w * inv_rbar;
+                    xs += fx * dvx; ys += fx * dvy;
+                }
+                if (!quick) { sh_list[wr] = (unsigned short)j; wr += NT; }
+            }
+#pragma unroll 1
+            for (int t = tid; t < wr; t += NT) interact(adj_tag, (int)sh_list[t]);
+            LIST_RESET();
+            return;
+        }
+#endif
 #if PAIR_PREFETCH_IDX
         const int nl = LIST_COUNT();
         int jn = nl > 0 ? (int)sh_list[tid] : 0;
@@ -784,6 +894,11 @@ static int pair_uh_constants(osph_ctx *ctx, PairArgs &a)
     return 1;
 }
 #endif
+
+int osph_pair_build_flags()
+{
+    return (PAIR_UH ? 1 : 0) | (PAIR_ISIGN ? 2 : 0) | (PAIR_UH && PAIR_UH_PIPE && PAIR_LEAN ? 4 : 0) | (PAIR_GEN_PIPE && PAIR_LEAN ? 8 : 0);
+}
 
 int osph_launch_pair(osph_ctx *ctx)
 {

@@ -57,6 +57,35 @@ __device__ __forceinline__ double rsqrt_fast(double x)
 }
 __device__ __forceinline__ float rsqrt_fast(float x) { return rsqrtf(x); }
 
+// rsqrt_fast in two halves, for a software-pipelined loop (pair.cu, PAIR_UH_PIPE): the seed and the first residual of entry
+// k + 1 are formed while entry k is evaluated.  Same operations as rsqrt_fast, hence the same bits.
+__device__ __forceinline__ void rsqrt_begin(double x, double &y, double &e)
+{
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if OSPH_NEWTON_STEPS == 0
+    e = fma(-(x * y), y, 1.0);
+#else
+    e = x;
+#endif
+}
+__device__ __forceinline__ double rsqrt_end(double y, double e)
+{
+#if OSPH_NEWTON_STEPS == 0
+    const double t = e * fma(e, 0.375, 0.5);
+    return fma(y, t, y);
+#else
+    const double hx = 0.5 * e;           // e carries x
+    double r = fma(-hx * y, y, 0.5); y = fma(y, r, y);
+    r = fma(-hx * y, y, 0.5); y = fma(y, r, y);
+#if OSPH_NEWTON_STEPS > 2
+    r = fma(-hx * y, y, 0.5); y = fma(y, r, y);
+#endif
+    return y;
+#endif
+}
+__device__ __forceinline__ void rsqrt_begin(float x, float &y, float &e) { y = rsqrtf(x); e = 0.f; }
+__device__ __forceinline__ float rsqrt_end(float y, float) { return y; }
+
 __device__ __forceinline__ double exp_neg(double x) { return exp(-x); }
 __device__ __forceinline__ float exp_neg(float x) { return __expf(-x); }
 

@@ -499,10 +499,11 @@ class Context:
         return int(self._L.osph_stream(self._h))
 
     def pair_kernel_info(self):
-        """(launches of the fused pair kernel so far, those that ran its uniform-smoothing-length instantiation)."""
-        out = (C.c_int64 * 2)()
+        """(launches of the fused pair kernel so far, those that ran its uniform-smoothing-length instantiation, build
+        flags: 1 that instantiation exists, 2 sign-bit clamps, 4 software-pipelined flush loop)."""
+        out = (C.c_int64 * 3)()
         self._ck(self._L.osph_pair_kernel_info(self._h, out))
-        return int(out[0]), int(out[1])
+        return int(out[0]), int(out[1]), int(out[2])
 
     def pair_kernel_time(self):
         us = C.c_double(0); n = C.c_int64(0)

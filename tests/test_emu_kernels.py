@@ -98,12 +98,20 @@ def test_pair_kernel_single_body_variant():
         capi.LIB_PATH, capi._lib = saved
 
 
-def test_pair_kernel_uniform_h_variant():
-    """-DPAIR_UH=1 -DPAIR_ISIGN=1: with Solver(h=value) the pair kernel's uniform-smoothing-length instantiation runs (loop
-    constants instead of the per-pair h terms for fluid neighbours, sign-bit clamps).  Same parity bar as the default build
-    on every golden case and oracle comparison, and the bits of the general instantiation (OSPH_UH=0) on the same input."""
+@pytest.mark.parametrize("defs,tag", [(("PAIR_UH=0", "PAIR_ISIGN=0", "PAIR_UH_PIPE=0", "PAIR_GEN_PIPE=0"), "_r2gate"),
+                                      (("PAIR_UH_PIPE=0", "PAIR_GEN_PIPE=0"), "_uhs"),
+                                      (("PAIR_GEN_PIPE=3", "PAIR_PIPE_UNROLL=1", "PAIR_CAP=96"), "_gp3cap96")])
+def test_pair_kernel_uniform_h_variant(defs, tag):
+    """The default build runs, with Solver(h=value), the pair kernel's uniform-smoothing-length instantiation (loop constants
+    instead of the per-pair h terms for fluid neighbours, sign-bit clamps) with a software-pipelined, branch-free flush loop
+    (the rare pairs deferred to the end of each flush), and pipelines the general double instantiation as well.  The other
+    settings of these knobs: `_r2gate` = the kernel of the round-2 hardware gate before them (no uniform-h instantiation, no
+    pipelining, FP64 clamps), `_uhs` = uniform-h without pipelining (bit-identical to the general instantiation), `_gp3cap96`
+    = every instantiation pipelined, on the batched staging path.  Same parity bar on every golden case and oracle comparison
+    (dynamic h, Gaussian, coupled rows and summation density included), and the bits of the general instantiation
+    (OSPH_UH=0) on the same input -- with pipelining up to the summation order of the deferred pairs."""
     from osph_b200 import capi
-    path = emu_build.build(defines=("PAIR_UH=1", "PAIR_ISIGN=1"), tag="_uhs")
+    path = emu_build.build(defines=defs, tag=tag)
     saved = (capi.LIB_PATH, capi._lib)
     capi.LIB_PATH, capi._lib = path, None
     mp = pytest.MonkeyPatch()
@@ -117,8 +125,9 @@ def test_pair_kernel_uniform_h_variant():
         _parity.test_dam_break_vs_oracle(150, 'cubic')
         _parity.test_dam_break_vs_oracle(150, 'gaussian')
         _parity.test_fp32_mode_close_to_fp64()
-        for kernel, precision in (('cubic', 'fp64'), ('wendland', 'fp64'), ('cubic', 'fp32'), ('wendland', 'fp32')):
-            _parity.test_uniform_h_instantiation_gives_the_bits_of_the_general_one(kernel, precision, mp)
+        if "PAIR_UH=0" not in defs:
+            for kernel, precision in (('cubic', 'fp64'), ('wendland', 'fp64'), ('cubic', 'fp32'), ('wendland', 'fp32')):
+                _parity.test_uniform_h_instantiation_gives_the_bits_of_the_general_one(kernel, precision, mp)
         _edges.test_coincident_particles_follow_the_reference_guards()
         _edges.test_cluster_denser_than_the_candidate_list()
         _edges.test_general_lennard_jones_exponents_and_beta_viscosity('cubic')

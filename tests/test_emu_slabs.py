@@ -101,9 +101,20 @@ def _worker(rank, world, port, lib, side, steps, kernel, fixed_dt, seq, q, sumde
                                                       (8, 'cubic', FIXED_DT, 'p2p')])
 def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt, seq):
     """fixed_dt None = the dynamic Courant / force time step, all-reduced every step (what bench.py --gpus N runs)."""
+    _slab_case(emu_build.build(), world, kernel, fixed_dt, seq)
+
+
+@pytest.mark.parametrize("world,kernel,fixed_dt,seq", [(2, 'cubic', None, 'p2p'), (3, 'wendland', FIXED_DT, 'python')])
+def test_emulated_slab_run_with_the_uniform_h_pair_kernel(world, kernel, fixed_dt, seq):
+    """The -DPAIR_UH=1 -DPAIR_ISIGN=1 build in slab mode: ghost fluid particles carry the smoothing length their owner wrote
+    (fixed_h on every rank), so the uniform-h instantiation serves owned and ghost neighbours alike; status stays 0
+    (OSPH_S_H_NOT_UNIFORM would show here) and the gathered result equals the single-rank run of the same build."""
+    _slab_case(emu_build.build(defines=("PAIR_UH=1", "PAIR_ISIGN=1"), tag="_uhs"), world, kernel, fixed_dt, seq)
+
+
+def _slab_case(lib, world, kernel, fixed_dt, seq):
     import queue
     import time
-    lib = emu_build.build()
     emu_build.build_fake_nccl()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

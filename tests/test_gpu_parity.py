@@ -283,24 +283,37 @@ def test_uniform_h_instantiation_gives_the_bits_of_the_general_one(kernel, preci
         cfg = capi.make_config(case['consts'], kernel, 'pec', prec, case['h'])
         with capi.Context(cfg) as ctx:
             ctx.upload(case['pA'])
+            ctx.compute()                                   # explicit-call path: one force evaluation of the uploaded state
+            first = ctx.download(case['pA'].copy())
             ctx.step(6, None, 0.05)
-            ctx.compute()                                   # explicit-call path as well
-            outs.append((ctx.download(case['pA'].copy()), ctx.dt_log(), ctx.pair_kernel_info()))
+            outs.append((ctx.download(case['pA'].copy()), ctx.dt_log(), ctx.pair_kernel_info(), first))
             assert ctx.sync() == 0
-    (a, dta, ia), (b, dtb, ib) = outs
-    assert ia == (7, 0)
-    if ib[1] == 0:
+    (a, dta, ia, a0), (b, dtb, ib, b0) = outs
+    assert ia[:2] == (7, 0)
+    if not ib[2] & 1:
         pytest.skip("library built without PAIR_UH: the general instantiation ran both times")
-    assert ib == (7, 7)
-    for f in STATE_FIELDS:
-        assert np.array_equal(a[f], b[f]), f              # -0 == +0: the sign-bit clamps may differ there
-    assert np.array_equal(dta, dtb)
+    assert ib[:2] == (7, 7)
+    if ib[2] & 4:
+        # software-pipelined flush loop: the rare pairs of a flush (wall and gate neighbours) are summed after its common ones
+        # -- equal to summation order, and bit-identical wherever a particle has no such neighbour
+        # (after a step the global dt carries the difference to every particle: the bitwise part looks at the first evaluation)
+        same = np.ones(len(a), bool)
+        for f in STATE_FIELDS:
+            assert field_err(b[f], a[f]) <= (1e-13 if precision == 'fp64' else 2e-6), f
+            assert field_err(b0[f], a0[f]) <= (1e-14 if precision == 'fp64' else 1e-6), f
+            same &= a0[f] == b0[f]
+        assert same.mean() > 0.8, same.mean()
+        assert np.allclose(dta, dtb, rtol=1e-12 if precision == 'fp64' else 1e-5, atol=0)
+    else:
+        for f in STATE_FIELDS:
+            assert np.array_equal(a[f], b[f]) and np.array_equal(a0[f], b0[f]), f       # -0 == +0: the sign-bit clamps may differ there
+        assert np.array_equal(dta, dtb)
     # smoothing length kept as uploaded: never the uniform-h instantiation, whatever the values are
     cfg = capi.make_config(case['consts'], kernel, 'pec', prec, case['h'], keep_h=True)
     with capi.Context(cfg) as ctx:
         ctx.upload(case['pA'])
         ctx.step(2, None, 0.05)
-        assert ctx.pair_kernel_info() == (2, 0)
+        assert ctx.pair_kernel_info()[:2] == (2, 0)
 
 
 def test_fp32_mode_close_to_fp64():
