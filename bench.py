@@ -298,6 +298,7 @@ def run_gpu(args):
     pair_us, pair_n = ctx.pair_kernel_time()
     status = ctx.sync()
     builds1, sorts1 = ctx.sort_stats()
+    pk_launches, pk_uniform, pk_flags = ctx.pair_kernel_info()
     value = n * args.steps / t_dev
 
     # ---- end to end through the plugin boundary, host buffers ---------------------------------
@@ -373,6 +374,9 @@ def run_gpu(args):
                    "l2": "per-step working set (%.0f MB state + sorted copies) exceeds the 126 MB L2" % (n * 19 * 8 / 1e6),
                    "neighbour_structure": "counting sort by cell; %d of the %d timed builds sorted, the others reused the binning "
                                           "(cells = pair radius + skin, OSPH_SKIN)" % (sorts1 - sorts0, builds1 - builds0),
+                   "pair_kernel": ("uniform-smoothing-length instantiation (Solver(h=value): h_ij terms of a fluid-fluid pair are loop "
+                                   "constants)" if pk_uniform == pk_launches else "general instantiation") +
+                                  (", software-pipelined flush loop" if pk_flags & (4 if pk_uniform == pk_launches else 8) else ""),
                    "parallelism": "1 GPU"},
         "clocks": clk, "gpu_launches": launches, "status_bits": status,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 154, "d2h_bytes_per_step": n * 154,

@@ -2,6 +2,7 @@
 # Hardware gate of HEAD (one B200):   gpurun --timeout 1500 -- 'bash tools/gpu_gate.sh [stage ...]'
 # Stages (default: tests sanitize bench):
 #   tests     pytest -m gpu (no -x: every failure is listed), smoke()
+#   memcheck  the memcheck runs of `sanitize` without the racecheck run
 #   sanitize  compute-sanitizer memcheck on the bench workload (1 M particles, both precisions, 2 steps) and on one golden
 #             case; racecheck on the golden case ("race detection")
 #   sanitize_multi  (needs 2 GPUs) memcheck over tests/multi_gpu_check.py: the three slab sequencers incl. the slab cadence
@@ -21,14 +22,14 @@ if has tests; then
   { echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25
     echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3; } >> $LOG 2>&1
 fi
-if has sanitize; then
+if has sanitize || has memcheck; then
   { for p in fp64 fp32; do
       echo "== memcheck bench $p"
       timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --precision $p 2>&1 | tail -12
       echo "rc=$?"
     done
     echo "== memcheck golden cases"; timeout 600 compute-sanitizer --tool memcheck --error-exitcode 99 python tools/sanitize_small.py 2>&1 | tail -8
-    echo "== racecheck golden case"; timeout 600 compute-sanitizer --tool racecheck --error-exitcode 99 python tools/sanitize_small.py 2>&1 | tail -8
+    if has sanitize; then echo "== racecheck golden case"; timeout 600 compute-sanitizer --tool racecheck --error-exitcode 99 python tools/sanitize_small.py 2>&1 | tail -8; fi
   } >> $LOG 2>&1
 fi
 if has sanitize_multi; then
