@@ -96,35 +96,53 @@ def time_oracle_step(case, kernel, budget_s=12.0, threads=None):
     from oracle import oracle as O
     threads = threads or host_threads()
     pA, c = case['pA'], case['consts']
-    P = O.Particles.from_aos(pA)
-    w = O.wcsph(c['height'], c['r0'], c['rho0'], True)
-    fluid = P.fluid
-    n_f = int(fluid.sum())
-    # cost model of the reference search: 9 cells of 1 m^2 -> candidates per particle (one thread: 3 ns per candidate,
-    # 36 ns per accepted pair, measured with this port; threads scale it by about 0.7 per thread)
+    n_f = int((pA['label'] == 0).sum())
+    # cost model of the reference search: 9 cells of 1 m^2 -> candidates per particle (one thread: 3-4 ns per candidate,
+    # 36 ns per accepted pair, measured with this port at 1 M and 16 M; threads scale it by about 0.7 per thread)
     cand = 9.0 * max(1.0, n_f / 625.0)
-    est = (n_f * cand * 3e-9 + n_f * 72 * 36e-9) / max(1.0, 0.7 * threads)
+    est = (n_f * cand * 4e-9 + n_f * 72 * 36e-9) / max(1.0, 0.7 * threads)
     stride = max(1, int(np.ceil(est / budget_s)))
     time_oracle_step.last_stride = stride
     time_oracle_step.last_threads = threads
-    t0 = time.perf_counter()
-    dt3 = O.timestep(P, fluid)
-    O.pec_predict(P, fluid, dt3[0], DAMPING, True, False)
-    grid = O.Grid(P, 2.0)
-    P.h[fluid.astype(bool)] = case['h']
-    t1 = time.perf_counter()
-    pairs = O.loop(P, w, grid, kernel, stride, 0, threads=threads)
-    t2 = time.perf_counter()
-    O.pec_correct(P, fluid, dt3[0], DAMPING, True, False)
-    t3 = time.perf_counter()
-    t_full = (t1 - t0) + (t3 - t2) + (t2 - t1) * stride
+    cache = getattr(time_oracle_step, "_cache", None)
+    if cache is not None and cache[0] is case and cache[1] == kernel:
+        # a later step of the same run: the phases outside the pair loop (time step, predictor, grid, corrector: 0.1 % of a
+        # step, all particles, one thread) are not repeated -- their time from the first step is added -- so that a run of
+        # many steps on 16 M particles stays within minutes; the pair loop is timed again on the same predicted state
+        _, _, P, w, grid, t_other = cache
+        t1 = time.perf_counter()
+        pairs = O.loop(P, w, grid, kernel, stride, 0, threads=threads)
+        t2 = time.perf_counter()
+        other_txt = "%.2f s, timed at the first step" % t_other
+    else:
+        P = O.Particles.from_aos(pA)
+        w = O.wcsph(c['height'], c['r0'], c['rho0'], True)
+        fluid = P.fluid
+        t0 = time.perf_counter()
+        dt3 = O.timestep(P, fluid)
+        O.pec_predict(P, fluid, dt3[0], DAMPING, True, False)
+        grid = O.Grid(P, 2.0)
+        P.h[fluid.astype(bool)] = case['h']
+        t1 = time.perf_counter()
+        pairs = O.loop(P, w, grid, kernel, stride, 0, threads=threads)
+        t2 = time.perf_counter()
+        # the corrector on a copy of the integrated fields: P stays the predicted state for the steps that follow
+        keep = {f: getattr(P, f).copy() for f in ('x', 'y', 'vx', 'vy', 'rho')}
+        O.pec_correct(P, fluid, dt3[0], DAMPING, True, False)
+        t3 = time.perf_counter()
+        for f, v in keep.items():
+            getattr(P, f)[:] = v
+        t_other = (t1 - t0) + (t3 - t2)
+        time_oracle_step._cache = (case, kernel, P, w, grid, t_other)
+        other_txt = "%.2f s" % t_other
+    t_full = t_other + (t2 - t1) * stride
     if stride == 1:
         sample = ("1 full step on all %d particles: pair loop on %d host threads (%d pairs, %.1f s), other phases on one "
-                  "thread (%.2f s)" % (P.n, threads, pairs, t2 - t1, (t1 - t0) + (t3 - t2)))
+                  "thread (%s)" % (P.n, threads, pairs, t2 - t1, other_txt))
     else:
         sample = ("1 step; pair loop on %d host threads over every %d-th fluid particle (%d of %d, %d pairs, %.1f s) scaled "
-                  "by %d; other phases on all %d particles (%.2f s)" % (threads, stride, (n_f + stride - 1) // stride, n_f,
-                                                                       pairs, t2 - t1, stride, P.n, (t1 - t0) + (t3 - t2)))
+                  "by %d; other phases on all %d particles (%s)" % (threads, stride, (n_f + stride - 1) // stride, n_f,
+                                                                    pairs, t2 - t1, stride, P.n, other_txt))
     return t_full, sample
 
 
