@@ -104,12 +104,12 @@ def test_emulated_slab_run_reproduces_single_rank_run(world, kernel, fixed_dt, s
     _slab_case(emu_build.build(), world, kernel, fixed_dt, seq)
 
 
-@pytest.mark.parametrize("world,kernel,fixed_dt,seq", [(2, 'cubic', None, 'p2p'), (3, 'wendland', FIXED_DT, 'python')])
-def test_emulated_slab_run_with_the_uniform_h_pair_kernel(world, kernel, fixed_dt, seq):
-    """The -DPAIR_UH=1 -DPAIR_ISIGN=1 build in slab mode: ghost fluid particles carry the smoothing length their owner wrote
-    (fixed_h on every rank), so the uniform-h instantiation serves owned and ghost neighbours alike; status stays 0
-    (OSPH_S_H_NOT_UNIFORM would show here) and the gathered result equals the single-rank run of the same build."""
-    _slab_case(emu_build.build(defines=("PAIR_UH=1", "PAIR_ISIGN=1"), tag="_uhs"), world, kernel, fixed_dt, seq)
+def test_emulated_slab_run_with_the_general_pair_kernel(monkeypatch):
+    """The default build runs the uniform-h instantiation of the pair kernel in every slab test of this file (fixed h: ghost
+    fluid particles carry the smoothing length their owner wrote, status stays 0 -- OSPH_S_H_NOT_UNIFORM would show).  Once with
+    OSPH_UH=0: the general (pipelined) instantiation in slab mode."""
+    monkeypatch.setenv("OSPH_UH", "0")
+    _slab_case(emu_build.build(), 2, 'cubic', None, 'p2p')
 
 
 def _slab_case(lib, world, kernel, fixed_dt, seq):
