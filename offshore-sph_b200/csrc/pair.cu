@@ -873,6 +873,10 @@ static int pair_uh_constants(osph_ctx *ctx, PairArgs &a)
     const bool off = env && env[0] == '0';
     const osph_config &c = ctx->cfg;
     if (off || c.dynamic_h != OSPH_H_FIXED || !(c.fixed_h > 0.0) || !std::isfinite(c.fixed_h) || c.kernel == OSPH_KERNEL_GAUSSIAN) return 0;
+    // The pipelined loop evaluates stage B for EVERY list entry and makes the operands of a non-common entry harmless with
+    // r^2 := 1 and m_j := 0; in this instantiation q is then 1 / h, and the Wendland polynomial (degree 8 in q) leaves the float
+    // range for h below about 1.5e-5: such a set-up runs the general instantiation, whose stand-in is q = 1 whatever h is.
+    if (c.precision == OSPH_FP32 && c.kernel == OSPH_KERNEL_WENDLAND && c.fixed_h < 1e-3) return 0;
     if (!(ctx->uh_ready && ctx->uh_for_h == c.fixed_h && ctx->uh_for_kernel == c.kernel && ctx->uh_for_prec == c.precision)) {
         if (!ctx->d_uh && cudaMalloc(&ctx->d_uh, 8 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return 0; }
         const bool cubic = c.kernel == OSPH_KERNEL_CUBIC;

@@ -316,6 +316,28 @@ def test_uniform_h_instantiation_gives_the_bits_of_the_general_one(kernel, preci
         assert ctx.pair_kernel_info()[:2] == (2, 0)
 
 
+def test_uniform_h_instantiation_is_not_used_where_its_float_stand_in_could_overflow():
+    """Float Wendland with a smoothing length below 1e-3: the pipelined uniform-h loop would evaluate its stand-in entries at
+    q = 1 / h, beyond the float range of the degree-8 polynomial for h < 1.5e-5 -- the host selects the general instantiation
+    there (its stand-in is q = 1).  Double, and float with the cubic spline, keep the uniform-h instantiation."""
+    case = W.dam_break_case(20, seed=3)
+    scale = 4e-4                                           # the same particle set shrunk to a spacing of 0.5 mm, h = 0.8 mm
+    pA = case['pA'].copy()
+    pA['x'] *= scale; pA['y'] *= scale
+    consts = dict(case['consts'], r0=case['consts']['r0'] * scale)
+    for kernel, prec, expect_uh in (('wendland', capi.FP32, False), ('wendland', capi.FP64, True), ('cubic', capi.FP32, True)):
+        cfg = capi.make_config(consts, kernel, 'pec', prec, case['h'] * scale)
+        with capi.Context(cfg) as ctx:
+            ctx.upload(pA)
+            ctx.step(2, None, 0.05)
+            launches, uniform, flags = ctx.pair_kernel_info()
+            cols = ctx.download_fields(['ax', 'ay', 'drho', 'x'])
+            assert ctx.sync() & capi.S_NONFINITE == 0
+        if flags & 1:
+            assert (uniform == launches) == expect_uh, (kernel, prec, launches, uniform)
+        assert all(np.all(np.isfinite(c)) for c in cols.values())
+
+
 def test_fp32_mode_close_to_fp64():
     """Performance mode: float pair arithmetic on anchor-relative positions; drift bounded and reported."""
     case = W.dam_break_case(100, seed=7)
