@@ -370,6 +370,11 @@ class Solver:
         if status & capi.S_NONFINITE and not getattr(self, '_warned_nonfinite', False):
             self._warned_nonfinite = True
             println('WARNING! non-finite particle state produced on the device.')
+        if status & capi.S_H_NOT_UNIFORM:
+            # the uniform-h pair kernel took h of every fluid particle from Solver(h=...), and one carried another value:
+            # the rates of its neighbours are wrong -- never continue silently (OSPH_UH=0 selects the general kernel)
+            raise RuntimeError('device status OSPH_S_H_NOT_UNIFORM: a fluid particle reached the pair kernel with a '
+                               'smoothing length other than Solver(h=...); rerun with OSPH_UH=0 and report this')
         return status
 
     def _export_drain(self):
