@@ -13,4 +13,14 @@ tools/build_variants.sh \
   scan2p   "-DPAIR_SCAN2=1 -DPAIR_LISTPTR=1" \
   scan2p8  "-DPAIR_SCAN2=1 -DPAIR_LISTPTR=1 -DPAIR_SCAN=8" \
   prep1    "-DPREP_ITEMS=1" \
-  prep4    "-DPREP_ITEMS=4"
+  prep4    "-DPREP_ITEMS=4" \
+  r2gate   "-DPAIR_UH=0 -DPAIR_ISIGN=0 -DPAIR_UH_PIPE=0 -DPAIR_GEN_PIPE=0" \
+  isign    "-DPAIR_UH=0 -DPAIR_UH_PIPE=0 -DPAIR_GEN_PIPE=0" \
+  uhs      "-DPAIR_UH_PIPE=0 -DPAIR_GEN_PIPE=0" \
+  uhp1     "-DPAIR_PIPE_UNROLL=1 -DPAIR_GEN_PIPE=0" \
+  uhp3     "-DPAIR_PIPE_UNROLL=3 -DPAIR_GEN_PIPE=0" \
+  gp2      "-DPAIR_GEN_PIPE=3 -DPAIR_GEN_PIPE_UNROLL=2" \
+  gp1f     "-DPAIR_GEN_PIPE=3"
+# (the last seven: the uniform-h / pipelined-flush knobs of the pair kernel against the default build = uniform-h instantiation
+#  pipelined in both precisions and unrolled by two, general double instantiation pipelined; r2gate = the kernel before them;
+#  measured with tools/gpu_uh_variants*.sh, profiles/r02/variants_uniform_h.log, variants_pipelined*.log)
